@@ -1,0 +1,140 @@
+/*
+ * pgmuvi_b200 - C ABI of the B200-native exact-GP training engine.
+ *
+ * Drop-in boundary for ONE path of ICSM/pgmuvi: spectral-mixture kernel build ->
+ * Cholesky exact marginal log-likelihood -> hyper-parameter gradient -> Adam step.
+ * The reference has no FFI of its own (it is pure Python on GPyTorch); each entry point
+ * below cites the reference interface it replaces.  A maintainer binds these with ctypes
+ * (see INTEGRATION.md); pgmuvi_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes; every pointer is a DEVICE pointer unless it says "host";
+ *  - all buffers are caller-owned, kernels never allocate, outputs are written in place;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return value: 0 ok, <0 bad argument / launch failure (pgm_last_error() has the text);
+ *  - per-light-curve status goes to info[B]:
+ *        0      Cholesky succeeded without jitter
+ *        1..3   succeeded after adding jitter 1e-8*10^(k-1) (f64) / 1e-6*10^(k-1) (f32)
+ *               to the diagonal (GPyTorch psd_safe_cholesky ladder)
+ *        -1     NaN encountered (GPyTorch NanError)
+ *        -2     not positive definite after 3 jitter tries (GPyTorch NotPSDError)
+ *
+ * Packed raw-parameter layout, P = 1 + Q + 2*Q*d (+1 if PGM_FLAG_LEARN_NOISE):
+ *     [ mean | w[0..Q) | mu[q*d+k] | sigma[q*d+k] | (learned noise) ]
+ * mirroring gpytorch's raw_constant, raw_mixture_weights [Q], raw_mixture_means [Q,1,d],
+ * raw_mixture_scales [Q,1,d], raw_noise [1] (pgmuvi/lightcurve.py:3847-3849, 6475-6480).
+ */
+#ifndef PGMUVI_B200_H
+#define PGMUVI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kernel kinds: gpytorch.kernels.SpectralMixtureKernel as instantiated at
+ * pgmuvi/gps.py:208 (1-D) and :305 (ard_num_dims=2). */
+#define PGM_KIND_SM1D 0          /* d = 1: sum_q w_q E_q C_q                               */
+#define PGM_KIND_SM_ARD_PRODSUM 1 /* d = 2: prod_d sum_q w_q E_qd C_qd  (GPyTorch order)    */
+#define PGM_KIND_SM_ARD_SUMPROD 2 /* d = 2: sum_q w_q prod_d E_qd C_qd  (switchable variant) */
+
+/* constraint kinds: gpytorch.constraints chosen at pgmuvi/lightcurve.py:3817-4008 */
+#define PGM_CON_NONE 0     /* value = raw                                         */
+#define PGM_CON_SOFTPLUS 1 /* Positive / GreaterThan(lb): softplus(raw) + lb      */
+#define PGM_CON_INTERVAL 2 /* Interval(lb, ub): lb + (ub - lb) * sigmoid(raw)     */
+
+/* flags */
+#define PGM_FLAG_GRAD 1          /* also compute d MLL / d raw (loss.backward, trainers.py:181) */
+#define PGM_FLAG_LEARN_NOISE 2   /* last slot is a learnable homoskedastic noise variance       */
+#define PGM_FLAG_BOUNDS_PER_LC 4 /* con_lb / con_ub are [B,P] (else [P], shared)                */
+
+/* optimiser kinds: torch.optim.* as selected at pgmuvi/trainers.py:141-147 */
+#define PGM_OPT_SGD 0
+#define PGM_OPT_ADAM 1
+#define PGM_OPT_ADAMW 2
+
+int pgm_version(void);
+const char* pgm_last_error(void); /* host string, thread-local */
+
+/* Bytes of device workspace the f64 / f32 entry points below need for light curves of up
+ * to n_max points (independent of B: the workspace is per resident thread block). */
+size_t pgm_workspace_bytes(int elem_size, int n_max, int d, int Q, int device);
+
+/*
+ * MLL (+ gradient) of B independent light curves.
+ * Replaces, per light curve, one pass of  model(train_x) -> -ExactMarginalLogLikelihood ->
+ * loss.backward()  (pgmuvi/trainers.py:179-181; gps.py:217-220, 315-318).
+ *
+ *  x            [B, n_max, d]  inputs (time [, wavelength]), row-major as train_x
+ *  n_valid      [B] or NULL    true n per light curve (ragged batches); NULL => n_max
+ *  y            [B, n_max]
+ *  fixed_noise  [B, n_max] or NULL  per-point noise VARIANCE (FixedNoiseGaussianLikelihood,
+ *                                   lightcurve.py:2780-2789), already clamped by the host
+ *  raw          [B, P]         packed raw parameters
+ *  con_kind     [P] (int32), con_lb / con_ub  [P] or [B,P]   constraint table
+ *  mll          [B]   out: per-datum marginal log-likelihood  (loss = -mll)
+ *  grad_raw     [B,P] out: d mll / d raw   (only with PGM_FLAG_GRAD; may be NULL otherwise)
+ *  info         [B]   out: see above
+ */
+int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y,
+                        const double* fixed_noise, const double* raw,
+                        const int32_t* con_kind, const double* con_lb, const double* con_ub,
+                        int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                        double* mll, double* grad_raw, int32_t* info,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Dense covariance K + D of each light curve, written to K_out [B, n_max, n_max] (rows /
+ * columns >= n_valid are left untouched).  Replaces SpectralMixtureKernel.forward(x, x) +
+ * likelihood noise (gps.py:208, 305; lightcurve.py:2786-2807).  Same device code as the
+ * fused path's on-the-fly builder; exists for parity tests and the large-n path.
+ */
+int pgm_sm_kernel_dense_f64(const double* x, const int32_t* n_valid, const double* fixed_noise,
+                            const double* raw, const int32_t* con_kind, const double* con_lb,
+                            const double* con_ub, int B, int n_max, int d, int Q,
+                            int kernel_kind, int flags, double* K_out, void* stream);
+
+/*
+ * One optimiser step on packed raw parameters of B light curves, in place.
+ * Replaces optimizer.step() (trainers.py:182) for torch.optim.SGD / Adam / AdamW with
+ * torch defaults (betas given, eps, weight_decay: Adam -> added to the gradient, AdamW ->
+ * decoupled).  grad_mll is d mll / d raw as produced above; the step minimises loss = -mll.
+ * `active` ([B] int32 or NULL) masks light curves that already stopped.  step counts from 1.
+ */
+int pgm_optim_step_f64(double* raw, const double* grad_mll, double* exp_avg, double* exp_avg_sq,
+                       const int32_t* active, int B, int P, int optim_kind, double lr,
+                       double beta1, double beta2, double eps, double weight_decay, int step,
+                       void* stream);
+
+/*
+ * Whole training loop on device: maxiter x (MLL+grad -> optimiser step), every light curve
+ * independent, no host synchronisation inside.  Replaces pgmuvi.trainers.train
+ * (trainers.py:12-209) for a batch: same loss/parameter history and early-stop rule
+ * (`stop and i > miniter and std(loss[-stopavg:]) < stop`, trainers.py:200-207).
+ *
+ *  raw           [B,P]  in: initial raw parameters; out: final
+ *  loss_hist     [maxiter, B] out: loss (= -mll) evaluated before each step; NaN after stop
+ *  raw_hist      [maxiter+1, B, P] or NULL  out: raw parameters, initial value first
+ *  n_iter        [B] out: iterations executed per light curve
+ *  opt_state     [2, B, P] scratch for exp_avg / exp_avg_sq (zeroed by the call)
+ */
+int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
+                   const double* fixed_noise, double* raw, const int32_t* con_kind,
+                   const double* con_lb, const double* con_ub, int B, int n_max, int d, int Q,
+                   int kernel_kind, int flags, int optim_kind, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int maxiter, int miniter,
+                   double stop, int stopavg, double* loss_hist, double* raw_hist,
+                   int32_t* n_iter, int32_t* info, double* opt_state, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Device yardsticks used by bench.py for the self-measured FP64 roofline: runs `iters`
+ * dependent-free DMMA (kind 0) or DFMA (kind 1) instructions per thread on every SM and
+ * returns achieved TFLOP/s in *tflops (host pointer). */
+int pgm_peak_probe(int kind, int iters, double* tflops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGMUVI_B200_H */

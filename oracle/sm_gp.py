@@ -1,0 +1,387 @@
+"""Torch-CPU restatement of the reference hot path (oracle + CPU baseline).
+
+TEST INFRASTRUCTURE - see ``oracle/__init__.py`` (parity unpinned at the GPyTorch
+boundary).  Every function cites what it follows.  Reference paths are relative to
+``/root/reference``; "A.n" is SURVEY.md Appendix A (restated GPyTorch maths, whose source
+is not vendored in the reference tree).
+
+The path (pgmuvi/trainers.py:177-182):
+
+    output = model(train_x)              # gps.py:217-220 ConstantMean + SpectralMixtureKernel
+    loss   = -ExactMLL(output, train_y)  # trainers.py:119,180  (Cholesky, per-datum)
+    loss.backward()                      # trainers.py:181
+    optimizer.step()                     # trainers.py:141-147,182 (SGD/Adam/AdamW on RAW params)
+
+Packed raw-parameter layout used by the oracle, the C ABI and the golden files
+(``P = 1 + Q + 2*Q*d (+1)``)::
+
+    [ mean | w[0..Q) | mu[q*d + k] | sigma[q*d + k] | (learned noise) ]
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+# kernel kinds -------------------------------------------------------------------------
+KIND_SM1D = 0              # gps.py:208  SMK(num_mixtures=Q)                       (d = 1)
+KIND_SM_ARD_PRODSUM = 1    # gps.py:305  SMK(ard_num_dims=2): prod_d sum_q (GPyTorch; F7)
+KIND_SM_ARD_SUMPROD = 2    # switchable variant: sum_q w_q prod_d (notebook tinygp cell; F7)
+
+# constraint kinds (A.2) ---------------------------------------------------------------
+CON_NONE = 0       # value = raw
+CON_SOFTPLUS = 1   # Positive / GreaterThan(lb): value = softplus(raw) + lb
+CON_INTERVAL = 2   # Interval(lb, ub):           value = lb + (ub - lb) * sigmoid(raw)
+
+TWO_PI = 2.0 * math.pi
+
+
+@dataclass(frozen=True)
+class ModelSpec:
+    """Static description of one model family on the path."""
+
+    d: int = 1                 # input dims (1: time; 2: time, wavelength)
+    Q: int = 4                 # num_mixtures (gps.py:205 default 4)
+    kind: int = KIND_SM1D
+    learn_noise: bool = False  # GaussianLikelihood / FixedNoise(learn_additional_noise)
+    # fixed per-point noise is a data argument (None -> absent)
+
+    @property
+    def P(self) -> int:
+        return 1 + self.Q + 2 * self.Q * self.d + (1 if self.learn_noise else 0)
+
+    # slot offsets in the packed layout
+    @property
+    def o_w(self):
+        return 1
+
+    @property
+    def o_mu(self):
+        return 1 + self.Q
+
+    @property
+    def o_sigma(self):
+        return 1 + self.Q + self.Q * self.d
+
+    @property
+    def o_noise(self):
+        return 1 + self.Q + 2 * self.Q * self.d
+
+
+# ---------------------------------------------------------------------------------------
+# constraints (A.2; chosen by lightcurve.py:3817-4008, SMK defaults Positive)
+# ---------------------------------------------------------------------------------------
+def constrain(raw, kinds, lb, ub):
+    """raw -> constrained value, elementwise.  kinds int tensor/array [P]."""
+    kinds = torch.as_tensor(kinds)
+    sp = torch.nn.functional.softplus(raw) + lb
+    iv = lb + (ub - lb) * torch.sigmoid(raw)
+    out = torch.where(kinds == CON_SOFTPLUS, sp, raw)
+    out = torch.where(kinds == CON_INTERVAL, iv, out)
+    return out
+
+
+def unconstrain(val, kinds, lb, ub):
+    """Inverse of :func:`constrain` (A.2: log(expm1(v-lb)); logit((v-lb)/(ub-lb)))."""
+    kinds = torch.as_tensor(kinds)
+    val = torch.as_tensor(val)
+    lb = torch.as_tensor(lb, dtype=val.dtype)
+    ub = torch.as_tensor(ub, dtype=val.dtype)
+    v = val - lb
+    # inv softplus: x + log(-expm1(-x)), stable for large x
+    sp = torch.where(v > 30, v, v + torch.log(-torch.expm1(-v.clamp(min=1e-300))))
+    u = (v / (ub - lb)).clamp(1e-300, 1 - 1e-16)
+    iv = torch.log(u) - torch.log1p(-u)
+    out = torch.where(kinds == CON_SOFTPLUS, sp, val)
+    out = torch.where(kinds == CON_INTERVAL, iv, out)
+    return out
+
+
+def unpack_params(theta, spec: ModelSpec):
+    """Split a packed (constrained or raw) vector [..., P] into named pieces."""
+    Q, d = spec.Q, spec.d
+    mean = theta[..., 0]
+    w = theta[..., spec.o_w:spec.o_w + Q]
+    mu = theta[..., spec.o_mu:spec.o_mu + Q * d].reshape(*theta.shape[:-1], Q, d)
+    sigma = theta[..., spec.o_sigma:spec.o_sigma + Q * d].reshape(*theta.shape[:-1], Q, d)
+    noise = theta[..., spec.o_noise] if spec.learn_noise else None
+    return mean, w, mu, sigma, noise
+
+
+# ---------------------------------------------------------------------------------------
+# kernel (A.3: gpytorch.kernels.SpectralMixtureKernel.forward, instantiated gps.py:208,305)
+# ---------------------------------------------------------------------------------------
+def sm_kernel_dense(x1, x2, w, mu, sigma, kind=KIND_SM1D):
+    """Dense spectral-mixture covariance, following GPyTorch's op order.
+
+    x1 [..., n, d], x2 [..., m, d]; w [..., Q]; mu, sigma [..., Q, d].
+    tau is formed as ``x1*p - x2*p`` (scale, then subtract) as GPyTorch does (F8).
+    Returns [..., n, m].
+    """
+    x1_ = x1.unsqueeze(-3)                         # [..., 1, n, d]
+    x2_ = x2.unsqueeze(-3)
+    sc = sigma.unsqueeze(-2)                       # [..., Q, 1, d]
+    mn = mu.unsqueeze(-2)
+    x1e, x2e = x1_ * sc, x2_ * sc                  # [..., Q, n, d]
+    x1c, x2c = x1_ * mn, x2_ * mn
+    exp_term = (x1e.unsqueeze(-2) - x2e.unsqueeze(-3)).pow(2).mul(-2 * math.pi ** 2)
+    cos_term = (x1c.unsqueeze(-2) - x2c.unsqueeze(-3)).mul(TWO_PI)
+    res = exp_term.exp() * cos_term.cos()          # [..., Q, n, m, d]
+    if kind in (KIND_SM1D, KIND_SM_ARD_PRODSUM):
+        # "Sum over mixtures" then "Product over dimensions" (F7 / A.3)
+        ww = w.unsqueeze(-1).unsqueeze(-1).unsqueeze(-1)
+        return (res * ww).sum(-4).prod(-1)
+    if kind == KIND_SM_ARD_SUMPROD:
+        ww = w.unsqueeze(-1).unsqueeze(-1)
+        return (res.prod(-1) * ww).sum(-3)
+    raise ValueError(f"unknown kernel kind {kind}")
+
+
+def noise_diag(n, fixed_noise, learned_noise, dtype):
+    """A.4: D = diag(fixed) (+ sigma^2 I).  fixed_noise is already squared/clamped by the
+    host layer (lightcurve.py:2780-2784; GPyTorch min_fixed_noise clamp)."""
+    dvec = torch.zeros(n, dtype=dtype)
+    if fixed_noise is not None:
+        dvec = dvec + fixed_noise
+    if learned_noise is not None:
+        dvec = dvec + learned_noise.unsqueeze(-1)
+    return dvec
+
+
+# ---------------------------------------------------------------------------------------
+# Cholesky with GPyTorch's jitter ladder (A.5: linear_operator psd_safe_cholesky)
+# ---------------------------------------------------------------------------------------
+def psd_safe_cholesky(A, max_tries=3):
+    """Try plain; on failure add jitter*10^i (1e-6 fp32 / 1e-8 fp64) to failed members only.
+
+    Returns (L, info) with info[b] = 0 ok without jitter, k>0 = succeeded at jitter try k,
+    -1 = NaN input (NanError), -2 = not PD after max_tries (NotPSDError).
+    """
+    batch = A.shape[:-2]
+    Af = A.reshape(-1, *A.shape[-2:]).clone()
+    info_out = torch.zeros(Af.shape[0], dtype=torch.int32)
+    nan = torch.isnan(Af).flatten(1).any(1)
+    info_out[nan] = -1
+    L, info = torch.linalg.cholesky_ex(Af)
+    bad = (info > 0) & ~nan
+    jitter = 1e-6 if A.dtype == torch.float32 else 1e-8
+    prev = 0.0
+    for i in range(max_tries):
+        if not bad.any():
+            break
+        jn = jitter * (10 ** i)
+        idx = torch.nonzero(bad).flatten()
+        Aj = Af[idx]
+        Aj.diagonal(dim1=-2, dim2=-1).add_(jn - prev)
+        Af[idx] = Aj
+        prev = jn
+        Lj, ij = torch.linalg.cholesky_ex(Aj)
+        L[idx] = Lj
+        ok = ij == 0
+        info_out[idx[ok]] = i + 1
+        bad[idx[ok]] = False
+    info_out[bad] = -2
+    return L.reshape(*batch, *A.shape[-2:]), info_out.reshape(batch)
+
+
+# ---------------------------------------------------------------------------------------
+# exact MLL (A.5: ExactMarginalLogLikelihood.forward -> MVN.log_prob, per datum)
+# ---------------------------------------------------------------------------------------
+def _mll_from_theta(x, y, fixed_noise, theta, spec: ModelSpec):
+    """Per-datum MLL from constrained theta.  x [n,d], y [n], theta [P]."""
+    n = y.shape[-1]
+    mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    K = sm_kernel_dense(x, x, w, mu, sigma, spec.kind)
+    Kt = K + torch.diag_embed(noise_diag(n, fixed_noise, noise, y.dtype))
+    L, info = psd_safe_cholesky(Kt.detach())
+    if int(info) > 0:  # re-apply the jitter that made it succeed, keeping the graph
+        jitter = (1e-6 if y.dtype == torch.float32 else 1e-8) * 10 ** (int(info) - 1)
+        Kt = Kt + jitter * torch.eye(n, dtype=y.dtype)
+    if int(info) < 0:
+        return torch.full((), float("nan"), dtype=y.dtype), info
+    L = torch.linalg.cholesky(Kt)
+    r = (y - mean).unsqueeze(-1)
+    z = torch.linalg.solve_triangular(L, r, upper=False)
+    inv_quad = (z * z).sum()
+    logdet = 2.0 * torch.log(torch.diagonal(L)).sum()
+    mll = -0.5 * (inv_quad + logdet + n * math.log(TWO_PI)) / n
+    return mll, info
+
+
+def mll_and_grad_autograd(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec):
+    """One light curve through GPyTorch's op sequence with torch autograd
+    (trainers.py:179-181).  Returns (mll, dmll/draw [P], info)."""
+    raw = raw.detach().clone().requires_grad_(True)
+    theta = constrain(raw, kinds, lb, ub)
+    mll, info = _mll_from_theta(x, y, fixed_noise, theta, spec)
+    if int(info) < 0:
+        return mll.detach(), torch.full_like(raw, float("nan")).detach(), info
+    (g,) = torch.autograd.grad(mll, raw)
+    return mll.detach(), g, info
+
+
+def constraint_jacobian(raw, kinds, lb, ub):
+    """d value / d raw (A.2)."""
+    kinds = torch.as_tensor(kinds)
+    s = torch.sigmoid(raw)
+    j = torch.ones_like(raw)
+    j = torch.where(kinds == CON_SOFTPLUS, s, j)
+    j = torch.where(kinds == CON_INTERVAL, (ub - lb) * s * (1 - s), j)
+    return j
+
+
+def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec):
+    """Same quantity via the closed form of A.5 (what the CUDA gradient kernel computes):
+
+        W = alpha alpha^T - Kt^-1,  dMLL/dtheta = (1/2n) sum_ij W_ij dK_ij/dtheta,
+        dMLL/dnoise = (1/2n) tr W,  dMLL/dc = (1/n) sum_i alpha_i,   then x Jacobian.
+    """
+    dt = y.dtype
+    n = y.shape[-1]
+    Q, d = spec.Q, spec.d
+    theta = constrain(raw, kinds, lb, ub)
+    mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    K = sm_kernel_dense(x, x, w, mu, sigma, spec.kind)
+    Kt = K + torch.diag_embed(noise_diag(n, fixed_noise, noise, dt))
+    L, info = psd_safe_cholesky(Kt)
+    if int(info) < 0:
+        nanv = torch.full((), float("nan"), dtype=dt)
+        return nanv, torch.full_like(raw, float("nan")), info
+    r = (y - mean).unsqueeze(-1)
+    alpha = torch.cholesky_solve(r, L)
+    Kinv = torch.cholesky_inverse(L)
+    inv_quad = (r * alpha).sum()
+    logdet = 2.0 * torch.log(torch.diagonal(L)).sum()
+    mll = -0.5 * (inv_quad + logdet + n * math.log(TWO_PI)) / n
+    W = alpha @ alpha.T - Kinv
+
+    tau = x.unsqueeze(-2) - x.unsqueeze(-3)                     # [n, n, d]
+    E = torch.exp(-2 * math.pi ** 2 * (tau.unsqueeze(0) * sigma[:, None, None, :]) ** 2)
+    ph = TWO_PI * tau.unsqueeze(0) * mu[:, None, None, :]       # [Q, n, n, d]
+    C, S = torch.cos(ph), torch.sin(ph)
+    EC = E * C
+    g = torch.zeros(spec.P, dtype=dt)
+    g[0] = alpha.sum() / n
+    half = 0.5 / n
+    if spec.kind in (KIND_SM1D, KIND_SM_ARD_PRODSUM):
+        Sd = (w[:, None, None, None] * EC).sum(0)               # [n, n, d]
+        for k in range(d):
+            R = torch.ones(n, n, dtype=dt)
+            for k2 in range(d):
+                if k2 != k:
+                    R = R * Sd[..., k2]
+            WR = W * R
+            for q in range(Q):
+                g[spec.o_w + q] += half * (WR * EC[q, ..., k]).sum()
+                g[spec.o_mu + q * d + k] = half * (
+                    WR * (-TWO_PI * tau[..., k] * w[q] * E[q, ..., k] * S[q, ..., k])).sum()
+                g[spec.o_sigma + q * d + k] = half * (
+                    WR * (-4 * math.pi ** 2 * tau[..., k] ** 2 * sigma[q, k] * w[q]
+                          * EC[q, ..., k])).sum()
+    else:  # sum over q of w_q prod_d
+        for q in range(Q):
+            Pq = EC[q].prod(-1)
+            g[spec.o_w + q] = half * (W * Pq).sum()
+            for k in range(d):
+                Rq = torch.ones(n, n, dtype=dt)
+                for k2 in range(d):
+                    if k2 != k:
+                        Rq = Rq * EC[q, ..., k2]
+                g[spec.o_mu + q * d + k] = half * (
+                    W * Rq * (-TWO_PI * tau[..., k] * w[q] * E[q, ..., k] * S[q, ..., k])).sum()
+                g[spec.o_sigma + q * d + k] = half * (
+                    W * Rq * (-4 * math.pi ** 2 * tau[..., k] ** 2 * sigma[q, k] * w[q]
+                              * EC[q, ..., k])).sum()
+    if spec.learn_noise:
+        g[spec.o_noise] = half * torch.diagonal(W).sum()
+    g = g * constraint_jacobian(raw, kinds, lb, ub)
+    return mll, g, info
+
+
+# ---------------------------------------------------------------------------------------
+# batched CPU baseline (torch batch mode; same op sequence, autograd) - BASELINE.md section 3
+# ---------------------------------------------------------------------------------------
+def batched_mll_and_grad(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec):
+    """x [B,n,d], y [B,n], fixed_noise [B,n] or None, raw/lb/ub [B,P].  No jitter ladder
+    (used for timing and for well-conditioned parity cases).  Returns (mll [B], grad [B,P])."""
+    raw = raw.detach().clone().requires_grad_(True)
+    theta = constrain(raw, kinds, lb, ub)
+    mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    n = y.shape[-1]
+    K = sm_kernel_dense(x, x, w, mu, sigma, spec.kind)
+    dvec = torch.zeros_like(y)
+    if fixed_noise is not None:
+        dvec = dvec + fixed_noise
+    if noise is not None:
+        dvec = dvec + noise.unsqueeze(-1)
+    Kt = K + torch.diag_embed(dvec)
+    L = torch.linalg.cholesky(Kt)
+    r = (y - mean.unsqueeze(-1)).unsqueeze(-1)
+    z = torch.linalg.solve_triangular(L, r, upper=False)
+    inv_quad = (z * z).sum((-2, -1))
+    logdet = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
+    mll = -0.5 * (inv_quad + logdet + n * math.log(TWO_PI)) / n
+    (g,) = torch.autograd.grad(mll.sum(), raw)
+    return mll.detach(), g
+
+
+# ---------------------------------------------------------------------------------------
+# optimisers (A.7: torch.optim defaults as used at trainers.py:141-147)
+# ---------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8, weight_decay=0.0,
+              decoupled=False):
+    """One Adam (decoupled=False, wd added to grad) / AdamW (decoupled=True) step, torch
+    semantics.  ``g`` is the gradient of the LOSS (= -MLL).  step counts from 1.
+    Works on numpy arrays or torch tensors; returns (p, m, v)."""
+    if decoupled:
+        p = p * (1.0 - lr * weight_decay)
+    elif weight_decay != 0.0:
+        g = g + weight_decay * p
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = (v ** 0.5) / math.sqrt(bc2) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v
+
+
+def train_loop(x, y, fixed_noise, raw0, kinds, lb, ub, spec: ModelSpec, maxiter=100,
+               miniter=10, stop=None, lr=1e-4, optim="SGD", eps=1e-8, stopavg=9,
+               use_torch_optim=True):
+    """trainers.py:167-209 restated for one light curve on packed raw parameters.
+
+    Returns dict(loss=[...], delta_loss=[...], raw=[P-vectors, initial first]).  The loss
+    recorded at iteration i is evaluated BEFORE that iteration's step (trainers.py:179-188);
+    parameters are recorded AFTER it (trainers.py:190-192).
+    """
+    raw = raw0.detach().clone().requires_grad_(True)
+    if optim == "SGD":
+        opt = torch.optim.SGD([raw], lr=lr)
+    elif optim == "Adam":
+        opt = torch.optim.Adam([raw], lr=lr, eps=eps)
+    elif optim == "AdamW":
+        opt = torch.optim.AdamW([raw], lr=lr, eps=eps)
+    else:
+        raise ValueError("optim must be 'SGD', 'Adam' or 'AdamW'")
+    res = {"loss": [], "delta_loss": [], "raw": [raw.detach().clone().numpy()]}
+    for i in range(maxiter):
+        opt.zero_grad()
+        theta = constrain(raw, kinds, lb, ub)
+        mll, info = _mll_from_theta(x, y, fixed_noise, theta, spec)
+        if int(info) < 0:
+            raise RuntimeError(f"Cholesky failed (info={int(info)}) at iteration {i}")
+        loss = -mll
+        loss.backward()
+        opt.step()
+        lv = loss.detach().numpy()
+        if i > 0:
+            res["delta_loss"].append(lv - res["loss"][-1])
+        res["loss"].append(lv)
+        res["raw"].append(raw.detach().clone().numpy())
+        if stop and i > miniter:
+            if np.std(res["loss"][-stopavg:]) < stop:
+                break
+    return res

@@ -1,0 +1,75 @@
+"""ctypes binding of libpgmuvi_b200.so (the C ABI in include/pgmuvi_b200.h).
+
+This is the binding a pgmuvi maintainer would add.  There is no CPU
+fallback: if the shared library is missing the import of any compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int32, c_size_t, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgmuvi_b200.so")
+
+# constants mirrored from include/pgmuvi_b200.h
+KIND_SM1D, KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD = 0, 1, 2
+CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2
+FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC = 1, 2, 4
+OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
+
+EXPORTS = (
+    "pgm_version", "pgm_last_error", "pgm_workspace_bytes", "pgm_sm_mll_grad_f64",
+    "pgm_sm_kernel_dense_f64", "pgm_optim_step_f64", "pgm_sm_fit_f64", "pgm_peak_probe",
+)
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """The CUDA engine rejected the call (bad argument or launch failure)."""
+
+
+def load():
+    """Load the shared library (once) and declare the prototypes.  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m pgmuvi_b200.build` "
+            "(pgmuvi_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    dp, ip, vp = c_void_p, c_void_p, c_void_p  # device pointers travel as integers
+    lib.pgm_version.restype = c_int
+    lib.pgm_last_error.restype = c_char_p
+    lib.pgm_workspace_bytes.restype = c_size_t
+    lib.pgm_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.pgm_sm_mll_grad_f64.restype = c_int
+    lib.pgm_sm_mll_grad_f64.argtypes = [dp, ip, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, dp, dp, ip, vp, c_size_t, vp]
+    lib.pgm_sm_kernel_dense_f64.restype = c_int
+    lib.pgm_sm_kernel_dense_f64.argtypes = [dp, ip, dp, dp, ip, dp, dp, c_int, c_int, c_int,
+                                            c_int, c_int, c_int, dp, vp]
+    lib.pgm_optim_step_f64.restype = c_int
+    lib.pgm_optim_step_f64.argtypes = [dp, dp, dp, dp, ip, c_int, c_int, c_int, c_double,
+                                       c_double, c_double, c_double, c_double, c_int, vp]
+    lib.pgm_sm_fit_f64.restype = c_int
+    lib.pgm_sm_fit_f64.argtypes = [dp, ip, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_double, c_double, c_double, c_double,
+                                   c_double, c_int, c_int, c_double, c_int, dp, dp, ip, ip, dp,
+                                   vp, c_size_t, vp]
+    lib.pgm_peak_probe.restype = c_int
+    lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EngineError(f"pgmuvi_b200 C ABI error {rc}: {load().pgm_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,294 @@
+// C ABI of pgmuvi_b200 (see include/pgmuvi_b200.h).  Host-side dispatch only; all device
+// code is in gp_fused.cuh.
+#include "gp_fused.cuh"
+#include "../../include/pgmuvi_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace pgm {
+// launchers are explicitly instantiated in inst.cu (one translation unit per config)
+template <int KIND, int QT, int D> int launch_eval(const EvalArgs& A0, cudaStream_t st);
+template <int KIND, int QT, int D> int launch_fit(const FitArgs& F, cudaStream_t st);
+template <int KIND, int QT, int D> int launch_dense(const EvalArgs& A, double* K, cudaStream_t st);
+
+thread_local std::string g_err;
+int fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+int cuda_fail(const char* what, cudaError_t e) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return -2;
+}
+int device_sms() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+}  // namespace pgm
+
+namespace pgm {
+__global__ void optim_step_kernel(double* raw, const double* grad_mll, double* m, double* v,
+                                  const int32_t* active, int B, int P, int kind, double lr,
+                                  double b1, double b2, double eps, double wd, int step) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * P) return;
+  if (active && !active[idx / P]) return;
+  double mm = m ? m[idx] : 0.0, vv = v ? v[idx] : 0.0;
+  raw[idx] = optim_update(raw[idx], -grad_mll[idx], mm, vv, kind, lr, b1, b2, eps, wd, step);
+  if (m) m[idx] = mm;
+  if (v) v[idx] = vv;
+}
+
+}  // namespace pgm
+
+namespace {
+using pgm::cuda_fail;
+using pgm::fail;
+using pgm::launch_dense;
+using pgm::launch_eval;
+using pgm::launch_fit;
+
+int pad_q(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
+
+// NF of the instantiated config serving (d, Q): sizes the workspace
+int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q) + 1; }
+
+#define PGM_DISPATCH_Q(KIND, D, FN, ...)                     \
+  switch (pad_q(Q)) {                                        \
+    case 1: return FN<KIND, 1, D>(__VA_ARGS__);              \
+    case 2: return FN<KIND, 2, D>(__VA_ARGS__);              \
+    case 4: return FN<KIND, 4, D>(__VA_ARGS__);              \
+    default: return FN<KIND, 8, D>(__VA_ARGS__);             \
+  }
+
+#define PGM_DISPATCH(FN, ...)                                                        \
+  do {                                                                               \
+    if (kernel_kind == PGM_KIND_SM1D) {                                              \
+      PGM_DISPATCH_Q(PGM_KIND_SM1D, 1, FN, __VA_ARGS__)                              \
+    } else if (kernel_kind == PGM_KIND_SM_ARD_PRODSUM) {                             \
+      PGM_DISPATCH_Q(PGM_KIND_SM_ARD_PRODSUM, 2, FN, __VA_ARGS__)                    \
+    } else {                                                                         \
+      PGM_DISPATCH_Q(PGM_KIND_SM_ARD_SUMPROD, 2, FN, __VA_ARGS__)                    \
+    }                                                                                \
+  } while (0)
+
+int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
+  if (B < 0 || n_max < 1) return fail("B must be >= 0 and n_max >= 1");
+  if (Q < 1 || Q > 8) return fail("Q (num_mixtures) must be in 1..8");
+  if (kernel_kind == PGM_KIND_SM1D) {
+    if (d != 1) return fail("PGM_KIND_SM1D needs d == 1");
+  } else if (kernel_kind == PGM_KIND_SM_ARD_PRODSUM || kernel_kind == PGM_KIND_SM_ARD_SUMPROD) {
+    if (d != 2) return fail("ARD spectral-mixture kinds need d == 2");
+  } else {
+    return fail("unknown kernel_kind");
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pgm_version(void) { return 100; }
+const char* pgm_last_error(void) { return pgm::g_err.c_str(); }
+
+size_t pgm_workspace_bytes(int elem_size, int n_max, int d, int Q, int device) {
+  (void)elem_size;
+  int sms = 148;
+  if (device >= 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  else { int dv = 0; if (cudaGetDevice(&dv) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dv); }
+  if (sms <= 0) sms = 148;
+  const size_t per_block = pgm::scratch_elems(n_max, nf_for(d, Q));
+  return per_block * sizeof(double) * (size_t)sms * 2;  // up to 2 resident blocks per SM
+}
+
+int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y,
+                        const double* fixed_noise, const double* raw, const int32_t* con_kind,
+                        const double* con_lb, const double* con_ub, int B, int n_max, int d,
+                        int Q, int kernel_kind, int flags, double* mll, double* grad_raw,
+                        int32_t* info, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
+    return fail("null pointer argument");
+  if ((flags & PGM_FLAG_GRAD) && !grad_raw) return fail("PGM_FLAG_GRAD needs grad_raw");
+  const size_t per_block = pgm::scratch_elems(n_max, nf_for(d, Q));
+  if (workspace_bytes < pgm_workspace_bytes(8, n_max, d, Q, -1))
+    return fail("workspace too small (see pgm_workspace_bytes)");
+  pgm::EvalArgs A;
+  A.x = x; A.n_valid = n_valid; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
+  A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
+  A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags;
+  A.mll = mll; A.grad = grad_raw; A.info = info;
+  A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGM_DISPATCH(launch_eval, A, st);
+  return 0;
+}
+
+int pgm_sm_kernel_dense_f64(const double* x, const int32_t* n_valid, const double* fixed_noise,
+                            const double* raw, const int32_t* con_kind, const double* con_lb,
+                            const double* con_ub, int B, int n_max, int d, int Q,
+                            int kernel_kind, int flags, double* K_out, void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !raw || !con_kind || !con_lb || !con_ub || !K_out) return fail("null pointer argument");
+  if (B > 65535) return fail("B > 65535 not supported by the dense builder");
+  pgm::EvalArgs A;
+  memset(&A, 0, sizeof(A));
+  A.x = x; A.n_valid = n_valid; A.fixed_noise = fixed_noise; A.raw = raw;
+  A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
+  A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGM_DISPATCH(launch_dense, A, K_out, st);
+  return 0;
+}
+
+int pgm_optim_step_f64(double* raw, const double* grad_mll, double* exp_avg, double* exp_avg_sq,
+                       const int32_t* active, int B, int P, int optim_kind, double lr,
+                       double beta1, double beta2, double eps, double weight_decay, int step,
+                       void* stream) {
+  if (B < 0 || P < 1) return fail("bad B / P");
+  if (B == 0) return 0;
+  if (!raw || !grad_mll) return fail("null pointer argument");
+  if (optim_kind != PGM_OPT_SGD && (!exp_avg || !exp_avg_sq))
+    return fail("Adam / AdamW need exp_avg and exp_avg_sq");
+  if (optim_kind < 0 || optim_kind > 2) return fail("unknown optim_kind");
+  if (step < 1) return fail("step counts from 1");
+  const int total = B * P;
+  const int threads = 256, blocks = (total + threads - 1) / threads;
+  pgm::optim_step_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      raw, grad_mll, exp_avg, exp_avg_sq, active, B, P, optim_kind, lr, beta1, beta2, eps,
+      weight_decay, step);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("optim_step_kernel launch", e);
+  return 0;
+}
+
+int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
+                   const double* fixed_noise, double* raw, const int32_t* con_kind,
+                   const double* con_lb, const double* con_ub, int B, int n_max, int d, int Q,
+                   int kernel_kind, int flags, int optim_kind, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int maxiter, int miniter,
+                   double stop, int stopavg, double* loss_hist, double* raw_hist,
+                   int32_t* n_iter, int32_t* info, double* opt_state, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  (void)opt_state;  // optimiser state lives in shared memory for the whole loop
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !loss_hist || !n_iter || !info ||
+      !workspace)
+    return fail("null pointer argument");
+  if (maxiter < 1) return fail("maxiter must be >= 1");
+  if (optim_kind < 0 || optim_kind > 2) return fail("unknown optim_kind");
+  if (stopavg < 1) stopavg = 1;
+  const size_t per_block = pgm::scratch_elems(n_max, nf_for(d, Q));
+  if (workspace_bytes < pgm_workspace_bytes(8, n_max, d, Q, -1))
+    return fail("workspace too small (see pgm_workspace_bytes)");
+  pgm::FitArgs F;
+  pgm::EvalArgs& A = F.e;
+  A.x = x; A.n_valid = n_valid; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
+  A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
+  A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags | PGM_FLAG_GRAD;
+  A.mll = nullptr; A.grad = nullptr; A.info = info;
+  A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
+  F.raw_io = raw; F.optim_kind = optim_kind; F.lr = lr; F.beta1 = beta1; F.beta2 = beta2;
+  F.eps = eps; F.weight_decay = weight_decay; F.stop = stop; F.maxiter = maxiter;
+  F.miniter = miniter; F.stopavg = stopavg; F.loss_hist = loss_hist; F.raw_hist = raw_hist;
+  F.n_iter = n_iter;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGM_DISPATCH(launch_fit, F, st);
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- FP64 yardsticks ---------------------------------------------------------------------
+namespace pgm {
+__global__ void __launch_bounds__(256) probe_dmma(int iters, double* out) {
+  double acc[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mma_f64(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) probe_dfma(int iters, double* out) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-9 + i;
+  const double a = 1.0000001, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) probe_ffma(int iters, double* out) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-9f + i;
+  const float a = 1.0000001f, b = 1e-9f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) out[0] = s;
+}
+}  // namespace pgm
+
+extern "C" int pgm_peak_probe(int kind, int iters, double* tflops_host, void* stream) {
+  if (!tflops_host || iters < 1) return fail("bad arguments");
+  const int sms = pgm::device_sms();
+  double* dout = nullptr;
+  cudaError_t e = cudaMalloc(&dout, 8);
+  if (e != cudaSuccess) return cuda_fail("cudaMalloc", e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8, threads = 256;
+  double flops_per_thread_iter = 0.0;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    if (kind == 0) {
+      pgm::probe_dmma<<<blocks, threads, 0, st>>>(iters, dout);
+      flops_per_thread_iter = 8.0 * (8 * 8 * 4 * 2) / 32.0;
+    } else if (kind == 1) {
+      pgm::probe_dfma<<<blocks, threads, 0, st>>>(iters, dout);
+      flops_per_thread_iter = 16.0 * 2;
+    } else {
+      pgm::probe_ffma<<<blocks, threads, 0, st>>>(iters, dout);
+      flops_per_thread_iter = 16.0 * 2;
+    }
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(dout); return cuda_fail("probe", e); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dout);
+  const double total = flops_per_thread_iter * (double)iters * (double)blocks * threads;
+  *tflops_host = total / (best * 1e-3) / 1e12;
+  return 0;
+}

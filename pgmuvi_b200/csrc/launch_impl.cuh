@@ -1,0 +1,62 @@
+// Host launchers of the fused kernels; explicitly instantiated per (KIND, QT, D) in inst.cu so
+// the heavy kernels compile in parallel translation units.
+#pragma once
+#include "gp_fused.cuh"
+#include <string>
+
+namespace pgm {
+int fail(const std::string& m);
+int cuda_fail(const char* what, cudaError_t e);
+int device_sms();
+
+template <int KIND, int QT, int D>
+int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
+  using C = pgm::Cfg<KIND, QT, D>;
+  pgm::EvalArgs A = A0;
+  auto kern = pgm::sm_mll_grad_kernel<KIND, QT, D>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pgm::NTHREADS, C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("occupancy", e);
+  if (occ < 1) return fail("kernel does not fit on an SM");
+  int grid = device_sms() * occ;
+  if (grid > A.B) grid = A.B;
+  kern<<<grid, pgm::NTHREADS, C::SMEM_BYTES, st>>>(A);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("sm_mll_grad_kernel launch", e);
+  return 0;
+}
+
+template <int KIND, int QT, int D>
+int launch_fit(const pgm::FitArgs& F, cudaStream_t st) {
+  using C = pgm::Cfg<KIND, QT, D>;
+  auto kern = pgm::sm_fit_kernel<KIND, QT, D>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pgm::NTHREADS, C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("occupancy", e);
+  if (occ < 1) return fail("kernel does not fit on an SM");
+  int grid = device_sms() * occ;
+  if (grid > F.e.B) grid = F.e.B;
+  kern<<<grid, pgm::NTHREADS, C::SMEM_BYTES, st>>>(F);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("sm_fit_kernel launch", e);
+  return 0;
+}
+
+template <int KIND, int QT, int D>
+int launch_dense(const pgm::EvalArgs& A, double* K, cudaStream_t st) {
+  const int N = (A.n_max + pgm::TS - 1) / pgm::TS;
+  dim3 grid(N, N, A.B);
+  pgm::sm_kernel_dense_kernel<KIND, QT, D><<<grid, pgm::NTHREADS, 0, st>>>(A, K);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("sm_kernel_dense_kernel launch", e);
+  return 0;
+}
+
+
+}  // namespace pgm

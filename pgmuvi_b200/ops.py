@@ -1,0 +1,182 @@
+"""Torch custom ops over the C ABI (device memory, streams: torch is plumbing only).
+
+``pgmuvi_b200::sm_mll_grad``, ``::sm_kernel_dense``, ``::optim_step``, ``::sm_fit`` take CUDA
+tensors, run on the current torch CUDA stream and never fall back to the CPU.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import (FLAG_BOUNDS_PER_LC, FLAG_GRAD, FLAG_LEARN_NOISE, KIND_SM1D,
+                   KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD, check, ptr)
+
+_workspaces = {}
+
+
+def param_count(Q: int, d: int, learn_noise: bool) -> int:
+    return 1 + Q + 2 * Q * d + (1 if learn_noise else 0)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pgmuvi_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _workspace(device, n_max, d, Q):
+    lib = _lib.load()
+    need = lib.pgm_workspace_bytes(8, n_max, d, Q, device.index if device.index is not None
+                                   else torch.cuda.current_device())
+    key = (device.index, )
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws, need
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _prep(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise):
+    _require_cuda(x, y, fixed_noise, raw, con_kind, con_lb, con_ub)
+    if x.dtype != torch.float64:
+        raise RuntimeError("only float64 is implemented in this build")
+    B, n = y.shape
+    d = 1 if kind == KIND_SM1D else 2
+    if x.shape != (B, n, d):
+        raise RuntimeError(f"x must be [B, n, {d}], got {tuple(x.shape)}")
+    P = param_count(Q, d, learn_noise)
+    if raw.shape != (B, P):
+        raise RuntimeError(f"raw must be [B, {P}], got {tuple(raw.shape)}")
+    flags = FLAG_LEARN_NOISE if learn_noise else 0
+    if con_lb.dim() == 2:
+        flags |= FLAG_BOUNDS_PER_LC
+        if con_lb.shape != (B, P) or con_ub.shape != (B, P):
+            raise RuntimeError("per-light-curve bounds must be [B, P]")
+    elif con_lb.shape != (P,) or con_ub.shape != (P,):
+        raise RuntimeError("shared bounds must be [P]")
+    if con_kind.shape != (P,) or con_kind.dtype != torch.int32:
+        raise RuntimeError("con_kind must be int32 [P]")
+    c = lambda t: None if t is None else t.contiguous()
+    return (c(x), c(y), c(fixed_noise), c(raw), c(con_kind), c(con_lb), c(con_ub), B, n, d, P,
+            flags)
+
+
+@torch.library.custom_op("pgmuvi_b200::sm_mll_grad", mutates_args=(), device_types="cuda")
+def sm_mll_grad(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
+                con_kind: Tensor, con_lb: Tensor, con_ub: Tensor, n_valid: Optional[Tensor],
+                kind: int, Q: int, learn_noise: bool, want_grad: bool
+                ) -> Tuple[Tensor, Tensor, Tensor]:
+    """Per-datum exact MLL, d MLL / d raw and Cholesky info for B light curves."""
+    (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+        x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    if want_grad:
+        flags |= FLAG_GRAD
+    mll = torch.empty(B, dtype=x.dtype, device=x.device)
+    grad = torch.zeros(B, P, dtype=x.dtype, device=x.device)
+    info = torch.zeros(B, dtype=torch.int32, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    ws, nbytes = _workspace(x.device, n, d, Q)
+    with torch.cuda.device(x.device):
+        check(_lib.load().pgm_sm_mll_grad_f64(
+            ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
+            ptr(con_ub), B, n, d, Q, kind, flags, ptr(mll), ptr(grad), ptr(info), ptr(ws),
+            ws.numel(), _stream()))
+    return mll, grad, info
+
+
+@sm_mll_grad.register_fake
+def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_noise,
+      want_grad):
+    B = y.shape[0]
+    return (y.new_empty(B), torch.empty_like(raw), y.new_empty(B, dtype=torch.int32))
+
+
+@torch.library.custom_op("pgmuvi_b200::sm_kernel_dense", mutates_args=(), device_types="cuda")
+def sm_kernel_dense(x: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con_kind: Tensor,
+                    con_lb: Tensor, con_ub: Tensor, n_valid: Optional[Tensor], kind: int, Q: int,
+                    learn_noise: bool) -> Tensor:
+    """Dense K + D [B, n, n] from the same device builder the fused path uses."""
+    B, n = x.shape[0], x.shape[1]
+    y = x.new_empty(B, n)
+    (x, _, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+        x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    K = torch.zeros(B, n, n, dtype=x.dtype, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    with torch.cuda.device(x.device):
+        check(_lib.load().pgm_sm_kernel_dense_f64(
+            ptr(x), ptr(n_valid), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
+            ptr(con_ub), B, n, d, Q, kind, flags, ptr(K), _stream()))
+    return K
+
+
+@sm_kernel_dense.register_fake
+def _(x, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_noise):
+    return x.new_empty(x.shape[0], x.shape[1], x.shape[1])
+
+
+@torch.library.custom_op("pgmuvi_b200::optim_step", mutates_args=("raw", "exp_avg", "exp_avg_sq"),
+                         device_types="cuda")
+def optim_step(raw: Tensor, grad_mll: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor,
+               active: Optional[Tensor], optim_kind: int, lr: float, beta1: float, beta2: float,
+               eps: float, weight_decay: float, step: int) -> None:
+    """In-place SGD / Adam / AdamW step on packed raw parameters [B, P] (minimises -MLL)."""
+    _require_cuda(raw, grad_mll, exp_avg, exp_avg_sq, active)
+    B, P = raw.shape
+    for t in (raw, grad_mll, exp_avg, exp_avg_sq):
+        if not t.is_contiguous() or t.dtype != torch.float64:
+            raise RuntimeError("optim_step needs contiguous float64 tensors")
+    with torch.cuda.device(raw.device):
+        check(_lib.load().pgm_optim_step_f64(
+            ptr(raw), ptr(grad_mll), ptr(exp_avg), ptr(exp_avg_sq), ptr(active), B, P, optim_kind,
+            lr, beta1, beta2, eps, weight_decay, step, _stream()))
+
+
+@torch.library.custom_op("pgmuvi_b200::sm_fit", mutates_args=("raw",), device_types="cuda")
+def sm_fit(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con_kind: Tensor,
+           con_lb: Tensor, con_ub: Tensor, n_valid: Optional[Tensor], kind: int, Q: int,
+           learn_noise: bool, optim_kind: int, lr: float, beta1: float, beta2: float, eps: float,
+           weight_decay: float, maxiter: int, miniter: int, stop: float, stopavg: int,
+           keep_history: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Whole optimisation loop on device.  Returns (loss_hist [maxiter,B],
+    raw_hist [maxiter+1,B,P] or empty, n_iter [B], info [B]); ``raw`` is updated in place."""
+    (x, y, fixed_noise, raw_c, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+        x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    if not raw.is_contiguous():
+        raise RuntimeError("raw must be contiguous (updated in place)")
+    loss_hist = torch.empty(maxiter, B, dtype=x.dtype, device=x.device)
+    raw_hist = torch.empty((maxiter + 1, B, P) if keep_history else (0,), dtype=x.dtype,
+                           device=x.device)
+    n_iter = torch.zeros(B, dtype=torch.int32, device=x.device)
+    info = torch.zeros(B, dtype=torch.int32, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    ws, _ = _workspace(x.device, n, d, Q)
+    with torch.cuda.device(x.device):
+        check(_lib.load().pgm_sm_fit_f64(
+            ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
+            ptr(con_ub), B, n, d, Q, kind, flags, optim_kind, lr, beta1, beta2, eps, weight_decay,
+            maxiter, miniter, stop, stopavg, ptr(loss_hist),
+            ptr(raw_hist) if keep_history else None, ptr(n_iter), ptr(info), None, ptr(ws),
+            ws.numel(), _stream()))
+    return loss_hist, raw_hist, n_iter, info
+
+
+def peak_probe(kind: int, iters: int = 4096) -> float:
+    """Self-measured FP64 DMMA (0) / DFMA (1) / FP32 FFMA (2) throughput in TFLOP/s."""
+    import ctypes
+    out = ctypes.c_double(0.0)
+    check(_lib.load().pgm_peak_probe(kind, iters, ctypes.byref(out), _stream()))
+    return out.value
+
+
+__all__ = ["sm_mll_grad", "sm_kernel_dense", "optim_step", "sm_fit", "peak_probe", "param_count",
+           "KIND_SM1D", "KIND_SM_ARD_PRODSUM", "KIND_SM_ARD_SUMPROD"]
