@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path on BASELINE.json's metric:
+
+    MLL+grad evals/s, 4096 x (n=512, SM-4) light curves (config C2), fp64, N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: K(x,x') build + Cholesky + solve +
+log-det + full raw-parameter gradient for every light curve of the batch (one "eval" per
+light curve).  Under torchrun every rank owns its own 4096-light-curve shard (independent
+light curves: no collective inside the step; weak scaling) and the only exchange is the
+result all-gather after the step.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, torch CPU with
+all host threads: GPyTorch itself is not installable in this image - SURVEY.md F3) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 512
+Q_MIX = 4
+LC_PER_GPU = 4096
+F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval
+METRIC = "MLL+grad evals/s, 4096x n=512 SM-4 lightcurves"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lightcurves", type=int, default=LC_PER_GPU, help="light curves per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="light curves in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": "C2: batch of synthetic 1-D light curves n=512, SM-4 kernel, "
+                        "FixedNoise likelihood, batched exact MLL+grad",
+            "lightcurves_per_gpu": args.lightcurves, "global_lightcurves": args.lightcurves * world,
+            "n": N_POINTS, "num_mixtures": Q_MIX, "params_per_lightcurve": 13,
+            "parallelism": f"independent light curves sharded over {world} GPU(s), "
+                           "no collective inside the step",
+            "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)"}
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU reference arm / baseline (oracle = torch-CPU restatement of the reference path)
+# ---------------------------------------------------------------------------------------
+def cpu_reference(sample, steps, warmup):
+    """evals/s of the reference's CPU path on `sample` C2 light curves per step.
+    Runs (i) the per-light-curve loop pgmuvi would run and (ii) torch batch mode, and
+    reports the faster (all host threads)."""
+    import torch
+    from oracle.sm_gp import ModelSpec, batched_mll_and_grad, mll_and_grad_autograd
+    from pgmuvi_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    bt = S.make_batch_1d(sample, N_POINTS, Q=Q_MIX)
+    spec = ModelSpec(d=1, Q=Q_MIX)
+    t = lambda a: torch.tensor(a, dtype=torch.float64)
+    x, y, nz, raw, lb, ub = (t(bt[k]) for k in ("x", "y", "noise", "raw", "lb", "ub"))
+    kinds = torch.tensor(bt["kinds"])
+
+    def step_batched():
+        return batched_mll_and_grad(x, y, nz, raw, kinds, lb, ub, spec)
+
+    def step_loop():
+        for b in range(sample):
+            mll_and_grad_autograd(x[b], y[b], nz[b], raw[b], kinds, lb[b], ub[b], spec)
+
+    results = {}
+    for name, fn in (("batched", step_batched), ("per_lightcurve_loop", step_loop)):
+        for _ in range(max(1, min(warmup, 2))):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / steps
+        results[name] = sample / dt
+    best = max(results, key=results.get)
+    return results[best], best, results, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    val, mode, both, cores = cpu_reference(args.cpu_sample, steps, args.warmup)
+    sample = (f"{args.cpu_sample} of the C2 light curves per step x {steps} steps, fp64, torch CPU "
+              f"{cores} threads, best of {both} (oracle restatement of GPyTorch's Cholesky path; "
+              "linear in the number of light curves)")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * args.cpu_sample / val, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample, "mode": mode},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pgmuvi_b200 import ops, synthetic as S
+    from pgmuvi_b200.batch import BatchEngine, HostBatch, gather_results
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.lightcurves
+    # distinct synthetic light curves per rank (seeded), C2 shape
+    distinct = min(B, 512)
+    bt = S.make_batch_1d(distinct, N_POINTS, Q=Q_MIX, seed0=1000 + rank * 100000)
+    rep = (B + distinct - 1) // distinct
+    for k in ("x", "y", "noise", "raw", "lb", "ub"):
+        bt[k] = np.concatenate([bt[k]] * rep, 0)[:B]
+    hb = HostBatch.from_numpy(bt, pin=True)
+    eng = BatchEngine(kind=ops.KIND_SM1D, Q=Q_MIX, learn_noise=False, device=dev)
+    d = eng.upload(hb)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        mll, grad, info = eng.evaluate_device(d, want_grad=True)
+        if world > 1:
+            res = gather_results(torch.cat([mll.unsqueeze(1), grad], 1))
+            return res
+        return mll
+
+    # ---- device-resident throughput ("value") -------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                   # L2 flush, outside the timed events
+        ev[i][0].record()
+        kev[i][0].record()
+        mll, grad, info = eng.evaluate_device(d, want_grad=True)
+        kev[i][1].record()
+        if world > 1:
+            gather_results(torch.cat([mll.unsqueeze(1), grad], 1))
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kern_ms = [a.elapsed_time(b) for a, b in kev]
+    total_ms = float(sum(step_ms))
+    bad = int((info != 0).sum().item())
+
+    # ---- end to end through the public host API ("e2e") -----------------------------------
+    for _ in range(2):
+        eng.evaluate(hb)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = eng.evaluate(hb)                         # H2D inputs, kernel, D2H results, sync
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    d2h = sum(t.numel() * t.element_size() for t in out)
+
+    tm = torch.tensor([total_ms, e2e_s * 1e3, float(np.mean(kern_ms))], dtype=torch.float64,
+                      device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kern_ms_avg = (float(v) for v in tm.tolist())
+
+    if rank == 0:
+        evals = B * world * args.steps
+        value = evals / (total_ms * 1e-3)
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        dmma = ops.peak_probe(0, 8192)
+        dfma = ops.peak_probe(1, 8192)
+        achieved = B * F_EVAL / (kern_ms_avg * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "pgm::sm_mll_grad_kernel<0,4,1>",
+                    "achieved": achieved, "peak": dmma, "unit": "TFLOP/s",
+                    "frac": achieved / dmma,
+                    "peak_source": "self-measured FP64 DMMA (mma.sync.m8n8k4.f64) probe in this "
+                                   "run; MEASURED_PEAKS.json holds no fp64 figure "
+                                   f"(its bf16 {peaks.get('bf16_tflops')} TF / HBM "
+                                   f"{peaks.get('hbm_gbs')} GB/s do not bound an fp64 kernel); "
+                                   "nominal B200 FP64 37 TFLOP/s",
+                    "dfma_probe_tflops": dfma,
+                    "algorithmic_flops_per_launch": B * F_EVAL,
+                    "kernel_ms_avg": kern_ms_avg, "traffic": None}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(args, world),
+                "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": d2h},
+                "gpu_launches": args.steps, "roofline": roofline, "clocks": clocks,
+                "cholesky_info_nonzero": bad, "wall_s_timed_loop": t_wall}
+        if world == 1 and not args.no_cpu_baseline:
+            val, mode, both, cores = cpu_reference(args.cpu_sample, 2, 1)
+            line["cpu_baseline"] = {
+                "value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_sample} of the C2 light curves x 2 steps, fp64, torch CPU "
+                          f"{cores} threads, best of {both}", "mode": mode}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

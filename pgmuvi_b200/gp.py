@@ -1,0 +1,258 @@
+"""GPyTorch-shaped model objects for the path (gpytorch itself is not in this image).
+
+The names, parameter names/shapes and registration order mirror what pgmuvi builds from
+GPyTorch, so that reference code written against
+``model.covar_module.raw_mixture_means``, ``register_constraint``, ``initialize(**hypers)``,
+``named_parameters()`` keeps working and the parity tests read like the reference's:
+
+    likelihood.noise_covar.raw_noise [1] | likelihood.second_noise_covar.raw_noise [1]
+    mean_module.raw_constant []
+    covar_module.raw_mixture_weights [Q], raw_mixture_means [Q,1,d], raw_mixture_scales [Q,1,d]
+
+Model classes follow pgmuvi/gps.py:175-220 (``SpectralMixtureGPModel``) and :270-318
+(``TwoDSpectralMixtureGPModel``).  Nothing here computes the GP on the CPU: the numbers come
+from ``B200ExactMarginalLogLikelihood`` (pgmuvi_b200/mll.py) -> CUDA.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+from torch import nn
+
+from .constraints import GreaterThan, Interval, Positive  # noqa: F401
+
+
+class NumericalWarning(RuntimeWarning):
+    """Mirrors linear_operator.utils.warnings.NumericalWarning."""
+
+
+class NotPSDError(RuntimeError):
+    """Mirrors linear_operator.utils.errors.NotPSDError."""
+
+
+class NanError(RuntimeError):
+    """Mirrors linear_operator.utils.errors.NanError."""
+
+
+def min_fixed_noise(dtype):
+    """gpytorch.settings.min_fixed_noise: 1e-4 (float), 1e-6 (double), 1e-3 (half)."""
+    return {torch.float32: 1e-4, torch.float64: 1e-6}.get(dtype, 1e-3)
+
+
+class Module(nn.Module):
+    """The slice of gpytorch.Module the path uses."""
+
+    def register_constraint(self, param_name, constraint, replace=True):
+        if param_name not in self._parameters:
+            raise RuntimeError(f"Attempting to register constraint for nonexistent parameter {param_name}")
+        cname = param_name + "_constraint"
+        if cname in self._modules and not replace:
+            return
+        # re-registering keeps the RAW value: the constrained value jumps (tutorial cells 32-37)
+        self.add_module(cname, constraint)
+
+    def constraint_for_parameter_name(self, param_name):
+        base, _, leaf = param_name.rpartition(".")
+        mod = self.get_submodule(base) if base else self
+        return mod._modules.get(leaf + "_constraint")
+
+    def named_parameters_and_constraints(self):
+        for name, p in self.named_parameters():
+            yield name, p, self.constraint_for_parameter_name(name)
+
+    def initialize(self, **kwargs):
+        """Set parameters by (possibly dotted, constrained or raw) name, as gpytorch does."""
+        for name, val in kwargs.items():
+            if "." in name:
+                head, rest = name.split(".", 1)
+                getattr(self, head).initialize(**{rest: val})
+                continue
+            if name in self._parameters:
+                p = self._parameters[name]
+                v = torch.as_tensor(val, dtype=p.dtype, device=p.device)
+                with torch.no_grad():
+                    p.copy_(v.expand_as(p) if v.numel() == 1 else v.reshape(p.shape))
+            elif "raw_" + name in self._parameters:
+                p = self._parameters["raw_" + name]
+                con = self._modules.get("raw_" + name + "_constraint")
+                v = torch.as_tensor(val, dtype=p.dtype, device=p.device)
+                v = v.expand_as(p) if v.numel() == 1 else v.reshape(p.shape)
+                with torch.no_grad():
+                    p.copy_(con.inverse_transform(v) if con is not None else v)
+            elif hasattr(self, name):
+                setattr(self, name, val)
+            else:
+                raise AttributeError(f"Unknown parameter {name} for {type(self).__name__}")
+        return self
+
+    def _constrained(self, raw_name):
+        p = self._parameters[raw_name]
+        con = self._modules.get(raw_name + "_constraint")
+        return con.transform(p) if con is not None else p
+
+
+# ---------------------------------------------------------------------------------------
+# mean, kernel, likelihoods
+# ---------------------------------------------------------------------------------------
+class ConstantMean(Module):
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("raw_constant", nn.Parameter(torch.zeros(())))
+
+    @property
+    def constant(self):
+        return self._constrained("raw_constant")
+
+    def forward(self, x):
+        return self.constant.expand(x.shape[:-1])
+
+
+class SpectralMixtureKernel(Module):
+    """gpytorch.kernels.SpectralMixtureKernel parameters (values computed on the GPU)."""
+
+    is_stationary = True
+
+    def __init__(self, num_mixtures=None, ard_num_dims=1, variant="prod_of_sums"):
+        super().__init__()
+        if num_mixtures is None:
+            raise RuntimeError("num_mixtures is a required argument")
+        self.num_mixtures = num_mixtures
+        self.ard_num_dims = ard_num_dims
+        self.variant = variant  # F7: GPyTorch = product over dims of per-dim mixture sums
+        Q, d = num_mixtures, ard_num_dims
+        self.register_parameter("raw_mixture_weights", nn.Parameter(torch.zeros(Q)))
+        self.register_parameter("raw_mixture_means", nn.Parameter(torch.zeros(Q, 1, d)))
+        self.register_parameter("raw_mixture_scales", nn.Parameter(torch.zeros(Q, 1, d)))
+        self.register_constraint("raw_mixture_weights", Positive())
+        self.register_constraint("raw_mixture_means", Positive())
+        self.register_constraint("raw_mixture_scales", Positive())
+
+    mixture_weights = property(lambda self: self._constrained("raw_mixture_weights"))
+    mixture_means = property(lambda self: self._constrained("raw_mixture_means"))
+    mixture_scales = property(lambda self: self._constrained("raw_mixture_scales"))
+
+    def initialize_from_data(self, train_x, train_y, **kwargs):
+        """A.3: scales <- 1/|N(0,1) max_dist|, means <- U(0,1) 0.5/min_dist, weights <-
+        std(y)/Q.  RANDOM (gps.py:209), so parity tests always set hypers explicitly."""
+        if train_x.dim() == 1:
+            train_x = train_x.unsqueeze(-1)
+        xs = train_x.sort(dim=-2)[0]
+        max_dist = xs[-1, :] - xs[0, :]
+        dists = xs[1:, :] - xs[:-1, :]
+        dists = torch.where(dists.eq(0.0), torch.tensor(1e10, dtype=xs.dtype, device=xs.device), dists)
+        min_dist = dists.sort(dim=-2)[0][0, :]
+        with torch.no_grad():
+            self.initialize(mixture_scales=torch.randn_like(self.raw_mixture_scales)
+                            .mul_(max_dist.to(self.raw_mixture_scales)).abs_().reciprocal_())
+            self.initialize(mixture_means=torch.rand_like(self.raw_mixture_means)
+                            .mul_(0.5).div(min_dist.to(self.raw_mixture_means)))
+            self.initialize(mixture_weights=train_y.std().to(self.raw_mixture_weights)
+                            / self.num_mixtures)
+
+    def forward(self, x1, x2=None, **params):
+        raise NotImplementedError(
+            "SpectralMixtureKernel values are produced on the GPU by pgmuvi_b200.ops "
+            "(sm_kernel_dense / the fused MLL); there is no CPU evaluation in this package")
+
+
+class _HomoskedasticNoise(Module):
+    def __init__(self, noise_constraint=None):
+        super().__init__()
+        self.register_parameter("raw_noise", nn.Parameter(torch.zeros(1)))
+        self.register_constraint("raw_noise", noise_constraint or GreaterThan(1e-4))
+
+    noise = property(lambda self: self._constrained("raw_noise"))
+
+
+class _FixedGaussianNoise(Module):
+    def __init__(self, noise):
+        super().__init__()
+        mfn = min_fixed_noise(noise.dtype)
+        if noise.lt(mfn).any():
+            warnings.warn(
+                "Very small noise values detected. This will likely lead to numerical "
+                f"instabilities. Rounding small noise values up to {mfn}.", NumericalWarning)
+            noise = noise.clamp_min(mfn)
+        self.register_buffer("noise", noise.clone().detach())
+
+
+class GaussianLikelihood(Module):
+    """gpytorch.likelihoods.GaussianLikelihood: learnable homoskedastic noise
+    (lightcurve.py:2805-2807)."""
+
+    def __init__(self, noise_constraint=None, learn_additional_noise=False, **kwargs):
+        super().__init__()
+        self.noise_covar = _HomoskedasticNoise(noise_constraint)
+
+    noise = property(lambda self: self.noise_covar.noise)
+
+
+class FixedNoiseGaussianLikelihood(Module):
+    """gpytorch.likelihoods.FixedNoiseGaussianLikelihood (lightcurve.py:2787-2794)."""
+
+    def __init__(self, noise, learn_additional_noise=False, **kwargs):
+        super().__init__()
+        self.noise_covar = _FixedGaussianNoise(torch.as_tensor(noise))
+        self.second_noise_covar = _HomoskedasticNoise() if learn_additional_noise else None
+
+    noise = property(lambda self: self.noise_covar.noise)
+
+    @property
+    def second_noise(self):
+        return 0 if self.second_noise_covar is None else self.second_noise_covar.noise
+
+
+# ---------------------------------------------------------------------------------------
+# models (pgmuvi/gps.py)
+# ---------------------------------------------------------------------------------------
+class PriorOutput:
+    """What ``model(train_x)`` returns in training mode: the (lazy) prior over the training
+    inputs.  GPyTorch returns a MultivariateNormal whose covariance is a lazy kernel tensor
+    (nothing computed yet, trainers.py:179); this carries the same references."""
+
+    def __init__(self, model, x):
+        self.model, self.x = model, x
+
+
+class ExactGP(Module):
+    def __init__(self, train_inputs, train_targets, likelihood):
+        super().__init__()
+        if torch.is_tensor(train_inputs):
+            train_inputs = (train_inputs,)
+        self.train_inputs = tuple(t.unsqueeze(-1) if t.dim() == 1 else t for t in train_inputs)
+        self.train_targets = train_targets
+        self.likelihood = likelihood
+
+    def __call__(self, *args, **kwargs):
+        x = args[0]
+        return self.forward(x.unsqueeze(-1) if x.dim() == 1 else x)
+
+
+class SpectralMixtureGPModel(ExactGP):
+    """pgmuvi/gps.py:175-220: ConstantMean + SMK(num_mixtures), initialize_from_data."""
+
+    def __init__(self, train_x, train_y, likelihood, num_mixtures=4):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean()
+        self.covar_module = SpectralMixtureKernel(num_mixtures=num_mixtures)
+        self.covar_module.initialize_from_data(train_x, train_y)
+        self.sci_kernel = self.covar_module
+
+    def forward(self, x):
+        return PriorOutput(self, x)
+
+
+class TwoDSpectralMixtureGPModel(ExactGP):
+    """pgmuvi/gps.py:270-318: ConstantMean + SMK(ard_num_dims=2); raw params start at 0."""
+
+    def __init__(self, train_x, train_y, likelihood, num_mixtures=4, variant="prod_of_sums"):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean()
+        self.covar_module = SpectralMixtureKernel(ard_num_dims=2, num_mixtures=num_mixtures,
+                                                  variant=variant)
+        self.sci_kernel = self.covar_module
+
+    def forward(self, x):
+        return PriorOutput(self, x)

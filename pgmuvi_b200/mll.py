@@ -1,0 +1,191 @@
+"""``B200ExactMarginalLogLikelihood``: the GPyTorch plug-in seam (SURVEY.md section 8b,
+seam #2).  Replaces ``gpytorch.mlls.ExactMarginalLogLikelihood(likelihood, model)`` as used
+at pgmuvi/trainers.py:119 so that the reference loop
+
+    output = model(train_x); loss = -mll(output, train_y); loss.backward(); optimizer.step()
+
+(trainers.py:179-182) runs unchanged with any ``torch.optim`` optimiser over
+``model.parameters()``: the returned scalar carries a ``grad_fn`` whose backward feeds the
+CUDA-computed d MLL / d raw into the individual ``raw_*`` Parameters.
+
+Model objects are duck-typed (ours from pgmuvi_b200.gp, or real GPyTorch ones): the wrapper
+reads ``mean_module.raw_constant``, ``covar_module.raw_mixture_{weights,means,scales}``, the
+likelihood's noise modules and each ``raw_*_constraint``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from ._lib import KIND_SM1D, KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD
+from .constraints import describe
+
+
+class UnsupportedModelError(NotImplementedError):
+    """The model/likelihood is outside the accelerated path."""
+
+
+@dataclass
+class PackedModel:
+    """Flat view of a model on the packed C-ABI layout
+    ``[mean | w[Q] | mu[Q*d] | sigma[Q*d] | (noise)]``."""
+    params: List[torch.nn.Parameter]      # in packed order
+    names: List[str]                      # their names under model.named_parameters()
+    kinds: torch.Tensor                   # [P] int32 (CPU)
+    lb: torch.Tensor                      # [P] float64 (CPU)
+    ub: torch.Tensor
+    kind: int
+    Q: int
+    d: int
+    learn_noise: bool
+    fixed_noise: Optional[torch.Tensor]   # [n] variance or None
+
+    @property
+    def P(self):
+        return int(self.kinds.numel())
+
+    def raw(self):
+        """[P] tensor tracking the Parameters (autograd flows back through the cat)."""
+        return torch.cat([p.reshape(-1) for p in self.params])
+
+    def scatter_raw_(self, flat):
+        """Write a packed [P] vector back into the Parameters (no grad)."""
+        o = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                p.copy_(flat[o:o + k].reshape(p.shape).to(dtype=p.dtype, device=p.device))
+                o += k
+
+
+def _constraint(mod, raw_name):
+    return getattr(mod, raw_name + "_constraint", None)
+
+
+def _find_name(model, param):
+    for n, p in model.named_parameters():
+        if p is param:
+            return n
+    return "?"
+
+
+def pack_model(model, likelihood=None) -> PackedModel:
+    """Recognise (ConstantMean, SpectralMixtureKernel, Gaussian | FixedNoise likelihood)."""
+    likelihood = likelihood if likelihood is not None else model.likelihood
+    mean, cov = getattr(model, "mean_module", None), getattr(model, "covar_module", None)
+    if mean is None or not hasattr(mean, "raw_constant"):
+        raise UnsupportedModelError("only ConstantMean is on the accelerated path")
+    for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
+        if cov is None or not hasattr(cov, nm):
+            raise UnsupportedModelError("covar_module must be a SpectralMixtureKernel")
+    Q = int(cov.raw_mixture_weights.numel())
+    d = int(cov.raw_mixture_means.shape[-1])
+    if d == 1:
+        kind = KIND_SM1D
+    elif d == 2:
+        kind = (KIND_SM_ARD_SUMPROD if getattr(cov, "variant", "prod_of_sums") == "sum_of_prods"
+                else KIND_SM_ARD_PRODSUM)
+    else:
+        raise UnsupportedModelError("ard_num_dims must be 1 or 2")
+    if Q > 8:
+        raise UnsupportedModelError("num_mixtures > 8 is not supported by the engine")
+    for m in (model, likelihood):
+        pri = getattr(m, "named_priors", None)
+        if pri is not None and len(list(pri())) > 0:
+            raise UnsupportedModelError("registered priors are not on the accelerated path")
+    params = [mean.raw_constant, cov.raw_mixture_weights, cov.raw_mixture_means,
+              cov.raw_mixture_scales]
+    cons = [_constraint(mean, "raw_constant"), _constraint(cov, "raw_mixture_weights"),
+            _constraint(cov, "raw_mixture_means"), _constraint(cov, "raw_mixture_scales")]
+    fixed, learn = None, False
+    nc = getattr(likelihood, "noise_covar", None)
+    snc = getattr(likelihood, "second_noise_covar", None)
+    if nc is not None and hasattr(nc, "raw_noise"):            # GaussianLikelihood
+        learn = True
+        params.append(nc.raw_noise)
+        cons.append(_constraint(nc, "raw_noise"))
+    elif nc is not None and hasattr(nc, "noise"):              # FixedNoiseGaussianLikelihood
+        fixed = nc.noise
+        if snc is not None and hasattr(snc, "raw_noise"):
+            learn = True
+            params.append(snc.raw_noise)
+            cons.append(_constraint(snc, "raw_noise"))
+    else:
+        raise UnsupportedModelError("likelihood must be Gaussian or FixedNoiseGaussian")
+    kinds, lb, ub = [], [], []
+    for p, c in zip(params, cons):
+        k, lo, hi = describe(c)
+        kinds += [k] * p.numel()
+        lb += [lo] * p.numel()
+        ub += [hi] * p.numel()
+    return PackedModel(params=params, names=[_find_name(model, p) for p in params],
+                       kinds=torch.tensor(kinds, dtype=torch.int32),
+                       lb=torch.tensor(lb, dtype=torch.float64),
+                       ub=torch.tensor(ub, dtype=torch.float64), kind=kind, Q=Q, d=d,
+                       learn_noise=learn, fixed_noise=fixed)
+
+
+def engine_device(t=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("pgmuvi_b200 needs a CUDA device: the engine has no CPU fallback")
+    if t is not None and t.is_cuda:
+        return t.device
+    return torch.device(f"cuda:{torch.cuda.current_device()}")
+
+
+def _sm_mll_setup_context(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _sm_mll_backward(ctx, g_mll, g_grad, g_info):
+    (grad,) = ctx.saved_tensors
+    g_raw = g_mll.unsqueeze(1) * grad if g_mll is not None else None
+    return (None, None, None, g_raw) + (None,) * 8
+
+
+ops.sm_mll_grad.register_autograd(_sm_mll_backward, setup_context=_sm_mll_setup_context)
+
+
+class B200ExactMarginalLogLikelihood(torch.nn.Module):
+    """Per-datum exact marginal log-likelihood of an SM exact GP, computed on the B200."""
+
+    def __init__(self, likelihood, model):
+        super().__init__()
+        self.likelihood = likelihood
+        self.model = model
+        self.last_info = 0
+
+    def forward(self, function_dist, target, *params):
+        from .gp import NanError, NotPSDError
+        model = self.model
+        pk = pack_model(model, self.likelihood)
+        x = getattr(function_dist, "x", None)
+        if x is None:                       # a real gpytorch MultivariateNormal: use the
+            x = model.train_inputs[0]       # training inputs it was built from
+        if x.dim() == 1:
+            x = x.unsqueeze(-1)
+        raw = pk.raw()
+        dev = engine_device(raw)
+        f64 = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float64)
+        mll, grad, info = ops.sm_mll_grad(
+            f64(x).unsqueeze(0).contiguous(), f64(target).unsqueeze(0).contiguous(),
+            None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
+            raw.to(device=dev, dtype=torch.float64).unsqueeze(0),
+            pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev), None, pk.kind, pk.Q, pk.learn_noise,
+            True)
+        code = int(info.item())
+        self.last_info = code
+        if code == -1:
+            raise NanError("cholesky_cpu: NaN values found in the covariance matrix")
+        if code == -2:
+            raise NotPSDError("Matrix not positive definite after repeatedly adding jitter "
+                              "up to 1.0e-06.")
+        if code > 0:
+            import warnings
+            from .gp import NumericalWarning
+            warnings.warn(f"A not p.d., added jitter of {1e-8 * 10 ** (code - 1):.1e} to the "
+                          "diagonal", NumericalWarning)
+        return mll[0].to(dtype=raw.dtype, device=raw.device)

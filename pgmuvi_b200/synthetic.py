@@ -28,6 +28,13 @@ def logit(u):
     return np.log(u) - np.log1p(-u)
 
 
+def fixed_noise_variance(yerr):
+    """yerr -> variance as the reference forms it: float32 ``yerr ** 2``
+    (lightcurve.py:2780-2784), clamped to GPyTorch's fp64 ``min_fixed_noise`` 1e-6."""
+    v = (np.asarray(yerr, dtype=np.float32) ** 2).astype(np.float64)
+    return np.maximum(v, 1e-6)
+
+
 def param_count(Q, d, learn_noise):
     return 1 + Q + 2 * Q * d + (1 if learn_noise else 0)
 
@@ -113,7 +120,7 @@ def make_batch_1d(B, n, Q=4, learn_noise=False, fixed_noise=True, seed0=1000):
         x[b, :, 0] = t01
         y[b] = yy
         if fixed_noise:
-            noise[b] = np.maximum(yerr ** 2, 1e-6)
+            noise[b] = fixed_noise_variance(yerr)
         kinds, lbb, ubb = default_constraints(t01, yy, yerr if fixed_noise else None, Q, d,
                                               learn_noise)
         lb[b], ub[b] = lbb, ubb
@@ -176,7 +183,7 @@ def make_batch_2d(B, n_bands, n_per_band, Q=4, learn_noise=False, seed0=5000):
         x01, yy, yerr, (period, span) = make_lightcurve_2d(seed0 + b, n_bands, n_per_band)
         rng = np.random.default_rng(20_000_000 + seed0 + b)
         x[b], y[b] = x01, yy
-        noise[b] = np.maximum(yerr ** 2, 1e-6)
+        noise[b] = fixed_noise_variance(yerr)
         kinds, lbb, ubb = default_constraints(x01, yy, yerr, Q, d, learn_noise)
         lb[b], ub[b] = lbb, ubb
         periods[b] = period

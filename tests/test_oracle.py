@@ -1,0 +1,155 @@
+"""CPU tests of the oracle: golden vectors, internal cross-checks, and the reference-produced
+known-answer test K3.  The oracle is the checker for the CUDA path."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import (ModelSpec, adam_step, constrain, mll_and_grad_analytic,
+                    mll_and_grad_autograd, psd_safe_cholesky, sm_kernel_dense, train_loop,
+                    unconstrain, unpack_params)
+from oracle.sm_gp import batched_mll_and_grad, noise_diag
+
+torch.set_default_dtype(torch.float64)
+
+
+def _case(g, b):
+    n = g["x"].shape[1] if g["n_valid"] is None else int(g["n_valid"][b])
+    t = lambda a: None if a is None else torch.tensor(a[b][:n])
+    spec = ModelSpec(d=g["d"], Q=g["Q"], kind=g["kind"], learn_noise=g["learn_noise"])
+    return (t(g["x"]), t(g["y"]), t(g["noise"]), torch.tensor(g["raw"][b]),
+            torch.tensor(g["kinds"]), torch.tensor(g["lb"][b]), torch.tensor(g["ub"][b]), spec)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_goldens(name):
+    g = load_golden(name)
+    for b in range(g["x"].shape[0]):
+        x, y, nz, raw, kinds, lb, ub, spec = _case(g, b)
+        m, gr, info = mll_and_grad_analytic(x, y, nz, raw, kinds, lb, ub, spec)
+        assert int(info) == int(g["info"][b])
+        assert abs(float(m) - g["mll"][b]) <= 1e-11 * abs(g["mll"][b])
+        scale = np.abs(g["grad_autograd"][b]).max()
+        assert np.abs(gr.numpy() - g["grad_autograd"][b]).max() <= 1e-8 * scale
+        assert np.abs(g["grad_analytic"][b] - g["grad_autograd"][b]).max() <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("name", ["sm1d_n100_q2_learn", "sm2d_prodsum_4x48_q4",
+                                  "sm2d_sumprod_4x48_q4"])
+def test_autograd_matches_closed_form(name):
+    g = load_golden(name)
+    x, y, nz, raw, kinds, lb, ub, spec = _case(g, 0)
+    m1, g1, _ = mll_and_grad_autograd(x, y, nz, raw, kinds, lb, ub, spec)
+    m2, g2, _ = mll_and_grad_analytic(x, y, nz, raw, kinds, lb, ub, spec)
+    assert abs(float(m1) - float(m2)) <= 1e-12 * abs(float(m1))
+    assert float((g1 - g2).abs().max()) <= 1e-10 * float(g1.abs().max())
+
+
+def test_kernel_symmetry_stationarity_and_diag():
+    g = load_golden("sm1d_n100_q2_learn")
+    x, y, nz, raw, kinds, lb, ub, spec = _case(g, 0)
+    mean, w, mu, sg, noise = unpack_params(constrain(raw, kinds, lb, ub), spec)
+    K = sm_kernel_dense(x, x, w, mu, sg, spec.kind)
+    assert torch.allclose(K, K.T, atol=1e-14)                       # tests/test_kernels.py:44-47
+    assert torch.allclose(torch.diagonal(K), w.sum().expand(len(y)), atol=1e-14)
+    Ks = sm_kernel_dense(x + 3.25, x + 3.25, w, mu, sg, spec.kind)  # stationary kernel
+    assert torch.allclose(K, Ks, atol=1e-11)
+
+
+def test_2d_variants_factorise():
+    """prod-of-sums with Q=1 equals sum-of-products with Q=1 equals K_t o K_lambda
+    (mirrors the ProductKernel identity of tests/test_kernels.py:130-139)."""
+    g = load_golden("sm2d_prodsum_4x48_q2_learn")
+    x = torch.tensor(g["x"][0])
+    w = torch.tensor([0.7])
+    mu = torch.tensor([[3.0, 0.4]])
+    sg = torch.tensor([[1.1, 0.6]])
+    K1 = sm_kernel_dense(x, x, w, mu, sg, 1)
+    K2 = sm_kernel_dense(x, x, w, mu, sg, 2)
+    Kt = sm_kernel_dense(x[:, :1], x[:, :1], torch.ones(1), mu[:, :1], sg[:, :1], 0)
+    Kl = sm_kernel_dense(x[:, 1:], x[:, 1:], torch.ones(1), mu[:, 1:], sg[:, 1:], 0)
+    assert torch.allclose(K2, 0.7 * Kt * Kl, atol=1e-13)
+    assert torch.allclose(K1, 0.49 * Kt * Kl, atol=1e-13)   # weight enters once per dimension
+
+
+def test_mll_is_per_datum_gaussian_logprob():
+    g = load_golden("sm1d_n40_q4")
+    x, y, nz, raw, kinds, lb, ub, spec = _case(g, 1)
+    mean, w, mu, sg, noise = unpack_params(constrain(raw, kinds, lb, ub), spec)
+    K = sm_kernel_dense(x, x, w, mu, sg, 0) + torch.diag_embed(noise_diag(len(y), nz, noise, y.dtype))
+    mvn = torch.distributions.MultivariateNormal(mean.expand(len(y)), covariance_matrix=K)
+    assert abs(float(mvn.log_prob(y)) / len(y) - g["mll"][1]) < 1e-10
+
+
+def test_constraint_roundtrip():
+    kinds = torch.tensor([0, 1, 1, 2])
+    lb = torch.tensor([0.0, 0.0, 1.5, -2.0])
+    ub = torch.tensor([0.0, 0.0, 0.0, 3.0])
+    raw = torch.tensor([0.3, -2.0, 40.0, 0.7])
+    v = constrain(raw, kinds, lb, ub)
+    assert torch.allclose(unconstrain(v, kinds, lb, ub), raw, atol=1e-10)
+    assert float(v[2]) == pytest.approx(41.5)
+    assert -2.0 < float(v[3]) < 3.0
+
+
+def test_jitter_ladder():
+    A = torch.eye(4).repeat(3, 1, 1)
+    A[1, 3, 3] = -1e-9          # rescued by the first jitter (1e-8)
+    A[2, 3, 3] = -1.0           # not PD even with 1e-6
+    L, info = psd_safe_cholesky(A)
+    assert info.tolist() == [0, 1, -2]
+    A[0, 0, 0] = float("nan")
+    assert psd_safe_cholesky(A)[1].tolist()[0] == -1
+
+
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (True, 0.01)])
+def test_adam_step_matches_torch(decoupled, wd):
+    p0 = torch.randn(7, generator=torch.Generator().manual_seed(1))
+    p = p0.clone().requires_grad_(True)
+    opt = (torch.optim.AdamW([p], lr=0.1, eps=1e-8) if decoupled
+           else torch.optim.Adam([p], lr=0.1, eps=1e-8))
+    q, m, v = p0.numpy().copy(), np.zeros(7), np.zeros(7)
+    for step in range(1, 5):
+        gr = torch.sin(p.detach() * step)
+        p.grad = gr.clone()
+        opt.step()
+        q, m, v = adam_step(q, gr.numpy(), m, v, step, 0.1, weight_decay=wd, decoupled=decoupled)
+        assert np.allclose(q, p.detach().numpy(), rtol=0, atol=1e-14)
+
+
+def test_train_loop_schema_and_goldens():
+    g = load_golden("sm1d_n100_q2_learn")
+    x, y, nz, raw, kinds, lb, ub, spec = _case(g, 0)
+    res = train_loop(x, y, nz, raw, kinds, lb, ub, spec, maxiter=3, miniter=3, lr=0.1,
+                     optim="AdamW")
+    assert len(res["loss"]) == 3 and len(res["delta_loss"]) == 2 and len(res["raw"]) == 4
+    assert np.allclose(np.stack(res["raw"]), g["adamw_raw"][0], atol=1e-12)
+    assert np.allclose(np.array(res["loss"], dtype=float), g["adamw_loss"][0], atol=1e-12)
+
+
+def test_batched_baseline_matches_single():
+    g = load_golden("sm1d_n200_q4")
+    t = torch.tensor
+    spec = ModelSpec(d=1, Q=4)
+    m, gr = batched_mll_and_grad(t(g["x"]), t(g["y"]), t(g["noise"]), t(g["raw"]), t(g["kinds"]),
+                                 t(g["lb"]), t(g["ub"]), spec)
+    assert np.allclose(m.numpy(), g["mll"], rtol=1e-11)
+    assert np.allclose(gr.numpy(), g["grad_autograd"], rtol=1e-7, atol=1e-12)
+
+
+def test_kat_k3_tutorial_fit():
+    """The only reference-produced numbers for the path (executed notebook): fp32, AdamW,
+    3000 iterations.  Published: loss -0.36470833, period 178.2802, weight 0.47454086."""
+    from oracle.kats import K3_PUBLISHED, k3_problem, k3_run
+    *_, meta = k3_problem()
+    assert meta["P"] == pytest.approx(178.17964606037768)          # cell 6 printout
+    assert meta["period_guess"] == pytest.approx(196.48998803679268)  # cell 21 printout
+    assert meta["ystd"] == pytest.approx(0.7348, abs(1e-4))        # cell 10: weights = std(y)
+    assert meta["ymid"] == pytest.approx(0.0200181, abs=1e-6)      # cell 10: constant
+    out, _ = k3_run(torch.float32)
+    assert out["loss"] == pytest.approx(K3_PUBLISHED["loss"], abs=1e-3)
+    assert out["period"] == pytest.approx(K3_PUBLISHED["period"], rel=1e-3)
+    assert out["weight"] == pytest.approx(K3_PUBLISHED["weight"], rel=5e-3)
+    assert out["noise"] == pytest.approx(K3_PUBLISHED["noise"], rel=5e-3)
