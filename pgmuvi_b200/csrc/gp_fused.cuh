@@ -13,7 +13,7 @@
 // by pgmuvi/trainers.py:177-182 and pgmuvi/gps.py:205-220, 302-318.
 //
 // Per-block scratch lives in a global workspace indexed by blockIdx.x (reused for every
-// light curve the block processes, so it stays L2-resident); only L / L^-1 tiles go there.
+// light curve the block processes); only L / L^-1 tiles go there.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,14 +23,12 @@ namespace pgm {
 
 constexpr int TS = 64;          // tile edge
 constexpr int TT = TS * TS;     // elements per tile
-constexpr int KC = 16;          // k-chunk per pipeline stage
+constexpr int KC = 32;          // k-chunk per pipeline stage
 constexpr int NTHREADS = 256;   // 8 warps: 2 (M) x 4 (N), warp tile 32 x 16
-constexpr int NSTAGES = 3;
-constexpr int LD_NT = 20;       // smem ld of a [64][KC] chunk   (ld % 16 == 4 -> conflict free)
-constexpr int LD_KM = 68;       // smem ld of a [KC][64] chunk
-constexpr int OPBUF = 1280;     // elements per operand per stage  (>= 64*20, 16*68)
-constexpr int LD_S = 68;        // smem ld of the 64x64 work tile
-constexpr int STAGE_ELEMS = NSTAGES * 2 * OPBUF;   // 7680
+constexpr int NSTAGES = 2;
+constexpr int OPBUF = TS * KC;  // elements per operand per stage (XOR-swizzled, no padding)
+constexpr int LD_S = 68;        // smem ld of the 64x64 work tile (diagonal blocks)
+constexpr int STAGE_ELEMS = NSTAGES * 2 * OPBUF;   // 8192 doubles = 64 KB
 constexpr int S_ELEMS = TS * LD_S;                 // 4352
 
 #define PGM_KIND_SM1D 0
@@ -67,12 +65,50 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
 
 __host__ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+// exp(x) for x <= 0, branch free: x = (64 e + j) ln2/64 + r, |r| <= ln2/128,
+// exp(x) = 2^e * T[j] * (1 + r + ... + r^5/120)   (truncation 3.5e-17 relative).
+// T = correctly rounded 2^(j/64), held in shared memory.
+__constant__ double c_exp2_tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
+  x = fmax(x, -700.0);
+  double t = fma(x, 0x1.71547652b82fep+6, 6755399441055744.0);  // round(x * 64/ln2)
+  const int k = __double2loint(t);
+  t -= 6755399441055744.0;
+  double r = fma(t, -0x1.62e42fee00000p-7, x);   // ln2/64 hi (33 significant bits)
+  r = fma(t, -0x1.a39ef35793c76p-39, r);         // ln2/64 lo
+  double p = fma(r, 8.33333333333333333e-03, 4.16666666666666667e-02);
+  p = fma(p, r, 1.66666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = tab[k & 63] * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
+
 // ------------------------------------------------------------------------------------
 // static configuration per (kernel kind, padded mixture count, input dims)
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
 struct Cfg {
-  static constexpr int NFB = D + 2 * D * QT;  // per-point fields: x[D], (cos,sin)[D][QT]
+  static constexpr int NCS = D * QT;          // (cos, sin) pairs per point
+  static constexpr int NFB = D + 2 * NCS;     // per-point doubles: x[D], (cos,sin)[D][QT]
   static constexpr int NF = NFB + 1;          // + alpha
   static constexpr int NG = QT + 2 * QT * D;  // kernel-gradient accumulators
   static constexpr int NV = NG + 1;           // + tr W
@@ -83,16 +119,18 @@ struct Cfg {
   static constexpr int SM_ROW = SM_S + S_ELEMS;
   static constexpr int SM_COL = SM_ROW + NF * TS;
   static constexpr int SM_PAR = SM_COL + NF * TS;
-  // par block: theta[PMAX] jac[PMAX] w[QT] a[QT*D] red[8*NV] fin[NV+4] tmp[64]
   static constexpr int PAR_THETA = 0;
   static constexpr int PAR_JAC = PAR_THETA + PMAX;
   static constexpr int PAR_W = PAR_JAC + PMAX;
   static constexpr int PAR_A = PAR_W + QT;
   static constexpr int PAR_RED = PAR_A + QT * D;
   static constexpr int PAR_FIN = PAR_RED + 8 * (NV + 2);
-  static constexpr int PAR_TMP = PAR_FIN + NV + 4;
-  static constexpr int PAR_RAW = PAR_TMP + 4 * TS;   // raw / adam state for the fit kernel
-  static constexpr int PAR_END = PAR_RAW + 3 * PMAX;
+  static constexpr int PAR_ZJ = (PAR_FIN + NV + 4 + 1) & ~1;   // z_j of the current block column [64], 16-B aligned
+  static constexpr int PAR_ZI = PAR_ZJ + TS;          // z_i of the current tile row / scratch [64]
+  static constexpr int PAR_DINV = PAR_ZI + TS;        // 1 / L_kk of the current diagonal block [64]
+  static constexpr int PAR_TAB = PAR_DINV + TS;       // 2^(j/64) table [64]
+  static constexpr int PAR_RAW = PAR_TAB + 64;        // raw / adam state / gradient (fit kernel)
+  static constexpr int PAR_END = PAR_RAW + 4 * PMAX;
   static constexpr int SM_TOTAL = SM_PAR + PAR_END + 8;
   static constexpr size_t SMEM_BYTES = (size_t)SM_TOTAL * sizeof(double);
 };
@@ -101,25 +139,63 @@ struct Cfg {
 struct Scratch {
   double* tiles;  // ntri * TT : L_ij (i>j) then X_ij; diagonal slots hold X_jj = L_jj^-1
   double* ctmp;   // TT
-  double* fld;    // NF * npad : x[D], trig, alpha
+  double* fx;     // D * npad      : centred inputs, [dd][i]
+  double* fcs;    // NCS * npad * 2: (cos, sin)(2 pi mu_qd x_id), [(dd*QT+q)][i][2]
+  double* alpha;  // npad
   double* rhs;    // npad  (y - mean)
   double* z;      // npad  (L^-1 rhs)
   double* dn;     // npad  (diagonal noise)
+  double* fpart;  // ntri * 4 * 64 : partial products L_ij z_j per warp column (forward solve)
+  double* apart;  // ntri * 2 * 64 : partial products X_ij^T z_i per warp row (alpha)
 };
 __host__ __device__ inline size_t scratch_elems(int n_max, int NF) {
   int N = (n_max + TS - 1) / TS;
   size_t npad = (size_t)N * TS;
-  return (size_t)tri(N, 0) * TT + TT + (size_t)NF * npad + 3 * npad + 64;
+  size_t ntri = (size_t)tri(N, 0);
+  return ntri * TT + TT + (size_t)(NF + 4) * npad + ntri * 6 * TS + 64;
 }
 
 // ------------------------------------------------------------------------------------
 // the tensor-core tile engine:  acc += sum_kt  opA(tileA(kt)) * opB(tileB(kt))^T
-//   opX element (row r of the product operand, k):   NT: tile[r*64 + k]   KM: tile[k*64 + r]
-// A,B tiles are global (L2-resident scratch); 3-stage cp.async pipeline into padded smem.
+//   opX element (u = row of the product operand, k):   NT: tile[u*64 + k]   KM: tile[k*64 + u]
+// Tiles are global (per-block scratch); 2-stage cp.async pipeline of 32-deep k-chunks into
+// XOR-swizzled shared memory; every fragment load is a conflict-free LDS.128.
+//
+// k <-> lane mapping of one 8-deep k-group (same for both operands): MMA step h in {0,1},
+// lane tq holds k = 8*k8 + 2*tq + h.
+// Accumulator layout acc[mi][ni][e] (lane = 4*g + tq):
+//   row:  A NT: wm*32 + mi*8 + g            A KM: wm*32 + (mi>>1)*16 + 2*g + (mi&1)
+//   col:  B NT: wn*16 + ni*8 + 2*tq + e     B KM: wn*16 + 4*tq + 2*e + ni
 // ------------------------------------------------------------------------------------
-template <bool A_KM, bool B_KM, typename FA, typename FB>
+template <bool KM>
+__device__ __forceinline__ int frag_row(int wm, int mi, int g) {
+  return KM ? (wm * 32 + (mi >> 1) * 16 + 2 * g + (mi & 1)) : (wm * 32 + mi * 8 + g);
+}
+template <bool KM>
+__device__ __forceinline__ int frag_col(int wn, int ni, int tq, int e) {
+  return KM ? (wn * 16 + 4 * tq + 2 * e + ni) : (wn * 16 + ni * 8 + 2 * tq + e);
+}
+
+template <bool KM>
+__device__ __forceinline__ void issue_operand(double* __restrict__ sbuf,
+                                              const double* __restrict__ gtile, int kc, int tid) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const int p = tid + h * NTHREADS;   // 1024 16-byte chunks per operand per stage
+    if (!KM) {
+      const int row = p >> 4, ch = p & 15;
+      cp_async16(sbuf + row * KC + ((ch ^ ((row & 1) << 2)) << 1), gtile + row * TS + kc * KC + ch * 2);
+    } else {
+      const int kk = p >> 5, ch = p & 31;
+      cp_async16(sbuf + kk * TS + ((ch ^ (((kk >> 1) & 3) << 1)) << 1),
+                 gtile + (kc * KC + kk) * TS + ch * 2);
+    }
+  }
+}
+
+template <bool A_KM, bool B_KM, typename FA, typename FB, typename FX>
 __device__ __forceinline__ void gemm_tiles(double (&acc)[4][2][2], int nk, FA tileA, FB tileB,
-                                           double* __restrict__ stages) {
+                                           double* __restrict__ stages, FX extra_prefetch) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
@@ -127,61 +203,75 @@ __device__ __forceinline__ void gemm_tiles(double (&acc)[4][2][2], int nk, FA ti
   const int nchunks = nk * (TS / KC);
 
   auto issue = [&](int c) {
-    const int kt = c >> 2, kc = c & 3;
-    double* sA = stages + (c % NSTAGES) * (2 * OPBUF);
-    double* sB = sA + OPBUF;
-    const double* gA = tileA(kt);
-    const double* gB = tileB(kt);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int p = tid + h * NTHREADS;
-      if (!A_KM) {
-        const int row = p >> 3, seg = p & 7;
-        cp_async16(sA + row * LD_NT + seg * 2, gA + row * TS + kc * KC + seg * 2);
-      } else {
-        const int kr = p >> 5, seg = p & 31;
-        cp_async16(sA + kr * LD_KM + seg * 2, gA + (kc * KC + kr) * TS + seg * 2);
-      }
-      if (!B_KM) {
-        const int row = p >> 3, seg = p & 7;
-        cp_async16(sB + row * LD_NT + seg * 2, gB + row * TS + kc * KC + seg * 2);
-      } else {
-        const int kr = p >> 5, seg = p & 31;
-        cp_async16(sB + kr * LD_KM + seg * 2, gB + (kc * KC + kr) * TS + seg * 2);
-      }
-    }
+    const int kt = c >> 1, kc = c & 1;
+    double* sA = stages + (c & 1) * (2 * OPBUF);
+    issue_operand<A_KM>(sA, tileA(kt), kc, tid);
+    issue_operand<B_KM>(sA + OPBUF, tileB(kt), kc, tid);
   };
 
   __syncthreads();  // previous users of the stage buffers / producers of the tiles are done
-#pragma unroll
-  for (int s = 0; s < NSTAGES - 1; ++s) {
-    if (s < nchunks) issue(s);
-    cp_async_commit();
-  }
+  extra_prefetch();
+  if (nchunks > 0) issue(0);
+  cp_async_commit();
   for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<NSTAGES - 2>();
+    cp_async_wait<0>();
     __syncthreads();
-    if (c + NSTAGES - 1 < nchunks) issue(c + NSTAGES - 1);
+    if (c + 1 < nchunks) issue(c + 1);
     cp_async_commit();
-    const double* sA = stages + (c % NSTAGES) * (2 * OPBUF);
+    const double* sA = stages + (c & 1) * (2 * OPBUF);
     const double* sB = sA + OPBUF;
 #pragma unroll
-    for (int k4 = 0; k4 < KC / 4; ++k4) {
-      double a[4], b[2];
+    for (int k8 = 0; k8 < KC / 8; ++k8) {
+      double a[2][4], b[2][2];
+      if (!A_KM) {
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi) {
-        const int r = wm * 32 + mi * 8 + g;
-        a[mi] = A_KM ? sA[(k4 * 4 + tq) * LD_KM + r] : sA[r * LD_NT + k4 * 4 + tq];
+        for (int mi = 0; mi < 4; ++mi) {
+          const int r = wm * 32 + mi * 8 + g;
+          const double2 v = *reinterpret_cast<const double2*>(
+              sA + r * KC + (((k8 * 4 + tq) ^ ((r & 1) << 2)) << 1));
+          a[0][mi] = v.x;
+          a[1][mi] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int kk = k8 * 8 + 2 * tq + h;   // ((kk >> 1) & 3) == tq
+#pragma unroll
+          for (int gp = 0; gp < 2; ++gp) {
+            const int u = wm * 32 + gp * 16 + 2 * g;
+            const double2 v = *reinterpret_cast<const double2*>(
+                sA + kk * TS + ((((u >> 1)) ^ (tq << 1)) << 1));
+            a[h][gp * 2] = v.x;
+            a[h][gp * 2 + 1] = v.y;
+          }
+        }
+      }
+      if (!B_KM) {
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          const int r = wn * 16 + ni * 8 + g;
+          const double2 v = *reinterpret_cast<const double2*>(
+              sB + r * KC + (((k8 * 4 + tq) ^ ((r & 1) << 2)) << 1));
+          b[0][ni] = v.x;
+          b[1][ni] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int kk = k8 * 8 + 2 * tq + h;
+          const int u = wn * 16 + 2 * g;
+          const double2 v = *reinterpret_cast<const double2*>(
+              sB + kk * TS + (((u >> 1) ^ (tq << 1)) << 1));
+          b[h][0] = v.x;
+          b[h][1] = v.y;
+        }
       }
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        const int r = wn * 16 + ni * 8 + g;
-        b[ni] = B_KM ? sB[(k4 * 4 + tq) * LD_KM + r] : sB[r * LD_NT + k4 * 4 + tq];
-      }
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni) mma_f64(acc[mi][ni], a[mi], b[ni]);
+          for (int ni = 0; ni < 2; ++ni) mma_f64(acc[mi][ni], a[h][mi], b[h][ni]);
     }
   }
   cp_async_wait<0>();
@@ -194,39 +284,47 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][2][2]) {
     for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 }
 
-// fragment entry -> (row, col) inside the 64x64 tile
-#define PGM_FRAG_LOOP(mi, ni, e, r, c)                                      \
-  _Pragma("unroll") for (int mi = 0; mi < 4; ++mi)                          \
-  _Pragma("unroll") for (int ni = 0; ni < 2; ++ni)                          \
-  _Pragma("unroll") for (int e = 0; e < 2; ++e)                             \
-    if (const int r = (threadIdx.x >> 7) * 32 + mi * 8 + ((threadIdx.x & 31) >> 2); true) \
-      if (const int c = ((threadIdx.x >> 5) & 3) * 16 + ni * 8 + (threadIdx.x & 3) * 2 + e; true)
-
+// accumulator -> row-major global tile (16-byte stores)
+template <bool A_KM, bool B_KM>
 __device__ __forceinline__ void store_acc_tile(const double (&acc)[4][2][2], double* tile,
                                                double sign) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r = frag_row<A_KM>(wm, mi, g);
+    if (!B_KM) {
 #pragma unroll
-    for (int ni = 0; ni < 2; ++ni) {
-      const int r = wm * 32 + mi * 8 + g, c = wn * 16 + ni * 8 + tq * 2;
-      double2 v = make_double2(sign * acc[mi][ni][0], sign * acc[mi][ni][1]);
-      *reinterpret_cast<double2*>(tile + r * TS + c) = v;
+      for (int ni = 0; ni < 2; ++ni) {
+        const int c = wn * 16 + ni * 8 + tq * 2;
+        *reinterpret_cast<double2*>(tile + r * TS + c) =
+            make_double2(sign * acc[mi][ni][0], sign * acc[mi][ni][1]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = wn * 16 + 4 * tq + 2 * e;
+        *reinterpret_cast<double2*>(tile + r * TS + c) =
+            make_double2(sign * acc[mi][0][e], sign * acc[mi][1][e]);
+      }
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------
 // kernel entry K(x_i, x_j) and its hyper-parameter derivatives.
-// rowv / colv: per-point fields of the 64 rows / cols of the tile, field-major [f][64]:
-//   f < D: centred x;  f = D + (dd*QT + q)*2 + {0,1}: cos / sin of 2 pi mu_qd x_d.
+// Per-point data of the 64 rows / cols of a tile in shared memory:
+//   xs[dd*64 + r] centred inputs;  cs[((dd*QT+q)*64 + r)] = (cos, sin)(2 pi mu_qd x_rd).
 // cos(2 pi mu tau) = c_i c_j + s_i s_j,  sin(2 pi mu tau) = s_i c_j - c_i s_j.
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
 __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
                                           const double* __restrict__ colv, int r, int c,
                                           const double* __restrict__ w,
-                                          const double* __restrict__ a) {
+                                          const double* __restrict__ a,
+                                          const double* __restrict__ tab) {
+  const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
+  const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
   double tau2[D];
 #pragma unroll
   for (int dd = 0; dd < D; ++dd) {
@@ -240,10 +338,8 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
       double pr = w[q];
 #pragma unroll
       for (int dd = 0; dd < D; ++dd) {
-        const int f = D + (dd * QT + q) * 2;
-        const double C = rowv[f * TS + r] * colv[f * TS + c] +
-                         rowv[(f + 1) * TS + r] * colv[(f + 1) * TS + c];
-        pr *= exp(-a[q * D + dd] * tau2[dd]) * C;
+        const double2 ri = rcs[(dd * QT + q) * TS + r], cj = ccs[(dd * QT + q) * TS + c];
+        pr *= exp_neg(-a[q * D + dd] * tau2[dd], tab) * (ri.x * cj.x + ri.y * cj.y);
       }
       k += pr;
     }
@@ -255,10 +351,8 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < QT; ++q) {
-        const int f = D + (dd * QT + q) * 2;
-        const double C = rowv[f * TS + r] * colv[f * TS + c] +
-                         rowv[(f + 1) * TS + r] * colv[(f + 1) * TS + c];
-        s += w[q] * exp(-a[q * D + dd] * tau2[dd]) * C;
+        const double2 ri = rcs[(dd * QT + q) * TS + r], cj = ccs[(dd * QT + q) * TS + c];
+        s += (w[q] * exp_neg(-a[q * D + dd] * tau2[dd], tab)) * (ri.x * cj.x + ri.y * cj.y);
       }
       k *= s;
     }
@@ -272,8 +366,11 @@ template <int KIND, int QT, int D>
 __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
                                              const double* __restrict__ colv, int r, int c,
                                              const double* __restrict__ w,
-                                             const double* __restrict__ a, double wgt,
+                                             const double* __restrict__ a,
+                                             const double* __restrict__ tab, double wgt,
                                              double (&ga)[QT + 2 * QT * D]) {
+  const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
+  const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
   double tau[D], EC[D][QT], ES[D][QT], Ssum[D];
 #pragma unroll
   for (int dd = 0; dd < D; ++dd) {
@@ -282,12 +379,10 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
     Ssum[dd] = 0.0;
 #pragma unroll
     for (int q = 0; q < QT; ++q) {
-      const int f = D + (dd * QT + q) * 2;
-      const double ci = rowv[f * TS + r], si = rowv[(f + 1) * TS + r];
-      const double cj = colv[f * TS + c], sj = colv[(f + 1) * TS + c];
-      const double E = exp(-a[q * D + dd] * t2);
-      EC[dd][q] = E * (ci * cj + si * sj);
-      ES[dd][q] = E * (si * cj - ci * sj);
+      const double2 ri = rcs[(dd * QT + q) * TS + r], cj = ccs[(dd * QT + q) * TS + c];
+      const double E = exp_neg(-a[q * D + dd] * t2, tab);
+      EC[dd][q] = E * (ri.x * cj.x + ri.y * cj.y);
+      ES[dd][q] = E * (ri.y * cj.x - ri.x * cj.y);
       Ssum[dd] += w[q] * EC[dd][q];
     }
   }
@@ -299,27 +394,27 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
     for (int q = 0; q < QT; ++q) {
       double R = 1.0;  // product of the other dimensions' factor
       if (D == 2) R = (KIND == PGM_KIND_SM_ARD_SUMPROD) ? EC[1 - dd][q] : Ssum[1 - dd];
-      const double ecr = EC[dd][q] * R;
+      const double ecr = (D == 2) ? EC[dd][q] * R : EC[dd][q];
       if (KIND == PGM_KIND_SM_ARD_SUMPROD) {
         if (dd == 0) ga[q] += wgt * ecr;
       } else {
         ga[q] += wgt * ecr;
       }
-      ga[QT + q * D + dd] += wt * (ES[dd][q] * R);
+      ga[QT + q * D + dd] += wt * ((D == 2) ? ES[dd][q] * R : ES[dd][q]);
       ga[QT + QT * D + q * D + dd] += wt2 * ecr;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------
-// 64x64 diagonal block:  S (lower) -> L in place,  X = L^-1 into S2.   256 threads.
-// Panel width 8: warp 0 factors the panel in registers (shuffles), everybody applies the
-// trailing update and forms the next 8 rows of L^-1 by block forward substitution.
-// Returns sum log(pivot) (= log det of the block) in *logdet_out (thread 0), sets *fail.
+// 64x64 diagonal block:  S (lower) -> L in place,  X = L^-1 into S2,  dinv[k] = 1/L_kk.
+// Panel width 8: warp 0 factors the panel in registers (shuffles); the trailing update and
+// the next 8 rows of L^-1 (block forward substitution) run on the tensor cores (DMMA 8x8x4).
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ void potrf_inv_64(double* __restrict__ S, double* __restrict__ S2,
-                                             int* fail, double* logdet_acc) {
+                                             double* __restrict__ dinv, int* fail) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
   for (int p = 0; p < 8; ++p) {
     const int c0 = p * 8;
     if (warp == 0) {
@@ -330,14 +425,14 @@ __device__ __forceinline__ void potrf_inv_64(double* __restrict__ S, double* __r
         a0[k] = (r0 < TS) ? S[r0 * LD_S + c0 + k] : 0.0;
         a1[k] = (r1 < TS) ? S[r1 * LD_S + c0 + k] : 0.0;
       }
-      double ld = 0.0;
       bool bad = false, isnan_ = false;
+      double myrs = 0.0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const double dpiv = shfl_d(a0[k], k);
         if (!(dpiv > 0.0)) { bad = true; if (dpiv != dpiv) isnan_ = true; }
         const double rs = bad ? 1.0 : rsqrt(dpiv);
-        ld += bad ? 0.0 : log(dpiv);
+        if (lane == k) myrs = rs;
         a0[k] *= rs;
         a1[k] *= rs;
 #pragma unroll
@@ -352,31 +447,40 @@ __device__ __forceinline__ void potrf_inv_64(double* __restrict__ S, double* __r
         if (r0 < TS) S[r0 * LD_S + c0 + k] = a0[k];
         if (r1 < TS) S[r1 * LD_S + c0 + k] = a1[k];
       }
-      if (lane == 0) {
-        *logdet_acc += ld;
-        if (bad) atomicOr(fail, isnan_ ? 2 : 1);
-      }
+      if (lane < 8) dinv[c0 + lane] = myrs;
+      if (lane == 0 && bad) atomicOr(fail, isnan_ ? 2 : 1);
     }
     __syncthreads();
-    // (i) trailing update of the lower triangle below/right of the panel
-    const int m = TS - c0 - 8;
-    for (int idx = tid; idx < m * m; idx += NTHREADS) {
-      const int rr = idx / m, cc = idx - rr * m;
-      if (cc <= rr) {
-        const int r = c0 + 8 + rr, c = c0 + 8 + cc;
-        double s = S[r * LD_S + c];
+    // (i) trailing SYRK on 8x8 MMA tiles (ti >= tj > p):  C -= P_ti P_tj^T,  P = S[:, c0:c0+8]
+    {
+      const int m8 = 7 - p;
+      const int cnt = m8 * (m8 + 1) / 2;
+      for (int t = warp; t < cnt; t += NTHREADS / 32) {
+        int a_ = 0;
+        while ((a_ + 1) * (a_ + 2) / 2 <= t) ++a_;
+        const int b_ = t - a_ * (a_ + 1) / 2;
+        const int ti = p + 1 + a_, tj = p + 1 + b_;
+        double2* cp = reinterpret_cast<double2*>(S + (8 * ti + g) * LD_S + 8 * tj + 2 * tq);
+        const double2 cv = *cp;
+        double c2[2] = {cv.x, cv.y};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s -= S[r * LD_S + c0 + k] * S[c * LD_S + c0 + k];
-        S[r * LD_S + c] = s;
+        for (int s = 0; s < 2; ++s)
+          mma_f64(c2, -S[(8 * ti + g) * LD_S + c0 + 4 * s + tq], S[(8 * tj + g) * LD_S + c0 + 4 * s + tq]);
+        *cp = make_double2(c2[0], c2[1]);
       }
     }
-    // (ii) rows c0..c0+7 of T = I - L[c0.., :c0] X[:c0, :]   (columns 0..c0+7)
-    for (int idx = tid; idx < 8 * (c0 + 8); idx += NTHREADS) {
-      const int rr = idx / (c0 + 8), c = idx - rr * (c0 + 8);
-      const int r = c0 + rr;
-      double s = (r == c) ? 1.0 : 0.0;
-      for (int k = c; k < c0; ++k) s -= S[r * LD_S + k] * S2[k * LD_S + c];
-      S2[r * LD_S + c] = s;
+    // (ii) rows c0..c0+7 of T = I - L[c0.., :c0] X[:c0, :]   (column tiles 0..p)
+    for (int nt = warp; nt <= p; nt += NTHREADS / 32) {
+      double c2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) c2[e] = (c0 + g == 8 * nt + 2 * tq + e) ? 1.0 : 0.0;
+      for (int kt = nt; kt < p; ++kt) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+          mma_f64(c2, -S[(c0 + g) * LD_S + 8 * kt + 4 * s + tq],
+                  S2[(8 * kt + 4 * s + tq) * LD_S + 8 * nt + g]);
+      }
+      *reinterpret_cast<double2*>(S2 + (c0 + g) * LD_S + 8 * nt + 2 * tq) = make_double2(c2[0], c2[1]);
     }
     __syncthreads();
     // (iii) 8x8 triangular solve per column (threads 32.., overlaps the next panel on warp 0)
@@ -390,7 +494,7 @@ __device__ __forceinline__ void potrf_inv_64(double* __restrict__ S, double* __r
         double s = v[rr];
 #pragma unroll
         for (int kk = 0; kk < rr; ++kk) s -= S[(c0 + rr) * LD_S + c0 + kk] * v[kk];
-        v[rr] = s / S[(c0 + rr) * LD_S + c0 + rr];
+        v[rr] = s * dinv[c0 + rr];
       }
 #pragma unroll
       for (int rr = 0; rr < 8; ++rr) S2[(c0 + rr) * LD_S + c] = v[rr];
@@ -457,8 +561,8 @@ __device__ __forceinline__ void block_reduce(double (&v)[NVAL], double* red, dou
 
 // ------------------------------------------------------------------------------------
 // one full evaluation of light curve b with raw parameters `raw` (global or shared).
-// Results: smem par[PAR_FIN..]: mll in fin[NV+0]; gradient written to grad_out[P] (may be
-// shared or global); returns info.
+// Writes the per-datum MLL to *mll_out and (PGM_FLAG_GRAD) d MLL / d raw to grad_out[P];
+// returns info.
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
 __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, double* sm,
@@ -485,7 +589,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double* aq = par + C::PAR_A;
   double* red = par + C::PAR_RED;
   double* fin = par + C::PAR_FIN;
-  double* tmpv = par + C::PAR_TMP;
+  double* zj = par + C::PAR_ZJ;
+  double* zi = par + C::PAR_ZI;
+  double* dinv = par + C::PAR_DINV;
+  double* tab = par + C::PAR_TAB;
   int* s_fail = reinterpret_cast<int*>(sm + C::SM_PAR + C::PAR_END);
   double* s_logdet = sm + C::SM_PAR + C::PAR_END + 1;
 
@@ -508,12 +615,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     theta[tid] = th;
     jac[tid] = jc;
   }
+  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
   __syncthreads();
   if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
   if (tid < QT * D) {
     const int q = tid / D, dd = tid - q * D;
     const double sg = (q < Q) ? theta[1 + Q + Q * D + q * D + dd] : 0.0;
-    aq[q * D + dd] = 2.0 * M_PI * M_PI * sg * sg;  // indexed [q*D + dd]
+    aq[q * D + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
   const double mean = theta[0];
   const double lnoise = learn_noise ? theta[P - 1] : 0.0;
@@ -526,13 +634,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
 #pragma unroll
     for (int dd = 0; dd < D; ++dd) {
       const double xc = valid ? (xb[(size_t)i * D + dd] - xb[dd]) : 0.0;
-      sc.fld[(size_t)dd * npad + i] = xc;
+      sc.fx[(size_t)dd * npad + i] = xc;
 #pragma unroll
       for (int q = 0; q < QT; ++q) {
         double sn = 0.0, cs = 1.0;
         if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * D + dd] * xc, &sn, &cs);
-        sc.fld[(size_t)(D + (dd * QT + q) * 2) * npad + i] = cs;
-        sc.fld[(size_t)(D + (dd * QT + q) * 2 + 1) * npad + i] = sn;
+        *reinterpret_cast<double2*>(sc.fcs + ((size_t)(dd * QT + q) * npad + i) * 2) =
+            make_double2(cs, sn);
       }
     }
     sc.rhs[i] = valid ? (yb[i] - mean) : 0.0;
@@ -540,16 +648,28 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   }
   __syncthreads();
 
-  auto load_side = [&](double* vec, int I, int nf) {
-    for (int idx = tid; idx < nf * TS; idx += NTHREADS) {
-      const int f = idx >> 6, r = idx & 63;
-      vec[idx] = sc.fld[(size_t)f * npad + I * TS + r];
+  // asynchronous prefetch of the per-point data of tile row/col I into rowv / colv
+  auto prefetch_side = [&](double* vec, int I, bool with_alpha) {
+    // x: D*64 doubles, cs: NCS*128 doubles, alpha: 64 doubles -> 16-byte chunks
+    constexpr int CH_X = D * 32, CH_CS = C::NCS * 64;
+    for (int ch = tid; ch < CH_X + CH_CS + 32; ch += NTHREADS) {
+      if (ch < CH_X) {
+        const int dd = ch >> 5, o = (ch & 31) * 2;
+        cp_async16(vec + dd * TS + o, sc.fx + (size_t)dd * npad + I * TS + o);
+      } else if (ch < CH_X + CH_CS) {
+        const int c2 = ch - CH_X, f = c2 >> 6, o = (c2 & 63) * 2;
+        cp_async16(vec + D * TS + f * 2 * TS + o, sc.fcs + ((size_t)f * npad + I * TS) * 2 + o);
+      } else if (with_alpha) {
+        const int o = (ch - CH_X - CH_CS) * 2;
+        cp_async16(vec + C::NFB * TS + o, sc.alpha + I * TS + o);
+      }
     }
   };
 
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
   double acc[4][2][2];
   double iq_part = 0.0;  // partial of z^T z
+  double ld_part = 0.0;  // partial of sum log L_kk
   int info = 0;
 
   // ================= phase P: Cholesky + forward solve, with the jitter ladder ========
@@ -559,30 +679,30 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       jitter = 1e-8;
       for (int t = 1; t < attempt; ++t) jitter *= 10.0;
     }
-    if (tid == 0) { *s_fail = 0; *s_logdet = 0.0; }
+    if (tid == 0) *s_fail = 0;
     iq_part = 0.0;
+    ld_part = 0.0;
     bool failed = false;
     for (int j = 0; j < N && !failed; ++j) {
       for (int i = j; i < N; ++i) {
         zero_acc(acc);
         gemm_tiles<false, false>(
             acc, j, [&](int k) { return sc.tiles + (size_t)tri(i, k) * TT; },
-            [&](int k) { return sc.tiles + (size_t)tri(j, k) * TT; }, stages);
-        // rowv/colv are free here: every reader passed the barrier inside gemm_tiles
-        load_side(rowv, i, C::NFB);
-        load_side(colv, j, C::NFB);
+            [&](int k) { return sc.tiles + (size_t)tri(j, k) * TT; }, stages,
+            [&]() { prefetch_side(rowv, i, false); prefetch_side(colv, j, false); });
         __syncthreads();
-        // epilogue: C = Ktilde_ij - acc
+        // epilogue: C = Ktilde_ij - acc   (diagonal tiles: lower triangle only)
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int r = wm * 32 + mi * 8 + g, c = wn * 16 + ni * 8 + tq * 2 + e;
+              const int r = frag_row<false>(wm, mi, g), c = frag_col<false>(wn, ni, tq, e);
               const int gi = i * TS + r, gj = j * TS + c;
               double kv = 0.0;
-              if (gi < n && gj < n) kv = k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq);
+              if (gi < n && gj < n && gj <= gi)
+                kv = k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab);
               if (gi == gj) kv = (gi < n) ? (kv + sc.dn[gi] + jitter) : 1.0;
               acc[mi][ni][e] = kv - acc[mi][ni][e];
             }
@@ -593,11 +713,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int r = wm * 32 + mi * 8 + g, c = wn * 16 + ni * 8 + tq * 2 + e;
+                const int r = frag_row<false>(wm, mi, g), c = frag_col<false>(wn, ni, tq, e);
                 S[r * LD_S + c] = acc[mi][ni][e];
               }
           __syncthreads();
-          potrf_inv_64(S, S2, s_fail, s_logdet);
+          potrf_inv_64(S, S2, dinv, s_fail);
           if (*s_fail) { failed = true; break; }
           // X_jj -> tile(j,j) (explicit zeros above the diagonal)
           double* dt = sc.tiles + (size_t)tri(j, j) * TT;
@@ -608,38 +728,52 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             v.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
             *reinterpret_cast<double2*>(dt + r * TS + c2) = v;
           }
-          // forward solve: z_j = X_jj (rhs_j - sum_{k<j} L_jk z_k)   (4 lanes per row)
+          // forward solve: z_j = X_jj (rhs_j - sum_{k<j} L_jk z_k); the products L_jk z_k
+          // were left in fpart by the epilogues of row j's tiles (4 partials per row).
+          {
+            const int r = tid & 63, part = tid >> 6;
+            double u = 0.0;
+            for (int k = 0; k < j; ++k) u += sc.fpart[((size_t)tri(j, k) * 4 + part) * TS + r];
+            S[part * TS + r] = u;     // S is free again (L_jj itself is not needed any more)
+          }
+          if (tid < TS) ld_part -= log(dinv[tid]);
+          __syncthreads();
+          if (tid < TS)
+            zi[tid] = sc.rhs[j * TS + tid] - ((S[tid] + S[TS + tid]) + (S[2 * TS + tid] + S[3 * TS + tid]));
+          __syncthreads();
           {
             const int r = tid >> 2, l4 = tid & 3;
-            double u = 0.0;
-            for (int k = 0; k < j; ++k) {
-              const double* Lt = sc.tiles + (size_t)tri(j, k) * TT + r * TS;
-              const double* zk = sc.z + k * TS;
-#pragma unroll 4
-              for (int c = l4; c < TS; c += 4) u += Lt[c] * zk[c];
-            }
-            u += shfl_xor_d(u, 1);
-            u += shfl_xor_d(u, 2);
-            if (l4 == 0) tmpv[r] = sc.rhs[j * TS + r] - u;
-            __syncthreads();
             double zz = 0.0;
-            for (int c = l4; c <= r; c += 4) zz += S2[r * LD_S + c] * tmpv[c];
+            for (int c = l4; c <= r; c += 4) zz += S2[r * LD_S + c] * zi[c];
             zz += shfl_xor_d(zz, 1);
             zz += shfl_xor_d(zz, 2);
             if (l4 == 0) {
               sc.z[j * TS + r] = zz;
+              zj[r] = zz;
               iq_part += zz * zz;
             }
           }
           __syncthreads();
         } else {
           // L_ij = C * X_jj^T  via the tile engine (C staged through the block's scratch)
-          store_acc_tile(acc, sc.ctmp, 1.0);
+          store_acc_tile<false, false>(acc, sc.ctmp, 1.0);
           zero_acc(acc);
           gemm_tiles<false, false>(
               acc, 1, [&](int) { return sc.ctmp; },
-              [&](int) { return sc.tiles + (size_t)tri(j, j) * TT; }, stages);
-          store_acc_tile(acc, sc.tiles + (size_t)tri(i, j) * TT, 1.0);
+              [&](int) { return sc.tiles + (size_t)tri(j, j) * TT; }, stages, []() {});
+          store_acc_tile<false, false>(acc, sc.tiles + (size_t)tri(i, j) * TT, 1.0);
+          // partial products L_ij z_j for the forward solve of row i (deterministic order)
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            double s = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) s += acc[mi][ni][e] * zj[frag_col<false>(wn, ni, tq, e)];
+            s += shfl_xor_d(s, 1);
+            s += shfl_xor_d(s, 2);
+            if (tq == 0) sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row<false>(wm, mi, g)] = s;
+          }
         }
       }
     }
@@ -653,11 +787,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
 
   // ---- MLL ---------------------------------------------------------------------------
   {
-    double v1[1] = {iq_part};
-    block_reduce<1>(v1, red, fin);
+    double v2[2] = {iq_part, ld_part};
+    block_reduce<2>(v2, red, fin);
   }
   const double inv_quad = fin[0];
-  const double logdet = *s_logdet;
+  const double logdet = 2.0 * fin[1];
   const double mll = (info >= 0)
                          ? -0.5 * (inv_quad + logdet + (double)n * 1.8378770664093454836) / n
                          : nan("");
@@ -675,32 +809,46 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       zero_acc(acc);
       gemm_tiles<false, true>(
           acc, i - j, [&](int kk) { return sc.tiles + (size_t)tri(i, j + kk) * TT; },
-          [&](int kk) { return sc.tiles + (size_t)tri(j + kk, j) * TT; }, stages);
-      store_acc_tile(acc, sc.ctmp, 1.0);
+          [&](int kk) { return sc.tiles + (size_t)tri(j + kk, j) * TT; }, stages,
+          [&]() { if (tid < TS / 2) cp_async16(zi + tid * 2, sc.z + i * TS + tid * 2); });
+      store_acc_tile<false, true>(acc, sc.ctmp, 1.0);
       zero_acc(acc);
       gemm_tiles<false, true>(
           acc, 1, [&](int) { return sc.tiles + (size_t)tri(i, i) * TT; },
-          [&](int) { return sc.ctmp; }, stages);
-      store_acc_tile(acc, sc.tiles + (size_t)tri(i, j) * TT, -1.0);
+          [&](int) { return sc.ctmp; }, stages, []() {});
+      store_acc_tile<false, true>(acc, sc.tiles + (size_t)tri(i, j) * TT, -1.0);
+      // partial products X_ij^T z_i for alpha_j  (X_ij = -acc); zi was prefetched above and
+      // is visible: every thread passed the barriers of the second gemm_tiles
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double s = 0.0;
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) s -= acc[mi][ni][e] * zi[frag_row<false>(wm, mi, g)];
+          s += shfl_xor_d(s, 4);
+          s += shfl_xor_d(s, 8);
+          s += shfl_xor_d(s, 16);
+          if (g == 0) sc.apart[((size_t)tri(i, j) * 2 + wm) * TS + frag_col<true>(wn, ni, tq, e)] = s;
+        }
     }
   }
   __syncthreads();
-  // ---- alpha = X^T z ------------------------------------------------------------------
-  double* alpha = sc.fld + (size_t)C::NFB * npad;
+  // ---- alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i -----------------------------------
   {
     const int c = tid & 63, rg = tid >> 6;
     for (int j = 0; j < N; ++j) {
+      const double* Xt = sc.tiles + (size_t)tri(j, j) * TT;
+      const double* zz = sc.z + j * TS;
       double s = 0.0;
-      for (int i = j; i < N; ++i) {
-        const double* Xt = sc.tiles + (size_t)tri(i, j) * TT;
-        const double* zi = sc.z + i * TS;
-#pragma unroll 4
-        for (int r = rg; r < TS; r += 4) s += Xt[r * TS + c] * zi[r];
-      }
-      tmpv[rg * TS + c] = s;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) s += Xt[(rg * 16 + r) * TS + c] * zz[rg * 16 + r];
+      if (rg < 2)
+        for (int i = j + 1; i < N; ++i) s += sc.apart[((size_t)tri(i, j) * 2 + rg) * TS + c];
+      S[rg * TS + c] = s;
       __syncthreads();
       if (tid < TS)
-        alpha[j * TS + tid] = tmpv[tid] + tmpv[TS + tid] + tmpv[2 * TS + tid] + tmpv[3 * TS + tid];
+        sc.alpha[j * TS + tid] = (S[tid] + S[TS + tid]) + (S[2 * TS + tid] + S[3 * TS + tid]);
       __syncthreads();
     }
   }
@@ -714,9 +862,8 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       zero_acc(acc);
       gemm_tiles<true, true>(
           acc, N - i, [&](int kk) { return sc.tiles + (size_t)tri(i + kk, i) * TT; },
-          [&](int kk) { return sc.tiles + (size_t)tri(i + kk, j) * TT; }, stages);
-      load_side(rowv, i, C::NF);
-      load_side(colv, j, C::NF);
+          [&](int kk) { return sc.tiles + (size_t)tri(i + kk, j) * TT; }, stages,
+          [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); });
       __syncthreads();
       const double* al_r = rowv + C::NFB * TS;
       const double* al_c = colv + C::NFB * TS;
@@ -726,13 +873,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int r = wm * 32 + mi * 8 + g, c = wn * 16 + ni * 8 + tq * 2 + e;
+            const int r = frag_row<true>(wm, mi, g), c = frag_col<true>(wn, ni, tq, e);
             const int gi = i * TS + r, gj = j * TS + c;
             if (gi < n && gj <= gi) {
               const double W = al_r[r] * al_c[c] - acc[mi][ni][e];
               if (gi == gj) trW += W;
               const double wgt = (gi == gj) ? W : 2.0 * W;
-              k_grad_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, wgt, ga);
+              k_grad_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab, wgt, ga);
             }
           }
     }
@@ -744,7 +891,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     for (int t = 0; t < C::NG; ++t) v[t] = ga[t];
     v[C::NG] = trW;
     double sa = 0.0;
-    for (int i2 = tid; i2 < n; i2 += NTHREADS) sa += alpha[i2];
+    for (int i2 = tid; i2 < n; i2 += NTHREADS) sa += sc.alpha[i2];
     v[C::NV] = sa;
     __syncthreads();
     block_reduce<C::NV + 1>(v, red, fin);
@@ -776,13 +923,18 @@ __device__ __forceinline__ Scratch make_scratch(double* base, int n_max) {
   using C = Cfg<KIND, QT, D>;
   const int N = (n_max + TS - 1) / TS;
   const size_t npad = (size_t)N * TS;
+  const size_t ntri = (size_t)tri(N, 0);
   Scratch sc;
   sc.tiles = base;
-  sc.ctmp = sc.tiles + (size_t)tri(N, 0) * TT;
-  sc.fld = sc.ctmp + TT;
-  sc.rhs = sc.fld + (size_t)C::NF * npad;
+  sc.ctmp = sc.tiles + ntri * TT;
+  sc.fx = sc.ctmp + TT;
+  sc.fcs = sc.fx + (size_t)D * npad;
+  sc.alpha = sc.fcs + (size_t)C::NCS * npad * 2;
+  sc.rhs = sc.alpha + npad;
   sc.z = sc.rhs + npad;
   sc.dn = sc.z + npad;
+  sc.fpart = sc.dn + npad;
+  sc.apart = sc.fpart + ntri * 4 * TS;
   return sc;
 }
 
@@ -793,8 +945,6 @@ template <int KIND, int QT, int D>
 __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
     sm_mll_grad_kernel(EvalArgs A) {
   extern __shared__ __align__(16) double sm[];
-  // NOTE: field layout of a light curve in scratch depends on ITS npad, so make_scratch is
-  // sized for n_max and eval_lightcurve only uses the leading part.
   Scratch sc = make_scratch<KIND, QT, D>(A.ws + (size_t)blockIdx.x * A.ws_per_block, A.n_max);
   const int P = 1 + A.Q + 2 * A.Q * D + ((A.flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0);
   for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
@@ -810,9 +960,9 @@ template <int KIND, int QT, int D>
 __global__ void __launch_bounds__(NTHREADS)
     sm_kernel_dense_kernel(EvalArgs A, double* __restrict__ Kout) {
   using C = Cfg<KIND, QT, D>;
-  __shared__ double rowv[C::NFB * TS];
-  __shared__ double colv[C::NFB * TS];
-  __shared__ double theta[C::PMAX], wq[QT], aq[QT * D];
+  __shared__ __align__(16) double rowv[C::NFB * TS];
+  __shared__ __align__(16) double colv[C::NFB * TS];
+  __shared__ double theta[C::PMAX], wq[QT], aq[QT * D], tab[64];
   const int tid = threadIdx.x;
   const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
   const int Q = A.Q;
@@ -830,6 +980,7 @@ __global__ void __launch_bounds__(NTHREADS)
     else if (kd == 2) th = lb + (ub - lb) * sigmoid_d(rv);
     theta[tid] = th;
   }
+  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
   __syncthreads();
   if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
   if (tid < QT * D) {
@@ -849,8 +1000,8 @@ __global__ void __launch_bounds__(NTHREADS)
       for (int q = 0; q < QT; ++q) {
         double sn = 0.0, cs = 1.0;
         if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * D + dd] * xc, &sn, &cs);
-        vec[(D + (dd * QT + q) * 2) * TS + r] = cs;
-        vec[(D + (dd * QT + q) * 2 + 1) * TS + r] = sn;
+        vec[D * TS + ((dd * QT + q) * TS + r) * 2] = cs;
+        vec[D * TS + ((dd * QT + q) * TS + r) * 2 + 1] = sn;
       }
     }
   }
@@ -862,7 +1013,9 @@ __global__ void __launch_bounds__(NTHREADS)
     const int r = idx >> 6, c = idx & 63;
     const int gi = ti * TS + r, gj = tj * TS + c;
     if (gi < n && gj < n) {
-      double kv = k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq);
+      // evaluate with the larger index as the row so that K_ij and K_ji are the same bits
+      double kv = (gi >= gj) ? k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab)
+                             : k_entry<KIND, QT, D>(colv, rowv, c, r, wq, aq, tab);
       if (gi == gj) kv += (fnb ? fnb[gi] : 0.0) + lnoise;
       Kb[(size_t)gi * A.n_max + gj] = kv;
     }
@@ -898,7 +1051,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* s_raw = par + C::PAR_RAW;
   double* s_m = s_raw + C::PMAX;
   double* s_v = s_m + C::PMAX;
-  double* s_grad = par + C::PAR_TMP + 2 * TS;  // tmpv upper half is free between evals
+  double* s_grad = s_v + C::PMAX;
   double* s_mll = par + C::PAR_FIN + C::NV + 2;
   const int tid = threadIdx.x;
   for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
