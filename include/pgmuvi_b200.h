@@ -130,8 +130,9 @@ int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
                    size_t workspace_bytes, void* stream);
 
 /* Device yardsticks used by bench.py for the self-measured FP64 roofline: runs `iters`
- * dependent-free DMMA (kind 0) or DFMA (kind 1) instructions per thread on every SM and
- * returns achieved TFLOP/s in *tflops (host pointer). */
+ * dependent-free FP64 DMMA (kind 0), FP64 DFMA (kind 1), FP32 FFMA (kind 2) or interleaved
+ * DMMA+DFMA (kind 3, equal flops each) instructions per thread on every SM and returns the
+ * achieved TFLOP/s in *tflops (host pointer). */
 int pgm_peak_probe(int kind, int iters, double* tflops_host, void* stream);
 
 #ifdef __cplusplus

@@ -237,6 +237,30 @@ __global__ void __launch_bounds__(256) probe_dfma(int iters, double* out) {
   for (int i = 0; i < 16; ++i) s += acc[i];
   if (s == 123.456) out[0] = s;
 }
+// DMMA and DFMA interleaved (equal flops each): tells whether they share one FP64 pipe
+__global__ void __launch_bounds__(256) probe_mixed(int iters, double* out) {
+  double acc[4][2], f[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = threadIdx.x * 1e-9 + i;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  const double fa = 1.0000001, fb = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mma_f64(acc[i], a, b);                        // 512 flops / warp
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[(i * 8 + j) & 15] = fma(f[(i * 8 + j) & 15], fa, fb);  // 8 x 64
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += acc[i][0] + acc[i][1];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += f[i];
+  if (s == 123.456) out[0] = s;
+}
 __global__ void __launch_bounds__(256) probe_ffma(int iters, double* out) {
   float acc[16];
 #pragma unroll
@@ -274,6 +298,9 @@ extern "C" int pgm_peak_probe(int kind, int iters, double* tflops_host, void* st
     } else if (kind == 1) {
       pgm::probe_dfma<<<blocks, threads, 0, st>>>(iters, dout);
       flops_per_thread_iter = 16.0 * 2;
+    } else if (kind == 3) {
+      pgm::probe_mixed<<<blocks, threads, 0, st>>>(iters, dout);
+      flops_per_thread_iter = 4.0 * (8 * 8 * 4 * 2) / 32.0 + 32.0 * 2;
     } else {
       pgm::probe_ffma<<<blocks, threads, 0, st>>>(iters, dout);
       flops_per_thread_iter = 16.0 * 2;

@@ -137,7 +137,8 @@ struct Cfg {
 
 // per-block global scratch layout (doubles)
 struct Scratch {
-  double* tiles;  // ntri * TT : L_ij (i>j) then X_ij; diagonal slots hold X_jj = L_jj^-1
+  double* tiles;  // ntri * TT : L_ij (i>j), later X_ij^T; diagonal slots hold X_jj = L_jj^-1
+  double* tilesT; // N * TT    : X_jj^T
   double* ctmp;   // TT
   double* fx;     // D * npad      : centred inputs, [dd][i]
   double* fcs;    // NCS * npad * 2: (cos, sin)(2 pi mu_qd x_id), [(dd*QT+q)][i][2]
@@ -152,48 +153,94 @@ __host__ __device__ inline size_t scratch_elems(int n_max, int NF) {
   int N = (n_max + TS - 1) / TS;
   size_t npad = (size_t)N * TS;
   size_t ntri = (size_t)tri(N, 0);
-  return ntri * TT + TT + (size_t)(NF + 4) * npad + ntri * 6 * TS + 64;
+  return ntri * TT + (size_t)N * TT + TT + (size_t)(NF + 4) * npad + ntri * 6 * TS + 64;
 }
 
 // ------------------------------------------------------------------------------------
-// the tensor-core tile engine:  acc += sum_kt  opA(tileA(kt)) * opB(tileB(kt))^T
-//   opX element (u = row of the product operand, k):   NT: tile[u*64 + k]   KM: tile[k*64 + u]
+// the tensor-core tile engine:  acc += sum_kt  A(kt) * B(kt)^T   on 64x64 row-major tiles
+//   A(kt)[m][k], B(kt)[n][k] with k contiguous ("NT").  Every product of the algorithm is
+//   brought to this form by storing the off-diagonal inverse tiles transposed.
 // Tiles are global (per-block scratch); 2-stage cp.async pipeline of 32-deep k-chunks into
 // XOR-swizzled shared memory; every fragment load is a conflict-free LDS.128.
 //
-// k <-> lane mapping of one 8-deep k-group (same for both operands): MMA step h in {0,1},
-// lane tq holds k = 8*k8 + 2*tq + h.
-// Accumulator layout acc[mi][ni][e] (lane = 4*g + tq):
-//   row:  A NT: wm*32 + mi*8 + g            A KM: wm*32 + (mi>>1)*16 + 2*g + (mi&1)
-//   col:  B NT: wn*16 + ni*8 + 2*tq + e     B KM: wn*16 + 4*tq + 2*e + ni
+// k <-> lane mapping of one 8-deep k-group: MMA step h in {0,1}, lane tq holds
+// k = 8*k8 + 2*tq + h  (both operands).
+// Accumulator layout acc[mi][ni][e] (lane = 4*g + tq), 8x8 MMA tiles interleaved over the
+// warps so that triangular operands / outputs give every warp the same amount of work:
+//   row = 8*mt + g,  mt = MT[wm][mi],  MT = {0,3,4,7} | {1,2,5,6}
+//   col = 8*nt + 2*tq + e,  nt = wn (ni = 0) | 7 - wn (ni = 1)
+//
+// MODE0 describes the zero structure of k-tile 0 (the others are dense):
+//   M_B_LE: B[n][k] = 0 for k > n   M_B_GE: B[n][k] = 0 for k < n
+//   M_A_LE: A[m][k] = 0 for k > m   M_A_GE: A[m][k] = 0 for k < m
+// LOWER: only MMA tiles with mt >= nt are computed (symmetric outputs).
 // ------------------------------------------------------------------------------------
-template <bool KM>
-__device__ __forceinline__ int frag_row(int wm, int mi, int g) {
-  return KM ? (wm * 32 + (mi >> 1) * 16 + 2 * g + (mi & 1)) : (wm * 32 + mi * 8 + g);
+enum { M_FULL = 0, M_B_LE = 1, M_B_GE = 2, M_A_LE = 3, M_A_GE = 4 };
+
+__device__ __forceinline__ int frag_mt(int wm, int mi) {
+  return wm ? ((mi == 0) ? 1 : (mi == 1) ? 2 : (mi == 2) ? 5 : 6)
+            : ((mi == 0) ? 0 : (mi == 1) ? 3 : (mi == 2) ? 4 : 7);
 }
-template <bool KM>
+__device__ __forceinline__ int frag_nt(int wn, int ni) { return ni ? 7 - wn : wn; }
+__device__ __forceinline__ int frag_row(int wm, int mi, int g) { return 8 * frag_mt(wm, mi) + g; }
 __device__ __forceinline__ int frag_col(int wn, int ni, int tq, int e) {
-  return KM ? (wn * 16 + 4 * tq + 2 * e + ni) : (wn * 16 + ni * 8 + 2 * tq + e);
+  return 8 * frag_nt(wn, ni) + 2 * tq + e;
 }
 
-template <bool KM>
 __device__ __forceinline__ void issue_operand(double* __restrict__ sbuf,
                                               const double* __restrict__ gtile, int kc, int tid) {
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
     const int p = tid + h * NTHREADS;   // 1024 16-byte chunks per operand per stage
-    if (!KM) {
-      const int row = p >> 4, ch = p & 15;
-      cp_async16(sbuf + row * KC + ((ch ^ ((row & 1) << 2)) << 1), gtile + row * TS + kc * KC + ch * 2);
-    } else {
-      const int kk = p >> 5, ch = p & 31;
-      cp_async16(sbuf + kk * TS + ((ch ^ (((kk >> 1) & 3) << 1)) << 1),
-                 gtile + (kc * KC + kk) * TS + ch * 2);
-    }
+    const int row = p >> 4, ch = p & 15;
+    cp_async16(sbuf + row * KC + ((ch ^ ((row & 1) << 2)) << 1), gtile + row * TS + kc * KC + ch * 2);
   }
 }
 
-template <bool A_KM, bool B_KM, typename FA, typename FB, typename FX>
+template <int MODE, bool LOWER>
+__device__ __forceinline__ void compute_chunk(double (&acc)[4][2][2], const double* __restrict__ sA,
+                                              const double* __restrict__ sB, int k8base, int wm,
+                                              int wn, int g, int tq) {
+#pragma unroll
+  for (int k8l = 0; k8l < KC / 8; ++k8l) {
+    const int k8g = k8base + k8l;
+    double a[2][4], b[2][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      const int r = frag_row(wm, mi, g);
+      const double2 v = *reinterpret_cast<const double2*>(
+          sA + r * KC + (((k8l * 4 + tq) ^ ((r & 1) << 2)) << 1));
+      a[0][mi] = v.x;
+      a[1][mi] = v.y;
+    }
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      const int r = 8 * frag_nt(wn, ni) + g;
+      const double2 v = *reinterpret_cast<const double2*>(
+          sB + r * KC + (((k8l * 4 + tq) ^ ((r & 1) << 2)) << 1));
+      b[0][ni] = v.x;
+      b[1][ni] = v.y;
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int mt = frag_mt(wm, mi), nt = frag_nt(wn, ni);
+        bool on = true;
+        if (LOWER) on = on && (mt >= nt);
+        if (MODE == M_B_LE) on = on && (k8g <= nt);
+        if (MODE == M_B_GE) on = on && (k8g >= nt);
+        if (MODE == M_A_LE) on = on && (k8g <= mt);
+        if (MODE == M_A_GE) on = on && (k8g >= mt);
+        if (on) {
+          mma_f64(acc[mi][ni], a[0][mi], b[0][ni]);
+          mma_f64(acc[mi][ni], a[1][mi], b[1][ni]);
+        }
+      }
+  }
+}
+
+template <int MODE0, bool LOWER, typename FA, typename FB, typename FX>
 __device__ __forceinline__ void gemm_tiles(double (&acc)[4][2][2], int nk, FA tileA, FB tileB,
                                            double* __restrict__ stages, FX extra_prefetch) {
   const int tid = threadIdx.x;
@@ -205,8 +252,8 @@ __device__ __forceinline__ void gemm_tiles(double (&acc)[4][2][2], int nk, FA ti
   auto issue = [&](int c) {
     const int kt = c >> 1, kc = c & 1;
     double* sA = stages + (c & 1) * (2 * OPBUF);
-    issue_operand<A_KM>(sA, tileA(kt), kc, tid);
-    issue_operand<B_KM>(sA + OPBUF, tileB(kt), kc, tid);
+    issue_operand(sA, tileA(kt), kc, tid);
+    issue_operand(sA + OPBUF, tileB(kt), kc, tid);
   };
 
   __syncthreads();  // previous users of the stage buffers / producers of the tiles are done
@@ -220,59 +267,10 @@ __device__ __forceinline__ void gemm_tiles(double (&acc)[4][2][2], int nk, FA ti
     cp_async_commit();
     const double* sA = stages + (c & 1) * (2 * OPBUF);
     const double* sB = sA + OPBUF;
-#pragma unroll
-    for (int k8 = 0; k8 < KC / 8; ++k8) {
-      double a[2][4], b[2][2];
-      if (!A_KM) {
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-          const int r = wm * 32 + mi * 8 + g;
-          const double2 v = *reinterpret_cast<const double2*>(
-              sA + r * KC + (((k8 * 4 + tq) ^ ((r & 1) << 2)) << 1));
-          a[0][mi] = v.x;
-          a[1][mi] = v.y;
-        }
-      } else {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int kk = k8 * 8 + 2 * tq + h;   // ((kk >> 1) & 3) == tq
-#pragma unroll
-          for (int gp = 0; gp < 2; ++gp) {
-            const int u = wm * 32 + gp * 16 + 2 * g;
-            const double2 v = *reinterpret_cast<const double2*>(
-                sA + kk * TS + ((((u >> 1)) ^ (tq << 1)) << 1));
-            a[h][gp * 2] = v.x;
-            a[h][gp * 2 + 1] = v.y;
-          }
-        }
-      }
-      if (!B_KM) {
-#pragma unroll
-        for (int ni = 0; ni < 2; ++ni) {
-          const int r = wn * 16 + ni * 8 + g;
-          const double2 v = *reinterpret_cast<const double2*>(
-              sB + r * KC + (((k8 * 4 + tq) ^ ((r & 1) << 2)) << 1));
-          b[0][ni] = v.x;
-          b[1][ni] = v.y;
-        }
-      } else {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int kk = k8 * 8 + 2 * tq + h;
-          const int u = wn * 16 + 2 * g;
-          const double2 v = *reinterpret_cast<const double2*>(
-              sB + kk * TS + (((u >> 1) ^ (tq << 1)) << 1));
-          b[h][0] = v.x;
-          b[h][1] = v.y;
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 2; ++ni) mma_f64(acc[mi][ni], a[h][mi], b[h][ni]);
-    }
+    if (MODE0 != M_FULL && c < 2)
+      compute_chunk<MODE0, LOWER>(acc, sA, sB, c * (KC / 8), wm, wn, g, tq);
+    else
+      compute_chunk<M_FULL, LOWER>(acc, sA, sB, 0, wm, wn, g, tq);
   }
   cp_async_wait<0>();
 }
@@ -284,28 +282,24 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][2][2]) {
     for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 }
 
-// accumulator -> row-major global tile (16-byte stores)
-template <bool A_KM, bool B_KM>
+// accumulator -> row-major global tile (TRANSPOSE: tile[c][r] = sign * acc(r, c))
+template <bool TRANSPOSE>
 __device__ __forceinline__ void store_acc_tile(const double (&acc)[4][2][2], double* tile,
                                                double sign) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) {
-    const int r = frag_row<A_KM>(wm, mi, g);
-    if (!B_KM) {
+    const int r = frag_row(wm, mi, g);
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        const int c = wn * 16 + ni * 8 + tq * 2;
+    for (int ni = 0; ni < 2; ++ni) {
+      const int c = frag_col(wn, ni, tq, 0);
+      if (!TRANSPOSE) {
         *reinterpret_cast<double2*>(tile + r * TS + c) =
             make_double2(sign * acc[mi][ni][0], sign * acc[mi][ni][1]);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = wn * 16 + 4 * tq + 2 * e;
-        *reinterpret_cast<double2*>(tile + r * TS + c) =
-            make_double2(sign * acc[mi][0][e], sign * acc[mi][1][e]);
+      } else {
+        tile[c * TS + r] = sign * acc[mi][ni][0];
+        tile[(c + 1) * TS + r] = sign * acc[mi][ni][1];
       }
     }
   }
@@ -686,10 +680,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     for (int j = 0; j < N && !failed; ++j) {
       for (int i = j; i < N; ++i) {
         zero_acc(acc);
-        gemm_tiles<false, false>(
-            acc, j, [&](int k) { return sc.tiles + (size_t)tri(i, k) * TT; },
-            [&](int k) { return sc.tiles + (size_t)tri(j, k) * TT; }, stages,
-            [&]() { prefetch_side(rowv, i, false); prefetch_side(colv, j, false); });
+        auto tA = [&](int k) { return sc.tiles + (size_t)tri(i, k) * TT; };
+        auto tB = [&](int k) { return sc.tiles + (size_t)tri(j, k) * TT; };
+        auto pf = [&]() { prefetch_side(rowv, i, false); prefetch_side(colv, j, false); };
+        if (i == j) gemm_tiles<M_FULL, true>(acc, j, tA, tB, stages, pf);
+        else gemm_tiles<M_FULL, false>(acc, j, tA, tB, stages, pf);
         __syncthreads();
         // epilogue: C = Ktilde_ij - acc   (diagonal tiles: lower triangle only)
 #pragma unroll
@@ -698,7 +693,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int r = frag_row<false>(wm, mi, g), c = frag_col<false>(wn, ni, tq, e);
+              const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, e);
               const int gi = i * TS + r, gj = j * TS + c;
               double kv = 0.0;
               if (gi < n && gj < n && gj <= gi)
@@ -713,20 +708,24 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int r = frag_row<false>(wm, mi, g), c = frag_col<false>(wn, ni, tq, e);
+                const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, e);
                 S[r * LD_S + c] = acc[mi][ni][e];
               }
           __syncthreads();
           potrf_inv_64(S, S2, dinv, s_fail);
           if (*s_fail) { failed = true; break; }
-          // X_jj -> tile(j,j) (explicit zeros above the diagonal)
+          // X_jj -> tile(j,j) and X_jj^T -> tilesT[j] (explicit zeros in the other triangle)
           double* dt = sc.tiles + (size_t)tri(j, j) * TT;
+          double* dtT = sc.tilesT + (size_t)j * TT;
           for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
             const int r = idx >> 5, c2 = (idx & 31) * 2;
-            double2 v;
+            double2 v, vt;
             v.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
             v.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
+            vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
+            vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
             *reinterpret_cast<double2*>(dt + r * TS + c2) = v;
+            *reinterpret_cast<double2*>(dtT + r * TS + c2) = vt;
           }
           // forward solve: z_j = X_jj (rhs_j - sum_{k<j} L_jk z_k); the products L_jk z_k
           // were left in fpart by the epilogues of row j's tiles (4 partials per row).
@@ -756,12 +755,12 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           __syncthreads();
         } else {
           // L_ij = C * X_jj^T  via the tile engine (C staged through the block's scratch)
-          store_acc_tile<false, false>(acc, sc.ctmp, 1.0);
+          store_acc_tile<false>(acc, sc.ctmp, 1.0);
           zero_acc(acc);
-          gemm_tiles<false, false>(
+          gemm_tiles<M_B_LE, false>(
               acc, 1, [&](int) { return sc.ctmp; },
               [&](int) { return sc.tiles + (size_t)tri(j, j) * TT; }, stages, []() {});
-          store_acc_tile<false, false>(acc, sc.tiles + (size_t)tri(i, j) * TT, 1.0);
+          store_acc_tile<false>(acc, sc.tiles + (size_t)tri(i, j) * TT, 1.0);
           // partial products L_ij z_j for the forward solve of row i (deterministic order)
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi) {
@@ -769,10 +768,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) s += acc[mi][ni][e] * zj[frag_col<false>(wn, ni, tq, e)];
+              for (int e = 0; e < 2; ++e) s += acc[mi][ni][e] * zj[frag_col(wn, ni, tq, e)];
             s += shfl_xor_d(s, 1);
             s += shfl_xor_d(s, 2);
-            if (tq == 0) sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row<false>(wm, mi, g)] = s;
+            if (tq == 0) sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
           }
         }
       }
@@ -807,16 +806,19 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   for (int j = 0; j < N - 1; ++j) {
     for (int i = j + 1; i < N; ++i) {
       zero_acc(acc);
-      gemm_tiles<false, true>(
+      // Tm = sum_kk L_{i,j+kk} X_{j+kk,j}:  B operand = X^T tiles (kk = 0: X_jj^T, upper tri.)
+      gemm_tiles<M_B_GE, false>(
           acc, i - j, [&](int kk) { return sc.tiles + (size_t)tri(i, j + kk) * TT; },
-          [&](int kk) { return sc.tiles + (size_t)tri(j + kk, j) * TT; }, stages,
+          [&](int kk) { return kk == 0 ? sc.tilesT + (size_t)j * TT
+                                       : sc.tiles + (size_t)tri(j + kk, j) * TT; }, stages,
           [&]() { if (tid < TS / 2) cp_async16(zi + tid * 2, sc.z + i * TS + tid * 2); });
-      store_acc_tile<false, true>(acc, sc.ctmp, 1.0);
+      store_acc_tile<true>(acc, sc.ctmp, 1.0);          // Tm^T
       zero_acc(acc);
-      gemm_tiles<false, true>(
+      // X_ij = -X_ii Tm  (A = X_ii lower triangular; B operand = Tm^T), stored transposed
+      gemm_tiles<M_A_LE, false>(
           acc, 1, [&](int) { return sc.tiles + (size_t)tri(i, i) * TT; },
           [&](int) { return sc.ctmp; }, stages, []() {});
-      store_acc_tile<false, true>(acc, sc.tiles + (size_t)tri(i, j) * TT, -1.0);
+      store_acc_tile<true>(acc, sc.tiles + (size_t)tri(i, j) * TT, -1.0);
       // partial products X_ij^T z_i for alpha_j  (X_ij = -acc); zi was prefetched above and
       // is visible: every thread passed the barriers of the second gemm_tiles
 #pragma unroll
@@ -825,11 +827,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         for (int e = 0; e < 2; ++e) {
           double s = 0.0;
 #pragma unroll
-          for (int mi = 0; mi < 4; ++mi) s -= acc[mi][ni][e] * zi[frag_row<false>(wm, mi, g)];
+          for (int mi = 0; mi < 4; ++mi) s -= acc[mi][ni][e] * zi[frag_row(wm, mi, g)];
           s += shfl_xor_d(s, 4);
           s += shfl_xor_d(s, 8);
           s += shfl_xor_d(s, 16);
-          if (g == 0) sc.apart[((size_t)tri(i, j) * 2 + wm) * TS + frag_col<true>(wn, ni, tq, e)] = s;
+          if (g == 0) sc.apart[((size_t)tri(i, j) * 2 + wm) * TS + frag_col(wn, ni, tq, e)] = s;
         }
     }
   }
@@ -860,10 +862,14 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   for (int i = 0; i < N; ++i) {
     for (int j = 0; j <= i; ++j) {
       zero_acc(acc);
-      gemm_tiles<true, true>(
-          acc, N - i, [&](int kk) { return sc.tiles + (size_t)tri(i + kk, i) * TT; },
-          [&](int kk) { return sc.tiles + (size_t)tri(i + kk, j) * TT; }, stages,
-          [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); });
+      // Kinv_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}: both operands are the stored X^T tiles
+      auto tA = [&](int kk) { return kk == 0 ? sc.tilesT + (size_t)i * TT
+                                             : sc.tiles + (size_t)tri(i + kk, i) * TT; };
+      auto tB = [&](int kk) { return (kk == 0 && i == j) ? sc.tilesT + (size_t)j * TT
+                                                         : sc.tiles + (size_t)tri(i + kk, j) * TT; };
+      auto pf = [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); };
+      if (i == j) gemm_tiles<M_A_GE, true>(acc, N - i, tA, tB, stages, pf);
+      else gemm_tiles<M_A_GE, false>(acc, N - i, tA, tB, stages, pf);
       __syncthreads();
       const double* al_r = rowv + C::NFB * TS;
       const double* al_c = colv + C::NFB * TS;
@@ -873,7 +879,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         for (int ni = 0; ni < 2; ++ni)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int r = frag_row<true>(wm, mi, g), c = frag_col<true>(wn, ni, tq, e);
+            const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, e);
             const int gi = i * TS + r, gj = j * TS + c;
             if (gi < n && gj <= gi) {
               const double W = al_r[r] * al_c[c] - acc[mi][ni][e];
@@ -926,7 +932,8 @@ __device__ __forceinline__ Scratch make_scratch(double* base, int n_max) {
   const size_t ntri = (size_t)tri(N, 0);
   Scratch sc;
   sc.tiles = base;
-  sc.ctmp = sc.tiles + ntri * TT;
+  sc.tilesT = sc.tiles + ntri * TT;
+  sc.ctmp = sc.tilesT + (size_t)N * TT;
   sc.fx = sc.ctmp + TT;
   sc.fcs = sc.fx + (size_t)D * npad;
   sc.alpha = sc.fcs + (size_t)C::NCS * npad * 2;

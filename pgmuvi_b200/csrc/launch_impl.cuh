@@ -2,6 +2,8 @@
 // the heavy kernels compile in parallel translation units.
 #pragma once
 #include "gp_fused.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include <string>
 
 namespace pgm {
@@ -14,16 +16,18 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   using C = pgm::Cfg<KIND, QT, D>;
   pgm::EvalArgs A = A0;
   auto kern = pgm::sm_mll_grad_kernel<KIND, QT, D>;
+  size_t smem = C::SMEM_BYTES;
+  if (const char* f = getenv("PGM_DEBUG_SMEM_KB")) smem = std::max(smem, (size_t)atoi(f) * 1024);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)C::SMEM_BYTES);
+                                       (int)smem);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pgm::NTHREADS, C::SMEM_BYTES);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pgm::NTHREADS, smem);
   if (e != cudaSuccess) return cuda_fail("occupancy", e);
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
   if (grid > A.B) grid = A.B;
-  kern<<<grid, pgm::NTHREADS, C::SMEM_BYTES, st>>>(A);
+  kern<<<grid, pgm::NTHREADS, smem, st>>>(A);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("sm_mll_grad_kernel launch", e);
   return 0;

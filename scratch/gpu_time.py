@@ -18,3 +18,5 @@ for want in (False, True):
         best = min(best, e0.elapsed_time(e1))
     fl = (512**3 + 4 * 512**2) if want else (512**3 / 3 + 2 * 512**2)
     print(f'time B={B} grad={want}: {best:.3f} ms  {B / best * 1e3:.0f} evals/s  {B * fl / best / 1e9:.2f} TFLOP/s  info-nonzero {int((info != 0).sum())}')
+for k, nm in [(0, 'DMMA'), (1, 'DFMA'), (3, 'DMMA+DFMA mixed')]:
+    print('peak', nm, ops.peak_probe(k, 8192), 'TFLOP/s')
