@@ -1,0 +1,326 @@
+"""Host-side mirror of the slice of ``pgmuvi.lightcurve.Lightcurve`` that CALLS the hot path
+(seam #0): data container + transforms, likelihood / model / default
+constraint / hyper-parameter setup and ``fit(model='1D'|'2D')``.
+
+The real class (pgmuvi/lightcurve.py:1677-10793) cannot be imported in this image
+(``import gpytorch`` / ``matplotlib`` at lightcurve.py:7,31), so this restates exactly the parts
+that fix the parameterisation the engine sees, each method citing what it follows.  Everything
+outside the path (ingest, Lomb-Scargle init, period summaries, plotting) is out of scope; with
+the real pgmuvi installed one uses its ``Lightcurve`` and only swaps ``train``.
+Nothing here computes the GP on the CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import gp
+from .constraints import GreaterThan, Interval
+from .trainers import train
+
+_SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPModel}
+CONSTRAINT_SETS = {"LPV": {"period": {"lower": (20.0, True), "upper": (None, False)}}}
+
+
+class Transformer(torch.nn.Module):
+    """pgmuvi/lightcurve.py:157-194."""
+
+    def transform(self, data, **kwargs):
+        raise NotImplementedError
+
+    def inverse(self, data, shift=True, **kwargs):
+        raise NotImplementedError
+
+
+class MinMax(Transformer):
+    """pgmuvi/lightcurve.py:196-243: rescale every column to [0, 1]."""
+
+    def transform(self, data, dim=0, apply_to=None, recalc=False, shift=True, **kwargs):
+        if recalc or not hasattr(self, "min"):
+            self.register_buffer("min", torch.min(data, dim=dim, keepdim=True)[0])
+            self.register_buffer("range", torch.max(data, dim=dim, keepdim=True)[0] - self.min)
+            shift = True
+        if apply_to is not None:
+            return (data - (shift * self.min[apply_to])) / self.range[apply_to]
+        return (data - (shift * self.min)) / self.range
+
+    def inverse(self, data, shift=True, **kwargs):
+        return (data * self.range) + (shift * self.min)
+
+
+class ZScore(Transformer):
+    """pgmuvi/lightcurve.py:245-288."""
+
+    def transform(self, data, dim=0, apply_to=None, recalc=False, shift=True, **kwargs):
+        if recalc or not hasattr(self, "mean"):
+            self.register_buffer("mean", torch.mean(data, dim=dim, keepdim=True))
+            self.register_buffer("sd", torch.std(data, dim=dim, keepdim=True))
+            shift = True
+        if apply_to is not None:
+            return (data - (shift * self.mean[apply_to])) / self.sd[apply_to]
+        return (data - shift * self.mean) / self.sd
+
+    def inverse(self, data, shift=True, **kwargs):
+        return (data * self.sd) + (self.mean * shift)
+
+
+def _make_transform(t):
+    if t is None or isinstance(t, Transformer):
+        return t
+    if t == "minmax":
+        return MinMax()
+    if t == "zscore":
+        return ZScore()
+    raise ValueError(f"unknown transform {t!r}")
+
+
+class Lightcurve(torch.nn.Module):
+    """``Lightcurve(xdata, ydata, yerr=None, xtransform='minmax', ytransform=None)``
+    (pgmuvi/lightcurve.py:1724-1742).  Data are stored float32 like the reference
+    (``_ensure_tensor``, :2434-2446); ``.double()`` opts into float64."""
+
+    def __init__(self, xdata, ydata, yerr=None, xtransform="minmax", ytransform=None, name=None,
+                 **kwargs):
+        super().__init__()
+        self.name = name
+        self.xtransform = _make_transform(xtransform)
+        self.ytransform = _make_transform(ytransform)
+        x = self._ensure_tensor(xdata)
+        y = self._ensure_tensor(ydata)
+        if x.dim() == 2 and x.shape[1] == 1:
+            x = x[:, 0]
+        if torch.isnan(x).any() or torch.isnan(y).any():
+            raise ValueError("The x / y values contain NaNs.")
+        self.register_buffer("_xdata_raw", x)
+        self.register_buffer("_xdata_transformed",
+                             x if self.xtransform is None else self.xtransform.transform(x))
+        self.register_buffer("_ydata_raw", y)
+        self.register_buffer("_ydata_transformed",
+                             y if self.ytransform is None else self.ytransform.transform(y))
+        if yerr is not None:
+            e = self._ensure_tensor(yerr)
+            self.register_buffer("_yerr_raw", e)
+            # the same transform object is applied to the errors (lightcurve.py:2421-2432)
+            self.register_buffer("_yerr_transformed",
+                                 e if self.ytransform is None else self.ytransform.transform(e))
+        self._constraints_set = False
+        self._fitted = False
+
+    @staticmethod
+    def _ensure_tensor(values):
+        return torch.as_tensor(np.asarray(values) if not torch.is_tensor(values) else values
+                               ).to(torch.float32)
+
+    @property
+    def ndim(self):
+        return 1 if self._xdata_raw.dim() == 1 else self._xdata_raw.shape[-1]
+
+    xdata = property(lambda self: self._xdata_raw)
+    ydata = property(lambda self: self._ydata_raw)
+    yerr = property(lambda self: self._yerr_raw)
+
+    # ---- likelihood (lightcurve.py:2718-2823) ------------------------------------------
+    def set_likelihood(self, likelihood=None, variance=False, **kwargs):
+        has_noise = hasattr(self, "_yerr_transformed")
+        if has_noise:
+            noise = self._yerr_transformed if variance else self._yerr_transformed ** 2
+        if has_noise and likelihood is None:
+            self.likelihood = gp.FixedNoiseGaussianLikelihood(noise)
+        elif has_noise and likelihood == "learn":
+            self.likelihood = gp.FixedNoiseGaussianLikelihood(noise, learn_additional_noise=True)
+        elif likelihood == "learn":
+            self.likelihood = gp.GaussianLikelihood(learn_additional_noise=True)
+        elif "Interval" in [t.__name__ for t in type(likelihood).__mro__]:
+            self.likelihood = gp.GaussianLikelihood(noise_constraint=likelihood)
+        elif likelihood is None:
+            self.likelihood = gp.GaussianLikelihood()
+        elif isinstance(likelihood, (gp.GaussianLikelihood, gp.FixedNoiseGaussianLikelihood)):
+            self.likelihood = likelihood
+        else:
+            raise ValueError(f"Expected a string, a constraint or a Likelihood instance, but got "
+                             f"{type(likelihood)}.")
+
+    # ---- model (lightcurve.py:2825-2974; only the SM exact models are on the path) -------
+    def set_model(self, model=None, likelihood=None, num_mixtures=None, variance=False, **kwargs):
+        if not hasattr(self, "likelihood") or likelihood is not None and not isinstance(
+                likelihood, torch.nn.Module):
+            self.set_likelihood(likelihood, variance=variance)
+        elif isinstance(likelihood, torch.nn.Module):
+            self.likelihood = likelihood
+        if isinstance(model, torch.nn.Module):
+            self.model = model
+        elif model in _SM_MODELS:
+            if model == "1D" and self.ndim > 1:
+                raise ValueError("You have selected a 1D model but your data has more than one "
+                                 "input dimension; use model='2D'.")   # tests/test_2d_integration.py:167-186
+            if model == "2D" and self.ndim != 2:
+                raise ValueError("model='2D' needs xdata of shape [n, 2] (time, wavelength)")
+            self.model = _SM_MODELS[model](self._xdata_transformed, self._ydata_transformed,
+                                           self.likelihood, num_mixtures=num_mixtures or 4,
+                                           **kwargs)
+        else:
+            raise UnsupportedModel(
+                f"model {model!r} is outside the accelerated path (SURVEY section 8a): "
+                "only '1D' and '2D' spectral-mixture exact GPs")
+        self._make_parameter_dict()
+        self._constraints_set = False
+
+    def _make_parameter_dict(self):
+        """name -> owning module, with the aliases of lightcurve.py:2976-3043."""
+        self._model_pars = {}
+        for name, p in self.model.named_parameters():
+            base, _, leaf = name.rpartition(".")
+            mod = self.model.get_submodule(base) if base else self.model
+            key = ".".join(c.lstrip("raw_") for c in name.split("."))
+            self._model_pars[key] = {"module": mod, "raw_name": leaf, "param": p}
+            for alias in ("noise", "mixture_means", "mixture_scales", "mixture_weights"):
+                if key.endswith(alias):
+                    self._model_pars[alias] = self._model_pars[key]
+
+    # ---- default constraints (lightcurve.py:3777-4011) -----------------------------------
+    def set_default_constraints(self, constraint_set=None, **kwargs):
+        y = self._ydata_transformed
+        if "noise" in self._model_pars:
+            if hasattr(self, "_yerr_transformed"):
+                noise_min = float(np.minimum(1e-4, float(self._yerr_transformed.min()) / 10))
+            else:
+                noise_min = 1e-4 * float(y.std())
+            self._model_pars["noise"]["module"].register_constraint(
+                "raw_noise", Interval(noise_min, float(y.std())))
+        for key, ent in self._model_pars.items():
+            if "mean_module.constant" in key:
+                ent["module"].register_constraint("raw_constant",
+                                                  Interval(float(y.min()), float(y.max())))
+        if "mixture_means" in self._model_pars:
+            xt = self._xdata_transformed
+            t = xt[:, 0] if self.ndim > 1 else xt
+            span = float(t.max() - t.min())
+            if span <= 0.0:
+                raise ValueError("set_default_constraints requires a dataset whose timestamps "
+                                 "span a positive time range")
+            if self.ndim > 1:
+                ts = t.sort().values
+                diffs = ts[1:] - ts[:-1]
+                con = Interval(1.0 / span, float(1 / (2 * diffs[diffs > 0].min())))
+            else:
+                con = GreaterThan(1.0 / span)
+            if constraint_set is not None:
+                cs = CONSTRAINT_SETS[constraint_set]
+                lower_val, lower_active = cs["period"]["lower"]
+                xr = self._xdata_raw[:, 0] if self.ndim > 1 else self._xdata_raw
+                freq_scale = float(xr.max() - xr.min()) / span
+                if lower_active and lower_val is not None:
+                    fmax = freq_scale / lower_val
+                    lo = float(con.lower_bound)
+                    if fmax > lo:
+                        hi = float(con.upper_bound)
+                        con = Interval(lo, min(hi, fmax))
+            self._model_pars["mixture_means"]["module"].register_constraint(
+                "raw_mixture_means", con)
+        self._constraints_set = True
+
+    # ---- hyper-parameters (lightcurve.py:4061-4156) --------------------------------------
+    def set_hypers(self, hypers=None, **kwargs):
+        if hypers is None:
+            return
+        hypers = {k: torch.as_tensor(v, dtype=self._ydata_transformed.dtype)
+                  for k, v in hypers.items()}
+        for key in hypers:
+            if any(p in key for p in ("mixture_means", "mixture_scales")):
+                if self.xtransform is not None:
+                    if hypers[key].dim() == 2:
+                        out = torch.zeros_like(hypers[key])
+                        for dim in range(hypers[key].shape[1]):
+                            out[:, dim] = 1 / ((1 / hypers[key][:, dim])
+                                               / self.xtransform.range[0, dim])
+                        hypers[key] = out
+                    else:
+                        hypers[key] = 1 / self.xtransform.transform(1 / hypers[key], shift=False)
+            elif any(p in key for p in ("noise", "mean_module")):
+                if self.ytransform is not None:
+                    hypers[key] = self.ytransform.transform(hypers[key])
+        for key, val in hypers.items():
+            par = self._lookup(key)
+            if par is not None and val.numel() == par.numel():
+                val = val.reshape(par.shape)
+            self.model.initialize(**{key: val})
+
+    def _lookup(self, key):
+        mod = self.model
+        parts = key.split(".")
+        for p in parts[:-1]:
+            mod = getattr(mod, p, None)
+            if mod is None:
+                return None
+        return mod._parameters.get("raw_" + parts[-1], mod._parameters.get(parts[-1]))
+
+    # ---- reporting (lightcurve.py:8999-9077, 6279-6343) ------------------------------------
+    def get_parameters(self, raw=False, transform=True):
+        pars = {}
+        for name, param in self.model.named_parameters():
+            if not raw and "raw" in name:
+                key = ".".join(c.lstrip("raw_") for c in name.split("."))
+                ent = self._model_pars[key]
+                con = ent["module"]._modules.get(ent["raw_name"] + "_constraint")
+                val = (con.transform(param) if con is not None else param).data
+            else:
+                key, val = name, param.data
+            if transform and self.xtransform is not None and any(
+                    p in key for p in ("mixture_means", "mixture_scales")):
+                val = 1 / self.xtransform.inverse(1 / val, shift=False)
+            elif transform and self.ytransform is not None and any(
+                    p in key for p in ("noise", "mean_module")):
+                val = self.ytransform.inverse(val)
+            pars[key] = val
+        return pars
+
+    def get_periods(self):
+        """Periods ``1/mu`` (time dimension), mixture weights and scales ``1/(2 pi sigma)`` in the
+        units of the raw x data (lightcurve.py:6279-6343)."""
+        pars = self.get_parameters()
+        mu = pars["covar_module.mixture_means"].detach().cpu()
+        sg = pars["covar_module.mixture_scales"].detach().cpu()
+        w = pars["covar_module.mixture_weights"].detach().cpu()
+        periods = (1 / mu[:, 0, 0]).numpy()
+        scales = (1 / (2 * np.pi * sg[:, 0, 0])).numpy()
+        return periods, w.numpy(), scales
+
+    # ---- fit (lightcurve.py:5211-5882) -------------------------------------------------
+    def fit(self, model=None, likelihood=None, num_mixtures=None, guess=None, periods=None,
+            constraint_set=None, cuda=False, training_iter=300, optim="AdamW", miniter=None,
+            stop=1e-5, lr=0.1, stopavg=30, variance=False, **kwargs):
+        """Same defaults as the reference: AdamW, lr 0.1, 300 iterations, stop 1e-5, stopavg 30,
+        ``miniter=None -> training_iter`` (so the early stop never fires).  The
+        Lomb-Scargle (MLS) initialisation is out of scope (astropy is absent; the reference then
+        falls back to ``num_mixtures`` 4 with a warning, lightcurve.py:5668-5688): pass
+        ``periods`` / ``guess`` for a deterministic start."""
+        if likelihood is not None or not hasattr(self, "likelihood"):
+            self.set_likelihood(likelihood, variance=variance)
+        if model is not None or not hasattr(self, "model"):
+            if model is None:
+                raise ValueError("""You must provide a model""")
+            if periods is not None and num_mixtures is None:
+                num_mixtures = len(periods)
+            self.set_model(model, self.likelihood, num_mixtures=num_mixtures, **kwargs)
+        if not self._constraints_set:
+            self.set_default_constraints(constraint_set=constraint_set)
+        hypers = {}
+        if periods is not None and self.ndim == 1:
+            hypers["covar_module.mixture_means"] = 1.0 / torch.as_tensor(
+                np.asarray(periods, dtype=np.float64))
+        if guess is not None:
+            hypers.update(guess)
+        if hypers:
+            self.set_hypers(hypers)
+        if miniter is None:
+            miniter = training_iter
+        self.model.train()
+        self.likelihood.train()
+        self.results = train(self, maxiter=training_iter, miniter=miniter, stop=stop, lr=lr,
+                             optim=optim, stopavg=stopavg)
+        self._fitted = True
+        return self.results
+
+
+class UnsupportedModel(NotImplementedError):
+    pass

@@ -1,0 +1,215 @@
+"""Host-side logic on CPU: the `train` seam (schema of pgmuvi/trainers.py:167-209), the
+Lightcurve mirror (likelihood / constraint / hyper set-up that fixes the parameterisation), the
+GPyTorch-shaped packing, and the multi-rank sharding (gloo, world_size 2).  The CUDA engine is
+replaced by the oracle here ONLY to drive the host code; the GPU twins of these tests are in
+test_gpu_parity.py / test_gpu_train.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ModelSpec, train_loop
+from pgmuvi_b200 import gp, trainers
+from pgmuvi_b200.batch import gather_results, shard_range
+from pgmuvi_b200.lightcurve import Lightcurve, UnsupportedModel
+from pgmuvi_b200.mll import UnsupportedModelError, pack_model
+
+OPT_NAMES = {0: "SGD", 1: "Adam", 2: "AdamW"}
+
+
+def fake_sm_fit(x, y, fixed_noise, raw, kinds, lb, ub, n_valid, kind, Q, learn_noise, optim_kind,
+                lr, b1, b2, eps, wd, maxiter, miniter, stop, stopavg, keep_history):
+    """Oracle stand-in with pgm_sm_fit_f64's contract (include/pgmuvi_b200.h)."""
+    B, P = raw.shape
+    d = x.shape[-1]
+    spec = ModelSpec(d=d, Q=Q, kind=kind, learn_noise=learn_noise)
+    loss = torch.full((maxiter, B), float("nan"), dtype=torch.float64)
+    hist = torch.zeros(maxiter + 1, B, P, dtype=torch.float64)
+    n_iter = torch.zeros(B, dtype=torch.int32)
+    for b in range(B):
+        res = train_loop(x[b], y[b], None if fixed_noise is None else fixed_noise[b], raw[b],
+                         kinds, lb if lb.dim() == 1 else lb[b], ub if ub.dim() == 1 else ub[b],
+                         spec, maxiter=maxiter, miniter=miniter, stop=stop or None, lr=lr,
+                         optim=OPT_NAMES[optim_kind], eps=eps, stopavg=stopavg)
+        k = len(res["loss"])
+        loss[:k, b] = torch.tensor(np.array(res["loss"], dtype=float))
+        hist[:k + 1, b] = torch.tensor(np.stack(res["raw"]))
+        n_iter[b] = k
+        raw[b] = hist[k, b]
+    return loss, hist, n_iter, torch.zeros(B, dtype=torch.int32)
+
+
+@pytest.fixture
+def cpu_engine(monkeypatch):
+    monkeypatch.setattr(trainers.ops, "sm_fit", fake_sm_fit)
+    monkeypatch.setattr(trainers, "engine_device", lambda t=None: torch.device("cpu"))
+
+
+def _lc_1d(n=60, yerr=True, seed=0, **kw):
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.uniform(2450000.0, 2450400.0, n))
+    y = np.sin(2 * np.pi * t / 57.0) + 0.1 * rng.standard_normal(n)
+    return Lightcurve(t, y, yerr=np.full(n, 0.1) if yerr else None, **kw), t, y
+
+
+def test_train_returns_the_reference_schema(cpu_engine):
+    lc, t, y = _lc_1d()
+    lc.set_model("1D", num_mixtures=2)
+    lc.set_default_constraints()
+    lc.set_hypers({"covar_module.mixture_means": torch.tensor([1 / 57.0, 1 / 110.0])})
+    before = {k: v.clone() for k, v in lc.get_parameters().items()}
+    res = trainers.train(lc, maxiter=5, miniter=5, stop=1e-5, lr=0.1, optim="AdamW", stopavg=3)
+    assert set(res) == {"loss", "delta_loss"} | set(before)              # trainers.py:167-171
+    assert len(res["loss"]) == 5 and len(res["delta_loss"]) == 4
+    for k, v0 in before.items():
+        assert len(res[k]) == 6                                          # initial value first
+        assert isinstance(res[k][0], np.ndarray) and res[k][0].shape == tuple(v0.shape)
+        assert np.allclose(res[k][0], v0.numpy(), rtol=1e-6)
+    after = lc.get_parameters()                                          # params were updated
+    for k in before:
+        assert np.allclose(res[k][-1], after[k].numpy(), rtol=1e-6)
+    assert set(before) == {"mean_module.constant", "covar_module.mixture_weights",
+                           "covar_module.mixture_means", "covar_module.mixture_scales"}
+    assert res["delta_loss"][0] == pytest.approx(float(res["loss"][1] - res["loss"][0]))
+    # reported frequencies are in raw (day^-1) units: 1/xtransform.inverse(1/v, shift=False)
+    assert res["covar_module.mixture_means"][0].reshape(-1)[0] == pytest.approx(1 / 57.0, rel=1e-4)
+
+
+def test_train_early_stop_and_argument_errors(cpu_engine, capsys):
+    lc, *_ = _lc_1d(n=40)
+    lc.set_model("1D", num_mixtures=1)
+    lc.set_default_constraints()
+    res = trainers.train(lc, maxiter=40, miniter=2, stop=10.0, lr=1e-3, optim="Adam", stopavg=3)
+    assert len(res["loss"]) == 4            # stop and i > miniter  ->  breaks at i = 3
+    assert "so we will end training here" in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        trainers.train(model=lc.model)                              # trainers.py:98-103
+    with pytest.raises(NotImplementedError):
+        trainers.train(lc, lossfn="elbo")
+    with pytest.raises(ValueError):
+        trainers.train(lc, optim="LBFGS")
+    with pytest.raises(NotImplementedError):
+        trainers.train(lc, optim="NUTS")
+
+
+def test_train_without_lightcurve_records_raw_parameters(cpu_engine):
+    lc, *_ = _lc_1d(n=30, yerr=False)
+    lc.set_model("1D", num_mixtures=1)
+    res = trainers.train(model=lc.model, likelihood=lc.likelihood,
+                         train_x=lc._xdata_transformed, train_y=lc._ydata_transformed,
+                         maxiter=3, optim="SGD", lr=1e-3)
+    names = [n for n, _ in lc.model.named_parameters()]
+    assert names[0] == "likelihood.noise_covar.raw_noise"             # SURVEY A.9 order
+    assert set(res) == {"loss", "delta_loss"} | set(names)
+    assert all(len(res[n]) == 4 for n in names)
+
+
+def test_likelihood_and_default_constraints_follow_the_reference():
+    lc, t, y = _lc_1d()
+    lc.set_likelihood()
+    assert isinstance(lc.likelihood, gp.FixedNoiseGaussianLikelihood)
+    assert torch.allclose(lc.likelihood.noise, torch.full((60,), 0.1) ** 2)   # tests/tests.py:144-154
+    lc.set_likelihood(variance=True)
+    assert torch.allclose(lc.likelihood.noise, torch.full((60,), 0.1))        # tests/tests.py:156-167
+    lc.set_model("1D", likelihood="learn", num_mixtures=3)
+    lc.set_default_constraints()
+    cov = lc.model.covar_module
+    assert type(cov.raw_mixture_means_constraint).__name__ == "GreaterThan"    # 1/span, :3920-3932
+    assert float(cov.raw_mixture_means_constraint.lower_bound) == pytest.approx(1.0)
+    nc = lc.likelihood.second_noise_covar.raw_noise_constraint
+    assert type(nc).__name__ == "Interval"
+    assert float(nc.lower_bound) == pytest.approx(1e-4)                      # min(1e-4, 0.1/10)
+    assert float(nc.upper_bound) == pytest.approx(float(lc._ydata_transformed.std()))
+    mc = lc.model.mean_module.raw_constant_constraint
+    assert float(mc.lower_bound) == pytest.approx(float(y.min()), rel=1e-6)
+    # re-registering a constraint keeps the RAW value (tutorial cells 32-37)
+    assert float(lc.model.mean_module.raw_constant) == 0.0
+    # no yerr -> GaussianLikelihood with noise >= 1e-4 * std(y)
+    lc2, *_ = _lc_1d(yerr=False)
+    lc2.set_model("1D", num_mixtures=2)
+    lc2.set_default_constraints()
+    assert isinstance(lc2.likelihood, gp.GaussianLikelihood)
+    nb = lc2.likelihood.noise_covar.raw_noise_constraint
+    assert float(nb.lower_bound) == pytest.approx(1e-4 * float(lc2._ydata_transformed.std()))
+
+
+def test_2d_constraints_and_dimension_checks():
+    rng = np.random.default_rng(1)
+    x = np.concatenate([np.stack([np.sort(rng.uniform(0, 300, 30)), np.full(30, wl)], 1)
+                        for wl in (0.8, 1.2, 2.2)])
+    y = rng.standard_normal(90)
+    lc = Lightcurve(x, y, yerr=np.full(90, 0.05))
+    with pytest.raises(ValueError):                           # tests/test_2d_integration.py:167-186
+        lc.set_model("1D", num_mixtures=2)
+    lc.set_model("2D", num_mixtures=3)
+    lc.set_default_constraints()
+    con = lc.model.covar_module.raw_mixture_means_constraint
+    assert type(con).__name__ == "Interval"                   # tests/test_2d_constraints.py:67-78
+    ts = np.sort(lc._xdata_transformed[:, 0].numpy())
+    dt = np.diff(ts)
+    assert float(con.upper_bound) == pytest.approx(1 / (2 * dt[dt > 0].min()), rel=1e-5)
+    assert lc.model.covar_module.raw_mixture_means.shape == (3, 1, 2)
+    lc.set_hypers({"covar_module.mixture_means": torch.tensor([[0.01, 1.0], [0.02, 1.0],
+                                                               [0.03, 1.0]])})
+    assert lc.model.covar_module.mixture_means.shape == (3, 1, 2)          # keeps [Q,1,2]
+    pk = pack_model(lc.model)
+    assert (pk.kind, pk.Q, pk.d, pk.P) == (1, 3, 2, 1 + 3 + 12)
+    with pytest.raises(UnsupportedModel):
+        lc.set_model("2DLinear")
+
+
+def test_pack_model_rejects_models_outside_the_path():
+    lc, *_ = _lc_1d(n=20)
+    lc.set_model("1D", num_mixtures=2)
+    pk = pack_model(lc.model)
+    assert pk.names == ["mean_module.raw_constant", "covar_module.raw_mixture_weights",
+                        "covar_module.raw_mixture_means", "covar_module.raw_mixture_scales"]
+    assert pk.fixed_noise is not None and not pk.learn_noise
+
+    class Linear(torch.nn.Module):
+        pass
+    lc.model.mean_module = Linear()
+    with pytest.raises(UnsupportedModelError):
+        pack_model(lc.model)
+
+
+def test_shard_range_covers_everything_once():
+    for total, world in ((4096, 8), (10, 3), (5, 8), (0, 2)):
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    total = 11                                                # uneven shards: 6 + 5
+    a, b = shard_range(total, rank, world)
+    local = torch.arange(a, b, dtype=torch.float64).unsqueeze(1) * torch.ones(1, 3)
+    counts = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0]
+              for r in range(world)]
+    full = gather_results(local, counts)
+    even = gather_results(torch.full((4, 2), float(rank)))
+    q.put((rank, full[:, 0].tolist(), even[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_gather_results_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, full, even in outs:
+        assert full == [float(i) for i in range(11)]
+        assert even == [0.0] * 4 + [1.0] * 4
