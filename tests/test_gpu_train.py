@@ -73,10 +73,15 @@ def test_torch_optimizer_instance_runs_the_reference_loop(cuda_device):
 
 
 def test_fit_1d_float32_recovers_the_period(cuda_device):
-    torch.manual_seed(1)
-    lc = _lc(n=200, period=57.0)                    # float32 data and parameters (reference default)
-    res = lc.fit(model="1D", num_mixtures=2, periods=[50.0, 140.0], training_iter=150,
-                 optim="AdamW", lr=0.1)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)          # the reference's default
+    try:
+        torch.manual_seed(1)
+        lc = _lc(n=200, period=57.0)                # float32 data and parameters
+        res = lc.fit(model="1D", num_mixtures=2, periods=[50.0, 140.0], training_iter=150,
+                     optim="AdamW", lr=0.1)
+    finally:
+        torch.set_default_dtype(prev)
     loss = np.array(res["loss"], dtype=float)
     assert len(loss) == 150 and np.isfinite(loss).all()
     assert loss[-5:].mean() < loss[:5].mean()

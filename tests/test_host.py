@@ -109,9 +109,9 @@ def test_likelihood_and_default_constraints_follow_the_reference():
     lc, t, y = _lc_1d()
     lc.set_likelihood()
     assert isinstance(lc.likelihood, gp.FixedNoiseGaussianLikelihood)
-    assert torch.allclose(lc.likelihood.noise, torch.full((60,), 0.1) ** 2)   # tests/tests.py:144-154
+    assert torch.allclose(lc.likelihood.noise, torch.full((60,), 0.1, dtype=torch.float32) ** 2)   # tests/tests.py:144-154
     lc.set_likelihood(variance=True)
-    assert torch.allclose(lc.likelihood.noise, torch.full((60,), 0.1))        # tests/tests.py:156-167
+    assert torch.allclose(lc.likelihood.noise, torch.full((60,), 0.1, dtype=torch.float32))        # tests/tests.py:156-167
     lc.set_model("1D", likelihood="learn", num_mixtures=3)
     lc.set_default_constraints()
     cov = lc.model.covar_module
