@@ -22,6 +22,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--threads", "1",
 ]
+if os.environ.get("PGM_DEBUG_HOOKS"):   # per-phase clock64 profile (PGM_DEBUG_PROF=1 at run time)
+    NVCC_FLAGS.append("-DPGM_DEBUG_HOOKS")
 # (KIND, QT, D) instantiations: 1-D SM, 2-D ARD product-of-sums, 2-D sum-of-products
 CONFIGS = [(k, q, d) for (k, d) in ((0, 1), (1, 2), (2, 2)) for q in (1, 2, 4, 8)]
 

@@ -13,7 +13,11 @@
 // by pgmuvi/trainers.py:177-182 and pgmuvi/gps.py:205-220, 302-318.
 //
 // Per-block scratch lives in a global workspace indexed by blockIdx.x (reused for every
-// light curve the block processes); only L / L^-1 tiles go there.
+// light curve the block processes); only L / L^-1 tiles go there, stored as the exact
+// shared-memory operand image (two 32-deep k-chunks, XOR-swizzled), so that a pipeline stage
+// is filled by ONE elected thread with two 16 KB bulk copies (cp.async.bulk -> SASS UBLKCP)
+// that complete on an mbarrier: no per-chunk block barrier, and the stream of chunks runs
+// ahead across tile boundaries.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,14 +51,53 @@ __device__ __forceinline__ void mma_f64(double (&d)[2], double a, double b) {
       : "+d"(d[0]), "+d"(d[1])
       : "d"(a), "d"(b));
 }
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// mbarrier + bulk-copy (TMA, non-tensor form) primitives: one elected thread streams whole
+// 16 KB operand chunks global -> shared, completion is counted in bytes on an mbarrier.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes,
+                                         unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+          "r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// generic-proxy writes (st.global / st.shared) -> visible to later async-proxy (bulk) reads
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async;\n" ::: "memory");
 }
 __device__ __forceinline__ double shfl_d(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
@@ -86,6 +129,22 @@ __constant__ double c_exp2_tab[64] = {
     0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
+#ifdef PGM_DEBUG_HOOKS
+// -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 (timing experiments only)
+__constant__ long long* c_prof = nullptr;
+#define PGM_PROF_START() long long prof_t = clock64()
+#define PGM_PROF(slot)                                                       \
+  do {                                                                       \
+    if (c_prof && threadIdx.x == 0) {                                        \
+      const long long t_ = clock64();                                        \
+      c_prof[blockIdx.x * 16 + (slot)] += t_ - prof_t;                       \
+      prof_t = t_;                                                           \
+    }                                                                        \
+  } while (0)
+#else
+#define PGM_PROF_START() do { } while (0)
+#define PGM_PROF(slot) do { } while (0)
+#endif
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
   x = fmax(x, -700.0);
   double t = fma(x, 0x1.71547652b82fep+6, 6755399441055744.0);  // round(x * 64/ln2)
@@ -130,7 +189,8 @@ struct Cfg {
   static constexpr int PAR_DINV = PAR_ZI + TS;        // 1 / L_kk of the current diagonal block [64]
   static constexpr int PAR_TAB = PAR_DINV + TS;       // 2^(j/64) table [64]
   static constexpr int PAR_RAW = PAR_TAB + 64;        // raw / adam state / gradient (fit kernel)
-  static constexpr int PAR_END = PAR_RAW + 4 * PMAX;
+  static constexpr int PAR_BAR = PAR_RAW + 4 * PMAX;  // 11 mbarriers (8 B each)
+  static constexpr int PAR_END = PAR_BAR + 12;
   static constexpr int SM_TOTAL = SM_PAR + PAR_END + 8;
   static constexpr size_t SMEM_BYTES = (size_t)SM_TOTAL * sizeof(double);
 };
@@ -139,7 +199,6 @@ struct Cfg {
 struct Scratch {
   double* tiles;  // ntri * TT : L_ij (i>j), later X_ij^T; diagonal slots hold X_jj = L_jj^-1
   double* tilesT; // N * TT    : X_jj^T
-  double* ctmp;   // TT
   double* fx;     // D * npad      : centred inputs, [dd][i]
   double* fcs;    // NCS * npad * 2: (cos, sin)(2 pi mu_qd x_id), [(dd*QT+q)][i][2]
   double* alpha;  // npad
@@ -147,21 +206,30 @@ struct Scratch {
   double* z;      // npad  (L^-1 rhs)
   double* dn;     // npad  (diagonal noise)
   double* fpart;  // ntri * 4 * 64 : partial products L_ij z_j per warp column (forward solve)
-  double* apart;  // ntri * 2 * 64 : partial products X_ij^T z_i per warp row (alpha)
+  double* apart;  // ntri * 4 * 64 : partial products X_ij^T z_i per warp column (alpha)
 };
 __host__ __device__ inline size_t scratch_elems(int n_max, int NF) {
   int N = (n_max + TS - 1) / TS;
   size_t npad = (size_t)N * TS;
   size_t ntri = (size_t)tri(N, 0);
-  return ntri * TT + (size_t)N * TT + TT + (size_t)(NF + 4) * npad + ntri * 6 * TS + 64;
+  return ntri * TT + (size_t)N * TT + (size_t)(NF + 4) * npad + ntri * 8 * TS + 64;
 }
 
 // ------------------------------------------------------------------------------------
-// the tensor-core tile engine:  acc += sum_kt  A(kt) * B(kt)^T   on 64x64 row-major tiles
+// the tensor-core tile engine:  acc += sum_kt  A(kt) * B(kt)^T   on 64x64 tiles
 //   A(kt)[m][k], B(kt)[n][k] with k contiguous ("NT").  Every product of the algorithm is
 //   brought to this form by storing the off-diagonal inverse tiles transposed.
-// Tiles are global (per-block scratch); 2-stage cp.async pipeline of 32-deep k-chunks into
-// XOR-swizzled shared memory; every fragment load is a conflict-free LDS.128.
+//
+// Tile image (global scratch == shared memory): two k-chunks of [64 rows][32 k] doubles,
+// 16-byte groups XOR-swizzled by the row parity so that every fragment load is a
+// conflict-free LDS.128:   img(r, k) below.
+//
+// Pipeline: a ring of NST stages (A chunk + B chunk = 32 KB each).  Thread 0 is the
+// producer: before computing chunk c it waits for empty[stage of chunk c+NST-1] (all 8 warps
+// released it) and issues that chunk's two bulk copies on full[stage]; every warp waits on
+// full[stage], computes, and releases with one arrive per warp.  The producer runs ahead into
+// the NEXT job's first chunks ("pre" of the following call) where the caller says the tiles
+// are final.
 //
 // k <-> lane mapping of one 8-deep k-group: MMA step h in {0,1}, lane tq holds
 // k = 8*k8 + 2*tq + h  (both operands).
@@ -177,6 +245,10 @@ __host__ __device__ inline size_t scratch_elems(int n_max, int NF) {
 // ------------------------------------------------------------------------------------
 enum { M_FULL = 0, M_B_LE = 1, M_B_GE = 2, M_A_LE = 3, M_A_GE = 4 };
 
+__host__ __device__ __forceinline__ int img(int r, int k) {
+  return (k >> 5) * OPBUF + r * KC + ((((k & 31) >> 1) ^ ((r & 1) << 2)) << 1) + (k & 1);
+}
+
 __device__ __forceinline__ int frag_mt(int wm, int mi) {
   return wm ? ((mi == 0) ? 1 : (mi == 1) ? 2 : (mi == 2) ? 5 : 6)
             : ((mi == 0) ? 0 : (mi == 1) ? 3 : (mi == 2) ? 4 : 7);
@@ -185,16 +257,6 @@ __device__ __forceinline__ int frag_nt(int wn, int ni) { return ni ? 7 - wn : wn
 __device__ __forceinline__ int frag_row(int wm, int mi, int g) { return 8 * frag_mt(wm, mi) + g; }
 __device__ __forceinline__ int frag_col(int wn, int ni, int tq, int e) {
   return 8 * frag_nt(wn, ni) + 2 * tq + e;
-}
-
-__device__ __forceinline__ void issue_operand(double* __restrict__ sbuf,
-                                              const double* __restrict__ gtile, int kc, int tid) {
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    const int p = tid + h * NTHREADS;   // 1024 16-byte chunks per operand per stage
-    const int row = p >> 4, ch = p & 15;
-    cp_async16(sbuf + row * KC + ((ch ^ ((row & 1) << 2)) << 1), gtile + row * TS + kc * KC + ch * 2);
-  }
 }
 
 template <int MODE, bool LOWER>
@@ -240,39 +302,74 @@ __device__ __forceinline__ void compute_chunk(double (&acc)[4][2][2], const doub
   }
 }
 
-template <int MODE0, bool LOWER, typename FA, typename FB, typename FX>
-__device__ __forceinline__ void gemm_tiles(double (&acc)[4][2][2], int nk, FA tileA, FB tileB,
-                                           double* __restrict__ stages, FX extra_prefetch) {
+// ring of NST stages; `gq` counts the chunks consumed on this ring since the barriers were
+// initialised (uniform over the block), which fixes the stage and the mbarrier phase.
+struct Ring {
+  unsigned full, empty;  // shared addresses of full[NST] / empty[NST]
+  double* stages;        // stage s at stages + s * 2 * OPBUF
+  int gq;
+};
+constexpr unsigned CHUNK_BYTES = OPBUF * sizeof(double);
+
+// acc += sum over this job's nk k-tiles.  `pre` chunks of the job are already in flight
+// (issued by the previous call); the first chunks of the next job (next_nk k-tiles, 0 = no
+// look-ahead) are issued from here.  Returns the number of next-job chunks issued.
+template <int MODE0, bool LOWER, int NST, typename FA, typename FB, typename FNA, typename FNB,
+          typename FX>
+__device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int nk, FA tileA,
+                                           FB tileB, int pre, int next_nk, FNA nextA, FNB nextB,
+                                           FX extra_prefetch) {
+  constexpr int LA = NST - 1;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;
-  const int nchunks = nk * (TS / KC);
+  const int n = 2 * nk, nn = 2 * next_nk;
 
-  auto issue = [&](int c) {
-    const int kt = c >> 1, kc = c & 1;
-    double* sA = stages + (c & 1) * (2 * OPBUF);
-    issue_operand(sA, tileA(kt), kc, tid);
-    issue_operand(sA + OPBUF, tileB(kt), kc, tid);
+  auto issue = [&](int t) {  // chunk t counted from this job's first chunk; thread 0 only
+    const double *ga, *gb;
+    if (t < n) {
+      ga = tileA(t >> 1) + (t & 1) * OPBUF;
+      gb = tileB(t >> 1) + (t & 1) * OPBUF;
+    } else {
+      const int u = t - n;
+      if (u >= nn) return;
+      ga = nextA(u >> 1) + (u & 1) * OPBUF;
+      gb = nextB(u >> 1) + (u & 1) * OPBUF;
+    }
+    const int q = rg.gq + t, s = q % NST, use = q / NST;
+    if (use > 0) mbar_wait(rg.empty + 8 * s, (use - 1) & 1);
+    const unsigned bar = rg.full + 8 * s;
+    const unsigned dst = smem_u32(rg.stages + s * 2 * OPBUF);
+    mbar_expect_tx(bar, 2 * CHUNK_BYTES);
+    bulk_g2s(dst, ga, CHUNK_BYTES, bar);
+    bulk_g2s(dst + CHUNK_BYTES, gb, CHUNK_BYTES, bar);
   };
 
-  __syncthreads();  // previous users of the stage buffers / producers of the tiles are done
+  fence_proxy_async();  // this thread's tile stores / staging writes before later bulk copies
+  __syncthreads();      // job boundary: producers of the tiles and users of the stages are done
   extra_prefetch();
-  if (nchunks > 0) issue(0);
   cp_async_commit();
-  for (int c = 0; c < nchunks; ++c) {
-    cp_async_wait<0>();
-    __syncthreads();
-    if (c + 1 < nchunks) issue(c + 1);
-    cp_async_commit();
-    const double* sA = stages + (c & 1) * (2 * OPBUF);
+  if (tid == 0) {
+    fence_proxy_async();
+    for (int t = pre; t < LA; ++t) issue(t);
+  }
+  for (int c = 0; c < n; ++c) {
+    if (tid == 0) issue(c + LA);
+    const int q = rg.gq + c, s = q % NST;
+    mbar_wait(rg.full + 8 * s, (q / NST) & 1);
+    const double* sA = rg.stages + s * 2 * OPBUF;
     const double* sB = sA + OPBUF;
     if (MODE0 != M_FULL && c < 2)
       compute_chunk<MODE0, LOWER>(acc, sA, sB, c * (KC / 8), wm, wn, g, tq);
     else
       compute_chunk<M_FULL, LOWER>(acc, sA, sB, 0, wm, wn, g, tq);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(rg.empty + 8 * s);
   }
+  rg.gq += n;
   cp_async_wait<0>();
+  return nn < LA ? nn : LA;
 }
 
 __device__ __forceinline__ void zero_acc(double (&acc)[4][2][2]) {
@@ -282,8 +379,7 @@ __device__ __forceinline__ void zero_acc(double (&acc)[4][2][2]) {
     for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 }
 
-// accumulator -> row-major global tile (TRANSPOSE: tile[c][r] = sign * acc(r, c))
-template <bool TRANSPOSE>
+// accumulator -> 64x64 tile image (global scratch or a shared-memory stage)
 __device__ __forceinline__ void store_acc_tile(const double (&acc)[4][2][2], double* tile,
                                                double sign) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -294,13 +390,8 @@ __device__ __forceinline__ void store_acc_tile(const double (&acc)[4][2][2], dou
 #pragma unroll
     for (int ni = 0; ni < 2; ++ni) {
       const int c = frag_col(wn, ni, tq, 0);
-      if (!TRANSPOSE) {
-        *reinterpret_cast<double2*>(tile + r * TS + c) =
-            make_double2(sign * acc[mi][ni][0], sign * acc[mi][ni][1]);
-      } else {
-        tile[c * TS + r] = sign * acc[mi][ni][0];
-        tile[(c + 1) * TS + r] = sign * acc[mi][ni][1];
-      }
+      *reinterpret_cast<double2*>(tile + img(r, c)) =
+          make_double2(sign * acc[mi][ni][0], sign * acc[mi][ni][1]);
     }
   }
 }
@@ -554,13 +645,38 @@ __device__ __forceinline__ void block_reduce(double (&v)[NVAL], double* red, dou
 }
 
 // ------------------------------------------------------------------------------------
+// pipeline state carried by a block across light curves (mbarrier phases keep running)
+// ------------------------------------------------------------------------------------
+struct PipeState {
+  int gq2;   // chunks consumed on the 2-stage ring (phases P, T)
+  int gq3;   // chunks consumed on the 3-stage ring (phase G)
+  int rcnt;  // bulk loads of the resident tile R completed so far
+};
+
+template <int KIND, int QT, int D>
+__device__ __forceinline__ void pipe_init(double* sm, PipeState& ps) {
+  using C = Cfg<KIND, QT, D>;
+  const unsigned bars = smem_u32(sm + C::SM_PAR + C::PAR_BAR);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (2 + s), NTHREADS / 32); }
+    for (int s = 0; s < 3; ++s) { mbar_init(bars + 8 * (4 + s), 1); mbar_init(bars + 8 * (7 + s), NTHREADS / 32); }
+    mbar_init(bars + 8 * 10, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  ps.gq2 = ps.gq3 = ps.rcnt = 0;
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------
 // one full evaluation of light curve b with raw parameters `raw` (global or shared).
 // Writes the per-datum MLL to *mll_out and (PGM_FLAG_GRAD) d MLL / d raw to grad_out[P];
 // returns info.
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
 __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, double* sm,
-                               const Scratch& sc, double* mll_out, double* grad_out) {
+                               const Scratch& sc, PipeState& ps, double* mll_out,
+                               double* grad_out) {
   using C = Cfg<KIND, QT, D>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Q = A.Q;
@@ -572,8 +688,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   const int npad = N * TS;
 
   double* stages = sm + C::SM_STAGES;
-  double* S2 = stages;  // aliases the pipeline buffers (idle during diagonal blocks)
-  double* S = sm + C::SM_S;
+  double* S2 = stages;         // diagonal blocks: X = L^-1 (aliases the idle pipeline stages)
+  double* S = sm + C::SM_S;    // diagonal blocks: C_jj -> L_jj
+  double* R = S;               // afterwards: resident X_jj / X_ii operand image (= stage 2 in G)
+  double* Cst = stages + 2 * OPBUF;   // stage 1: staging of the register-resident A operand
+  double* scr = stages + S_ELEMS;     // 256 doubles behind S2
   double* rowv = sm + C::SM_ROW;
   double* colv = sm + C::SM_COL;
   double* par = sm + C::SM_PAR;
@@ -588,8 +707,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double* dinv = par + C::PAR_DINV;
   double* tab = par + C::PAR_TAB;
   int* s_fail = reinterpret_cast<int*>(sm + C::SM_PAR + C::PAR_END);
-  double* s_logdet = sm + C::SM_PAR + C::PAR_END + 1;
+  const unsigned bars = smem_u32(par + C::PAR_BAR);
+  const unsigned rbar = bars + 8 * 10;
 
+  PGM_PROF_START();
   __syncthreads();
   // ---- constraints: raw -> theta, d theta / d raw  (A.2) -----------------------------
   if (tid < P) {
@@ -659,12 +780,26 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       }
     }
   };
+  auto tile = [&](int i, int j) { return sc.tiles + (size_t)tri(i, j) * TT; };
+  auto tileT = [&](int j) { return sc.tilesT + (size_t)j * TT; };
 
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  PGM_PROF(0);
   double acc[4][2][2];
   double iq_part = 0.0;  // partial of z^T z
   double ld_part = 0.0;  // partial of sum log L_kk
   int info = 0;
+  Ring r2{bars, bars + 16, stages, ps.gq2};
+
+  // the register-resident 64x64 result times the resident triangular tile R:
+  //   acc <- acc_as_A * R^T   (R[n][k] = 0 for k > n), A staged through stage 1
+  auto times_resident = [&]() {
+    store_acc_tile(acc, Cst, 1.0);
+    __syncthreads();
+    zero_acc(acc);
+    compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+    compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+  };
 
   // ================= phase P: Cholesky + forward solve, with the jitter ladder ========
   for (int attempt = 0; attempt <= 3; ++attempt) {
@@ -677,46 +812,58 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     iq_part = 0.0;
     ld_part = 0.0;
     bool failed = false;
+    int pre = 0;
     for (int j = 0; j < N && !failed; ++j) {
       for (int i = j; i < N; ++i) {
         zero_acc(acc);
-        auto tA = [&](int k) { return sc.tiles + (size_t)tri(i, k) * TT; };
-        auto tB = [&](int k) { return sc.tiles + (size_t)tri(j, k) * TT; };
+        // next job in column-major order; its k-tile 0 is final as soon as column 0 is
+        // done.  No look-ahead across diagonal jobs (S2 aliases the stages there).
+        int ni = i + 1, nj = j;
+        if (ni >= N) { ni = j + 1; nj = j + 1; }
+        const int nnk = (j >= 1 && i != j && ni < N) ? nj : 0;
+        auto tA = [&](int k) { return tile(i, k); };
+        auto tB = [&](int k) { return tile(j, k); };
+        auto nA = [&](int k) { return tile(ni, k); };
+        auto nB = [&](int k) { return tile(nj, k); };
         auto pf = [&]() { prefetch_side(rowv, i, false); prefetch_side(colv, j, false); };
-        if (i == j) gemm_tiles<M_FULL, true>(acc, j, tA, tB, stages, pf);
-        else gemm_tiles<M_FULL, false>(acc, j, tA, tB, stages, pf);
+        if (i == j) pre = gemm_stream<M_FULL, true, 2>(acc, r2, j, tA, tB, pre, nnk, nA, nB, pf);
+        else pre = gemm_stream<M_FULL, false, 2>(acc, r2, j, tA, tB, pre, nnk, nA, nB, pf);
         __syncthreads();
+        PGM_PROF(1);
         // epilogue: C = Ktilde_ij - acc   (diagonal tiles: lower triangle only)
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-          for (int ni = 0; ni < 2; ++ni)
+          for (int ni2 = 0; ni2 < 2; ++ni2)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, e);
+              const int r = frag_row(wm, mi, g), c = frag_col(wn, ni2, tq, e);
               const int gi = i * TS + r, gj = j * TS + c;
               double kv = 0.0;
               if (gi < n && gj < n && gj <= gi)
                 kv = k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab);
               if (gi == gj) kv = (gi < n) ? (kv + sc.dn[gi] + jitter) : 1.0;
-              acc[mi][ni][e] = kv - acc[mi][ni][e];
+              acc[mi][ni2][e] = kv - acc[mi][ni2][e];
             }
+        PGM_PROF(2);
         if (i == j) {
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni)
+            for (int ni2 = 0; ni2 < 2; ++ni2)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, e);
-                S[r * LD_S + c] = acc[mi][ni][e];
+                const int r = frag_row(wm, mi, g), c = frag_col(wn, ni2, tq, e);
+                S[r * LD_S + c] = acc[mi][ni2][e];
               }
           __syncthreads();
           potrf_inv_64(S, S2, dinv, s_fail);
+          PGM_PROF(3);
           if (*s_fail) { failed = true; break; }
-          // X_jj -> tile(j,j) and X_jj^T -> tilesT[j] (explicit zeros in the other triangle)
-          double* dt = sc.tiles + (size_t)tri(j, j) * TT;
-          double* dtT = sc.tilesT + (size_t)j * TT;
+          // X_jj -> tile(j,j) and the resident R, X_jj^T -> tilesT[j]  (tile images with
+          // explicit zeros in the other triangle); L_jj itself is not needed any more
+          double* dt = tile(j, j);
+          double* dtT = tileT(j);
           for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
             const int r = idx >> 5, c2 = (idx & 31) * 2;
             double2 v, vt;
@@ -724,8 +871,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             v.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
             vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
             vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
-            *reinterpret_cast<double2*>(dt + r * TS + c2) = v;
-            *reinterpret_cast<double2*>(dtT + r * TS + c2) = vt;
+            const int o = img(r, c2);
+            *reinterpret_cast<double2*>(dt + o) = v;
+            *reinterpret_cast<double2*>(R + o) = v;
+            *reinterpret_cast<double2*>(dtT + o) = vt;
           }
           // forward solve: z_j = X_jj (rhs_j - sum_{k<j} L_jk z_k); the products L_jk z_k
           // were left in fpart by the epilogues of row j's tiles (4 partials per row).
@@ -733,12 +882,12 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             const int r = tid & 63, part = tid >> 6;
             double u = 0.0;
             for (int k = 0; k < j; ++k) u += sc.fpart[((size_t)tri(j, k) * 4 + part) * TS + r];
-            S[part * TS + r] = u;     // S is free again (L_jj itself is not needed any more)
+            scr[part * TS + r] = u;
           }
           if (tid < TS) ld_part -= log(dinv[tid]);
           __syncthreads();
           if (tid < TS)
-            zi[tid] = sc.rhs[j * TS + tid] - ((S[tid] + S[TS + tid]) + (S[2 * TS + tid] + S[3 * TS + tid]));
+            zi[tid] = sc.rhs[j * TS + tid] - ((scr[tid] + scr[TS + tid]) + (scr[2 * TS + tid] + scr[3 * TS + tid]));
           __syncthreads();
           {
             const int r = tid >> 2, l4 = tid & 3;
@@ -753,26 +902,24 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             }
           }
           __syncthreads();
+          PGM_PROF(4);
         } else {
-          // L_ij = C * X_jj^T  via the tile engine (C staged through the block's scratch)
-          store_acc_tile<false>(acc, sc.ctmp, 1.0);
-          zero_acc(acc);
-          gemm_tiles<M_B_LE, false>(
-              acc, 1, [&](int) { return sc.ctmp; },
-              [&](int) { return sc.tiles + (size_t)tri(j, j) * TT; }, stages, []() {});
-          store_acc_tile<false>(acc, sc.tiles + (size_t)tri(i, j) * TT, 1.0);
+          // L_ij = C * X_jj^T  straight from registers / shared memory
+          times_resident();
+          store_acc_tile(acc, tile(i, j), 1.0);
           // partial products L_ij z_j for the forward solve of row i (deterministic order)
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi) {
             double s = 0.0;
 #pragma unroll
-            for (int ni = 0; ni < 2; ++ni)
+            for (int ni2 = 0; ni2 < 2; ++ni2)
 #pragma unroll
-              for (int e = 0; e < 2; ++e) s += acc[mi][ni][e] * zj[frag_col(wn, ni, tq, e)];
+              for (int e = 0; e < 2; ++e) s += acc[mi][ni2][e] * zj[frag_col(wn, ni2, tq, e)];
             s += shfl_xor_d(s, 1);
             s += shfl_xor_d(s, 2);
             if (tq == 0) sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
           }
+          PGM_PROF(5);
         }
       }
     }
@@ -795,100 +942,128 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
                          ? -0.5 * (inv_quad + logdet + (double)n * 1.8378770664093454836) / n
                          : nan("");
   __syncthreads();
+  PGM_PROF(6);
   if (tid == 0) *mll_out = mll;
-  if (!want_grad) return info;
-  if (info < 0) {
-    if (tid < P) grad_out[tid] = nan("");
+  if (!want_grad || info < 0) {
+    if (want_grad && tid < P) grad_out[tid] = nan("");
+    ps.gq2 = r2.gq;
     return info;
   }
 
-  // ================= phase T: X = L^-1 (in place, column by column) ===================
-  for (int j = 0; j < N - 1; ++j) {
-    for (int i = j + 1; i < N; ++i) {
-      zero_acc(acc);
-      // Tm = sum_kk L_{i,j+kk} X_{j+kk,j}:  B operand = X^T tiles (kk = 0: X_jj^T, upper tri.)
-      gemm_tiles<M_B_GE, false>(
-          acc, i - j, [&](int kk) { return sc.tiles + (size_t)tri(i, j + kk) * TT; },
-          [&](int kk) { return kk == 0 ? sc.tilesT + (size_t)j * TT
-                                       : sc.tiles + (size_t)tri(j + kk, j) * TT; }, stages,
-          [&]() { if (tid < TS / 2) cp_async16(zi + tid * 2, sc.z + i * TS + tid * 2); });
-      store_acc_tile<true>(acc, sc.ctmp, 1.0);          // Tm^T
-      zero_acc(acc);
-      // X_ij = -X_ii Tm  (A = X_ii lower triangular; B operand = Tm^T), stored transposed
-      gemm_tiles<M_A_LE, false>(
-          acc, 1, [&](int) { return sc.tiles + (size_t)tri(i, i) * TT; },
-          [&](int) { return sc.ctmp; }, stages, []() {});
-      store_acc_tile<true>(acc, sc.tiles + (size_t)tri(i, j) * TT, -1.0);
-      // partial products X_ij^T z_i for alpha_j  (X_ij = -acc); zi was prefetched above and
-      // is visible: every thread passed the barriers of the second gemm_tiles
+  // ================= phase T: X = L^-1 in place, row by row ============================
+  // Tm^T = sum_{k=j}^{i-1} X_kj^T L_ik^T (k = j: X_jj^T from tilesT), X_ij^T = -Tm^T X_ii^T
+  // with X_ii resident in R for the whole row; the off-diagonal tiles keep holding X^T.
+  {
+    int pre = 0;
+    for (int i = 1; i < N; ++i) {
+      fence_proxy_async();
+      __syncthreads();  // the previous row is done with R and zi
+      if (tid == 0) {
+        mbar_expect_tx(rbar, 2 * CHUNK_BYTES);
+        bulk_g2s(smem_u32(R), tile(i, i), 2 * CHUNK_BYTES, rbar);
+      }
+      if (tid < TS) zi[tid] = sc.z[i * TS + tid];
+      bool rwait = true;
+      for (int j = 0; j < i; ++j) {
+        zero_acc(acc);
+        int ni = i, nj = j + 1;
+        if (nj >= i) { ni = i + 1; nj = 0; }
+        const int nnk = (ni < N) ? ni - nj : 0;
+        auto tA = [&](int kk) { return kk == 0 ? tileT(j) : tile(j + kk, j); };
+        auto tB = [&](int kk) { return tile(i, j + kk); };
+        auto nA = [&](int kk) { return kk == 0 ? tileT(nj) : tile(nj + kk, nj); };
+        auto nB = [&](int kk) { return tile(ni, nj + kk); };
+        pre = gemm_stream<M_A_GE, false, 2>(acc, r2, i - j, tA, tB, pre, nnk, nA, nB, []() {});
+        __syncthreads();
+        PGM_PROF(7);
+        if (rwait) {
+          mbar_wait(rbar, ps.rcnt & 1);
+          ++ps.rcnt;
+          rwait = false;
+        }
+        times_resident();
+        store_acc_tile(acc, tile(i, j), -1.0);
+        // partial products X_ij^T z_i for alpha_j  (X_ij^T = -acc)
 #pragma unroll
-      for (int ni = 0; ni < 2; ++ni)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int mi = 0; mi < 4; ++mi) {
           double s = 0.0;
 #pragma unroll
-          for (int mi = 0; mi < 4; ++mi) s -= acc[mi][ni][e] * zi[frag_row(wm, mi, g)];
-          s += shfl_xor_d(s, 4);
-          s += shfl_xor_d(s, 8);
-          s += shfl_xor_d(s, 16);
-          if (g == 0) sc.apart[((size_t)tri(i, j) * 2 + wm) * TS + frag_col(wn, ni, tq, e)] = s;
+          for (int ni2 = 0; ni2 < 2; ++ni2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) s -= acc[mi][ni2][e] * zi[frag_col(wn, ni2, tq, e)];
+          s += shfl_xor_d(s, 1);
+          s += shfl_xor_d(s, 2);
+          if (tq == 0) sc.apart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
         }
+        PGM_PROF(8);
+      }
     }
   }
+  ps.gq2 = r2.gq;
   __syncthreads();
   // ---- alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i -----------------------------------
   {
     const int c = tid & 63, rg = tid >> 6;
     for (int j = 0; j < N; ++j) {
-      const double* Xt = sc.tiles + (size_t)tri(j, j) * TT;
+      const double* Xt = tile(j, j);
       const double* zz = sc.z + j * TS;
       double s = 0.0;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) s += Xt[(rg * 16 + r) * TS + c] * zz[rg * 16 + r];
-      if (rg < 2)
-        for (int i = j + 1; i < N; ++i) s += sc.apart[((size_t)tri(i, j) * 2 + rg) * TS + c];
-      S[rg * TS + c] = s;
+      for (int r = 0; r < 16; ++r) s += Xt[img(rg * 16 + r, c)] * zz[rg * 16 + r];
+      for (int i = j + 1; i < N; ++i) s += sc.apart[((size_t)tri(i, j) * 4 + rg) * TS + c];
+      scr[rg * TS + c] = s;
       __syncthreads();
       if (tid < TS)
-        sc.alpha[j * TS + tid] = (S[tid] + S[TS + tid]) + (S[2 * TS + tid] + S[3 * TS + tid]);
+        sc.alpha[j * TS + tid] = (scr[tid] + scr[TS + tid]) + (scr[2 * TS + tid] + scr[3 * TS + tid]);
       __syncthreads();
     }
   }
+  PGM_PROF(9);
   // ================= phase G: K^-1 tiles -> gradient contraction =======================
   double ga[C::NG];
 #pragma unroll
   for (int t = 0; t < C::NG; ++t) ga[t] = 0.0;
   double trW = 0.0;
-  for (int i = 0; i < N; ++i) {
-    for (int j = 0; j <= i; ++j) {
-      zero_acc(acc);
-      // Kinv_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}: both operands are the stored X^T tiles
-      auto tA = [&](int kk) { return kk == 0 ? sc.tilesT + (size_t)i * TT
-                                             : sc.tiles + (size_t)tri(i + kk, i) * TT; };
-      auto tB = [&](int kk) { return (kk == 0 && i == j) ? sc.tilesT + (size_t)j * TT
-                                                         : sc.tiles + (size_t)tri(i + kk, j) * TT; };
-      auto pf = [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); };
-      if (i == j) gemm_tiles<M_A_GE, true>(acc, N - i, tA, tB, stages, pf);
-      else gemm_tiles<M_A_GE, false>(acc, N - i, tA, tB, stages, pf);
-      __syncthreads();
-      const double* al_r = rowv + C::NFB * TS;
-      const double* al_c = colv + C::NFB * TS;
+  {
+    Ring r3{bars + 32, bars + 56, stages, ps.gq3};
+    int pre = 0;
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j <= i; ++j) {
+        zero_acc(acc);
+        int ni = i, nj = j + 1;
+        if (nj > i) { ni = i + 1; nj = 0; }
+        const int nnk = (ni < N) ? N - ni : 0;
+        // Kinv_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}: both operands are the stored X^T tiles
+        auto tA = [&](int kk) { return kk == 0 ? tileT(i) : tile(i + kk, i); };
+        auto tB = [&](int kk) { return (kk == 0 && i == j) ? tileT(j) : tile(i + kk, j); };
+        auto nA = [&](int kk) { return kk == 0 ? tileT(ni) : tile(ni + kk, ni); };
+        auto nB = [&](int kk) { return (kk == 0 && ni == nj) ? tileT(nj) : tile(ni + kk, nj); };
+        auto pf = [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); };
+        if (i == j) pre = gemm_stream<M_A_GE, true, 3>(acc, r3, N - i, tA, tB, pre, nnk, nA, nB, pf);
+        else pre = gemm_stream<M_A_GE, false, 3>(acc, r3, N - i, tA, tB, pre, nnk, nA, nB, pf);
+        __syncthreads();
+        PGM_PROF(10);
+        const double* al_r = rowv + C::NFB * TS;
+        const double* al_c = colv + C::NFB * TS;
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 2; ++ni)
+          for (int ni2 = 0; ni2 < 2; ++ni2)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, e);
-            const int gi = i * TS + r, gj = j * TS + c;
-            if (gi < n && gj <= gi) {
-              const double W = al_r[r] * al_c[c] - acc[mi][ni][e];
-              if (gi == gj) trW += W;
-              const double wgt = (gi == gj) ? W : 2.0 * W;
-              k_grad_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab, wgt, ga);
+            for (int e = 0; e < 2; ++e) {
+              const int r = frag_row(wm, mi, g), c = frag_col(wn, ni2, tq, e);
+              const int gi = i * TS + r, gj = j * TS + c;
+              if (gi < n && gj <= gi) {
+                const double W = al_r[r] * al_c[c] - acc[mi][ni2][e];
+                if (gi == gj) trW += W;
+                const double wgt = (gi == gj) ? W : 2.0 * W;
+                k_grad_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab, wgt, ga);
+              }
             }
-          }
+        PGM_PROF(11);
+      }
     }
+    ps.gq3 = r3.gq;
   }
   // ---- reduce, apply constants and the constraint Jacobian ----------------------------
   {
@@ -921,6 +1096,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     grad_out[tid] = gv * jac[tid];
   }
   __syncthreads();
+  PGM_PROF(12);
   return info;
 }
 
@@ -933,8 +1109,7 @@ __device__ __forceinline__ Scratch make_scratch(double* base, int n_max) {
   Scratch sc;
   sc.tiles = base;
   sc.tilesT = sc.tiles + ntri * TT;
-  sc.ctmp = sc.tilesT + (size_t)N * TT;
-  sc.fx = sc.ctmp + TT;
+  sc.fx = sc.tilesT + (size_t)N * TT;
   sc.fcs = sc.fx + (size_t)D * npad;
   sc.alpha = sc.fcs + (size_t)C::NCS * npad * 2;
   sc.rhs = sc.alpha + npad;
@@ -954,10 +1129,12 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   extern __shared__ __align__(16) double sm[];
   Scratch sc = make_scratch<KIND, QT, D>(A.ws + (size_t)blockIdx.x * A.ws_per_block, A.n_max);
   const int P = 1 + A.Q + 2 * A.Q * D + ((A.flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0);
+  PipeState ps;
+  pipe_init<KIND, QT, D>(sm, ps);
   for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
     double* gout = A.grad ? A.grad + (size_t)b * P : nullptr;
     const int info =
-        eval_lightcurve<KIND, QT, D>(A, b, A.raw + (size_t)b * P, sm, sc, A.mll + b, gout);
+        eval_lightcurve<KIND, QT, D>(A, b, A.raw + (size_t)b * P, sm, sc, ps, A.mll + b, gout);
     if (threadIdx.x == 0) A.info[b] = info;
   }
 }
@@ -1061,6 +1238,8 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* s_grad = s_v + C::PMAX;
   double* s_mll = par + C::PAR_FIN + C::NV + 2;
   const int tid = threadIdx.x;
+  PipeState ps;
+  pipe_init<KIND, QT, D>(sm, ps);
   for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
     __syncthreads();
     if (tid < P) {
@@ -1072,7 +1251,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
     int it = 0, info = 0;
     for (; it < F.maxiter; ++it) {
       __syncthreads();
-      info = eval_lightcurve<KIND, QT, D>(A, b, s_raw, sm, sc, s_mll, s_grad);
+      info = eval_lightcurve<KIND, QT, D>(A, b, s_raw, sm, sc, ps, s_mll, s_grad);
       __syncthreads();
       const double loss = -(*s_mll);
       if (tid == 0) F.loss_hist[(size_t)it * A.B + b] = loss;

@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <string>
+#include <vector>
+#include <cstdio>
 
 namespace pgm {
 int fail(const std::string& m);
@@ -27,9 +29,32 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
   if (grid > A.B) grid = A.B;
+#ifdef PGM_DEBUG_HOOKS
+  long long* dprof = nullptr;
+  if (getenv("PGM_DEBUG_PROF")) {
+    cudaMalloc(&dprof, (size_t)grid * 16 * sizeof(long long));
+    cudaMemsetAsync(dprof, 0, (size_t)grid * 16 * sizeof(long long), st);
+  }
+  cudaMemcpyToSymbolAsync(pgm::c_prof, &dprof, sizeof(dprof), 0, cudaMemcpyHostToDevice, st);
+#endif
   kern<<<grid, pgm::NTHREADS, smem, st>>>(A);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("sm_mll_grad_kernel launch", e);
+#ifdef PGM_DEBUG_HOOKS
+  if (dprof) {
+    cudaStreamSynchronize(st);
+    std::vector<long long> h((size_t)grid * 16);
+    cudaMemcpy(h.data(), dprof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dprof);
+    static const char* nm[13] = {"setup", "P.gemm", "P.kepi", "P.potrf", "P.diagpost", "P.trsm", "mll",
+                                 "T.gemm1", "T.gemm2", "alpha", "G.gemm", "G.epi", "final"};
+    double tot = 0, v[13];
+    for (int s2 = 0; s2 < 13; ++s2) { v[s2] = 0; for (int b = 0; b < grid; ++b) v[s2] += (double)h[(size_t)b * 16 + s2]; v[s2] /= grid; tot += v[s2]; }
+    fprintf(stderr, "[pgm prof] per-CTA cycles (avg over %d CTAs), total %.0f:", grid, tot);
+    for (int s2 = 0; s2 < 13; ++s2) fprintf(stderr, " %s %.0f (%.1f%%)", nm[s2], v[s2], 100 * v[s2] / tot);
+    fprintf(stderr, "\n");
+  }
+#endif
   return 0;
 }
 
