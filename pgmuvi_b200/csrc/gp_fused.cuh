@@ -259,46 +259,56 @@ __device__ __forceinline__ int frag_col(int wn, int ni, int tq, int e) {
   return 8 * frag_nt(wn, ni) + 2 * tq + e;
 }
 
+// Fragment loads of k-group k8l+1 are issued (and pinned in program order by an empty
+// volatile asm) before the MMAs of k-group k8l; the two MMA steps of one accumulator are
+// separated by the 7 other accumulators so that no DMMA waits on the one issued just before.
+__device__ __forceinline__ void load_frags(double2 (&fa)[4], double2 (&fb)[2],
+                                           const double* __restrict__ sA,
+                                           const double* __restrict__ sB, int k8l, int wm, int wn,
+                                           int g, int tq) {
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    const int r = frag_row(wm, mi, g);
+    fa[mi] = *reinterpret_cast<const double2*>(sA + r * KC + (((k8l * 4 + tq) ^ ((r & 1) << 2)) << 1));
+  }
+#pragma unroll
+  for (int ni = 0; ni < 2; ++ni) {
+    const int r = 8 * frag_nt(wn, ni) + g;
+    fb[ni] = *reinterpret_cast<const double2*>(sB + r * KC + (((k8l * 4 + tq) ^ ((r & 1) << 2)) << 1));
+  }
+  asm volatile("" : "+d"(fa[0].x), "+d"(fa[0].y), "+d"(fa[1].x), "+d"(fa[1].y), "+d"(fa[2].x),
+                    "+d"(fa[2].y), "+d"(fa[3].x), "+d"(fa[3].y), "+d"(fb[0].x), "+d"(fb[0].y),
+                    "+d"(fb[1].x), "+d"(fb[1].y));
+}
+
 template <int MODE, bool LOWER>
 __device__ __forceinline__ void compute_chunk(double (&acc)[4][2][2], const double* __restrict__ sA,
                                               const double* __restrict__ sB, int k8base, int wm,
                                               int wn, int g, int tq) {
+  double2 fa[2][4], fb[2][2];
+  load_frags(fa[0], fb[0], sA, sB, 0, wm, wn, g, tq);
 #pragma unroll
   for (int k8l = 0; k8l < KC / 8; ++k8l) {
     const int k8g = k8base + k8l;
-    double a[2][4], b[2][2];
+    const int cur = k8l & 1;
+    if (k8l + 1 < KC / 8) load_frags(fa[cur ^ 1], fb[cur ^ 1], sA, sB, k8l + 1, wm, wn, g, tq);
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      const int r = frag_row(wm, mi, g);
-      const double2 v = *reinterpret_cast<const double2*>(
-          sA + r * KC + (((k8l * 4 + tq) ^ ((r & 1) << 2)) << 1));
-      a[0][mi] = v.x;
-      a[1][mi] = v.y;
-    }
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int ni = 0; ni < 2; ++ni) {
-      const int r = 8 * frag_nt(wn, ni) + g;
-      const double2 v = *reinterpret_cast<const double2*>(
-          sB + r * KC + (((k8l * 4 + tq) ^ ((r & 1) << 2)) << 1));
-      b[0][ni] = v.x;
-      b[1][ni] = v.y;
-    }
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 2; ++ni) {
-        const int mt = frag_mt(wm, mi), nt = frag_nt(wn, ni);
-        bool on = true;
-        if (LOWER) on = on && (mt >= nt);
-        if (MODE == M_B_LE) on = on && (k8g <= nt);
-        if (MODE == M_B_GE) on = on && (k8g >= nt);
-        if (MODE == M_A_LE) on = on && (k8g <= mt);
-        if (MODE == M_A_GE) on = on && (k8g >= mt);
-        if (on) {
-          mma_f64(acc[mi][ni], a[0][mi], b[0][ni]);
-          mma_f64(acc[mi][ni], a[1][mi], b[1][ni]);
+        for (int ni = 0; ni < 2; ++ni) {
+          const int mt = frag_mt(wm, mi), nt = frag_nt(wn, ni);
+          bool on = true;
+          if (LOWER) on = on && (mt >= nt);
+          if (MODE == M_B_LE) on = on && (k8g <= nt);
+          if (MODE == M_B_GE) on = on && (k8g >= nt);
+          if (MODE == M_A_LE) on = on && (k8g <= mt);
+          if (MODE == M_A_GE) on = on && (k8g >= mt);
+          if (on)
+            mma_f64(acc[mi][ni], h ? fa[cur][mi].y : fa[cur][mi].x,
+                    h ? fb[cur][ni].y : fb[cur][ni].x);
         }
-      }
   }
 }
 
@@ -405,8 +415,7 @@ __device__ __forceinline__ void store_acc_tile(const double (&acc)[4][2][2], dou
 template <int KIND, int QT, int D>
 __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
                                           const double* __restrict__ colv, int r, int c,
-                                          const double* __restrict__ w,
-                                          const double* __restrict__ a,
+                                          const double (&w)[QT], const double (&a)[QT * D],
                                           const double* __restrict__ tab) {
   const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
   const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
@@ -450,8 +459,7 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
 template <int KIND, int QT, int D>
 __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
                                              const double* __restrict__ colv, int r, int c,
-                                             const double* __restrict__ w,
-                                             const double* __restrict__ a,
+                                             const double (&w)[QT], const double (&a)[QT * D],
                                              const double* __restrict__ tab, double wgt,
                                              double (&ga)[QT + 2 * QT * D]) {
   const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
@@ -784,6 +792,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   auto tileT = [&](int j) { return sc.tilesT + (size_t)j * TT; };
 
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  double wreg[QT], areg[QT * D];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) wreg[q] = wq[q];
+#pragma unroll
+  for (int q = 0; q < QT * D; ++q) areg[q] = aq[q];
   PGM_PROF(0);
   double acc[4][2][2];
   double iq_part = 0.0;  // partial of z^T z
@@ -830,32 +843,38 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         else pre = gemm_stream<M_FULL, false, 2>(acc, r2, j, tA, tB, pre, nnk, nA, nB, pf);
         __syncthreads();
         PGM_PROF(1);
-        // epilogue: C = Ktilde_ij - acc   (diagonal tiles: lower triangle only)
+        // epilogue: C = Ktilde_ij - acc (diagonal tiles: lower triangle only).  The
+        // accumulators are parked in stage 1 (the image the next product reads as its A
+        // operand) so that the registers go to the exp / cos chains: one rolled loop over the
+        // 8 MMA tiles of the warp, 2 entries x QT mixtures in flight, no per-entry branches
+        // (padded points carry finite dummy fields); MMA tiles above the diagonal are skipped.
+        store_acc_tile(acc, Cst, 1.0);
+#pragma unroll 1
+        for (int p8 = 0; p8 < 8; ++p8) {
+          const int mi = p8 >> 1, ni2 = p8 & 1;
+          if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+          const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+          const int gi = i * TS + r;
+          double2* cp = reinterpret_cast<double2*>(Cst + img(r, c0));
+          const double2 cv = *cp;
+          double out[2];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni2 = 0; ni2 < 2; ++ni2)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int r = frag_row(wm, mi, g), c = frag_col(wn, ni2, tq, e);
-              const int gi = i * TS + r, gj = j * TS + c;
-              double kv = 0.0;
-              if (gi < n && gj < n && gj <= gi)
-                kv = k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab);
-              if (gi == gj) kv = (gi < n) ? (kv + sc.dn[gi] + jitter) : 1.0;
-              acc[mi][ni2][e] = kv - acc[mi][ni2][e];
-            }
+          for (int e = 0; e < 2; ++e) {
+            const int gj = j * TS + c0 + e;
+            double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, tab);
+            kv = (gi < n && gj <= gi) ? kv : 0.0;
+            if (gi == gj) kv = (gi < n) ? (kv + sc.dn[gi] + jitter) : 1.0;
+            out[e] = kv - (e ? cv.y : cv.x);
+          }
+          if (i == j) {
+            S[r * LD_S + c0] = out[0];
+            S[r * LD_S + c0 + 1] = out[1];
+          } else {
+            *cp = make_double2(out[0], out[1]);
+          }
+        }
         PGM_PROF(2);
         if (i == j) {
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni2 = 0; ni2 < 2; ++ni2)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int r = frag_row(wm, mi, g), c = frag_col(wn, ni2, tq, e);
-                S[r * LD_S + c] = acc[mi][ni2][e];
-              }
           __syncthreads();
           potrf_inv_64(S, S2, dinv, s_fail);
           PGM_PROF(3);
@@ -904,8 +923,11 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           __syncthreads();
           PGM_PROF(4);
         } else {
-          // L_ij = C * X_jj^T  straight from registers / shared memory
-          times_resident();
+          // L_ij = C * X_jj^T  straight from shared memory (C in stage 1, X_jj resident)
+          __syncthreads();
+          zero_acc(acc);
+          compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+          compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
           store_acc_tile(acc, tile(i, j), 1.0);
           // partial products L_ij z_j for the forward solve of row i (deterministic order)
 #pragma unroll
@@ -999,7 +1021,6 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       }
     }
   }
-  ps.gq2 = r2.gq;
   __syncthreads();
   // ---- alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i -----------------------------------
   {
@@ -1025,7 +1046,6 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   for (int t = 0; t < C::NG; ++t) ga[t] = 0.0;
   double trW = 0.0;
   {
-    Ring r3{bars + 32, bars + 56, stages, ps.gq3};
     int pre = 0;
     for (int i = 0; i < N; ++i) {
       for (int j = 0; j <= i; ++j) {
@@ -1039,31 +1059,35 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         auto nA = [&](int kk) { return kk == 0 ? tileT(ni) : tile(ni + kk, ni); };
         auto nB = [&](int kk) { return (kk == 0 && ni == nj) ? tileT(nj) : tile(ni + kk, nj); };
         auto pf = [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); };
-        if (i == j) pre = gemm_stream<M_A_GE, true, 3>(acc, r3, N - i, tA, tB, pre, nnk, nA, nB, pf);
-        else pre = gemm_stream<M_A_GE, false, 3>(acc, r3, N - i, tA, tB, pre, nnk, nA, nB, pf);
+        if (i == j) pre = gemm_stream<M_A_GE, true, 2>(acc, r2, N - i, tA, tB, pre, nnk, nA, nB, pf);
+        else pre = gemm_stream<M_A_GE, false, 2>(acc, r2, N - i, tA, tB, pre, nnk, nA, nB, pf);
         __syncthreads();
         PGM_PROF(10);
+        // K^-1 tile parked in R (free in this phase); rolled, branch-free contraction
+        store_acc_tile(acc, R, 1.0);
         const double* al_r = rowv + C::NFB * TS;
         const double* al_c = colv + C::NFB * TS;
+#pragma unroll 1
+        for (int p8 = 0; p8 < 8; ++p8) {
+          const int mi = p8 >> 1, ni2 = p8 & 1;
+          if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+          const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+          const int gi = i * TS + r;
+          const double2 kinv = *reinterpret_cast<const double2*>(R + img(r, c0));
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni2 = 0; ni2 < 2; ++ni2)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int r = frag_row(wm, mi, g), c = frag_col(wn, ni2, tq, e);
-              const int gi = i * TS + r, gj = j * TS + c;
-              if (gi < n && gj <= gi) {
-                const double W = al_r[r] * al_c[c] - acc[mi][ni2][e];
-                if (gi == gj) trW += W;
-                const double wgt = (gi == gj) ? W : 2.0 * W;
-                k_grad_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab, wgt, ga);
-              }
-            }
+          for (int e = 0; e < 2; ++e) {
+            const int gj = j * TS + c0 + e;
+            double W = al_r[r] * al_c[c0 + e] - (e ? kinv.y : kinv.x);
+            W = (gi < n && gj <= gi) ? W : 0.0;
+            if (gi == gj) trW += W;
+            const double wgt = (gi == gj) ? W : 2.0 * W;
+            k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, tab, wgt, ga);
+          }
+        }
         PGM_PROF(11);
       }
     }
-    ps.gq3 = r3.gq;
+    ps.gq2 = r2.gq;
   }
   // ---- reduce, apply constants and the constraint Jacobian ----------------------------
   {
