@@ -95,9 +95,30 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
           "r"(dst), "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
-// generic-proxy writes (st.global / st.shared) -> visible to later async-proxy (bulk) reads
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+               "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+// source shared memory of all committed bulk stores has been read
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+// all committed bulk stores are complete (visible to later bulk loads of this thread)
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+}
+// generic-proxy writes (st.global / st.shared) -> visible to later async-proxy (bulk) reads.
+// The full fence drains the thread's global stores (slow): only the 64x64 diagonal blocks use
+// it; off-diagonal tiles leave through shared memory + bulk store (shared-only fence).
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
 __device__ __forceinline__ double shfl_d(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
@@ -130,7 +151,11 @@ __constant__ double c_exp2_tab[64] = {
     0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
 
 #ifdef PGM_DEBUG_HOOKS
-// -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 (timing experiments only)
+// -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 and decomposition switches
+// (PGM_DEBUG_MODE: 0x100 no operand loads, 0x200 no MMAs, 0x800 ignore potrf failures) -
+// timing experiments only, results are garbage
+__constant__ int c_dbg = 0;
+#define PGM_DBG(bit) (c_dbg & (bit))
 __constant__ long long* c_prof = nullptr;
 #define PGM_PROF_START() long long prof_t = clock64()
 #define PGM_PROF(slot)                                                       \
@@ -142,6 +167,7 @@ __constant__ long long* c_prof = nullptr;
     }                                                                        \
   } while (0)
 #else
+#define PGM_DBG(bit) 0
 #define PGM_PROF_START() do { } while (0)
 #define PGM_PROF(slot) do { } while (0)
 #endif
@@ -229,7 +255,9 @@ __host__ __device__ inline size_t scratch_elems(int n_max, int NF) {
 // released it) and issues that chunk's two bulk copies on full[stage]; every warp waits on
 // full[stage], computes, and releases with one arrive per warp.  The producer runs ahead into
 // the NEXT job's first chunks ("pre" of the following call) where the caller says the tiles
-// are final.
+// are final.  Off-diagonal result tiles leave through shared memory and ONE bulk store
+// (async proxy on both sides, no generic->async fence on global memory); the producer waits
+// for that store before it issues anything beyond k-tile 0 of the following job.
 //
 // k <-> lane mapping of one 8-deep k-group: MMA step h in {0,1}, lane tq holds
 // k = 8*k8 + 2*tq + h  (both operands).
@@ -351,26 +379,33 @@ __device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int
     if (use > 0) mbar_wait(rg.empty + 8 * s, (use - 1) & 1);
     const unsigned bar = rg.full + 8 * s;
     const unsigned dst = smem_u32(rg.stages + s * 2 * OPBUF);
+    if (PGM_DBG(0x100)) { mbar_arrive(bar); return; }
     mbar_expect_tx(bar, 2 * CHUNK_BYTES);
     bulk_g2s(dst, ga, CHUNK_BYTES, bar);
     bulk_g2s(dst + CHUNK_BYTES, gb, CHUNK_BYTES, bar);
   };
 
-  fence_proxy_async();  // this thread's tile stores / staging writes before later bulk copies
-  __syncthreads();      // job boundary: producers of the tiles and users of the stages are done
+  __syncthreads();  // job boundary: users of the stages / rowv / colv are done
   extra_prefetch();
   cp_async_commit();
   if (tid == 0) {
-    fence_proxy_async();
+    // the previous job's bulk store has left its staging buffer; a cold start (nothing in
+    // flight) also waits for every earlier store to be complete
+    if (pre == 0) bulk_wait_all(); else bulk_wait_read();
     for (int t = pre; t < LA; ++t) issue(t);
   }
   for (int c = 0; c < n; ++c) {
-    if (tid == 0) issue(c + LA);
+    if (tid == 0) {
+      // chunks >= 2 (k-tile 1 onwards) may read the tile the previous job stored
+      if (c + LA == 2 || (c == 0 && LA > 2)) bulk_wait_all();
+      issue(c + LA);
+    }
     const int q = rg.gq + c, s = q % NST;
     mbar_wait(rg.full + 8 * s, (q / NST) & 1);
     const double* sA = rg.stages + s * 2 * OPBUF;
     const double* sB = sA + OPBUF;
-    if (MODE0 != M_FULL && c < 2)
+    if (PGM_DBG(0x200)) {
+    } else if (MODE0 != M_FULL && c < 2)
       compute_chunk<MODE0, LOWER>(acc, sA, sB, c * (KC / 8), wm, wn, g, tq);
     else
       compute_chunk<M_FULL, LOWER>(acc, sA, sB, 0, wm, wn, g, tq);
@@ -403,6 +438,20 @@ __device__ __forceinline__ void store_acc_tile(const double (&acc)[4][2][2], dou
       *reinterpret_cast<double2*>(tile + img(r, c)) =
           make_double2(sign * acc[mi][ni][0], sign * acc[mi][ni][1]);
     }
+  }
+}
+
+// accumulator -> global tile through a shared staging buffer (every warp must be done reading
+// `stage`): image written by all threads, one bulk store issued by thread 0.
+__device__ __forceinline__ void store_tile_bulk(const double (&acc)[4][2][2], double* stage,
+                                                double* gtile, double sign) {
+  __syncthreads();
+  store_acc_tile(acc, stage, sign);
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bulk_s2g(gtile, smem_u32(stage), 2 * OPBUF * sizeof(double));
+    bulk_commit();
   }
 }
 
@@ -878,7 +927,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           __syncthreads();
           potrf_inv_64(S, S2, dinv, s_fail);
           PGM_PROF(3);
-          if (*s_fail) { failed = true; break; }
+          if (*s_fail && !PGM_DBG(0x800)) { failed = true; break; }
           // X_jj -> tile(j,j) and the resident R, X_jj^T -> tilesT[j]  (tile images with
           // explicit zeros in the other triangle); L_jj itself is not needed any more
           double* dt = tile(j, j);
@@ -895,6 +944,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             *reinterpret_cast<double2*>(R + o) = v;
             *reinterpret_cast<double2*>(dtT + o) = vt;
           }
+          fence_proxy_async();  // dt / dtT are read by bulk copies later (barriers follow)
           // forward solve: z_j = X_jj (rhs_j - sum_{k<j} L_jk z_k); the products L_jk z_k
           // were left in fpart by the epilogues of row j's tiles (4 partials per row).
           {
@@ -928,7 +978,6 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           zero_acc(acc);
           compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
           compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
-          store_acc_tile(acc, tile(i, j), 1.0);
           // partial products L_ij z_j for the forward solve of row i (deterministic order)
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi) {
@@ -941,12 +990,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             s += shfl_xor_d(s, 2);
             if (tq == 0) sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
           }
+          store_tile_bulk(acc, Cst, tile(i, j), 1.0);
           PGM_PROF(5);
         }
       }
     }
     __syncthreads();
-    const int fl = *s_fail;
+    const int fl = PGM_DBG(0x800) ? 0 : *s_fail;
     if (!fl) { info = attempt; break; }
     if (fl & 2) { info = -1; break; }
     info = -2;
@@ -978,7 +1028,6 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   {
     int pre = 0;
     for (int i = 1; i < N; ++i) {
-      fence_proxy_async();
       __syncthreads();  // the previous row is done with R and zi
       if (tid == 0) {
         mbar_expect_tx(rbar, 2 * CHUNK_BYTES);
@@ -1004,7 +1053,6 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           rwait = false;
         }
         times_resident();
-        store_acc_tile(acc, tile(i, j), -1.0);
         // partial products X_ij^T z_i for alpha_j  (X_ij^T = -acc)
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
@@ -1017,6 +1065,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           s += shfl_xor_d(s, 2);
           if (tq == 0) sc.apart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
         }
+        store_tile_bulk(acc, Cst, tile(i, j), -1.0);
         PGM_PROF(8);
       }
     }
@@ -1047,6 +1096,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double trW = 0.0;
   {
     int pre = 0;
+    if (tid == 0) bulk_wait_all();
     for (int i = 0; i < N; ++i) {
       for (int j = 0; j <= i; ++j) {
         zero_acc(acc);
@@ -1161,6 +1211,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
         eval_lightcurve<KIND, QT, D>(A, b, A.raw + (size_t)b * P, sm, sc, ps, A.mll + b, gout);
     if (threadIdx.x == 0) A.info[b] = info;
   }
+  if (threadIdx.x == 0) bulk_wait_all();  // no bulk store may outlive the block's shared memory
 }
 
 // dense K + D for parity tests / large-n path: one block per (light curve, 64x64 tile)
@@ -1304,6 +1355,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
     // mark the unused tail of the history
     for (int t = it + tid; t < F.maxiter; t += NTHREADS) F.loss_hist[(size_t)t * A.B + b] = nan("");
   }
+  if (threadIdx.x == 0) bulk_wait_all();
 }
 
 }  // namespace pgm

@@ -30,6 +30,11 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   int grid = device_sms() * occ;
   if (grid > A.B) grid = A.B;
 #ifdef PGM_DEBUG_HOOKS
+  {
+    int dbg = 0;
+    if (const char* f = getenv("PGM_DEBUG_MODE")) dbg = (int)strtol(f, nullptr, 0);
+    cudaMemcpyToSymbolAsync(pgm::c_dbg, &dbg, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+  }
   long long* dprof = nullptr;
   if (getenv("PGM_DEBUG_PROF")) {
     cudaMalloc(&dprof, (size_t)grid * 16 * sizeof(long long));
