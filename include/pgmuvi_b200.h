@@ -19,10 +19,13 @@
  *        -1     NaN encountered (GPyTorch NanError)
  *        -2     not positive definite after 3 jitter tries (GPyTorch NotPSDError)
  *
- * Packed raw-parameter layout, P = 1 + Q + 2*Q*d (+1 if PGM_FLAG_LEARN_NOISE):
- *     [ mean | w[0..Q) | mu[q*d+k] | sigma[q*d+k] | (learned noise) ]
- * mirroring gpytorch's raw_constant, raw_mixture_weights [Q], raw_mixture_means [Q,1,d],
- * raw_mixture_scales [Q,1,d], raw_noise [1] (pgmuvi/lightcurve.py:3847-3849, 6475-6480).
+ * Packed raw-parameter layout, P = 1 + Q + 2*Q*ds (+1 if PGM_FLAG_LEARN_NOISE) + NL:
+ *     [ mean | w[0..Q) | mu[q*ds+k] | sigma[q*ds+k] | (learned noise) | lam[0..NL) ]
+ * mirroring gpytorch's raw_constant, raw_mixture_weights [Q], raw_mixture_means [Q,1,ds],
+ * raw_mixture_scales [Q,1,ds], raw_noise [1] (pgmuvi/lightcurve.py:3847-3849, 6475-6480).
+ * ds = d for the plain spectral-mixture kinds; the separable kinds (d = 2, pgmuvi/gps.py:
+ * 1327-1336: SM(time) * k(wavelength)) have ds = 1 and NL wavelength-kernel parameters
+ *     lam = [ raw_outputscale, raw_lengthscale (, raw_alpha) ]  or  [ raw_constant ].
  */
 #ifndef PGMUVI_B200_H
 #define PGMUVI_B200_H
@@ -39,6 +42,11 @@ extern "C" {
 #define PGM_KIND_SM1D 0          /* d = 1: sum_q w_q E_q C_q                               */
 #define PGM_KIND_SM_ARD_PRODSUM 1 /* d = 2: prod_d sum_q w_q E_qd C_qd  (GPyTorch order)    */
 #define PGM_KIND_SM_ARD_SUMPROD 2 /* d = 2: sum_q w_q prod_d E_qd C_qd  (switchable variant) */
+/* separable SM(time) * wavelength kernel, gps.py:990-1002 x 1045-1072, product at :1327-1336 */
+#define PGM_KIND_SEP_RBF 3      /* ScaleKernel(RBFKernel):        os exp(-tau^2 / 2 l^2)       NL=2 */
+#define PGM_KIND_SEP_MATERN15 4 /* ScaleKernel(MaternKernel 1.5): os (1+s3 r) exp(-s3 r)       NL=2 */
+#define PGM_KIND_SEP_RQ 5       /* ScaleKernel(RQKernel):         os (1+tau^2/2 a l^2)^-a      NL=3 */
+#define PGM_KIND_SEP_CONST 6    /* ConstantKernel (AchromaticGPModel, gps.py:1414-1415)        NL=1 */
 
 /* constraint kinds: gpytorch.constraints chosen at pgmuvi/lightcurve.py:3817-4008 */
 #define PGM_CON_NONE 0     /* value = raw                                         */

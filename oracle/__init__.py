@@ -18,6 +18,14 @@ from .sm_gp import (  # noqa: F401
     KIND_SM1D,
     KIND_SM_ARD_PRODSUM,
     KIND_SM_ARD_SUMPROD,
+    KIND_SEP_RBF,
+    KIND_SEP_MATERN15,
+    KIND_SEP_RQ,
+    KIND_SEP_CONST,
+    SEP_KINDS,
+    kernel_dense,
+    wavelength_kernel_dense,
+    unpack_lam,
     CON_NONE,
     CON_SOFTPLUS,
     CON_INTERVAL,

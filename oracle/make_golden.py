@@ -17,8 +17,8 @@ import torch
 
 from pgmuvi_b200 import synthetic as S
 
-from .sm_gp import (ModelSpec, constrain, mll_and_grad_analytic, mll_and_grad_autograd,
-                    noise_diag, sm_kernel_dense, train_loop, unpack_params)
+from .sm_gp import (ModelSpec, constrain, kernel_dense, mll_and_grad_analytic,
+                    mll_and_grad_autograd, noise_diag, train_loop, unpack_params)
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 
@@ -38,6 +38,12 @@ CASES = [
     ("sm2d_sumprod_4x48_q4", dict(dim=2, kind=2, B=2, bands=4, per=48, Q=4, learn_noise=False)),
     ("sm2d_prodsum_4x256_q4", dict(dim=2, kind=1, B=1, bands=4, per=256, Q=4, learn_noise=False)),  # C5 shape
     ("sm1d_ragged_q4", dict(dim=1, B=4, n=200, Q=4, learn_noise=False, n_valid=[200, 130, 64, 77])),
+    # separable SM(time) x wavelength kernel (gps.py:1274-1342), kinds 3..6
+    ("sep_rbf_4x48_q4", dict(dim=2, kind=3, B=2, bands=4, per=48, Q=4, learn_noise=False)),
+    ("sep_matern_4x48_q2_learn", dict(dim=2, kind=4, B=2, bands=4, per=48, Q=2, learn_noise=True)),
+    ("sep_rq_4x48_q4", dict(dim=2, kind=5, B=2, bands=4, per=48, Q=4, learn_noise=False)),
+    ("sep_const_3x40_q3_learn", dict(dim=2, kind=6, B=2, bands=3, per=40, Q=3, learn_noise=True)),
+    ("sep_rbf_4x128_q8", dict(dim=2, kind=3, B=1, bands=4, per=128, Q=8, learn_noise=False)),
 ]
 
 
@@ -49,6 +55,9 @@ def make_case(name, kw):
     if dim == 1:
         bt = S.make_batch_1d(kw["B"], kw["n"], Q=kw["Q"], learn_noise=kw["learn_noise"],
                              fixed_noise=kw.get("fixed_noise", True))
+    elif kind >= 3:
+        bt = S.make_batch_sep(kw["B"], kw["bands"], kw["per"], Q=kw["Q"], kind=kind,
+                              learn_noise=kw["learn_noise"])
     else:
         bt = S.make_batch_2d(kw["B"], kw["bands"], kw["per"], Q=kw["Q"],
                              learn_noise=kw["learn_noise"])
@@ -78,7 +87,7 @@ def make_case(name, kw):
         mll[b], g_auto[b], g_ana[b], info[b] = float(m1), g1.numpy(), g2.numpy(), int(i1)
         th = constrain(raw, kinds, lb, ub)
         mean, w, mu, sg, noise = unpack_params(th, spec)
-        K = sm_kernel_dense(x, x, w, mu, sg, kind) + torch.diag_embed(
+        K = kernel_dense(x, x, th, spec) + torch.diag_embed(
             noise_diag(nb, nz, noise, y.dtype))
         ii = np.minimum(kidx[0], nb - 1)
         ksamp[b] = K[ii][:, ii].numpy()
@@ -98,9 +107,13 @@ def make_case(name, kw):
 
 
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_default_dtype(torch.float64)
+    only = sys.argv[1:]          # optional name prefixes: regenerate a subset
     for name, kw in CASES:
+        if only and not any(name.startswith(o) for o in only):
+            continue
         out = make_case(name, kw)
         # x / y / noise hold float32-representable values: store them as float32 to keep the
         # fixtures small (exactly recoverable); everything else float64.

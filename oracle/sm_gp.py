@@ -13,9 +13,12 @@ The path (pgmuvi/trainers.py:177-182):
     optimizer.step()                     # trainers.py:141-147,182 (SGD/Adam/AdamW on RAW params)
 
 Packed raw-parameter layout used by the oracle, the C ABI and the golden files
-(``P = 1 + Q + 2*Q*d (+1)``)::
+(``P = 1 + Q + 2*Q*ds (+1) + NL``)::
 
-    [ mean | w[0..Q) | mu[q*d + k] | sigma[q*d + k] | (learned noise) ]
+    [ mean | w[0..Q) | mu[q*ds + k] | sigma[q*ds + k] | (learned noise) | lam[0..NL) ]
+
+``ds`` = dims the spectral mixture acts on (= d, or 1 for the separable kinds whose
+wavelength factor has the ``NL`` parameters ``lam``).
 """
 from __future__ import annotations
 
@@ -29,6 +32,14 @@ import torch
 KIND_SM1D = 0              # gps.py:208  SMK(num_mixtures=Q)                       (d = 1)
 KIND_SM_ARD_PRODSUM = 1    # gps.py:305  SMK(ard_num_dims=2): prod_d sum_q (GPyTorch; F7)
 KIND_SM_ARD_SUMPROD = 2    # switchable variant: sum_q w_q prod_d (notebook tinygp cell; F7)
+# separable 2-D models (gps.py:1327-1336  covar = time_kernel * wavelength_kernel with
+# active_dims [0] / [1]); time kernel = SMK(Q, ard_num_dims=1) (gps.py:990-1002)
+KIND_SEP_RBF = 3           # x ScaleKernel(RBFKernel())          gps.py:1045-1048, 1063-1064
+KIND_SEP_MATERN15 = 4      # x ScaleKernel(MaternKernel(nu=1.5)) gps.py:1049-1052
+KIND_SEP_RQ = 5            # x ScaleKernel(RQKernel())           gps.py:1053-1056
+KIND_SEP_CONST = 6         # x ConstantKernel()                  gps.py:1414-1415 (Achromatic)
+SEP_KINDS = (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)
+NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST: 1}
 
 # constraint kinds (A.2) ---------------------------------------------------------------
 CON_NONE = 0       # value = raw
@@ -49,8 +60,18 @@ class ModelSpec:
     # fixed per-point noise is a data argument (None -> absent)
 
     @property
+    def ds(self) -> int:
+        """dims the spectral mixture acts on (separable kinds: time only)."""
+        return 1 if self.kind in SEP_KINDS else self.d
+
+    @property
+    def NL(self) -> int:
+        """wavelength-kernel parameters of the separable kinds."""
+        return NUM_LAM.get(self.kind, 0)
+
+    @property
     def P(self) -> int:
-        return 1 + self.Q + 2 * self.Q * self.d + (1 if self.learn_noise else 0)
+        return 1 + self.Q + 2 * self.Q * self.ds + (1 if self.learn_noise else 0) + self.NL
 
     # slot offsets in the packed layout
     @property
@@ -63,11 +84,15 @@ class ModelSpec:
 
     @property
     def o_sigma(self):
-        return 1 + self.Q + self.Q * self.d
+        return 1 + self.Q + self.Q * self.ds
 
     @property
     def o_noise(self):
-        return 1 + self.Q + 2 * self.Q * self.d
+        return 1 + self.Q + 2 * self.Q * self.ds
+
+    @property
+    def o_lam(self):
+        return self.o_noise + (1 if self.learn_noise else 0)
 
 
 # ---------------------------------------------------------------------------------------
@@ -101,7 +126,7 @@ def unconstrain(val, kinds, lb, ub):
 
 def unpack_params(theta, spec: ModelSpec):
     """Split a packed (constrained or raw) vector [..., P] into named pieces."""
-    Q, d = spec.Q, spec.d
+    Q, d = spec.Q, spec.ds
     mean = theta[..., 0]
     w = theta[..., spec.o_w:spec.o_w + Q]
     mu = theta[..., spec.o_mu:spec.o_mu + Q * d].reshape(*theta.shape[:-1], Q, d)
@@ -137,6 +162,44 @@ def sm_kernel_dense(x1, x2, w, mu, sigma, kind=KIND_SM1D):
         ww = w.unsqueeze(-1).unsqueeze(-1)
         return (res.prod(-1) * ww).sum(-3)
     raise ValueError(f"unknown kernel kind {kind}")
+
+
+def unpack_lam(theta, spec: ModelSpec):
+    """Wavelength-kernel parameters [..., NL] of the separable kinds."""
+    return theta[..., spec.o_lam:spec.o_lam + spec.NL]
+
+
+def wavelength_kernel_dense(l1, l2, lam, kind):
+    """Wavelength factor of the separable kinds, following GPyTorch's kernels (A.3):
+    ScaleKernel: outputscale * base;  RBF exp(-tau^2 / (2 l^2));  Matern-1.5
+    (1 + sqrt3 r) exp(-sqrt3 r), r = |tau| / l;  RQ (1 + tau^2 / (2 alpha l^2))^-alpha;
+    ConstantKernel: constant.   l1 [..., n], l2 [..., m]; lam [..., NL]."""
+    tau = l1.unsqueeze(-1) - l2.unsqueeze(-2)
+    ex = lambda t: t.unsqueeze(-1).unsqueeze(-1)
+    if kind == KIND_SEP_CONST:
+        return ex(lam[..., 0]) * torch.ones_like(tau)
+    os_, ell = ex(lam[..., 0]), ex(lam[..., 1])
+    if kind == KIND_SEP_RBF:
+        return os_ * torch.exp(-0.5 * (tau / ell) ** 2)
+    if kind == KIND_SEP_MATERN15:
+        r = math.sqrt(3.0) * (tau / ell).abs()
+        return os_ * (1.0 + r) * torch.exp(-r)
+    if kind == KIND_SEP_RQ:
+        al = ex(lam[..., 2])
+        return os_ * (1.0 + (tau / ell) ** 2 / (2.0 * al)) ** (-al)
+    raise ValueError(f"not a separable kind: {kind}")
+
+
+def kernel_dense(x1, x2, theta, spec: ModelSpec):
+    """Dense covariance of any kind from a constrained packed vector theta [..., P].
+    Separable kinds: ProductKernel restricted by active_dims (gps.py:1319-1336), i.e. the
+    elementwise product K_t(x[:, 0]) * K_l(x[:, 1])  (tests/test_kernels.py:130-139)."""
+    mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    if spec.kind in SEP_KINDS:
+        Kt = sm_kernel_dense(x1[..., :1], x2[..., :1], w, mu, sigma, KIND_SM1D)
+        Kl = wavelength_kernel_dense(x1[..., 1], x2[..., 1], unpack_lam(theta, spec), spec.kind)
+        return Kt * Kl
+    return sm_kernel_dense(x1, x2, w, mu, sigma, spec.kind)
 
 
 def noise_diag(n, fixed_noise, learned_noise, dtype):
@@ -193,7 +256,7 @@ def _mll_from_theta(x, y, fixed_noise, theta, spec: ModelSpec):
     """Per-datum MLL from constrained theta.  x [n,d], y [n], theta [P]."""
     n = y.shape[-1]
     mean, w, mu, sigma, noise = unpack_params(theta, spec)
-    K = sm_kernel_dense(x, x, w, mu, sigma, spec.kind)
+    K = kernel_dense(x, x, theta, spec)
     Kt = K + torch.diag_embed(noise_diag(n, fixed_noise, noise, y.dtype))
     L, info = psd_safe_cholesky(Kt.detach())
     if int(info) > 0:  # re-apply the jitter that made it succeed, keeping the graph
@@ -240,10 +303,10 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
     """
     dt = y.dtype
     n = y.shape[-1]
-    Q, d = spec.Q, spec.d
+    Q, d = spec.Q, spec.ds
     theta = constrain(raw, kinds, lb, ub)
     mean, w, mu, sigma, noise = unpack_params(theta, spec)
-    K = sm_kernel_dense(x, x, w, mu, sigma, spec.kind)
+    K = kernel_dense(x, x, theta, spec)
     Kt = K + torch.diag_embed(noise_diag(n, fixed_noise, noise, dt))
     L, info = psd_safe_cholesky(Kt)
     if int(info) < 0:
@@ -257,7 +320,16 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
     mll = -0.5 * (inv_quad + logdet + n * math.log(TWO_PI)) / n
     W = alpha @ alpha.T - Kinv
 
-    tau = x.unsqueeze(-2) - x.unsqueeze(-3)                     # [n, n, d]
+    sep = spec.kind in SEP_KINDS
+    if sep:
+        # K = Kt o Kl: the time-kernel parameters see W o Kl, the wavelength ones W o Kt
+        lam = unpack_lam(theta, spec)
+        Kl = wavelength_kernel_dense(x[:, 1], x[:, 1], lam, spec.kind)
+        Ktime = K / Kl
+        W_full = W
+        W = W * Kl
+        x_full, x = x, x[:, :1]
+    tau = x.unsqueeze(-2) - x.unsqueeze(-3)                     # [n, n, ds]
     E = torch.exp(-2 * math.pi ** 2 * (tau.unsqueeze(0) * sigma[:, None, None, :]) ** 2)
     ph = TWO_PI * tau.unsqueeze(0) * mu[:, None, None, :]       # [Q, n, n, d]
     C, S = torch.cos(ph), torch.sin(ph)
@@ -265,7 +337,7 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
     g = torch.zeros(spec.P, dtype=dt)
     g[0] = alpha.sum() / n
     half = 0.5 / n
-    if spec.kind in (KIND_SM1D, KIND_SM_ARD_PRODSUM):
+    if spec.kind in (KIND_SM1D, KIND_SM_ARD_PRODSUM) or sep:
         Sd = (w[:, None, None, None] * EC).sum(0)               # [n, n, d]
         for k in range(d):
             R = torch.ones(n, n, dtype=dt)
@@ -294,6 +366,27 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
                 g[spec.o_sigma + q * d + k] = half * (
                     W * Rq * (-4 * math.pi ** 2 * tau[..., k] ** 2 * sigma[q, k] * w[q]
                               * EC[q, ..., k])).sum()
+    if sep:
+        W = W_full
+        tl = x_full[:, 1].unsqueeze(-1) - x_full[:, 1].unsqueeze(-2)
+        WK = W * Ktime
+        if spec.kind == KIND_SEP_CONST:
+            g[spec.o_lam] = half * WK.sum()
+        else:
+            os_, ell = lam[0], lam[1]
+            f = Kl / os_
+            g[spec.o_lam] = half * (WK * f).sum()
+            if spec.kind == KIND_SEP_RBF:
+                dfdl = f * tl ** 2 / ell ** 3
+            elif spec.kind == KIND_SEP_MATERN15:
+                u = math.sqrt(3.0) * tl.abs() / ell
+                dfdl = u ** 2 * torch.exp(-u) / ell
+            else:
+                al = lam[2]
+                u = tl ** 2 / (2.0 * al * ell ** 2)
+                dfdl = 2.0 * al * f * u / ((1.0 + u) * ell)
+                g[spec.o_lam + 2] = half * (WK * os_ * f * (u / (1.0 + u) - torch.log1p(u))).sum()
+            g[spec.o_lam + 1] = half * (WK * os_ * dfdl).sum()
     if spec.learn_noise:
         g[spec.o_noise] = half * torch.diagonal(W).sum()
     g = g * constraint_jacobian(raw, kinds, lb, ub)
@@ -310,7 +403,7 @@ def batched_mll_and_grad(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec)
     theta = constrain(raw, kinds, lb, ub)
     mean, w, mu, sigma, noise = unpack_params(theta, spec)
     n = y.shape[-1]
-    K = sm_kernel_dense(x, x, w, mu, sigma, spec.kind)
+    K = kernel_dense(x, x, theta, spec)
     dvec = torch.zeros_like(y)
     if fixed_noise is not None:
         dvec = dvec + fixed_noise

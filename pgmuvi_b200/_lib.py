@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(_HERE, "libpgmuvi_b200.so")
 
 # constants mirrored from include/pgmuvi_b200.h
 KIND_SM1D, KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD = 0, 1, 2
+KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST = 3, 4, 5, 6
+SEP_KINDS = (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)
+NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST: 1}
 CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2
 FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC = 1, 2, 4
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2

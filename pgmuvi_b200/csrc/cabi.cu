@@ -54,8 +54,8 @@ using pgm::launch_fit;
 
 int pad_q(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
 
-// NF of the instantiated config serving (d, Q): sizes the workspace
-int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q) + 1; }
+// NF of the instantiated config serving (d, Q): sizes the workspace (upper bound over kinds)
+int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q <= 4 ? 4 : Q) + 1; }
 
 #define PGM_DISPATCH_Q(KIND, D, FN, ...)                     \
   switch (pad_q(Q)) {                                        \
@@ -65,14 +65,26 @@ int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q) + 1; }
     default: return FN<KIND, 8, D>(__VA_ARGS__);             \
   }
 
+#define PGM_DISPATCH_Q48(KIND, D, FN, ...)                   \
+  if (Q <= 4) return FN<KIND, 4, D>(__VA_ARGS__);            \
+  return FN<KIND, 8, D>(__VA_ARGS__);
+
 #define PGM_DISPATCH(FN, ...)                                                        \
   do {                                                                               \
     if (kernel_kind == PGM_KIND_SM1D) {                                              \
       PGM_DISPATCH_Q(PGM_KIND_SM1D, 1, FN, __VA_ARGS__)                              \
     } else if (kernel_kind == PGM_KIND_SM_ARD_PRODSUM) {                             \
       PGM_DISPATCH_Q(PGM_KIND_SM_ARD_PRODSUM, 2, FN, __VA_ARGS__)                    \
-    } else {                                                                         \
+    } else if (kernel_kind == PGM_KIND_SM_ARD_SUMPROD) {                             \
       PGM_DISPATCH_Q(PGM_KIND_SM_ARD_SUMPROD, 2, FN, __VA_ARGS__)                    \
+    } else if (kernel_kind == PGM_KIND_SEP_RBF) {                                    \
+      PGM_DISPATCH_Q48(PGM_KIND_SEP_RBF, 2, FN, __VA_ARGS__)                         \
+    } else if (kernel_kind == PGM_KIND_SEP_MATERN15) {                               \
+      PGM_DISPATCH_Q48(PGM_KIND_SEP_MATERN15, 2, FN, __VA_ARGS__)                    \
+    } else if (kernel_kind == PGM_KIND_SEP_RQ) {                                     \
+      PGM_DISPATCH_Q48(PGM_KIND_SEP_RQ, 2, FN, __VA_ARGS__)                          \
+    } else {                                                                         \
+      PGM_DISPATCH_Q48(PGM_KIND_SEP_CONST, 2, FN, __VA_ARGS__)                       \
     }                                                                                \
   } while (0)
 
@@ -83,6 +95,8 @@ int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
     if (d != 1) return fail("PGM_KIND_SM1D needs d == 1");
   } else if (kernel_kind == PGM_KIND_SM_ARD_PRODSUM || kernel_kind == PGM_KIND_SM_ARD_SUMPROD) {
     if (d != 2) return fail("ARD spectral-mixture kinds need d == 2");
+  } else if (kernel_kind >= PGM_KIND_SEP_RBF && kernel_kind <= PGM_KIND_SEP_CONST) {
+    if (d != 2) return fail("separable kinds need d == 2 (time, wavelength)");
   } else {
     return fail("unknown kernel_kind");
   }

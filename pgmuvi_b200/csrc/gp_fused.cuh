@@ -38,6 +38,11 @@ constexpr int S_ELEMS = TS * LD_S;                 // 4352
 #define PGM_KIND_SM1D 0
 #define PGM_KIND_SM_ARD_PRODSUM 1
 #define PGM_KIND_SM_ARD_SUMPROD 2
+// separable 2-D models (gps.py:1327-1336): SM(time, Q mixtures) x wavelength kernel
+#define PGM_KIND_SEP_RBF 3        // ScaleKernel(RBFKernel)           gps.py:1045-1048, 1063
+#define PGM_KIND_SEP_MATERN15 4   // ScaleKernel(MaternKernel(1.5))   gps.py:1049-1052
+#define PGM_KIND_SEP_RQ 5         // ScaleKernel(RQKernel)            gps.py:1053-1056
+#define PGM_KIND_SEP_CONST 6      // ConstantKernel (achromatic)      gps.py:1414-1415
 #define PGM_FLAG_GRAD 1
 #define PGM_FLAG_LEARN_NOISE 2
 #define PGM_FLAG_BOUNDS_PER_LC 4
@@ -192,12 +197,17 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
 struct Cfg {
-  static constexpr int NCS = D * QT;          // (cos, sin) pairs per point
-  static constexpr int NFB = D + 2 * NCS;     // per-point doubles: x[D], (cos,sin)[D][QT]
+  static constexpr bool SEP = KIND >= PGM_KIND_SEP_RBF;
+  static constexpr int DS = SEP ? 1 : D;      // dims the spectral mixture acts on
+  // wavelength-kernel parameters: (outputscale, lengthscale[, alpha]) or (constant)
+  static constexpr int NL = (KIND == PGM_KIND_SEP_RBF || KIND == PGM_KIND_SEP_MATERN15) ? 2
+                            : (KIND == PGM_KIND_SEP_RQ) ? 3 : (KIND == PGM_KIND_SEP_CONST) ? 1 : 0;
+  static constexpr int NCS = DS * QT;         // (cos, sin) pairs per point
+  static constexpr int NFB = D + 2 * NCS;     // per-point doubles: x[D], (cos,sin)[DS][QT]
   static constexpr int NF = NFB + 1;          // + alpha
-  static constexpr int NG = QT + 2 * QT * D;  // kernel-gradient accumulators
+  static constexpr int NG = QT + 2 * QT * DS + NL;  // kernel-gradient accumulators
   static constexpr int NV = NG + 1;           // + tr W
-  static constexpr int PMAX = 2 + QT + 2 * QT * D;
+  static constexpr int PMAX = 2 + QT + 2 * QT * DS + NL;
   // shared memory (doubles)
   static constexpr int SM_STAGES = 0;
   static constexpr int SM_S = STAGE_ELEMS;
@@ -208,7 +218,8 @@ struct Cfg {
   static constexpr int PAR_JAC = PAR_THETA + PMAX;
   static constexpr int PAR_W = PAR_JAC + PMAX;
   static constexpr int PAR_A = PAR_W + QT;
-  static constexpr int PAR_RED = PAR_A + QT * D;
+  static constexpr int PAR_LAM = PAR_A + QT * DS;   // wavelength-kernel constants [4]
+  static constexpr int PAR_RED = PAR_LAM + 4;
   static constexpr int PAR_FIN = PAR_RED + 8 * (NV + 2);
   static constexpr int PAR_ZJ = (PAR_FIN + NV + 4 + 1) & ~1;   // z_j of the current block column [64], 16-B aligned
   static constexpr int PAR_ZI = PAR_ZJ + TS;          // z_i of the current tile row / scratch [64]
@@ -461,16 +472,55 @@ __device__ __forceinline__ void store_tile_bulk(const double (&acc)[4][2][2], do
 //   xs[dd*64 + r] centred inputs;  cs[((dd*QT+q)*64 + r)] = (cos, sin)(2 pi mu_qd x_rd).
 // cos(2 pi mu tau) = c_i c_j + s_i s_j,  sin(2 pi mu tau) = s_i c_j - c_i s_j.
 // ------------------------------------------------------------------------------------
+// wavelength factor f(tau) of the separable kinds and the two derivative carriers
+//   lam = { outputscale | constant, c1, alpha, lengthscale }
+//   RBF:     c1 = 1/(2 l^2)        f = exp(-c1 tau^2)          df/dl = f tau^2 / l^3
+//   Matern:  c1 = sqrt(3)/l        f = (1+u) e^-u, u = c1|tau|  df/dl = u^2 e^-u / l
+//   RQ:      c1 = 1/(2 alpha l^2)  f = (1+u)^-alpha, u = c1 tau^2
+//            df/dl = 2 alpha f u / ((1+u) l),  df/dalpha = f (u/(1+u) - log1p(u))
+// gl / ga_ return df/dl and df/dalpha WITHOUT their constant factors (applied once per light
+// curve in the final assembly).
+template <int KIND>
+__device__ __forceinline__ double lam_factor(double tl, const double (&lam)[4],
+                                             const double* __restrict__ tab, double& gl,
+                                             double& ga_) {
+  gl = 0.0;
+  ga_ = 0.0;
+  if (KIND == PGM_KIND_SEP_RBF) {
+    const double t2 = tl * tl;
+    const double f = exp_neg(-lam[1] * t2, tab);
+    gl = f * t2;
+    return f;
+  } else if (KIND == PGM_KIND_SEP_MATERN15) {
+    const double u = lam[1] * fabs(tl);
+    const double e = exp_neg(-u, tab);
+    gl = u * u * e;
+    return (1.0 + u) * e;
+  } else if (KIND == PGM_KIND_SEP_RQ) {
+    const double u = lam[1] * tl * tl;
+    const double l1 = log1p(u);
+    const double f = exp(-lam[2] * l1);
+    const double uu = u / (1.0 + u);
+    gl = f * uu;
+    ga_ = f * (uu - l1);
+    return f;
+  }
+  return 1.0;
+}
+
 template <int KIND, int QT, int D>
 __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
                                           const double* __restrict__ colv, int r, int c,
-                                          const double (&w)[QT], const double (&a)[QT * D],
+                                          const double (&w)[QT],
+                                          const double (&a)[QT * Cfg<KIND, QT, D>::DS],
+                                          const double (&lam)[4],
                                           const double* __restrict__ tab) {
+  constexpr int DS = Cfg<KIND, QT, D>::DS;
   const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
   const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
-  double tau2[D];
+  double tau2[DS];
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) {
+  for (int dd = 0; dd < DS; ++dd) {
     const double tau = rowv[dd * TS + r] - colv[dd * TS + c];
     tau2[dd] = tau * tau;
   }
@@ -480,9 +530,9 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
     for (int q = 0; q < QT; ++q) {
       double pr = w[q];
 #pragma unroll
-      for (int dd = 0; dd < D; ++dd) {
+      for (int dd = 0; dd < DS; ++dd) {
         const double2 ri = rcs[(dd * QT + q) * TS + r], cj = ccs[(dd * QT + q) * TS + c];
-        pr *= exp_neg(-a[q * D + dd] * tau2[dd], tab) * (ri.x * cj.x + ri.y * cj.y);
+        pr *= exp_neg(-a[q * DS + dd] * tau2[dd], tab) * (ri.x * cj.x + ri.y * cj.y);
       }
       k += pr;
     }
@@ -490,60 +540,87 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
   } else {
     double k = 1.0;
 #pragma unroll
-    for (int dd = 0; dd < D; ++dd) {
+    for (int dd = 0; dd < DS; ++dd) {
       double s = 0.0;
 #pragma unroll
       for (int q = 0; q < QT; ++q) {
         const double2 ri = rcs[(dd * QT + q) * TS + r], cj = ccs[(dd * QT + q) * TS + c];
-        s += (w[q] * exp_neg(-a[q * D + dd] * tau2[dd], tab)) * (ri.x * cj.x + ri.y * cj.y);
+        s += (w[q] * exp_neg(-a[q * DS + dd] * tau2[dd], tab)) * (ri.x * cj.x + ri.y * cj.y);
       }
       k *= s;
+    }
+    if (Cfg<KIND, QT, D>::SEP) {
+      double gl, ga_;
+      k *= lam[0] * lam_factor<KIND>(rowv[TS + r] - colv[TS + c], lam, tab, gl, ga_);
     }
     return k;
   }
 }
 
-// accumulate  wgt * dK/dtheta  into ga[NG] = { gw[q], gmu[q*D+dd], gsg[q*D+dd] } (raw sums;
-// the constant factors -2 pi w_q and -4 pi^2 sigma w_q are applied once at the end).
+// accumulate  wgt * dK/dtheta  into ga[NG] = { gw[q], gmu[q*DS+dd], gsg[q*DS+dd], glam[NL] }
+// (raw sums; the constant factors -2 pi w_q, -4 pi^2 sigma w_q and those of the wavelength
+// kernel are applied once at the end).
 template <int KIND, int QT, int D>
 __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
                                              const double* __restrict__ colv, int r, int c,
-                                             const double (&w)[QT], const double (&a)[QT * D],
+                                             const double (&w)[QT],
+                                             const double (&a)[QT * Cfg<KIND, QT, D>::DS],
+                                             const double (&lam)[4],
                                              const double* __restrict__ tab, double wgt,
-                                             double (&ga)[QT + 2 * QT * D]) {
+                                             double (&ga)[Cfg<KIND, QT, D>::NG]) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
   const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
   const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
-  double tau[D], EC[D][QT], ES[D][QT], Ssum[D];
+  double tau[DS], EC[DS][QT], ES[DS][QT], Ssum[DS];
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) {
+  for (int dd = 0; dd < DS; ++dd) {
     tau[dd] = rowv[dd * TS + r] - colv[dd * TS + c];
     const double t2 = tau[dd] * tau[dd];
     Ssum[dd] = 0.0;
 #pragma unroll
     for (int q = 0; q < QT; ++q) {
       const double2 ri = rcs[(dd * QT + q) * TS + r], cj = ccs[(dd * QT + q) * TS + c];
-      const double E = exp_neg(-a[q * D + dd] * t2, tab);
+      const double E = exp_neg(-a[q * DS + dd] * t2, tab);
       EC[dd][q] = E * (ri.x * cj.x + ri.y * cj.y);
       ES[dd][q] = E * (ri.y * cj.x - ri.x * cj.y);
       Ssum[dd] += w[q] * EC[dd][q];
     }
   }
+  if (C::SEP) {
+    // K = kt * kl,  kt = Ssum[0],  kl = lam0 * f
+    double gl, ga_;
+    const double f = lam_factor<KIND>(rowv[TS + r] - colv[TS + c], lam, tab, gl, ga_);
+    const double wk = wgt * (lam[0] * f);         // weight seen by the time-kernel parameters
+    const double wt = wk * tau[0], wt2 = wt * tau[0];
 #pragma unroll
-  for (int dd = 0; dd < D; ++dd) {
+    for (int q = 0; q < QT; ++q) {
+      ga[q] += wk * EC[0][q];
+      ga[QT + q] += wt * ES[0][q];
+      ga[2 * QT + q] += wt2 * EC[0][q];
+    }
+    const double wkt = wgt * Ssum[0];
+    ga[3 * QT] += wkt * f;                          // d/d outputscale  (or d/d constant)
+    if (C::NL >= 2) ga[3 * QT + 1] += wkt * gl;     // d/d lengthscale  (x const at the end)
+    if (C::NL >= 3) ga[3 * QT + 2] += wkt * ga_;    // d/d alpha
+    return;
+  }
+#pragma unroll
+  for (int dd = 0; dd < DS; ++dd) {
     const double wt = wgt * tau[dd];
     const double wt2 = wt * tau[dd];
 #pragma unroll
     for (int q = 0; q < QT; ++q) {
       double R = 1.0;  // product of the other dimensions' factor
-      if (D == 2) R = (KIND == PGM_KIND_SM_ARD_SUMPROD) ? EC[1 - dd][q] : Ssum[1 - dd];
-      const double ecr = (D == 2) ? EC[dd][q] * R : EC[dd][q];
+      if (DS == 2) R = (KIND == PGM_KIND_SM_ARD_SUMPROD) ? EC[1 - dd][q] : Ssum[1 - dd];
+      const double ecr = (DS == 2) ? EC[dd][q] * R : EC[dd][q];
       if (KIND == PGM_KIND_SM_ARD_SUMPROD) {
         if (dd == 0) ga[q] += wgt * ecr;
       } else {
         ga[q] += wgt * ecr;
       }
-      ga[QT + q * D + dd] += wt * ((D == 2) ? ES[dd][q] * R : ES[dd][q]);
-      ga[QT + QT * D + q * D + dd] += wt2 * ecr;
+      ga[QT + q * DS + dd] += wt * ((DS == 2) ? ES[dd][q] * R : ES[dd][q]);
+      ga[QT + QT * DS + q * DS + dd] += wt2 * ecr;
     }
   }
 }
@@ -701,6 +778,29 @@ __device__ __forceinline__ void block_reduce(double (&v)[NVAL], double* red, dou
   __syncthreads();
 }
 
+// packed raw-parameter layout:  [ mean | w[Q] | mu[Q*DS] | sigma[Q*DS] | (noise) | lam[NL] ]
+template <int KIND, int QT, int D>
+__host__ __device__ __forceinline__ int param_count(int Q, bool learn_noise) {
+  using C = Cfg<KIND, QT, D>;
+  return 1 + Q + 2 * Q * C::DS + (learn_noise ? 1 : 0) + C::NL;
+}
+
+// constants of the wavelength kernel from its constrained parameters (lam_factor above)
+template <int KIND>
+__device__ __forceinline__ void lam_setup(const double* th /* NL constrained values */,
+                                          double* lam /* [4] */) {
+  lam[0] = 1.0; lam[1] = 0.0; lam[2] = 1.0; lam[3] = 1.0;
+  if (KIND == PGM_KIND_SEP_RBF) {
+    lam[0] = th[0]; lam[3] = th[1]; lam[1] = 0.5 / (th[1] * th[1]);
+  } else if (KIND == PGM_KIND_SEP_MATERN15) {
+    lam[0] = th[0]; lam[3] = th[1]; lam[1] = 1.7320508075688772935 / th[1];
+  } else if (KIND == PGM_KIND_SEP_RQ) {
+    lam[0] = th[0]; lam[3] = th[1]; lam[2] = th[2]; lam[1] = 0.5 / (th[2] * th[1] * th[1]);
+  } else if (KIND == PGM_KIND_SEP_CONST) {
+    lam[0] = th[0];
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // pipeline state carried by a block across light curves (mbarrier phases keep running)
 // ------------------------------------------------------------------------------------
@@ -739,7 +839,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   const int Q = A.Q;
   const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
   const bool want_grad = (A.flags & PGM_FLAG_GRAD) != 0;
-  const int P = 1 + Q + 2 * Q * D + (learn_noise ? 1 : 0);
+  constexpr int DS = C::DS;
+  const int P = param_count<KIND, QT, D>(Q, learn_noise);
+  const int o_noise = 1 + Q + 2 * Q * DS;             // learned-noise slot (if any)
+  const int o_lam = o_noise + (learn_noise ? 1 : 0);  // wavelength-kernel slots
   const int n = A.n_valid ? A.n_valid[b] : A.n_max;
   const int N = (n + TS - 1) / TS;
   const int npad = N * TS;
@@ -757,6 +860,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double* jac = par + C::PAR_JAC;
   double* wq = par + C::PAR_W;
   double* aq = par + C::PAR_A;
+  double* lamq = par + C::PAR_LAM;
   double* red = par + C::PAR_RED;
   double* fin = par + C::PAR_FIN;
   double* zj = par + C::PAR_ZJ;
@@ -790,13 +894,14 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
   __syncthreads();
   if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
-  if (tid < QT * D) {
-    const int q = tid / D, dd = tid - q * D;
-    const double sg = (q < Q) ? theta[1 + Q + Q * D + q * D + dd] : 0.0;
-    aq[q * D + dd] = 2.0 * M_PI * M_PI * sg * sg;
+  if (tid < QT * DS) {
+    const int q = tid / DS, dd = tid - q * DS;
+    const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
+    aq[q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
+  if (tid == 32) lam_setup<KIND>(theta + o_lam, lamq);
   const double mean = theta[0];
-  const double lnoise = learn_noise ? theta[P - 1] : 0.0;
+  const double lnoise = learn_noise ? theta[o_noise] : 0.0;
   // ---- per-point fields into the block's scratch ------------------------------------
   const double* xb = A.x + (size_t)b * A.n_max * D;
   const double* yb = A.y + (size_t)b * A.n_max;
@@ -807,12 +912,14 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     for (int dd = 0; dd < D; ++dd) {
       const double xc = valid ? (xb[(size_t)i * D + dd] - xb[dd]) : 0.0;
       sc.fx[(size_t)dd * npad + i] = xc;
+      if (dd < DS) {
 #pragma unroll
-      for (int q = 0; q < QT; ++q) {
-        double sn = 0.0, cs = 1.0;
-        if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * D + dd] * xc, &sn, &cs);
-        *reinterpret_cast<double2*>(sc.fcs + ((size_t)(dd * QT + q) * npad + i) * 2) =
-            make_double2(cs, sn);
+        for (int q = 0; q < QT; ++q) {
+          double sn = 0.0, cs = 1.0;
+          if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * DS + dd] * xc, &sn, &cs);
+          *reinterpret_cast<double2*>(sc.fcs + ((size_t)(dd * QT + q) * npad + i) * 2) =
+              make_double2(cs, sn);
+        }
       }
     }
     sc.rhs[i] = valid ? (yb[i] - mean) : 0.0;
@@ -841,11 +948,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   auto tileT = [&](int j) { return sc.tilesT + (size_t)j * TT; };
 
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
-  double wreg[QT], areg[QT * D];
+  double wreg[QT], areg[QT * DS], lam[4];
 #pragma unroll
   for (int q = 0; q < QT; ++q) wreg[q] = wq[q];
 #pragma unroll
-  for (int q = 0; q < QT * D; ++q) areg[q] = aq[q];
+  for (int q = 0; q < QT * DS; ++q) areg[q] = aq[q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) lam[q] = lamq[q];
   PGM_PROF(0);
   double acc[4][2][2];
   double iq_part = 0.0;  // partial of z^T z
@@ -910,7 +1019,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int gj = j * TS + c0 + e;
-            double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, tab);
+            double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
             kv = (gi < n && gj <= gi) ? kv : 0.0;
             if (gi == gj) kv = (gi < n) ? (kv + sc.dn[gi] + jitter) : 1.0;
             out[e] = kv - (e ? cv.y : cv.x);
@@ -1131,7 +1240,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             W = (gi < n && gj <= gi) ? W : 0.0;
             if (gi == gj) trW += W;
             const double wgt = (gi == gj) ? W : 2.0 * W;
-            k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, tab, wgt, ga);
+            k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
           }
         }
         PGM_PROF(11);
@@ -1158,14 +1267,26 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       gv = fin[C::NV] / (double)n;
     } else if (tid < 1 + Q) {
       gv = half * fin[tid - 1];
-    } else if (tid < 1 + Q + Q * D) {
-      const int t = tid - 1 - Q, q = t / D, dd = t - q * D;
-      gv = half * (-2.0 * M_PI * wq[q]) * fin[QT + q * D + dd];
-    } else if (tid < 1 + Q + 2 * Q * D) {
-      const int t = tid - 1 - Q - Q * D, q = t / D, dd = t - q * D;
-      gv = half * (-4.0 * M_PI * M_PI * theta[tid] * wq[q]) * fin[QT + QT * D + q * D + dd];
+    } else if (tid < 1 + Q + Q * DS) {
+      const int t = tid - 1 - Q, q = t / DS, dd = t - q * DS;
+      gv = half * (-2.0 * M_PI * wq[q]) * fin[QT + q * DS + dd];
+    } else if (tid < o_noise) {
+      const int t = tid - 1 - Q - Q * DS, q = t / DS, dd = t - q * DS;
+      gv = half * (-4.0 * M_PI * M_PI * theta[tid] * wq[q]) * fin[QT + QT * DS + q * DS + dd];
+    } else if (tid < o_lam) {
+      gv = half * fin[C::NG];   // learned noise: tr W
     } else {
-      gv = half * fin[C::NG];
+      // wavelength kernel: constant factors of lam_factor's derivative carriers
+      const int t = tid - o_lam;
+      double cf = 1.0;
+      if (t == 1) {
+        if (KIND == PGM_KIND_SEP_RBF) cf = lamq[0] / (lamq[3] * lamq[3] * lamq[3]);
+        else if (KIND == PGM_KIND_SEP_MATERN15) cf = lamq[0] / lamq[3];
+        else cf = lamq[0] * 2.0 * lamq[2] / lamq[3];
+      } else if (t == 2) {
+        cf = lamq[0];
+      }
+      gv = half * cf * fin[QT + 2 * QT * DS + t];
     }
     grad_out[tid] = gv * jac[tid];
   }
@@ -1202,7 +1323,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
     sm_mll_grad_kernel(EvalArgs A) {
   extern __shared__ __align__(16) double sm[];
   Scratch sc = make_scratch<KIND, QT, D>(A.ws + (size_t)blockIdx.x * A.ws_per_block, A.n_max);
-  const int P = 1 + A.Q + 2 * A.Q * D + ((A.flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0);
+  const int P = param_count<KIND, QT, D>(A.Q, (A.flags & PGM_FLAG_LEARN_NOISE) != 0);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
   for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
@@ -1219,14 +1340,16 @@ template <int KIND, int QT, int D>
 __global__ void __launch_bounds__(NTHREADS)
     sm_kernel_dense_kernel(EvalArgs A, double* __restrict__ Kout) {
   using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
   __shared__ __align__(16) double rowv[C::NFB * TS];
   __shared__ __align__(16) double colv[C::NFB * TS];
-  __shared__ double theta[C::PMAX], wq[QT], aq[QT * D], tab[64];
+  __shared__ double theta[C::PMAX], wq[QT], aq[QT * DS], lamq[4], tab[64];
   const int tid = threadIdx.x;
   const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
   const int Q = A.Q;
   const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
-  const int P = 1 + Q + 2 * Q * D + (learn_noise ? 1 : 0);
+  const int P = param_count<KIND, QT, D>(Q, learn_noise);
+  const int o_noise = 1 + Q + 2 * Q * DS, o_lam = o_noise + (learn_noise ? 1 : 0);
   const int n = A.n_valid ? A.n_valid[b] : A.n_max;
   if (ti * TS >= n || tj * TS >= n) return;
   if (tid < P) {
@@ -1242,11 +1365,12 @@ __global__ void __launch_bounds__(NTHREADS)
   if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
   __syncthreads();
   if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
-  if (tid < QT * D) {
-    const int q = tid / D, dd = tid - q * D;
-    const double sg = (q < Q) ? theta[1 + Q + Q * D + q * D + dd] : 0.0;
-    aq[q * D + dd] = 2.0 * M_PI * M_PI * sg * sg;
+  if (tid < QT * DS) {
+    const int q = tid / DS, dd = tid - q * DS;
+    const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
+    aq[q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
+  if (tid == 32) lam_setup<KIND>(theta + o_lam, lamq);
   const double* xb = A.x + (size_t)b * A.n_max * D;
   for (int idx = tid; idx < 2 * TS; idx += NTHREADS) {
     const int side = idx >> 6, r = idx & 63;
@@ -1256,25 +1380,30 @@ __global__ void __launch_bounds__(NTHREADS)
     for (int dd = 0; dd < D; ++dd) {
       const double xc = valid ? (xb[(size_t)gi * D + dd] - xb[dd]) : 0.0;
       vec[dd * TS + r] = xc;
+      if (dd >= DS) continue;
       for (int q = 0; q < QT; ++q) {
         double sn = 0.0, cs = 1.0;
-        if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * D + dd] * xc, &sn, &cs);
+        if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * DS + dd] * xc, &sn, &cs);
         vec[D * TS + ((dd * QT + q) * TS + r) * 2] = cs;
         vec[D * TS + ((dd * QT + q) * TS + r) * 2 + 1] = sn;
       }
     }
   }
   __syncthreads();
-  const double lnoise = learn_noise ? theta[P - 1] : 0.0;
+  const double lnoise = learn_noise ? theta[o_noise] : 0.0;
   const double* fnb = A.fixed_noise ? A.fixed_noise + (size_t)b * A.n_max : nullptr;
   double* Kb = Kout + (size_t)b * A.n_max * A.n_max;
+  double wreg[QT], areg[QT * DS], lam[4];
+  for (int q = 0; q < QT; ++q) wreg[q] = wq[q];
+  for (int q = 0; q < QT * DS; ++q) areg[q] = aq[q];
+  for (int q = 0; q < 4; ++q) lam[q] = lamq[q];
   for (int idx = tid; idx < TT; idx += NTHREADS) {
     const int r = idx >> 6, c = idx & 63;
     const int gi = ti * TS + r, gj = tj * TS + c;
     if (gi < n && gj < n) {
       // evaluate with the larger index as the row so that K_ij and K_ji are the same bits
-      double kv = (gi >= gj) ? k_entry<KIND, QT, D>(rowv, colv, r, c, wq, aq, tab)
-                             : k_entry<KIND, QT, D>(colv, rowv, c, r, wq, aq, tab);
+      double kv = (gi >= gj) ? k_entry<KIND, QT, D>(rowv, colv, r, c, wreg, areg, lam, tab)
+                             : k_entry<KIND, QT, D>(colv, rowv, c, r, wreg, areg, lam, tab);
       if (gi == gj) kv += (fnb ? fnb[gi] : 0.0) + lnoise;
       Kb[(size_t)gi * A.n_max + gj] = kv;
     }
@@ -1305,7 +1434,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   extern __shared__ __align__(16) double sm[];
   const EvalArgs& A = F.e;
   Scratch sc = make_scratch<KIND, QT, D>(A.ws + (size_t)blockIdx.x * A.ws_per_block, A.n_max);
-  const int P = 1 + A.Q + 2 * A.Q * D + ((A.flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0);
+  const int P = param_count<KIND, QT, D>(A.Q, (A.flags & PGM_FLAG_LEARN_NOISE) != 0);
   double* par = sm + C::SM_PAR;
   double* s_raw = par + C::PAR_RAW;
   double* s_m = s_raw + C::PMAX;

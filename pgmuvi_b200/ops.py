@@ -12,12 +12,15 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import (FLAG_BOUNDS_PER_LC, FLAG_GRAD, FLAG_LEARN_NOISE, KIND_SM1D,
-                   KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD, check, ptr)
+                   KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD, NUM_LAM, SEP_KINDS, check, ptr)
 
 _workspaces = {}
 
 
-def param_count(Q: int, d: int, learn_noise: bool) -> int:
+def param_count(Q: int, d: int, learn_noise: bool, kind: int = -1) -> int:
+    """P of the packed layout ``[mean | w | mu | sigma | (noise) | lam]`` (pgmuvi_b200.h)."""
+    if kind in SEP_KINDS:
+        return 1 + 3 * Q + (1 if learn_noise else 0) + NUM_LAM[kind]
     return 1 + Q + 2 * Q * d + (1 if learn_noise else 0)
 
 
@@ -51,7 +54,7 @@ def _prep(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise
     d = 1 if kind == KIND_SM1D else 2
     if x.shape != (B, n, d):
         raise RuntimeError(f"x must be [B, n, {d}], got {tuple(x.shape)}")
-    P = param_count(Q, d, learn_noise)
+    P = param_count(Q, d, learn_noise, kind)
     if raw.shape != (B, P):
         raise RuntimeError(f"raw must be [B, {P}], got {tuple(raw.shape)}")
     flags = FLAG_LEARN_NOISE if learn_noise else 0

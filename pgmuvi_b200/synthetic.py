@@ -35,7 +35,13 @@ def fixed_noise_variance(yerr):
     return np.maximum(v, 1e-6)
 
 
-def param_count(Q, d, learn_noise):
+NUM_LAM = {3: 2, 4: 2, 5: 3, 6: 1}   # wavelength-kernel parameters of the separable kinds
+
+
+def param_count(Q, d, learn_noise, kind=None):
+    """P of the packed layout (include/pgmuvi_b200.h); ``kind`` >= 3: separable models."""
+    if kind is not None and kind >= 3:
+        return 1 + Q + 2 * Q + (1 if learn_noise else 0) + NUM_LAM[kind]
     return 1 + Q + 2 * Q * d + (1 if learn_noise else 0)
 
 
@@ -202,3 +208,53 @@ def make_batch_2d(B, n_bands, n_per_band, Q=4, learn_noise=False, seed0=5000):
         raw[b, o_sg:o_sg + Q * d] = inv_softplus(sig.ravel())
     return dict(x=x, y=y, noise=noise, raw=raw, kinds=kinds, lb=lb, ub=ub, periods=periods,
                 Q=Q, d=d, learn_noise=learn_noise)
+
+
+def make_batch_sep(B, n_bands, n_per_band, Q=4, kind=3, learn_noise=False, seed0=7000):
+    """Separable models (pgmuvi/gps.py:1274-1342): SM-Q in time x {RBF, Matern-1.5, RQ,
+    Constant} in wavelength on the 2-D synthetic light curves of :func:`make_batch_2d`.
+    Constraints: mean Interval(min y, max y); SM means GreaterThan(1/span) as for the 1-D
+    model; everything else GPyTorch's default Positive; learned noise Interval."""
+    n = n_bands * n_per_band
+    P = param_count(Q, 2, learn_noise, kind)
+    NL = NUM_LAM[kind]
+    o_mu, o_sg, o_noise = 1 + Q, 1 + 2 * Q, 1 + 3 * Q
+    o_lam = o_noise + (1 if learn_noise else 0)
+    x = np.zeros((B, n, 2))
+    y = np.zeros((B, n))
+    noise = np.zeros((B, n))
+    raw = np.zeros((B, P))
+    lb = np.zeros((B, P))
+    ub = np.zeros((B, P))
+    kinds = np.full(P, CON_SOFTPLUS, dtype=np.int32)
+    kinds[0] = CON_INTERVAL
+    if learn_noise:
+        kinds[o_noise] = CON_INTERVAL
+    for b in range(B):
+        x01, yy, yerr, (period, span) = make_lightcurve_2d(seed0 + b, n_bands, n_per_band)
+        rng = np.random.default_rng(30_000_000 + seed0 + b)
+        x[b], y[b] = x01, yy
+        noise[b] = fixed_noise_variance(yerr)
+        lb[b, 0], ub[b, 0] = float(yy.min()), float(yy.max())
+        tspan = float(x01[:, 0].max() - x01[:, 0].min())
+        lb[b, o_mu:o_mu + Q] = 1.0 / tspan
+        f1 = span / period
+        mu = f1 * np.array([1.0, 2.0, 0.5, 3.0, 1.5, 4.0, 0.75, 2.5])[np.arange(Q) % 8] \
+            * (1.0 + 0.05 * rng.standard_normal(Q))
+        mu = np.maximum(mu, lb[b, o_mu] * 1.01 + 1e-3)
+        sig = rng.uniform(0.3, 2.0, Q)
+        wv = np.full(Q, np.std(yy, ddof=1) / Q)
+        raw[b, 1:1 + Q] = inv_softplus(wv)
+        raw[b, o_mu:o_mu + Q] = inv_softplus(mu - lb[b, o_mu])
+        raw[b, o_sg:o_sg + Q] = inv_softplus(sig)
+        if learn_noise:
+            ystd = float(np.std(yy, ddof=1))
+            lb[b, o_noise], ub[b, o_noise] = min(1e-4, float(yerr.min()) / 10.0), ystd
+        lamv = [rng.uniform(0.6, 1.5)]                       # outputscale / constant
+        if NL >= 2:
+            lamv.append(rng.uniform(0.3, 1.2))               # lengthscale (x in [0, 1])
+        if NL >= 3:
+            lamv.append(rng.uniform(0.5, 3.0))               # RQ alpha
+        raw[b, o_lam:o_lam + NL] = inv_softplus(np.array(lamv))
+    return dict(x=x, y=y, noise=noise, raw=raw, kinds=kinds, lb=lb, ub=ub, Q=Q, d=2,
+                kind=kind, learn_noise=learn_noise)
