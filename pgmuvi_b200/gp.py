@@ -66,8 +66,8 @@ class Module(nn.Module):
         """Set parameters by (possibly dotted, constrained or raw) name, as gpytorch does."""
         for name, val in kwargs.items():
             if "." in name:
-                head, rest = name.split(".", 1)
-                getattr(self, head).initialize(**{rest: val})
+                base, _, leaf = name.rpartition(".")
+                self.get_submodule(base).initialize(**{leaf: val})   # walks ModuleLists too
                 continue
             if name in self._parameters:
                 p = self._parameters[name]
@@ -155,6 +155,88 @@ class SpectralMixtureKernel(Module):
         raise NotImplementedError(
             "SpectralMixtureKernel values are produced on the GPU by pgmuvi_b200.ops "
             "(sm_kernel_dense / the fused MLL); there is no CPU evaluation in this package")
+
+
+class _ParamKernel(Module):
+    """Kernel parameter holder; ``k1 * k2`` builds a ProductKernel as gpytorch does."""
+
+    is_stationary = True
+
+    def __mul__(self, other):
+        return ProductKernel(self, other)
+
+    def forward(self, x1, x2=None, **params):
+        raise NotImplementedError(
+            f"{type(self).__name__} values are produced on the GPU by pgmuvi_b200.ops; there is "
+            "no CPU evaluation in this package")
+
+
+class RBFKernel(_ParamKernel):
+    """gpytorch.kernels.RBFKernel: exp(-tau^2 / (2 l^2)); raw_lengthscale [1, 1], Positive."""
+    lam_kind = "rbf"
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("raw_lengthscale", nn.Parameter(torch.zeros(1, 1)))
+        self.register_constraint("raw_lengthscale", Positive())
+
+    lengthscale = property(lambda self: self._constrained("raw_lengthscale"),
+                           lambda self, v: self.initialize(lengthscale=v))
+
+
+class MaternKernel(RBFKernel):
+    """gpytorch.kernels.MaternKernel; only nu = 1.5 is on the accelerated path."""
+    lam_kind = "matern"
+
+    def __init__(self, nu=1.5):
+        super().__init__()
+        self.nu = nu
+
+
+class RQKernel(RBFKernel):
+    """gpytorch.kernels.RQKernel: (1 + tau^2 / (2 alpha l^2))^-alpha; raw_alpha [1]."""
+    lam_kind = "rq"
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("raw_alpha", nn.Parameter(torch.zeros(1)))
+        self.register_constraint("raw_alpha", Positive())
+
+    alpha = property(lambda self: self._constrained("raw_alpha"))
+
+
+class ScaleKernel(_ParamKernel):
+    """gpytorch.kernels.ScaleKernel: outputscale * base_kernel; raw_outputscale [], Positive."""
+
+    def __init__(self, base_kernel):
+        super().__init__()
+        self.base_kernel = base_kernel
+        self.register_parameter("raw_outputscale", nn.Parameter(torch.zeros(())))
+        self.register_constraint("raw_outputscale", Positive())
+
+    outputscale = property(lambda self: self._constrained("raw_outputscale"))
+
+
+class ConstantKernel(_ParamKernel):
+    """gpytorch.kernels.ConstantKernel: k = constant; raw_constant [], Positive."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("raw_constant", nn.Parameter(torch.zeros(())))
+        self.register_constraint("raw_constant", Positive())
+
+    constant = property(lambda self: self._constrained("raw_constant"))
+
+
+class ProductKernel(_ParamKernel):
+    """gpytorch.kernels.ProductKernel: parameters live under ``kernels.0`` / ``kernels.1``."""
+
+    def __init__(self, *kernels):
+        super().__init__()
+        self.kernels = nn.ModuleList(kernels)
+
+
+SpectralMixtureKernel.__mul__ = lambda self, other: ProductKernel(self, other)
 
 
 class _HomoskedasticNoise(Module):
@@ -256,3 +338,96 @@ class TwoDSpectralMixtureGPModel(ExactGP):
 
     def forward(self, x):
         return PriorOutput(self, x)
+
+
+def _build_time_kernel(time_kernel_type, num_mixtures):
+    """pgmuvi/gps.py:938-1007; only the spectral-mixture time kernel is on the path."""
+    if isinstance(time_kernel_type, nn.Module):
+        return time_kernel_type
+    if time_kernel_type in ("spectral_mixture", "sm"):
+        return SpectralMixtureKernel(num_mixtures=num_mixtures, ard_num_dims=1)
+    raise NotImplementedError(
+        f"time_kernel_type {time_kernel_type!r} is outside the accelerated path "
+        "(SURVEY.md section 8a row a4: only 'spectral_mixture' / 'sm')")
+
+
+def _build_wavelength_kernel(wavelength_kernel_type, wavelength_lengthscale,
+                             scaling="constant"):
+    """pgmuvi/gps.py:1010-1072 (scaling='constant': ScaleKernel(base))."""
+    if isinstance(wavelength_kernel_type, nn.Module):
+        return wavelength_kernel_type
+    if wavelength_kernel_type == "rbf":
+        k = RBFKernel()
+    elif wavelength_kernel_type == "matern":
+        k = MaternKernel(nu=1.5)
+    elif wavelength_kernel_type in ("rational_quadratic", "rq"):
+        k = RQKernel()
+    else:
+        raise ValueError(
+            f"Unknown wavelength_kernel_type '{wavelength_kernel_type}'. "
+            "Choose from 'rbf', 'matern', 'rational_quadratic'/'rq', "
+            "or supply a gpytorch.kernels.Kernel instance.")
+    k.lengthscale = wavelength_lengthscale
+    if scaling == "constant":
+        return ScaleKernel(k)
+    if scaling == "linear":
+        raise NotImplementedError("scaling='linear' (LinearKernel * k) is outside the "
+                                  "accelerated path")
+    raise ValueError(f"Unknown scaling type '{scaling}'. Available options are 'constant' or "
+                     "'linear'")
+
+
+class SeparableGPModel(ExactGP):
+    """pgmuvi/gps.py:1274-1342: k((t,l),(t',l')) = k_time(t,t') * k_wavelength(l,l') as a
+    ProductKernel whose factors carry active_dims [0] / [1]."""
+
+    def __init__(self, train_x, train_y, likelihood, time_kernel=None, wavelength_kernel=None,
+                 mean_module=None, num_mixtures=4, **kwargs):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean() if mean_module is None else mean_module
+        if time_kernel is None:      # the reference defaults to Matern here (gps.py:1316-1317)
+            time_kernel = SpectralMixtureKernel(num_mixtures=num_mixtures, ard_num_dims=1)
+        if wavelength_kernel is None:
+            wavelength_kernel = ScaleKernel(RBFKernel())
+        time_kernel.register_buffer("active_dims", torch.tensor([0], dtype=torch.long))
+        wavelength_kernel.register_buffer("active_dims", torch.tensor([1], dtype=torch.long))
+        self.covar_module = time_kernel * wavelength_kernel
+        self.sci_kernel = self.covar_module
+
+    def forward(self, x):
+        return PriorOutput(self, x)
+
+
+class AchromaticGPModel(SeparableGPModel):
+    """pgmuvi/gps.py:1345-1423: ConstantKernel in wavelength (all bands share the temporal
+    variability)."""
+
+    def __init__(self, train_x, train_y, likelihood, time_kernel_type="sm", period=None,
+                 num_mixtures=4, mean_module=None, **kwargs):
+        super().__init__(train_x, train_y, likelihood,
+                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures),
+                         wavelength_kernel=ConstantKernel())
+
+
+class WavelengthDependentGPModel(SeparableGPModel):
+    """pgmuvi/gps.py:1476-1628 with the spectral-mixture time kernel and a ConstantMean (the
+    reference's default quadratic mean is outside the accelerated path)."""
+
+    def __init__(self, train_x, train_y, likelihood, time_kernel_type="sm",
+                 wavelength_kernel_type="rbf", period=None, wavelength_lengthscale=None,
+                 num_mixtures=4, mean_module="constant", add_flicker=False,
+                 wavelength_scaling="constant", **kwargs):
+        if wavelength_lengthscale is None:
+            wl_span = float(train_x[:, 1].max() - train_x[:, 1].min())
+            wavelength_lengthscale = max(wl_span / 2.0, 1.0)       # gps.py:1576-1578
+        if mean_module not in ("constant", "constant_mean") and not isinstance(mean_module,
+                                                                               ConstantMean):
+            raise NotImplementedError("only mean_module='constant' is on the accelerated path")
+        if add_flicker:
+            raise NotImplementedError("add_flicker is outside the accelerated path")
+        super().__init__(train_x, train_y, likelihood,
+                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures),
+                         wavelength_kernel=_build_wavelength_kernel(
+                             wavelength_kernel_type, wavelength_lengthscale,
+                             scaling=wavelength_scaling),
+                         mean_module=ConstantMean())

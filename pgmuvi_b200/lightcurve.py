@@ -18,7 +18,11 @@ from . import gp
 from .constraints import GreaterThan, Interval
 from .trainers import train
 
-_SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPModel}
+# lightcurve.py:2901-2930 - the spectral-mixture exact models; the separable ones are built
+# with the spectral-mixture time kernel
+_SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPModel,
+              "2DSeparable": gp.SeparableGPModel, "2DAchromatic": gp.AchromaticGPModel,
+              "2DWavelengthDependent": gp.WavelengthDependentGPModel}
 CONSTRAINT_SETS = {"LPV": {"period": {"lower": (20.0, True), "upper": (None, False)}}}
 
 
@@ -153,15 +157,17 @@ class Lightcurve(torch.nn.Module):
             if model == "1D" and self.ndim > 1:
                 raise ValueError("You have selected a 1D model but your data has more than one "
                                  "input dimension; use model='2D'.")   # tests/test_2d_integration.py:167-186
-            if model == "2D" and self.ndim != 2:
-                raise ValueError("model='2D' needs xdata of shape [n, 2] (time, wavelength)")
+            if model.startswith("2D") and self.ndim != 2:
+                raise ValueError(f"model={model!r} needs xdata of shape [n, 2] (time, wavelength)")
             self.model = _SM_MODELS[model](self._xdata_transformed, self._ydata_transformed,
                                            self.likelihood, num_mixtures=num_mixtures or 4,
                                            **kwargs)
         else:
             raise UnsupportedModel(
                 f"model {model!r} is outside the accelerated path (SURVEY section 8a): "
-                "only '1D' and '2D' spectral-mixture exact GPs")
+                "only '1D' / '2D' spectral-mixture exact GPs and the separable '2DSeparable' / "
+                "'2DAchromatic' / '2DWavelengthDependent' models with a spectral-mixture time "
+                "kernel")
         self._make_parameter_dict()
         self._constraints_set = False
 
@@ -278,9 +284,8 @@ class Lightcurve(torch.nn.Module):
         """Periods ``1/mu`` (time dimension), mixture weights and scales ``1/(2 pi sigma)`` in the
         units of the raw x data (lightcurve.py:6279-6343)."""
         pars = self.get_parameters()
-        mu = pars["covar_module.mixture_means"].detach().cpu()
-        sg = pars["covar_module.mixture_scales"].detach().cpu()
-        w = pars["covar_module.mixture_weights"].detach().cpu()
+        pick = lambda leaf: next(v for k, v in pars.items() if k.endswith(leaf)).detach().cpu()
+        mu, sg, w = pick("mixture_means"), pick("mixture_scales"), pick("mixture_weights")
         periods = (1 / mu[:, 0, 0]).numpy()
         scales = (1 / (2 * np.pi * sg[:, 0, 0])).numpy()
         return periods, w.numpy(), scales

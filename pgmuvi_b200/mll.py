@@ -20,7 +20,8 @@ from typing import List, Optional
 import torch
 
 from . import ops
-from ._lib import KIND_SM1D, KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD
+from ._lib import (KIND_SEP_CONST, KIND_SEP_MATERN15, KIND_SEP_RBF, KIND_SEP_RQ, KIND_SM1D,
+                   KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD)
 from .constraints import describe
 
 
@@ -31,7 +32,7 @@ class UnsupportedModelError(NotImplementedError):
 @dataclass
 class PackedModel:
     """Flat view of a model on the packed C-ABI layout
-    ``[mean | w[Q] | mu[Q*d] | sigma[Q*d] | (noise)]``."""
+    ``[mean | w[Q] | mu[Q*ds] | sigma[Q*ds] | (noise) | lam[NL]]``."""
     params: List[torch.nn.Parameter]      # in packed order
     names: List[str]                      # their names under model.named_parameters()
     kinds: torch.Tensor                   # [P] int32 (CPU)
@@ -78,12 +79,52 @@ def pack_model(model, likelihood=None) -> PackedModel:
     mean, cov = getattr(model, "mean_module", None), getattr(model, "covar_module", None)
     if mean is None or not hasattr(mean, "raw_constant"):
         raise UnsupportedModelError("only ConstantMean is on the accelerated path")
+    lam_params, lam_cons, sep_kind = [], [], None
+    factors = getattr(cov, "kernels", None)
+    if factors is not None:
+        # ProductKernel(time_kernel, wavelength_kernel) with active_dims [0] / [1]
+        # (pgmuvi/gps.py:1319-1333)
+        if len(factors) != 2 or not hasattr(factors[0], "raw_mixture_weights"):
+            raise UnsupportedModelError(
+                "separable models need covar_module = SpectralMixtureKernel * wavelength kernel")
+        wl = factors[1]
+        cov = factors[0]
+        if hasattr(wl, "raw_constant") and not hasattr(wl, "base_kernel"):
+            sep_kind = KIND_SEP_CONST
+            lam_params, lam_cons = [wl.raw_constant], [_constraint(wl, "raw_constant")]
+        elif hasattr(wl, "raw_outputscale") and hasattr(wl, "base_kernel"):
+            base = wl.base_kernel
+            bname = type(base).__name__
+            if not hasattr(base, "raw_lengthscale"):
+                raise UnsupportedModelError(f"wavelength base kernel {bname} is not supported")
+            lam_params = [wl.raw_outputscale, base.raw_lengthscale]
+            lam_cons = [_constraint(wl, "raw_outputscale"), _constraint(base, "raw_lengthscale")]
+            if hasattr(base, "raw_alpha"):
+                sep_kind = KIND_SEP_RQ
+                lam_params.append(base.raw_alpha)
+                lam_cons.append(_constraint(base, "raw_alpha"))
+            elif "Matern" in bname:
+                if float(getattr(base, "nu", 1.5)) != 1.5:
+                    raise UnsupportedModelError("only MaternKernel(nu=1.5) is supported")
+                sep_kind = KIND_SEP_MATERN15
+            elif "RBF" in bname:
+                sep_kind = KIND_SEP_RBF
+            else:
+                raise UnsupportedModelError(f"wavelength base kernel {bname} is not supported")
+        else:
+            raise UnsupportedModelError("wavelength kernel must be ScaleKernel(RBF | Matern-1.5 "
+                                        "| RQ) or ConstantKernel")
     for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
         if cov is None or not hasattr(cov, nm):
             raise UnsupportedModelError("covar_module must be a SpectralMixtureKernel")
     Q = int(cov.raw_mixture_weights.numel())
     d = int(cov.raw_mixture_means.shape[-1])
-    if d == 1:
+    if sep_kind is not None:
+        if d != 1:
+            raise UnsupportedModelError("the time kernel of a separable model needs "
+                                        "ard_num_dims=1")
+        kind, d = sep_kind, 2
+    elif d == 1:
         kind = KIND_SM1D
     elif d == 2:
         kind = (KIND_SM_ARD_SUMPROD if getattr(cov, "variant", "prod_of_sums") == "sum_of_prods"
@@ -115,6 +156,8 @@ def pack_model(model, likelihood=None) -> PackedModel:
             cons.append(_constraint(snc, "raw_noise"))
     else:
         raise UnsupportedModelError("likelihood must be Gaussian or FixedNoiseGaussian")
+    params += lam_params
+    cons += lam_cons
     kinds, lb, ub = [], [], []
     for p, c in zip(params, cons):
         k, lo, hi = describe(c)

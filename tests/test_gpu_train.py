@@ -108,3 +108,43 @@ def test_fit_2d_loss_decreases(cuda_device):
     assert loss[-5:].mean() < loss[:5].mean()
     assert res["covar_module.mixture_means"][0].shape == (3, 1, 2)
     assert {"loss", "delta_loss", "mean_module.constant"} <= set(res)
+
+
+def _lc_2d(seed=5, n_per=40, **kw):
+    from pgmuvi_b200.lightcurve import Lightcurve
+    rng = np.random.default_rng(seed)
+    xs, ys = [], []
+    for wl, amp in ((0.8, 1.0), (1.2, 0.7), (2.2, 0.45)):
+        t = np.sort(rng.uniform(0.0, 400.0, n_per))
+        xs.append(np.stack([t, np.full(n_per, wl)], 1))
+        ys.append(amp * np.sin(2 * np.pi * t / 83.0 + 0.1 * wl) + 0.05 * rng.standard_normal(n_per))
+    x, y = np.concatenate(xs), np.concatenate(ys)
+    return Lightcurve(x, y, yerr=np.full(len(y), 0.05), **kw)
+
+
+@pytest.mark.parametrize("model,kw", [("2DWavelengthDependent", dict(wavelength_kernel_type="rbf")),
+                                      ("2DWavelengthDependent", dict(wavelength_kernel_type="matern")),
+                                      ("2DWavelengthDependent", dict(wavelength_kernel_type="rq")),
+                                      ("2DAchromatic", {}), ("2DSeparable", {})])
+def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
+    """SM(time) x wavelength kernel through Lightcurve -> train (seam #1) against the oracle's
+    restatement of the same loop, and the loss goes down (tests/test_2d_integration.py:112-135)."""
+    from oracle import train_loop
+    from pgmuvi_b200.trainers import train
+    torch.manual_seed(0)
+    lc = _lc_2d().double()
+    lc.set_model(model, num_mixtures=2, **kw)
+    lc.double()
+    lc.set_default_constraints()
+    # hypers in the min-max-scaled units of the time axis (span ~400 d)
+    lc.model.initialize(**{"covar_module.kernels.0.mixture_means": torch.tensor([4.8, 9.7]),
+                           "covar_module.kernels.0.mixture_scales": torch.tensor([1.5, 1.0])})
+    args, pk = _oracle_inputs(lc)
+    assert pk.kind >= 3
+    ref = train_loop(*args, maxiter=5, miniter=5, stop=None, lr=0.05, optim="AdamW")
+    res = train(lc, maxiter=5, miniter=5, stop=None, lr=0.05, optim="AdamW")
+    assert np.allclose(np.array(res["loss"], dtype=float), np.array(ref["loss"], dtype=float),
+                       rtol=1e-9, atol=1e-12)
+    assert np.allclose(pk.raw().detach().numpy(), ref["raw"][-1], rtol=1e-8, atol=1e-10)
+    res = train(lc, maxiter=40, miniter=40, stop=None, lr=0.05, optim="AdamW")
+    assert res["loss"][-1] < res["loss"][0]

@@ -159,6 +159,48 @@ def test_2d_constraints_and_dimension_checks():
         lc.set_model("2DLinear")
 
 
+def test_separable_models_pack_onto_the_separable_kinds():
+    """pgmuvi/gps.py:1274-1423 (SeparableGPModel / AchromaticGPModel / WavelengthDependentGPModel
+    with the spectral-mixture time kernel): parameter names as GPyTorch registers them under
+    ``covar_module.kernels.{0,1}``, packed as [mean | w | mu | sigma | (noise) | lam]."""
+    rng = np.random.default_rng(2)
+    x = np.concatenate([np.stack([np.sort(rng.uniform(0, 300, 25)), np.full(25, wl)], 1)
+                        for wl in (0.8, 1.2, 2.2)])
+    y = rng.standard_normal(75)
+    expect = {"rbf": (3, 2), "matern": (4, 2), "rq": (5, 3)}
+    for wk, (kind, nl) in expect.items():
+        lc = Lightcurve(x, y, yerr=np.full(75, 0.05))
+        lc.set_model("2DWavelengthDependent", num_mixtures=3, wavelength_kernel_type=wk)
+        lc.set_default_constraints()
+        pk = pack_model(lc.model)
+        assert (pk.kind, pk.Q, pk.d, pk.P) == (kind, 3, 2, 1 + 9 + nl)
+        assert pk.names[:4] == ["mean_module.raw_constant",
+                                "covar_module.kernels.0.raw_mixture_weights",
+                                "covar_module.kernels.0.raw_mixture_means",
+                                "covar_module.kernels.0.raw_mixture_scales"]
+        assert pk.names[4:6] == ["covar_module.kernels.1.raw_outputscale",
+                                 "covar_module.kernels.1.base_kernel.raw_lengthscale"]
+        # the time-kernel means get the 2-D Interval constraint, the wavelength kernel keeps
+        # GPyTorch's Positive defaults; the initial lengthscale is max(span/2, 1) (gps.py:1576)
+        assert type(lc.model.covar_module.kernels[0].raw_mixture_means_constraint).__name__ == "Interval"
+        assert float(lc.model.covar_module.kernels[1].base_kernel.lengthscale) == pytest.approx(1.0)
+        assert pk.kinds.tolist()[-nl:] == [1] * nl
+        keys = set(lc.get_parameters())
+        assert "covar_module.kernels.1.base_kernel.lengthscale" in keys
+        if wk == "rq":       # the reference's str.lstrip("raw_") quirk (SURVEY A.9)
+            assert "covar_module.kernels.1.base_kernel.lpha" in keys
+    lc = Lightcurve(x, y)                                   # Gaussian likelihood: learned noise
+    lc.set_model("2DAchromatic", num_mixtures=2)
+    pk = pack_model(lc.model)
+    assert (pk.kind, pk.P, pk.learn_noise) == (6, 1 + 6 + 1 + 1, True)
+    assert pk.names[-2:] == ["likelihood.noise_covar.raw_noise",
+                             "covar_module.kernels.1.raw_constant"]
+    with pytest.raises(NotImplementedError):
+        lc.set_model("2DAchromatic", time_kernel_type="matern")
+    with pytest.raises(ValueError):
+        Lightcurve(x[:, 0], y).set_model("2DSeparable")
+
+
 def test_pack_model_rejects_models_outside_the_path():
     lc, *_ = _lc_1d(n=20)
     lc.set_model("1D", num_mixtures=2)
