@@ -1,6 +1,7 @@
 // C ABI of pgmuvi_b200 (see include/pgmuvi_b200.h).  Host-side dispatch only; all device
 // code is in gp_fused.cuh.
 #include "gp_fused.cuh"
+#include "gp_large.cuh"
 #include "../../include/pgmuvi_b200.h"
 
 #include <cstdio>
@@ -12,6 +13,8 @@ namespace pgm {
 template <int KIND, int QT, int D> int launch_eval(const EvalArgs& A0, cudaStream_t st);
 template <int KIND, int QT, int D> int launch_fit(const FitArgs& F, cudaStream_t st);
 template <int KIND, int QT, int D> int launch_dense(const EvalArgs& A, double* K, cudaStream_t st);
+template <int KIND, int QT, int D>
+int launch_large(const LargeArgs& A, int want_grad, int32_t* info_host, cudaStream_t st);
 
 thread_local std::string g_err;
 int fail(const std::string& m) {
@@ -51,6 +54,7 @@ using pgm::fail;
 using pgm::launch_dense;
 using pgm::launch_eval;
 using pgm::launch_fit;
+using pgm::launch_large;
 
 int pad_q(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
 
@@ -141,6 +145,33 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
   A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGM_DISPATCH(launch_eval, A, st);
+  return 0;
+}
+
+size_t pgm_large_workspace_bytes(int n) {
+  return n < 1 ? 0 : pgm::large_ws_elems(n) * sizeof(double);
+}
+
+int pgm_sm_mll_grad_large_f64(const double* x, const double* y, const double* fixed_noise,
+                              const double* raw, const int32_t* con_kind, const double* con_lb,
+                              const double* con_ub, int n, int d, int Q, int kernel_kind,
+                              int flags, double* mll, double* grad_raw, int32_t* info_host,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (int r = check_common(1, n, d, Q, kernel_kind)) return r;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info_host || !workspace)
+    return fail("null pointer argument");
+  if ((flags & PGM_FLAG_GRAD) && !grad_raw) return fail("PGM_FLAG_GRAD needs grad_raw");
+  if (flags & PGM_FLAG_BOUNDS_PER_LC) return fail("the large-GP entry takes shared bounds [P]");
+  if (workspace_bytes < pgm_large_workspace_bytes(n))
+    return fail("workspace too small (see pgm_large_workspace_bytes)");
+  pgm::LargeArgs A;
+  A.x = x; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
+  A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
+  A.n = n; A.Q = Q; A.flags = flags; A.mll = mll; A.grad = grad_raw;
+  A.ws = static_cast<double*>(workspace);
+  const int want_grad = (flags & PGM_FLAG_GRAD) ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGM_DISPATCH(launch_large, A, want_grad, info_host, st);
   return 0;
 }
 

@@ -1,0 +1,615 @@
+// pgmuvi_b200 - single large exact GP (n in the thousands .. tens of thousands) on ONE B200.
+//
+// BASELINE configs C3 (n = 8000, 2-D) and C4 (n = 32768): the factor no longer fits one
+// block's scratch, so the whole GPU works on one matrix.  K~ lives in HBM as the lower
+// triangle of 64x64 tile images (the shared-memory operand image of gp_fused.cuh) and every
+// product runs through the same bulk-copy + mbarrier DMMA tile engine, one output tile per
+// thread block, one kernel launch per dependency stage:
+//
+//   P  right-looking blocked Cholesky, panels of NB tile columns:
+//        lg_update (column of the panel, k inside the panel)  -> lg_diag (64x64 potrf +
+//        inverse, z_j, log-det)  -> lg_trsm (L_ij = C_ij X_jj^T, rhs_i -= L_ij z_j)
+//        ... then ONE lg_update over the whole trailing triangle (k = the panel).
+//      The first touch of a tile generates K~ in the epilogue (never a separate build pass).
+//   T  X = L^-1 row by row (lg_inv_row: one block per tile of the row), alpha = X^T z.
+//   G  K^-1_ij = sum_k X_ki^T X_kj per tile, contracted at once with W = alpha alpha^T - K^-1
+//      and the regenerated dK/dtheta; per-tile partial sums, deterministic final reduction.
+//
+// Reference semantics as gp_fused.cuh (pgmuvi/trainers.py:177-182);
+// the exact-Cholesky branch for n > 800 is the north star's definition of the path (F6).
+#pragma once
+#include "gp_fused.cuh"
+
+namespace pgm {
+
+constexpr int LG_NFB_MAX = 2 + 2 * 16;   // per-point doubles upper bound: x[2], (cos,sin)[16]
+constexpr int LG_PAR = 160;              // theta[64] jac[64] wq[8] aq[16] lam[4] (+pad)
+constexpr int LG_GP = 48;                // doubles per job in the gradient partials
+constexpr int LG_PAR_TH = 0, LG_PAR_JC = 64, LG_PAR_WQ = 128, LG_PAR_AQ = 136, LG_PAR_LM = 152;
+
+struct LargeWs {
+  double *tilesL, *tilesX, *tilesT;
+  double *fx, *fcs, *alpha, *rhs, *z, *dn, *par, *ldz, *gpart;
+  int* fail;
+};
+
+__host__ __device__ inline size_t large_ws_elems(int n) {
+  const size_t N = (n + TS - 1) / TS, npad = N * TS, ntri = N * (N + 1) / 2;
+  return 2 * ntri * TT + N * TT + (size_t)(LG_NFB_MAX + 4) * npad + LG_PAR + 2 * N +
+         ntri * LG_GP + 16;
+}
+__host__ __device__ inline LargeWs make_large_ws(double* base, int n) {
+  const size_t N = (n + TS - 1) / TS, npad = N * TS, ntri = N * (N + 1) / 2;
+  LargeWs w;
+  w.tilesL = base;
+  w.tilesX = w.tilesL + ntri * TT;
+  w.tilesT = w.tilesX + ntri * TT;
+  w.fx = w.tilesT + N * TT;
+  w.fcs = w.fx + 2 * npad;
+  w.alpha = w.fcs + 32 * npad;
+  w.rhs = w.alpha + npad;
+  w.z = w.rhs + npad;
+  w.dn = w.z + npad;
+  w.par = w.dn + npad;
+  w.ldz = w.par + LG_PAR;
+  w.gpart = w.ldz + 2 * N;
+  w.fail = reinterpret_cast<int*>(w.gpart + ntri * LG_GP);
+  return w;
+}
+
+struct LargeArgs {
+  const double* x;
+  const double* y;
+  const double* fixed_noise;
+  const double* raw;
+  const int32_t* con_kind;
+  const double* con_lb;
+  const double* con_ub;
+  int n, Q, flags;
+  double* mll;
+  double* grad;
+  double* ws;
+};
+
+__device__ __forceinline__ double* lg_tile(double* base, int i, int j) {
+  return base + ((size_t)i * (i + 1) / 2 + j) * TT;
+}
+// linear index t -> (a, b) with a >= b >= 0 (row-major lower triangle)
+__device__ __forceinline__ void tri_unrank(int t, int& a, int& b) {
+  a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= t) ++a;
+  while (a * (a + 1) / 2 > t) --a;
+  b = t - a * (a + 1) / 2;
+}
+
+// ------------------------------------------------------------------------------------
+// setup: constraints -> parameter block; per-point fields, rhs, noise diagonal
+// ------------------------------------------------------------------------------------
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
+  __shared__ double theta[64], jac[64];
+  const int tid = threadIdx.x;
+  const int Q = A.Q;
+  const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
+  const int P = param_count<KIND, QT, D>(Q, learn_noise);
+  const int o_noise = 1 + Q + 2 * Q * DS, o_lam = o_noise + (learn_noise ? 1 : 0);
+  LargeWs w = make_large_ws(A.ws, A.n);
+  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  if (tid < P) {
+    const double rv = A.raw[tid];
+    const int kd = A.con_kind[tid];
+    const double lb = A.con_lb[tid], ub = A.con_ub[tid];
+    double th = rv, jc = 1.0;
+    if (kd == 1) {
+      th = softplus_d(rv) + lb;
+      jc = sigmoid_d(rv);
+    } else if (kd == 2) {
+      const double s = sigmoid_d(rv);
+      th = lb + (ub - lb) * s;
+      jc = (ub - lb) * s * (1.0 - s);
+    }
+    theta[tid] = th;
+    jac[tid] = jc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (tid < P) {
+      w.par[LG_PAR_TH + tid] = theta[tid];
+      w.par[LG_PAR_JC + tid] = jac[tid];
+    }
+    if (tid < QT) w.par[LG_PAR_WQ + tid] = (tid < Q) ? theta[1 + tid] : 0.0;
+    if (tid < QT * DS) {
+      const int q = tid / DS, dd = tid - q * DS;
+      const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
+      w.par[LG_PAR_AQ + q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
+    }
+    if (tid == 32) lam_setup<KIND>(theta + o_lam, w.par + LG_PAR_LM);
+  }
+  const double mean = theta[0];
+  const double lnoise = learn_noise ? theta[o_noise] : 0.0;
+  const int i = blockIdx.x * NTHREADS + tid;
+  if (i >= npad) return;
+  const bool valid = i < n;
+#pragma unroll
+  for (int dd = 0; dd < D; ++dd) {
+    const double xc = valid ? (A.x[(size_t)i * D + dd] - A.x[dd]) : 0.0;
+    w.fx[(size_t)dd * npad + i] = xc;
+    if (dd < DS) {
+#pragma unroll
+      for (int q = 0; q < QT; ++q) {
+        double sn = 0.0, cs = 1.0;
+        if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * DS + dd] * xc, &sn, &cs);
+        *reinterpret_cast<double2*>(w.fcs + ((size_t)(dd * QT + q) * npad + i) * 2) =
+            make_double2(cs, sn);
+      }
+    }
+  }
+  w.rhs[i] = valid ? (A.y[i] - mean) : 0.0;
+  w.dn[i] = valid ? ((A.fixed_noise ? A.fixed_noise[i] : 0.0) + lnoise) : 0.0;
+}
+
+// per-point data of tile row / col I -> rowv / colv (cp.async, as in the fused kernel)
+template <int KIND, int QT, int D>
+__device__ __forceinline__ void lg_prefetch_side(double* vec, const LargeWs& w, int npad, int I,
+                                                 bool with_alpha) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int CH_X = D * 32, CH_CS = C::NCS * 64;
+  for (int ch = threadIdx.x; ch < CH_X + CH_CS + 32; ch += NTHREADS) {
+    if (ch < CH_X) {
+      const int dd = ch >> 5, o = (ch & 31) * 2;
+      cp_async16(vec + dd * TS + o, w.fx + (size_t)dd * npad + I * TS + o);
+    } else if (ch < CH_X + CH_CS) {
+      const int c2 = ch - CH_X, f = c2 >> 6, o = (c2 & 63) * 2;
+      cp_async16(vec + D * TS + f * 2 * TS + o, w.fcs + ((size_t)f * npad + I * TS) * 2 + o);
+    } else if (with_alpha) {
+      const int o = (ch - CH_X - CH_CS) * 2;
+      cp_async16(vec + C::NFB * TS + o, w.alpha + I * TS + o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// C_ij -= sum_{k0 <= k < k1} L_ik L_jk^T   (build: C_ij = K~_ij - sum, first touch)
+//   mode 0: one tile column j = jj, i = jj + blockIdx.x
+//   mode 1: the whole trailing triangle i >= j >= jj, blockIdx.x -> (i - jj, j - jj)
+// ------------------------------------------------------------------------------------
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+    lg_update(LargeArgs A, int mode, int jj, int k0, int k1, int build, double jitter) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  LargeWs w = make_large_ws(A.ws, A.n);
+  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  int i, j;
+  if (mode == 0) {
+    j = jj;
+    i = jj + blockIdx.x;
+  } else {
+    int a, b;
+    tri_unrank(blockIdx.x, a, b);
+    i = jj + a;
+    j = jj + b;
+  }
+  double* stages = sm + C::SM_STAGES;
+  double* Cst = stages + 2 * OPBUF;
+  double* rowv = sm + C::SM_ROW;
+  double* colv = sm + C::SM_COL;
+  double* par = sm + C::SM_PAR;
+  double* tab = par + C::PAR_TAB;
+  const unsigned bars = smem_u32(par + C::PAR_BAR);
+  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  PipeState ps;
+  pipe_init<KIND, QT, D>(sm, ps);
+  Ring r2{bars, bars + 16, stages, 0};
+  double acc[4][2][2];
+  zero_acc(acc);
+  auto tA = [&](int kk) { return lg_tile(w.tilesL, i, k0 + kk); };
+  auto tB = [&](int kk) { return lg_tile(w.tilesL, j, k0 + kk); };
+  auto none = [&](int) { return (double*)nullptr; };
+  auto pf = [&]() {
+    if (build) {
+      lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
+      lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, false);
+    }
+  };
+  if (i == j) gemm_stream<M_FULL, true, 2>(acc, r2, k1 - k0, tA, tB, 0, 0, none, none, pf);
+  else gemm_stream<M_FULL, false, 2>(acc, r2, k1 - k0, tA, tB, 0, 0, none, none, pf);
+  __syncthreads();
+  double* out = lg_tile(w.tilesL, i, j);
+  if (!build) {
+    // read-modify-write of this block's own tile (thread-private entries)
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, 0);
+        double2* p = reinterpret_cast<double2*>(out + img(r, c));
+        double2 v = *p;
+        v.x -= acc[mi][ni][0];
+        v.y -= acc[mi][ni][1];
+        *p = v;
+      }
+    return;
+  }
+  double wreg[QT], areg[QT * DS], lam[4];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) wreg[q] = w.par[LG_PAR_WQ + q];
+#pragma unroll
+  for (int q = 0; q < QT * DS; ++q) areg[q] = w.par[LG_PAR_AQ + q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) lam[q] = w.par[LG_PAR_LM + q];
+  store_acc_tile(acc, Cst, 1.0);
+#pragma unroll 1
+  for (int p8 = 0; p8 < 8; ++p8) {
+    const int mi = p8 >> 1, ni2 = p8 & 1;
+    if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+    const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+    const int gi = i * TS + r;
+    double2* cp = reinterpret_cast<double2*>(Cst + img(r, c0));
+    const double2 cv = *cp;
+    double o2[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int gj = j * TS + c0 + e;
+      double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
+      kv = (gi < n && gj <= gi) ? kv : 0.0;
+      if (gi == gj) kv = (gi < n) ? (kv + w.dn[gi] + jitter) : 1.0;
+      o2[e] = kv - (e ? cv.y : cv.x);
+    }
+    *cp = make_double2(o2[0], o2[1]);
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    bulk_s2g(out, smem_u32(Cst), 2 * OPBUF * sizeof(double));
+    bulk_commit();
+    bulk_wait_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// diagonal block j: C_jj -> X_jj = L_jj^-1 (tilesL / tilesX diagonal slots), X_jj^T (tilesT),
+// z_j = X_jj rhs_j, log-det and z^T z partials
+// ------------------------------------------------------------------------------------
+constexpr size_t LG_DIAG_SMEM = (size_t)(2 * S_ELEMS + 4 * TS + 8) * sizeof(double);
+static __global__ void __launch_bounds__(NTHREADS) lg_diag(double* ws, int n, int j) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;
+  double* S2 = sm + S_ELEMS;
+  double* dinv = S2 + S_ELEMS;
+  double* zi = dinv + TS;
+  double* red = zi + TS;   // [2 * 64]
+  int* s_fail = reinterpret_cast<int*>(red + 2 * TS);
+  const int tid = threadIdx.x;
+  LargeWs w = make_large_ws(ws, n);
+  double* tl = lg_tile(w.tilesL, j, j);
+  if (tid == 0) *s_fail = 0;
+  for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
+    const int r = idx >> 5, c2 = (idx & 31) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(tl + img(r, c2));
+    S[r * LD_S + c2] = v.x;
+    S[r * LD_S + c2 + 1] = v.y;
+  }
+  if (tid < TS) zi[tid] = w.rhs[j * TS + tid];
+  __syncthreads();
+  potrf_inv_64(S, S2, dinv, s_fail);
+  if (*s_fail) {
+    if (tid == 0) atomicOr(w.fail, *s_fail);
+    return;
+  }
+  double* tx = lg_tile(w.tilesX, j, j);
+  double* tt = w.tilesT + (size_t)j * TT;
+  for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
+    const int r = idx >> 5, c2 = (idx & 31) * 2;
+    double2 v, vt;
+    v.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
+    v.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
+    vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
+    vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
+    const int o = img(r, c2);
+    *reinterpret_cast<double2*>(tl + o) = v;
+    *reinterpret_cast<double2*>(tx + o) = v;
+    *reinterpret_cast<double2*>(tt + o) = vt;
+  }
+  {
+    const int r = tid >> 2, l4 = tid & 3;
+    double zz = 0.0;
+    for (int c = l4; c <= r; c += 4) zz += S2[r * LD_S + c] * zi[c];
+    zz += shfl_xor_d(zz, 1);
+    zz += shfl_xor_d(zz, 2);
+    if (l4 == 0) {
+      w.z[j * TS + r] = zz;
+      red[r] = zz * zz;
+      red[TS + r] = -log(dinv[r]);
+    }
+  }
+  __syncthreads();
+  if (tid < 2) {
+    double s = 0.0;
+    for (int r = 0; r < TS; ++r) s += red[tid * TS + r];
+    w.ldz[2 * j + (tid ? 0 : 1)] = s;   // ldz[2j] = sum log L_kk, ldz[2j+1] = z_j^T z_j
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// L_ij = C_ij X_jj^T for i > j;  rhs_i -= L_ij z_j
+// ------------------------------------------------------------------------------------
+constexpr size_t LG_TRSM_SMEM = (size_t)(4 * OPBUF + 5 * TS + 8) * sizeof(double);
+static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(double* ws, int n, int j) {
+  extern __shared__ __align__(16) double sm[];
+  double* Cst = sm;
+  double* R = sm + 2 * OPBUF;
+  double* zj = R + 2 * OPBUF;
+  double* red = zj + TS;   // [4][64]
+  const unsigned bar = smem_u32(red + 4 * TS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  LargeWs w = make_large_ws(ws, n);
+  const int i = j + 1 + blockIdx.x;
+  double* tij = lg_tile(w.tilesL, i, j);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  if (tid < TS) zj[tid] = w.z[j * TS + tid];
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, 4 * CHUNK_BYTES);
+    bulk_g2s(smem_u32(Cst), tij, 2 * CHUNK_BYTES, bar);
+    bulk_g2s(smem_u32(R), lg_tile(w.tilesL, j, j), 2 * CHUNK_BYTES, bar);
+  }
+  mbar_wait(bar, 0);
+  double acc[4][2][2];
+  zero_acc(acc);
+  compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+  compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    double s = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) s += acc[mi][ni][e] * zj[frag_col(wn, ni, tq, e)];
+    s += shfl_xor_d(s, 1);
+    s += shfl_xor_d(s, 2);
+    if (tq == 0) red[wn * TS + frag_row(wm, mi, g)] = s;
+  }
+  store_tile_bulk(acc, Cst, tij, 1.0);   // barriers inside also publish `red`
+  if (tid < TS)
+    w.rhs[i * TS + tid] -= (red[tid] + red[TS + tid]) + (red[2 * TS + tid] + red[3 * TS + tid]);
+  if (tid == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------
+// row i of X = L^-1:  X_ij^T = -(sum_{k=j}^{i-1} X_kj^T L_ik^T) X_ii^T,  j = blockIdx.x < i
+// (reads L from tilesL, writes X^T tiles to tilesX: blocks of one launch never conflict)
+// ------------------------------------------------------------------------------------
+constexpr size_t LG_INV_SMEM = (size_t)(6 * OPBUF + 16) * sizeof(double);
+static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(double* ws, int n, int i) {
+  extern __shared__ __align__(16) double sm[];
+  double* stages = sm;
+  double* Cst = stages + 2 * OPBUF;
+  double* R = sm + 4 * OPBUF;
+  const unsigned bars = smem_u32(sm + 6 * OPBUF);
+  const unsigned rbar = bars + 8 * 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  LargeWs w = make_large_ws(ws, n);
+  const int j = blockIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (2 + s), NTHREADS / 32); }
+    mbar_init(rbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(rbar, 2 * CHUNK_BYTES);
+    bulk_g2s(smem_u32(R), lg_tile(w.tilesX, i, i), 2 * CHUNK_BYTES, rbar);
+  }
+  Ring r2{bars, bars + 16, stages, 0};
+  double acc[4][2][2];
+  zero_acc(acc);
+  auto tA = [&](int kk) { return kk == 0 ? w.tilesT + (size_t)j * TT : lg_tile(w.tilesX, j + kk, j); };
+  auto tB = [&](int kk) { return lg_tile(w.tilesL, i, j + kk); };
+  auto none = [&](int) { return (double*)nullptr; };
+  gemm_stream<M_A_GE, false, 2>(acc, r2, i - j, tA, tB, 0, 0, none, none, []() {});
+  __syncthreads();
+  store_acc_tile(acc, Cst, 1.0);
+  __syncthreads();
+  mbar_wait(rbar, 0);
+  zero_acc(acc);
+  compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+  compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+  store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);
+  if (tid == 0) bulk_wait_all();
+}
+
+// alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i   (tilesX holds X_jj and the X_ij^T tiles)
+static __global__ void __launch_bounds__(NTHREADS) lg_alpha(double* ws, int n) {
+  __shared__ double scr[4 * TS];
+  const int tid = threadIdx.x;
+  LargeWs w = make_large_ws(ws, n);
+  const int N = (n + TS - 1) / TS, j = blockIdx.x;
+  const int m = tid & 63, part = tid >> 6;
+  double s = 0.0;
+  {
+    const double* Xd = lg_tile(w.tilesX, j, j);
+    const double* zz = w.z + j * TS;
+#pragma unroll 4
+    for (int r = part * 16; r < part * 16 + 16; ++r) s += Xd[img(r, m)] * zz[r];
+  }
+  for (int i = j + 1; i < N; ++i) {
+    const double* Xt = lg_tile(w.tilesX, i, j);
+    const double* zz = w.z + i * TS;
+#pragma unroll 4
+    for (int c = part * 16; c < part * 16 + 16; ++c) s += Xt[img(m, c)] * zz[c];
+  }
+  scr[part * TS + m] = s;
+  __syncthreads();
+  if (tid < TS)
+    w.alpha[j * TS + tid] = (scr[tid] + scr[TS + tid]) + (scr[2 * TS + tid] + scr[3 * TS + tid]);
+}
+
+// ------------------------------------------------------------------------------------
+// gradient partials of tile (i, j), i >= j:  K^-1_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}
+// ------------------------------------------------------------------------------------
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+    lg_grad(LargeArgs A) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
+  static_assert(C::NV <= LG_GP, "gradient partial slot too small");
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  LargeWs w = make_large_ws(A.ws, A.n);
+  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  int i, j;
+  tri_unrank(blockIdx.x, i, j);
+  double* stages = sm + C::SM_STAGES;
+  double* R = sm + C::SM_S;
+  double* rowv = sm + C::SM_ROW;
+  double* colv = sm + C::SM_COL;
+  double* par = sm + C::SM_PAR;
+  double* red = par + C::PAR_RED;
+  double* fin = par + C::PAR_FIN;
+  double* tab = par + C::PAR_TAB;
+  const unsigned bars = smem_u32(par + C::PAR_BAR);
+  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  PipeState ps;
+  pipe_init<KIND, QT, D>(sm, ps);
+  Ring r2{bars, bars + 16, stages, 0};
+  double acc[4][2][2];
+  zero_acc(acc);
+  auto tA = [&](int kk) { return kk == 0 ? w.tilesT + (size_t)i * TT : lg_tile(w.tilesX, i + kk, i); };
+  auto tB = [&](int kk) {
+    return (kk == 0 && i == j) ? w.tilesT + (size_t)j * TT : lg_tile(w.tilesX, i + kk, j);
+  };
+  auto none = [&](int) { return (double*)nullptr; };
+  auto pf = [&]() {
+    lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, true);
+    lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, true);
+  };
+  if (i == j) gemm_stream<M_A_GE, true, 2>(acc, r2, N - i, tA, tB, 0, 0, none, none, pf);
+  else gemm_stream<M_A_GE, false, 2>(acc, r2, N - i, tA, tB, 0, 0, none, none, pf);
+  __syncthreads();
+  double wreg[QT], areg[QT * DS], lam[4];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) wreg[q] = w.par[LG_PAR_WQ + q];
+#pragma unroll
+  for (int q = 0; q < QT * DS; ++q) areg[q] = w.par[LG_PAR_AQ + q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) lam[q] = w.par[LG_PAR_LM + q];
+  store_acc_tile(acc, R, 1.0);
+  double ga[C::NG];
+#pragma unroll
+  for (int t = 0; t < C::NG; ++t) ga[t] = 0.0;
+  double trW = 0.0;
+  const double* al_r = rowv + C::NFB * TS;
+  const double* al_c = colv + C::NFB * TS;
+#pragma unroll 1
+  for (int p8 = 0; p8 < 8; ++p8) {
+    const int mi = p8 >> 1, ni2 = p8 & 1;
+    if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+    const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+    const int gi = i * TS + r;
+    const double2 kinv = *reinterpret_cast<const double2*>(R + img(r, c0));
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int gj = j * TS + c0 + e;
+      double W = al_r[r] * al_c[c0 + e] - (e ? kinv.y : kinv.x);
+      W = (gi < n && gj <= gi) ? W : 0.0;
+      if (gi == gj) trW += W;
+      const double wgt = (gi == gj) ? W : 2.0 * W;
+      k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
+    }
+  }
+  double v[C::NV];
+#pragma unroll
+  for (int t = 0; t < C::NG; ++t) v[t] = ga[t];
+  v[C::NG] = trW;
+  __syncthreads();
+  block_reduce<C::NV>(v, red, fin);
+  if (tid < C::NV) w.gpart[(size_t)blockIdx.x * LG_GP + tid] = fin[tid];
+}
+
+// ------------------------------------------------------------------------------------
+// final reduction (fixed order), MLL, gradient assembly
+// ------------------------------------------------------------------------------------
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int info, int want_grad) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
+  __shared__ double red[8 * (C::NV + 4)], fin[C::NV + 4];
+  const int tid = threadIdx.x;
+  LargeWs w = make_large_ws(A.ws, A.n);
+  const int n = A.n, N = (n + TS - 1) / TS;
+  const int Q = A.Q;
+  const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
+  const int P = param_count<KIND, QT, D>(Q, learn_noise);
+  const int o_noise = 1 + Q + 2 * Q * DS, o_lam = o_noise + (learn_noise ? 1 : 0);
+  if (info < 0) {
+    if (tid == 0) *A.mll = nan("");
+    if (want_grad && tid < P) A.grad[tid] = nan("");
+    return;
+  }
+  double v[C::NV + 3];
+#pragma unroll
+  for (int t = 0; t < C::NV + 3; ++t) v[t] = 0.0;
+  for (int jb = tid; jb < N; jb += NTHREADS) {
+    v[C::NV + 1] += w.ldz[2 * jb];
+    v[C::NV + 2] += w.ldz[2 * jb + 1];
+  }
+  if (want_grad) {
+    const int njobs = N * (N + 1) / 2;
+    for (int t = tid; t < njobs; t += NTHREADS)
+#pragma unroll
+      for (int k = 0; k < C::NV; ++k) v[k] += w.gpart[(size_t)t * LG_GP + k];
+    for (int i2 = tid; i2 < n; i2 += NTHREADS) v[C::NV] += w.alpha[i2];
+  }
+  block_reduce<C::NV + 3>(v, red, fin);
+  if (tid == 0) {
+    const double logdet = 2.0 * fin[C::NV + 1], inv_quad = fin[C::NV + 2];
+    *A.mll = -0.5 * (inv_quad + logdet + (double)n * 1.8378770664093454836) / n;
+  }
+  if (!want_grad || tid >= P) return;
+  const double* theta = w.par + LG_PAR_TH;
+  const double* wq = w.par + LG_PAR_WQ;
+  const double* lamq = w.par + LG_PAR_LM;
+  const double half = 0.5 / (double)n;
+  double gv;
+  if (tid == 0) {
+    gv = fin[C::NV] / (double)n;
+  } else if (tid < 1 + Q) {
+    gv = half * fin[tid - 1];
+  } else if (tid < 1 + Q + Q * DS) {
+    const int t = tid - 1 - Q, q = t / DS, dd = t - q * DS;
+    gv = half * (-2.0 * M_PI * wq[q]) * fin[QT + q * DS + dd];
+  } else if (tid < o_noise) {
+    const int t = tid - 1 - Q - Q * DS, q = t / DS, dd = t - q * DS;
+    gv = half * (-4.0 * M_PI * M_PI * theta[tid] * wq[q]) * fin[QT + QT * DS + q * DS + dd];
+  } else if (tid < o_lam) {
+    gv = half * fin[C::NG];
+  } else {
+    const int t = tid - o_lam;
+    double cf = 1.0;
+    if (t == 1) {
+      if (KIND == PGM_KIND_SEP_RBF) cf = lamq[0] / (lamq[3] * lamq[3] * lamq[3]);
+      else if (KIND == PGM_KIND_SEP_MATERN15) cf = lamq[0] / lamq[3];
+      else cf = lamq[0] * 2.0 * lamq[2] / lamq[3];
+    } else if (t == 2) {
+      cf = lamq[0];
+    }
+    gv = half * cf * fin[QT + 2 * QT * DS + t];
+  }
+  A.grad[tid] = gv * w.par[LG_PAR_JC + tid];
+}
+
+}  // namespace pgm

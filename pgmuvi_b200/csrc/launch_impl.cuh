@@ -2,6 +2,7 @@
 // the heavy kernels compile in parallel translation units.
 #pragma once
 #include "gp_fused.cuh"
+#include "gp_large.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -92,5 +93,65 @@ int launch_dense(const pgm::EvalArgs& A, double* K, cudaStream_t st) {
   return 0;
 }
 
+
+// Single large GP: the whole device factors one K~ (gp_large.cuh).  Host-orchestrated stage
+// by stage on `st`; synchronises once per Cholesky attempt to read the failure flag (the
+// jitter ladder of psd_safe_cholesky) - the call is blocking.
+template <int KIND, int QT, int D>
+int launch_large(const pgm::LargeArgs& A, int want_grad, int32_t* info_host, cudaStream_t st) {
+  using C = pgm::Cfg<KIND, QT, D>;
+  using namespace pgm;
+  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  constexpr int NB = 8;   // tile columns per panel
+  auto k_upd = lg_update<KIND, QT, D>;
+  auto k_grad = lg_grad<KIND, QT, D>;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_update)", e);
+  e = cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_grad)", e);
+  cudaFuncSetAttribute(lg_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_DIAG_SMEM);
+  cudaFuncSetAttribute(lg_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_TRSM_SMEM);
+  cudaFuncSetAttribute(lg_inv_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_INV_SMEM);
+  LargeWs w = make_large_ws(A.ws, n);
+  int info = 0;
+  for (int attempt = 0; attempt <= 3; ++attempt) {
+    double jitter = 0.0;
+    if (attempt > 0) { jitter = 1e-8; for (int t = 1; t < attempt; ++t) jitter *= 10.0; }
+    cudaMemsetAsync(w.fail, 0, sizeof(int), st);
+    lg_setup<KIND, QT, D><<<(npad + NTHREADS - 1) / NTHREADS, NTHREADS, 0, st>>>(A);
+    for (int J0 = 0; J0 < N; J0 += NB) {
+      const int J1 = std::min(J0 + NB, N);
+      const int build = (J0 == 0) ? 1 : 0;
+      for (int j = J0; j < J1; ++j) {
+        if (build || j > J0)
+          k_upd<<<N - j, NTHREADS, C::SMEM_BYTES, st>>>(A, 0, j, J0, j, build, jitter);
+        lg_diag<<<1, NTHREADS, LG_DIAG_SMEM, st>>>(A.ws, n, j);
+        if (j + 1 < N) lg_trsm<<<N - j - 1, NTHREADS, LG_TRSM_SMEM, st>>>(A.ws, n, j);
+      }
+      if (J1 < N) {
+        const int M = N - J1;
+        k_upd<<<M * (M + 1) / 2, NTHREADS, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build, jitter);
+      }
+    }
+    int fl = 0;
+    e = cudaMemcpyAsync(&fl, w.fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail("large-GP Cholesky phase", e);
+    if (!fl) { info = attempt; break; }
+    if (fl & 2) { info = -1; break; }
+    info = -2;
+  }
+  if (info >= 0 && want_grad) {
+    for (int i = 1; i < N; ++i) lg_inv_row<<<i, NTHREADS, LG_INV_SMEM, st>>>(A.ws, n, i);
+    lg_alpha<<<N, NTHREADS, 0, st>>>(A.ws, n);
+    k_grad<<<N * (N + 1) / 2, NTHREADS, C::SMEM_BYTES, st>>>(A);
+  }
+  lg_finish<KIND, QT, D><<<1, NTHREADS, 0, st>>>(A, info, want_grad);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("large-GP launch", e);
+  *info_host = info;
+  return 0;
+}
 
 }  // namespace pgm

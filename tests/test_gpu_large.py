@@ -1,0 +1,79 @@
+"""GPU tests of the single-large-GP path (pgm_sm_mll_grad_large_f64; BASELINE configs C3 / C4):
+the whole device factors ONE K~.  Checked against the oracle's golden vectors (every kernel
+kind, ragged last tile), against the fused one-block-per-light-curve kernel at n = 1500, and -
+at n = 8000 (C3's size) - through size-independent properties (finite differences of the MLL
+along the gradient; permutation invariance)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev, dt=torch.float64):
+    return None if a is None else torch.tensor(np.asarray(a), dtype=dt, device=dev)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_large_path_matches_goldens(name, cuda_device):
+    from pgmuvi_b200 import ops
+    g = load_golden(name)
+    dev = cuda_device
+    n = g["x"].shape[1]
+    for b in range(g["x"].shape[0]):
+        nb = n if g["n_valid"] is None else int(g["n_valid"][b])
+        lb = g["lb"][b] if np.ndim(g["lb"]) == 2 else g["lb"]
+        ub = g["ub"][b] if np.ndim(g["ub"]) == 2 else g["ub"]
+        mll, grad, info = ops.sm_mll_grad_large(
+            _t(g["x"][b][:nb], dev), _t(g["y"][b][:nb], dev),
+            None if g["noise"] is None else _t(g["noise"][b][:nb], dev), _t(g["raw"][b], dev),
+            _t(g["kinds"], dev, torch.int32), _t(lb, dev), _t(ub, dev), g["kind"], g["Q"],
+            g["learn_noise"], True)
+        assert info == int(g["info"][b])
+        assert abs(float(mll) - g["mll"][b]) <= 1e-9 * abs(g["mll"][b])
+        scale = np.abs(g["grad_autograd"][b]).max()
+        assert np.abs(grad.cpu().numpy() - g["grad_autograd"][b]).max() <= 1e-7 * scale
+
+
+def test_large_path_matches_fused_kernel_n1500(cuda_device):
+    from pgmuvi_b200 import ops, synthetic as S
+    bt = S.make_batch_1d(1, 1500, Q=4, learn_noise=True, seed0=4242)
+    dev = cuda_device
+    x, y, nz, raw = (_t(bt[k], dev) for k in ("x", "y", "noise", "raw"))
+    kinds, lb, ub = _t(bt["kinds"], dev, torch.int32), _t(bt["lb"], dev), _t(bt["ub"], dev)
+    m0, g0, i0 = ops.sm_mll_grad(x, y, nz, raw, kinds, lb, ub, None, 0, 4, True, True)
+    m1, g1, i1 = ops.sm_mll_grad_large(x[0], y[0], nz[0], raw[0], kinds, lb[0], ub[0], 0, 4, True)
+    assert i1 == int(i0[0]) == 0
+    assert abs(float(m1) - float(m0[0])) <= 1e-10 * abs(float(m0[0]))
+    assert float((g1 - g0[0]).abs().max()) <= 1e-8 * float(g0[0].abs().max())
+    # MLL-only entry
+    m2, _, _ = ops.sm_mll_grad_large(x[0], y[0], nz[0], raw[0], kinds, lb[0], ub[0], 0, 4, True,
+                                     want_grad=False)
+    assert float(m2) == float(m1)
+
+
+def test_large_path_c3_size_properties(cuda_device):
+    """C3: 8 bands x 1000 epochs (n = 8000), 2-D SM-4, FixedNoise, fp64.  The gradient agrees
+    with a central finite difference of the MLL along a random direction, and the MLL does not
+    depend on the order of the points."""
+    from pgmuvi_b200 import ops, synthetic as S
+    bt = S.make_batch_2d(1, 8, 1000, Q=4, learn_noise=False, seed0=31)
+    dev = cuda_device
+    x, y, nz, raw = (_t(bt[k][0], dev) for k in ("x", "y", "noise", "raw"))
+    kinds, lb, ub = _t(bt["kinds"], dev, torch.int32), _t(bt["lb"][0], dev), _t(bt["ub"][0], dev)
+    ev = lambda r, wg=False, xx=x, yy=y, nn=nz: ops.sm_mll_grad_large(
+        xx, yy, nn, r, kinds, lb, ub, 1, 4, False, want_grad=wg)
+    mll, grad, info = ev(raw, True)
+    assert info == 0 and np.isfinite(float(mll)) and bool(torch.isfinite(grad).all())
+    gen = torch.Generator().manual_seed(0)
+    u = torch.randn(raw.shape, generator=gen, dtype=torch.float64).to(dev)
+    u = u / u.norm()
+    h = 1e-5
+    fd = (float(ev(raw + h * u)[0]) - float(ev(raw - h * u)[0])) / (2 * h)
+    an = float((grad * u).sum())
+    assert abs(fd - an) <= 1e-5 * max(1.0, abs(an))
+    perm = torch.randperm(x.shape[0], generator=gen).to(dev)
+    mp = float(ev(raw, False, x[perm], y[perm], nz[perm])[0])
+    assert abs(mp - float(mll)) <= 1e-9 * abs(float(mll))
