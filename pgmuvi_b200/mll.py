@@ -192,6 +192,23 @@ def _sm_mll_backward(ctx, g_mll, g_grad, g_info):
 ops.sm_mll_grad.register_autograd(_sm_mll_backward, setup_context=_sm_mll_setup_context)
 
 
+class _LargeMLL(torch.autograd.Function):
+    """MLL of ONE large GP through the whole-device path (``ops.sm_mll_grad_large``)."""
+
+    @staticmethod
+    def forward(ctx, raw, x, y, fixed, kinds, lb, ub, kind, Q, learn_noise, holder):
+        mll, grad, info = ops.sm_mll_grad_large(x, y, fixed, raw, kinds, lb, ub, kind, Q,
+                                                learn_noise, True)
+        holder.append(info)
+        ctx.save_for_backward(grad)
+        return mll
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (g * grad,) + (None,) * 10
+
+
 class B200ExactMarginalLogLikelihood(torch.nn.Module):
     """Per-datum exact marginal log-likelihood of an SM exact GP, computed on the B200."""
 
@@ -213,13 +230,27 @@ class B200ExactMarginalLogLikelihood(torch.nn.Module):
         raw = pk.raw()
         dev = engine_device(raw)
         f64 = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float64)
+        from .trainers import LARGE_N
+        if x.shape[0] > LARGE_N:
+            holder = []
+            mll = _LargeMLL.apply(raw.to(device=dev, dtype=torch.float64), f64(x).contiguous(),
+                                  f64(target).contiguous(),
+                                  None if pk.fixed_noise is None else f64(pk.fixed_noise),
+                                  pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev), pk.kind, pk.Q,
+                                  pk.learn_noise, holder)
+            self._raise_for(holder[0])
+            return mll.to(dtype=raw.dtype, device=raw.device)
         mll, grad, info = ops.sm_mll_grad(
             f64(x).unsqueeze(0).contiguous(), f64(target).unsqueeze(0).contiguous(),
             None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
             raw.to(device=dev, dtype=torch.float64).unsqueeze(0),
             pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev), None, pk.kind, pk.Q, pk.learn_noise,
             True)
-        code = int(info.item())
+        self._raise_for(int(info.item()))
+        return mll[0].to(dtype=raw.dtype, device=raw.device)
+
+    def _raise_for(self, code):
+        from .gp import NanError, NotPSDError
         self.last_info = code
         if code == -1:
             raise NanError("cholesky_cpu: NaN values found in the covariance matrix")
@@ -231,4 +262,3 @@ class B200ExactMarginalLogLikelihood(torch.nn.Module):
             from .gp import NumericalWarning
             warnings.warn(f"A not p.d., added jitter of {1e-8 * 10 ** (code - 1):.1e} to the "
                           "diagonal", NumericalWarning)
-        return mll[0].to(dtype=raw.dtype, device=raw.device)

@@ -28,6 +28,10 @@ from .batch import optimizer_defaults
 from .mll import (B200ExactMarginalLogLikelihood, UnsupportedModelError, engine_device,  # noqa: F401
                   pack_model)
 
+# light curves longer than this are factored by the whole device (pgm_sm_mll_grad_large_f64)
+# instead of one thread block (the fused kernel's per-block scratch grows with n^2)
+LARGE_N = 2048
+
 _X_KEYS = ("mixture_means", "mixture_scales")      # lightcurve.py:9036-9041
 _Y_KEYS = ("noise", "mean_module")
 
@@ -135,6 +139,9 @@ def train(lightcurve=None, model=None, likelihood=None, train_x=None, train_y=No
     x = train_x if train_x.dim() > 1 else train_x.unsqueeze(-1)
     raw = f64(pk.raw()).unsqueeze(0).contiguous()
     od = optimizer_defaults(optim, eps)
+    if x.shape[0] > LARGE_N:
+        return _train_large(lightcurve, model, pk, f64(x), f64(train_y), raw[0], od, float(lr),
+                            int(maxiter), int(miniter), stop, int(stopavg), dev)
     loss_hist, raw_hist, n_iter, info = ops.sm_fit(
         f64(x).unsqueeze(0).contiguous(), f64(train_y).unsqueeze(0).contiguous(),
         None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
@@ -162,6 +169,42 @@ def train(lightcurve=None, model=None, likelihood=None, train_x=None, train_y=No
         stopval = np.std(results["loss"][-stopavg:])
         print(f"""Average change in loss over the last {stopavg} iterations
                     was {stopval}.\n This is < {stop}, so we will end training here.""")
+    return results
+
+
+def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, stop, stopavg, dev):
+    """trainers.py:177-207 for ONE large GP: each iteration is a whole-device MLL+gradient
+    (``ops.sm_mll_grad_large``) followed by the batched optimiser kernel on the [1, P] raw
+    vector; the loss is read back once per iteration (the early-stop rule needs it)."""
+    from .gp import NanError, NotPSDError
+    fixed = None if pk.fixed_noise is None else pk.fixed_noise.detach().to(device=dev,
+                                                                           dtype=torch.float64)
+    kinds, lb, ub = pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev)
+    raw = raw.clone().reshape(1, -1)
+    m, v = torch.zeros_like(raw), torch.zeros_like(raw)
+    raws, losses = [raw[0].cpu().clone()], []
+    for i in range(maxiter):
+        mll, grad, code = ops.sm_mll_grad_large(x, y, fixed, raw[0], kinds, lb, ub, pk.kind, pk.Q,
+                                                pk.learn_noise, True)
+        if code < 0:
+            pk.scatter_raw_(raws[-1])
+            if code == -1:
+                raise NanError("cholesky_cpu: NaN values found in the covariance matrix "
+                               f"at training iteration {i}")
+            raise NotPSDError("Matrix not positive definite after repeatedly adding jitter up "
+                              f"to 1.0e-06 (training iteration {i}).")
+        ops.optim_step(raw, grad.reshape(1, -1), m, v, None, od["optim_kind"], lr, od["beta1"],
+                       od["beta2"], od["eps"], od["weight_decay"], i + 1)
+        losses.append(np.asarray(-float(mll), dtype=np.float64))
+        raws.append(raw[0].cpu().clone())
+        if stop and i > miniter and np.std(losses[-stopavg:]) < stop:
+            print(f"""Average change in loss over the last {stopavg} iterations
+                    was {np.std(losses[-stopavg:])}.\n This is < {stop}, so we will end training here.""")
+            break
+    pk.scatter_raw_(raws[-1])
+    results = {"loss": losses,
+               "delta_loss": [losses[i] - losses[i - 1] for i in range(1, len(losses))]}
+    results.update(history_from_raw(torch.stack(raws), pk, model, lightcurve))
     return results
 
 

@@ -77,3 +77,43 @@ def test_large_path_c3_size_properties(cuda_device):
     perm = torch.randperm(x.shape[0], generator=gen).to(dev)
     mp = float(ev(raw, False, x[perm], y[perm], nz[perm])[0])
     assert abs(mp - float(mll)) <= 1e-9 * abs(float(mll))
+
+
+def test_train_routes_long_light_curves_through_the_large_path(cuda_device):
+    """trainers.train on n = 2600 > LARGE_N: host loop over the whole-device MLL+gradient and
+    the optimiser kernel, against the oracle's restatement of pgmuvi/trainers.py:177-207; the
+    torch-optimizer seam (loss.backward with a stock optimiser) follows the same trajectory."""
+    from oracle import ModelSpec, train_loop
+    from pgmuvi_b200.lightcurve import Lightcurve
+    from pgmuvi_b200.mll import pack_model
+    from pgmuvi_b200.trainers import LARGE_N, train
+    n = 2600
+    assert n > LARGE_N
+    outs = []
+    for use_instance in (False, True):
+        rng = np.random.default_rng(11)
+        t = np.sort(rng.uniform(0.0, 900.0, n))
+        y = np.sin(2 * np.pi * t / 61.0) + 0.1 * rng.standard_normal(n)
+        lc = Lightcurve(t, y, yerr=np.full(n, 0.1), max_samples=None).double()
+        lc.set_model("1D", num_mixtures=2)
+        lc.double()
+        lc.set_default_constraints()
+        lc.model.initialize(**{"covar_module.mixture_means": torch.tensor([14.5, 30.0]),
+                               "covar_module.mixture_scales": torch.tensor([1.5, 1.0])})
+        pk = pack_model(lc.model)
+        if not use_instance:
+            spec = ModelSpec(d=1, Q=2, kind=0, learn_noise=False)
+            ref = train_loop(lc._xdata_transformed.double().unsqueeze(-1),
+                             lc._ydata_transformed.double(), pk.fixed_noise.double(),
+                             pk.raw().detach().double(), pk.kinds, pk.lb, pk.ub, spec, maxiter=3,
+                             miniter=3, stop=None, lr=0.05, optim="Adam")
+            res = train(lc, maxiter=3, miniter=3, stop=None, lr=0.05, optim="Adam")
+            assert np.allclose(np.array(res["loss"], dtype=float),
+                               np.array(ref["loss"], dtype=float), rtol=1e-9, atol=1e-12)
+            assert np.allclose(pk.raw().detach().numpy(), ref["raw"][-1], rtol=1e-7, atol=1e-9)
+        else:
+            opt = torch.optim.Adam(lc.model.parameters(), lr=0.05)
+            res = train(lc, maxiter=3, miniter=3, stop=None, optim=opt)
+        outs.append(np.array(res["loss"], dtype=float))
+        assert len(res["covar_module.mixture_means"]) == 4
+    assert np.allclose(outs[0], outs[1], rtol=1e-9, atol=1e-12)
