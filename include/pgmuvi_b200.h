@@ -94,26 +94,27 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * ONE large exact GP (BASELINE configs C3 n = 8000 / C4 n = 32768; "single large GPs stay on
- * one GPU"): same quantities as pgm_sm_mll_grad_f64 for B = 1, but the whole device factors
- * the one K~ (HBM-resident lower triangle of 64x64 tile images, right-looking blocked
- * Cholesky + inverse + gradient contraction, one output tile per thread block).  Replaces
- * the same reference calls (pgmuvi/trainers.py:179-181) under
+ * Staged engine: the same quantities as pgm_sm_mll_grad_f64 (same arguments), computed stage
+ * by stage over the whole device: K~ of every light curve lives in HBM as the lower triangle
+ * of 64x64 tile images (right-looking blocked Cholesky + inverse + gradient contraction, one
+ * output tile per thread block, one launch per dependency stage carrying B x tiles blocks).
+ *   B = 1, n_max large: ONE large exact GP (BASELINE configs C3 n = 8000 / C4 n = 32768;
+ *                       "single large GPs stay on one GPU");
+ *   B large:            batches whose light curves are too long for one block's scratch.
+ * Replaces the same reference calls (pgmuvi/trainers.py:179-181) under
  * gpytorch.settings.fast_computations(False, False, False), i.e. the exact Cholesky branch
  * the reference takes only for n <= 800.
- *
- *  x [n,d], y [n], fixed_noise [n] or NULL, raw [P], con_* [P]   device pointers
- *  mll [1], grad_raw [P]                                          device, out
- *  info_host                                                      HOST int32, out
- * The call is BLOCKING (it synchronises `stream` once per Cholesky attempt to read the
- * failure flag of the jitter ladder).
+ * The call is BLOCKING: it synchronises `stream` once per Cholesky pass to learn whether any
+ * light curve must repeat it with more jitter.  B <= 65535.
  */
-size_t pgm_large_workspace_bytes(int n);
-int pgm_sm_mll_grad_large_f64(const double* x, const double* y, const double* fixed_noise,
-                              const double* raw, const int32_t* con_kind, const double* con_lb,
-                              const double* con_ub, int n, int d, int Q, int kernel_kind,
-                              int flags, double* mll, double* grad_raw, int32_t* info_host,
-                              void* workspace, size_t workspace_bytes, void* stream);
+size_t pgm_staged_workspace_bytes(int n_max, int B);
+int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const double* y,
+                               const double* fixed_noise, const double* raw,
+                               const int32_t* con_kind, const double* con_lb,
+                               const double* con_ub, int B, int n_max, int d, int Q,
+                               int kernel_kind, int flags, double* mll, double* grad_raw,
+                               int32_t* info, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /*
  * Dense covariance K + D of each light curve, written to K_out [B, n_max, n_max] (rows /

@@ -24,7 +24,7 @@ OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 EXPORTS = (
     "pgm_version", "pgm_last_error", "pgm_workspace_bytes", "pgm_sm_mll_grad_f64",
     "pgm_sm_kernel_dense_f64", "pgm_optim_step_f64", "pgm_sm_fit_f64", "pgm_peak_probe",
-    "pgm_large_workspace_bytes", "pgm_sm_mll_grad_large_f64",
+    "pgm_staged_workspace_bytes", "pgm_sm_mll_grad_staged_f64",
 )
 
 _lib = None
@@ -63,12 +63,10 @@ def load():
                                    c_int, c_int, c_int, c_double, c_double, c_double, c_double,
                                    c_double, c_int, c_int, c_double, c_int, dp, dp, ip, ip, dp,
                                    vp, c_size_t, vp]
-    lib.pgm_large_workspace_bytes.restype = c_size_t
-    lib.pgm_large_workspace_bytes.argtypes = [c_int]
-    lib.pgm_sm_mll_grad_large_f64.restype = c_int
-    lib.pgm_sm_mll_grad_large_f64.argtypes = [dp, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int,
-                                              c_int, c_int, dp, dp, POINTER(c_int32), vp,
-                                              c_size_t, vp]
+    lib.pgm_staged_workspace_bytes.restype = c_size_t
+    lib.pgm_staged_workspace_bytes.argtypes = [c_int, c_int]
+    lib.pgm_sm_mll_grad_staged_f64.restype = c_int
+    lib.pgm_sm_mll_grad_staged_f64.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
     lib.pgm_peak_probe.restype = c_int
     lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
     _lib = lib

@@ -14,7 +14,7 @@ template <int KIND, int QT, int D> int launch_eval(const EvalArgs& A0, cudaStrea
 template <int KIND, int QT, int D> int launch_fit(const FitArgs& F, cudaStream_t st);
 template <int KIND, int QT, int D> int launch_dense(const EvalArgs& A, double* K, cudaStream_t st);
 template <int KIND, int QT, int D>
-int launch_large(const LargeArgs& A, int want_grad, int32_t* info_host, cudaStream_t st);
+int launch_large(const LargeArgs& A, int want_grad, cudaStream_t st);
 
 thread_local std::string g_err;
 int fail(const std::string& m) {
@@ -148,30 +148,33 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
   return 0;
 }
 
-size_t pgm_large_workspace_bytes(int n) {
-  return n < 1 ? 0 : pgm::large_ws_elems(n) * sizeof(double);
+size_t pgm_staged_workspace_bytes(int n_max, int B) {
+  return (n_max < 1 || B < 1) ? 0 : pgm::large_ws_bytes(n_max, B);
 }
 
-int pgm_sm_mll_grad_large_f64(const double* x, const double* y, const double* fixed_noise,
-                              const double* raw, const int32_t* con_kind, const double* con_lb,
-                              const double* con_ub, int n, int d, int Q, int kernel_kind,
-                              int flags, double* mll, double* grad_raw, int32_t* info_host,
-                              void* workspace, size_t workspace_bytes, void* stream) {
-  if (int r = check_common(1, n, d, Q, kernel_kind)) return r;
-  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info_host || !workspace)
+int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const double* y,
+                               const double* fixed_noise, const double* raw,
+                               const int32_t* con_kind, const double* con_lb,
+                               const double* con_ub, int B, int n_max, int d, int Q,
+                               int kernel_kind, int flags, double* mll, double* grad_raw,
+                               int32_t* info, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
     return fail("null pointer argument");
   if ((flags & PGM_FLAG_GRAD) && !grad_raw) return fail("PGM_FLAG_GRAD needs grad_raw");
-  if (flags & PGM_FLAG_BOUNDS_PER_LC) return fail("the large-GP entry takes shared bounds [P]");
-  if (workspace_bytes < pgm_large_workspace_bytes(n))
-    return fail("workspace too small (see pgm_large_workspace_bytes)");
+  if (workspace_bytes < pgm_staged_workspace_bytes(n_max, B))
+    return fail("workspace too small (see pgm_staged_workspace_bytes)");
   pgm::LargeArgs A;
-  A.x = x; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
+  A.x = x; A.n_valid = n_valid; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
   A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
-  A.n = n; A.Q = Q; A.flags = flags; A.mll = mll; A.grad = grad_raw;
+  A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags;
+  A.mll = mll; A.grad = grad_raw; A.info = info;
   A.ws = static_cast<double*>(workspace);
   const int want_grad = (flags & PGM_FLAG_GRAD) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PGM_DISPATCH(launch_large, A, want_grad, info_host, st);
+  PGM_DISPATCH(launch_large, A, want_grad, st);
   return 0;
 }
 

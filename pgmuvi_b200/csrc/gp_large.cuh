@@ -15,6 +15,13 @@
 //   G  K^-1_ij = sum_k X_ki^T X_kj per tile, contracted at once with W = alpha alpha^T - K^-1
 //      and the regenerated dK/dtheta; per-tile partial sums, deterministic final reduction.
 //
+// The same kernels take a batch index (blockIdx.y = light curve): a batch of B light curves
+// advances stage by stage in lock step, every launch carrying B x (tiles of the stage)
+// independent blocks for the hardware scheduler to balance ("staged" engine; the fused
+// one-block-per-light-curve kernel of gp_fused.cuh is the other engine).  The jitter ladder of
+// psd_safe_cholesky is per light curve: state[b] / attempt[b] / fail[b] live behind the
+// per-light-curve workspaces and failed members alone repeat the P phase.
+//
 // Reference semantics as gp_fused.cuh (pgmuvi/trainers.py:177-182);
 // the exact-Cholesky branch for n > 800 is the north star's definition of the path (F6).
 #pragma once
@@ -30,13 +37,31 @@ constexpr int LG_PAR_TH = 0, LG_PAR_JC = 64, LG_PAR_WQ = 128, LG_PAR_AQ = 136, L
 struct LargeWs {
   double *tilesL, *tilesX, *tilesT;
   double *fx, *fcs, *alpha, *rhs, *z, *dn, *par, *ldz, *gpart;
-  int* fail;
 };
+// batch state behind the B per-light-curve workspaces
+struct BatchState {
+  int *state;     // 0 = needs the P phase, 1 = factored, 2 = failed
+  int *attempt;   // jitter rung 0..3
+  int *fail;      // potrf failure bits of the current pass
+  int *count;     // light curves that must repeat the P phase
+};
+enum { LG_ACTIVE = 0, LG_FACTORED = 1, LG_FAILED = 2 };
 
 __host__ __device__ inline size_t large_ws_elems(int n) {
   const size_t N = (n + TS - 1) / TS, npad = N * TS, ntri = N * (N + 1) / 2;
   return 2 * ntri * TT + N * TT + (size_t)(LG_NFB_MAX + 4) * npad + LG_PAR + 2 * N +
          ntri * LG_GP + 16;
+}
+__host__ __device__ inline size_t large_ws_bytes(int n_max, int B) {
+  return large_ws_elems(n_max) * sizeof(double) * (size_t)B + (size_t)(3 * B + 4) * sizeof(int);
+}
+__host__ __device__ inline BatchState make_batch_state(double* base, int n_max, int B) {
+  BatchState st;
+  st.state = reinterpret_cast<int*>(base + large_ws_elems(n_max) * (size_t)B);
+  st.attempt = st.state + B;
+  st.fail = st.attempt + B;
+  st.count = st.fail + B;
+  return st;
 }
 __host__ __device__ inline LargeWs make_large_ws(double* base, int n) {
   const size_t N = (n + TS - 1) / TS, npad = N * TS, ntri = N * (N + 1) / 2;
@@ -53,23 +78,47 @@ __host__ __device__ inline LargeWs make_large_ws(double* base, int n) {
   w.par = w.dn + npad;
   w.ldz = w.par + LG_PAR;
   w.gpart = w.ldz + 2 * N;
-  w.fail = reinterpret_cast<int*>(w.gpart + ntri * LG_GP);
   return w;
 }
 
 struct LargeArgs {
-  const double* x;
-  const double* y;
-  const double* fixed_noise;
-  const double* raw;
+  const double* x;            // [B, n_max, D]
+  const int32_t* n_valid;     // [B] or null
+  const double* y;            // [B, n_max]
+  const double* fixed_noise;  // [B, n_max] or null
+  const double* raw;          // [B, P]
   const int32_t* con_kind;
   const double* con_lb;
   const double* con_ub;
-  int n, Q, flags;
-  double* mll;
-  double* grad;
+  int B, n_max, Q, flags;
+  double* mll;                // [B]
+  double* grad;               // [B, P]
+  int32_t* info;              // [B] (device)
   double* ws;
 };
+
+// the light curve of this block: its size and workspace
+struct LcView {
+  int b, n, N, npad;
+  LargeWs w;
+  BatchState st;
+};
+__device__ __forceinline__ LcView lc_view(const LargeArgs& A) {
+  LcView v;
+  v.b = blockIdx.y;
+  v.n = A.n_valid ? A.n_valid[v.b] : A.n_max;
+  v.N = (v.n + TS - 1) / TS;
+  v.npad = v.N * TS;
+  v.w = make_large_ws(A.ws + large_ws_elems(A.n_max) * (size_t)v.b, A.n_max);
+  v.st = make_batch_state(A.ws, A.n_max, A.B);
+  return v;
+}
+__device__ __forceinline__ double lg_jitter(int attempt) {
+  if (attempt <= 0) return 0.0;
+  double j = 1e-8;
+  for (int t = 1; t < attempt; ++t) j *= 10.0;
+  return j;
+}
 
 __device__ __forceinline__ double* lg_tile(double* base, int i, int j) {
   return base + ((size_t)i * (i + 1) / 2 + j) * TT;
@@ -91,16 +140,20 @@ __global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
   constexpr int DS = C::DS;
   __shared__ double theta[64], jac[64];
   const int tid = threadIdx.x;
+  const LcView v = lc_view(A);
+  if (v.st.state[v.b] != LG_ACTIVE) return;
+  const LargeWs& w = v.w;
   const int Q = A.Q;
   const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
   const int P = param_count<KIND, QT, D>(Q, learn_noise);
   const int o_noise = 1 + Q + 2 * Q * DS, o_lam = o_noise + (learn_noise ? 1 : 0);
-  LargeWs w = make_large_ws(A.ws, A.n);
-  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  const int n = v.n, npad = v.npad;
+  if (blockIdx.x * NTHREADS >= npad) return;
   if (tid < P) {
-    const double rv = A.raw[tid];
+    const double rv = A.raw[(size_t)v.b * P + tid];
     const int kd = A.con_kind[tid];
-    const double lb = A.con_lb[tid], ub = A.con_ub[tid];
+    const size_t bo = (A.flags & PGM_FLAG_BOUNDS_PER_LC) ? (size_t)v.b * P : 0;
+    const double lb = A.con_lb[bo + tid], ub = A.con_ub[bo + tid];
     double th = rv, jc = 1.0;
     if (kd == 1) {
       th = softplus_d(rv) + lb;
@@ -132,9 +185,12 @@ __global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
   const int i = blockIdx.x * NTHREADS + tid;
   if (i >= npad) return;
   const bool valid = i < n;
+  const double* xb = A.x + (size_t)v.b * A.n_max * D;
+  const double* yb = A.y + (size_t)v.b * A.n_max;
+  const double* fnb = A.fixed_noise ? A.fixed_noise + (size_t)v.b * A.n_max : nullptr;
 #pragma unroll
   for (int dd = 0; dd < D; ++dd) {
-    const double xc = valid ? (A.x[(size_t)i * D + dd] - A.x[dd]) : 0.0;
+    const double xc = valid ? (xb[(size_t)i * D + dd] - xb[dd]) : 0.0;
     w.fx[(size_t)dd * npad + i] = xc;
     if (dd < DS) {
 #pragma unroll
@@ -146,8 +202,8 @@ __global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
       }
     }
   }
-  w.rhs[i] = valid ? (A.y[i] - mean) : 0.0;
-  w.dn[i] = valid ? ((A.fixed_noise ? A.fixed_noise[i] : 0.0) + lnoise) : 0.0;
+  w.rhs[i] = valid ? (yb[i] - mean) : 0.0;
+  w.dn[i] = valid ? ((fnb ? fnb[i] : 0.0) + lnoise) : 0.0;
 }
 
 // per-point data of tile row / col I -> rowv / colv (cp.async, as in the fused kernel)
@@ -177,14 +233,16 @@ __device__ __forceinline__ void lg_prefetch_side(double* vec, const LargeWs& w, 
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
 __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
-    lg_update(LargeArgs A, int mode, int jj, int k0, int k1, int build, double jitter) {
+    lg_update(LargeArgs A, int mode, int jj, int k0, int k1, int build) {
   using C = Cfg<KIND, QT, D>;
   constexpr int DS = C::DS;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
-  LargeWs w = make_large_ws(A.ws, A.n);
-  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  const LcView v = lc_view(A);
+  if (v.st.state[v.b] != LG_ACTIVE) return;
+  const LargeWs& w = v.w;
+  const int n = v.n, N = v.N, npad = v.npad;
   int i, j;
   if (mode == 0) {
     j = jj;
@@ -195,6 +253,9 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
     i = jj + a;
     j = jj + b;
   }
+  if (i >= N || j >= N) return;
+  if (v.st.fail[v.b]) return;
+  const double jitter = lg_jitter(v.st.attempt[v.b]);
   double* stages = sm + C::SM_STAGES;
   double* Cst = stages + 2 * OPBUF;
   double* rowv = sm + C::SM_ROW;
@@ -229,10 +290,10 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
       for (int ni = 0; ni < 2; ++ni) {
         const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, 0);
         double2* p = reinterpret_cast<double2*>(out + img(r, c));
-        double2 v = *p;
-        v.x -= acc[mi][ni][0];
-        v.y -= acc[mi][ni][1];
-        *p = v;
+        double2 vv = *p;
+        vv.x -= acc[mi][ni][0];
+        vv.y -= acc[mi][ni][1];
+        *p = vv;
       }
     return;
   }
@@ -277,7 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
 // z_j = X_jj rhs_j, log-det and z^T z partials
 // ------------------------------------------------------------------------------------
 constexpr size_t LG_DIAG_SMEM = (size_t)(2 * S_ELEMS + 4 * TS + 8) * sizeof(double);
-static __global__ void __launch_bounds__(NTHREADS) lg_diag(double* ws, int n, int j) {
+static __global__ void __launch_bounds__(NTHREADS) lg_diag(LargeArgs A, int j) {
   extern __shared__ __align__(16) double sm[];
   double* S = sm;
   double* S2 = sm + S_ELEMS;
@@ -286,34 +347,37 @@ static __global__ void __launch_bounds__(NTHREADS) lg_diag(double* ws, int n, in
   double* red = zi + TS;   // [2 * 64]
   int* s_fail = reinterpret_cast<int*>(red + 2 * TS);
   const int tid = threadIdx.x;
-  LargeWs w = make_large_ws(ws, n);
+  const LcView v = lc_view(A);
+  if (v.st.state[v.b] != LG_ACTIVE || j >= v.N) return;
+  if (v.st.fail[v.b]) return;   // an earlier diagonal block failed: keep its failure bits
+  const LargeWs& w = v.w;
   double* tl = lg_tile(w.tilesL, j, j);
   if (tid == 0) *s_fail = 0;
   for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
     const int r = idx >> 5, c2 = (idx & 31) * 2;
-    const double2 v = *reinterpret_cast<const double2*>(tl + img(r, c2));
-    S[r * LD_S + c2] = v.x;
-    S[r * LD_S + c2 + 1] = v.y;
+    const double2 vv = *reinterpret_cast<const double2*>(tl + img(r, c2));
+    S[r * LD_S + c2] = vv.x;
+    S[r * LD_S + c2 + 1] = vv.y;
   }
   if (tid < TS) zi[tid] = w.rhs[j * TS + tid];
   __syncthreads();
   potrf_inv_64(S, S2, dinv, s_fail);
   if (*s_fail) {
-    if (tid == 0) atomicOr(w.fail, *s_fail);
+    if (tid == 0) atomicOr(v.st.fail + v.b, *s_fail);
     return;
   }
   double* tx = lg_tile(w.tilesX, j, j);
   double* tt = w.tilesT + (size_t)j * TT;
   for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
     const int r = idx >> 5, c2 = (idx & 31) * 2;
-    double2 v, vt;
-    v.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
-    v.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
+    double2 vv, vt;
+    vv.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
+    vv.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
     vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
     vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
     const int o = img(r, c2);
-    *reinterpret_cast<double2*>(tl + o) = v;
-    *reinterpret_cast<double2*>(tx + o) = v;
+    *reinterpret_cast<double2*>(tl + o) = vv;
+    *reinterpret_cast<double2*>(tx + o) = vv;
     *reinterpret_cast<double2*>(tt + o) = vt;
   }
   {
@@ -340,7 +404,7 @@ static __global__ void __launch_bounds__(NTHREADS) lg_diag(double* ws, int n, in
 // L_ij = C_ij X_jj^T for i > j;  rhs_i -= L_ij z_j
 // ------------------------------------------------------------------------------------
 constexpr size_t LG_TRSM_SMEM = (size_t)(4 * OPBUF + 5 * TS + 8) * sizeof(double);
-static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(double* ws, int n, int j) {
+static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(LargeArgs A, int j) {
   extern __shared__ __align__(16) double sm[];
   double* Cst = sm;
   double* R = sm + 2 * OPBUF;
@@ -349,8 +413,11 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(double* ws, int n,
   const unsigned bar = smem_u32(red + 4 * TS);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
-  LargeWs w = make_large_ws(ws, n);
+  const LcView v = lc_view(A);
   const int i = j + 1 + blockIdx.x;
+  if (v.st.state[v.b] != LG_ACTIVE || i >= v.N) return;
+  if (v.st.fail[v.b]) return;   // a diagonal block of this light curve already failed
+  const LargeWs& w = v.w;
   double* tij = lg_tile(w.tilesL, i, j);
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -386,12 +453,35 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(double* ws, int n,
   if (tid == 0) bulk_wait_all();
 }
 
+// per-light-curve jitter ladder (psd_safe_cholesky, A.5) after a P pass
+static __global__ void lg_ladder(LargeArgs A) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= A.B) return;
+  BatchState st = make_batch_state(A.ws, A.n_max, A.B);
+  if (st.state[b] != LG_ACTIVE) return;
+  const int fl = st.fail[b];
+  if (!fl) {
+    st.state[b] = LG_FACTORED;
+    A.info[b] = st.attempt[b];
+  } else if (fl & 2) {
+    st.state[b] = LG_FAILED;
+    A.info[b] = -1;
+  } else if (st.attempt[b] < 3) {
+    st.attempt[b] += 1;
+    st.fail[b] = 0;
+    atomicAdd(st.count, 1);
+  } else {
+    st.state[b] = LG_FAILED;
+    A.info[b] = -2;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // row i of X = L^-1:  X_ij^T = -(sum_{k=j}^{i-1} X_kj^T L_ik^T) X_ii^T,  j = blockIdx.x < i
 // (reads L from tilesL, writes X^T tiles to tilesX: blocks of one launch never conflict)
 // ------------------------------------------------------------------------------------
 constexpr size_t LG_INV_SMEM = (size_t)(6 * OPBUF + 16) * sizeof(double);
-static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(double* ws, int n, int i) {
+static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(LargeArgs A, int i) {
   extern __shared__ __align__(16) double sm[];
   double* stages = sm;
   double* Cst = stages + 2 * OPBUF;
@@ -400,7 +490,9 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(double* ws, int
   const unsigned rbar = bars + 8 * 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
-  LargeWs w = make_large_ws(ws, n);
+  const LcView v = lc_view(A);
+  if (v.st.state[v.b] != LG_FACTORED || i >= v.N) return;
+  const LargeWs& w = v.w;
   const int j = blockIdx.x;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (2 + s), NTHREADS / 32); }
@@ -432,11 +524,13 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(double* ws, int
 }
 
 // alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i   (tilesX holds X_jj and the X_ij^T tiles)
-static __global__ void __launch_bounds__(NTHREADS) lg_alpha(double* ws, int n) {
+static __global__ void __launch_bounds__(NTHREADS) lg_alpha(LargeArgs A) {
   __shared__ double scr[4 * TS];
   const int tid = threadIdx.x;
-  LargeWs w = make_large_ws(ws, n);
-  const int N = (n + TS - 1) / TS, j = blockIdx.x;
+  const LcView v = lc_view(A);
+  const int N = v.N, j = blockIdx.x;
+  if (v.st.state[v.b] != LG_FACTORED || j >= N) return;
+  const LargeWs& w = v.w;
   const int m = tid & 63, part = tid >> 6;
   double s = 0.0;
   {
@@ -469,10 +563,13 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
-  LargeWs w = make_large_ws(A.ws, A.n);
-  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  const LcView v = lc_view(A);
+  if (v.st.state[v.b] != LG_FACTORED) return;
+  const LargeWs& w = v.w;
+  const int n = v.n, N = v.N, npad = v.npad;
   int i, j;
   tri_unrank(blockIdx.x, i, j);
+  if (i >= N) return;
   double* stages = sm + C::SM_STAGES;
   double* R = sm + C::SM_S;
   double* rowv = sm + C::SM_ROW;
@@ -531,53 +628,56 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
       k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
     }
   }
-  double v[C::NV];
+  double vv[C::NV];
 #pragma unroll
-  for (int t = 0; t < C::NG; ++t) v[t] = ga[t];
-  v[C::NG] = trW;
+  for (int t = 0; t < C::NG; ++t) vv[t] = ga[t];
+  vv[C::NG] = trW;
   __syncthreads();
-  block_reduce<C::NV>(v, red, fin);
+  block_reduce<C::NV>(vv, red, fin);
   if (tid < C::NV) w.gpart[(size_t)blockIdx.x * LG_GP + tid] = fin[tid];
 }
 
 // ------------------------------------------------------------------------------------
-// final reduction (fixed order), MLL, gradient assembly
+// final reduction (fixed order), MLL, gradient assembly: one block per light curve
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int info, int want_grad) {
+__global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int want_grad) {
   using C = Cfg<KIND, QT, D>;
   constexpr int DS = C::DS;
   __shared__ double red[8 * (C::NV + 4)], fin[C::NV + 4];
   const int tid = threadIdx.x;
-  LargeWs w = make_large_ws(A.ws, A.n);
-  const int n = A.n, N = (n + TS - 1) / TS;
+  const LcView v = lc_view(A);
+  const LargeWs& w = v.w;
+  const int n = v.n, N = v.N;
   const int Q = A.Q;
   const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
   const int P = param_count<KIND, QT, D>(Q, learn_noise);
   const int o_noise = 1 + Q + 2 * Q * DS, o_lam = o_noise + (learn_noise ? 1 : 0);
-  if (info < 0) {
-    if (tid == 0) *A.mll = nan("");
-    if (want_grad && tid < P) A.grad[tid] = nan("");
+  double* mll_out = A.mll + v.b;
+  double* grad_out = A.grad ? A.grad + (size_t)v.b * P : nullptr;
+  if (v.st.state[v.b] != LG_FACTORED) {
+    if (tid == 0) *mll_out = nan("");
+    if (want_grad && tid < P) grad_out[tid] = nan("");
     return;
   }
-  double v[C::NV + 3];
+  double vv[C::NV + 3];
 #pragma unroll
-  for (int t = 0; t < C::NV + 3; ++t) v[t] = 0.0;
+  for (int t = 0; t < C::NV + 3; ++t) vv[t] = 0.0;
   for (int jb = tid; jb < N; jb += NTHREADS) {
-    v[C::NV + 1] += w.ldz[2 * jb];
-    v[C::NV + 2] += w.ldz[2 * jb + 1];
+    vv[C::NV + 1] += w.ldz[2 * jb];
+    vv[C::NV + 2] += w.ldz[2 * jb + 1];
   }
   if (want_grad) {
     const int njobs = N * (N + 1) / 2;
     for (int t = tid; t < njobs; t += NTHREADS)
 #pragma unroll
-      for (int k = 0; k < C::NV; ++k) v[k] += w.gpart[(size_t)t * LG_GP + k];
-    for (int i2 = tid; i2 < n; i2 += NTHREADS) v[C::NV] += w.alpha[i2];
+      for (int k = 0; k < C::NV; ++k) vv[k] += w.gpart[(size_t)t * LG_GP + k];
+    for (int i2 = tid; i2 < n; i2 += NTHREADS) vv[C::NV] += w.alpha[i2];
   }
-  block_reduce<C::NV + 3>(v, red, fin);
+  block_reduce<C::NV + 3>(vv, red, fin);
   if (tid == 0) {
     const double logdet = 2.0 * fin[C::NV + 1], inv_quad = fin[C::NV + 2];
-    *A.mll = -0.5 * (inv_quad + logdet + (double)n * 1.8378770664093454836) / n;
+    *mll_out = -0.5 * (inv_quad + logdet + (double)n * 1.8378770664093454836) / n;
   }
   if (!want_grad || tid >= P) return;
   const double* theta = w.par + LG_PAR_TH;
@@ -609,7 +709,7 @@ __global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int info, int
     }
     gv = half * cf * fin[QT + 2 * QT * DS + t];
   }
-  A.grad[tid] = gv * w.par[LG_PAR_JC + tid];
+  grad_out[tid] = gv * w.par[LG_PAR_JC + tid];
 }
 
 }  // namespace pgm

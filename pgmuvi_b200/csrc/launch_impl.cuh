@@ -94,14 +94,16 @@ int launch_dense(const pgm::EvalArgs& A, double* K, cudaStream_t st) {
 }
 
 
-// Single large GP: the whole device factors one K~ (gp_large.cuh).  Host-orchestrated stage
-// by stage on `st`; synchronises once per Cholesky attempt to read the failure flag (the
-// jitter ladder of psd_safe_cholesky) - the call is blocking.
+// Staged engine (gp_large.cuh): B light curves advance stage by stage, one launch per
+// dependency stage with B x (tiles of the stage) blocks; B = 1 is the single large GP.
+// Host-orchestrated on `st`; synchronises once per Cholesky pass to read how many light curves
+// must repeat it with more jitter (psd_safe_cholesky's ladder) - the call is blocking.
 template <int KIND, int QT, int D>
-int launch_large(const pgm::LargeArgs& A, int want_grad, int32_t* info_host, cudaStream_t st) {
+int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st) {
   using C = pgm::Cfg<KIND, QT, D>;
   using namespace pgm;
-  const int n = A.n, N = (n + TS - 1) / TS, npad = N * TS;
+  const int n = A.n_max, N = (n + TS - 1) / TS, npad = N * TS, B = A.B;
+  if (B > 65535) return fail("staged engine: B > 65535 (split the batch)");
   constexpr int NB = 8;   // tile columns per panel
   auto k_upd = lg_update<KIND, QT, D>;
   auto k_grad = lg_grad<KIND, QT, D>;
@@ -113,44 +115,41 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, int32_t* info_host, cud
   cudaFuncSetAttribute(lg_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_DIAG_SMEM);
   cudaFuncSetAttribute(lg_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_TRSM_SMEM);
   cudaFuncSetAttribute(lg_inv_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_INV_SMEM);
-  LargeWs w = make_large_ws(A.ws, n);
-  int info = 0;
-  for (int attempt = 0; attempt <= 3; ++attempt) {
-    double jitter = 0.0;
-    if (attempt > 0) { jitter = 1e-8; for (int t = 1; t < attempt; ++t) jitter *= 10.0; }
-    cudaMemsetAsync(w.fail, 0, sizeof(int), st);
-    lg_setup<KIND, QT, D><<<(npad + NTHREADS - 1) / NTHREADS, NTHREADS, 0, st>>>(A);
+  BatchState bs = make_batch_state(A.ws, n, B);
+  cudaMemsetAsync(bs.state, 0, (size_t)(3 * B + 4) * sizeof(int), st);
+  const dim3 blk(NTHREADS);
+  for (int pass = 0; pass <= 3; ++pass) {
+    cudaMemsetAsync(bs.count, 0, sizeof(int), st);
+    lg_setup<KIND, QT, D><<<dim3((npad + NTHREADS - 1) / NTHREADS, B), blk, 0, st>>>(A);
     for (int J0 = 0; J0 < N; J0 += NB) {
       const int J1 = std::min(J0 + NB, N);
       const int build = (J0 == 0) ? 1 : 0;
       for (int j = J0; j < J1; ++j) {
         if (build || j > J0)
-          k_upd<<<N - j, NTHREADS, C::SMEM_BYTES, st>>>(A, 0, j, J0, j, build, jitter);
-        lg_diag<<<1, NTHREADS, LG_DIAG_SMEM, st>>>(A.ws, n, j);
-        if (j + 1 < N) lg_trsm<<<N - j - 1, NTHREADS, LG_TRSM_SMEM, st>>>(A.ws, n, j);
+          k_upd<<<dim3(N - j, B), blk, C::SMEM_BYTES, st>>>(A, 0, j, J0, j, build);
+        lg_diag<<<dim3(1, B), blk, LG_DIAG_SMEM, st>>>(A, j);
+        if (j + 1 < N) lg_trsm<<<dim3(N - j - 1, B), blk, LG_TRSM_SMEM, st>>>(A, j);
       }
       if (J1 < N) {
         const int M = N - J1;
-        k_upd<<<M * (M + 1) / 2, NTHREADS, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build, jitter);
+        k_upd<<<dim3(M * (M + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build);
       }
     }
-    int fl = 0;
-    e = cudaMemcpyAsync(&fl, w.fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+    lg_ladder<<<(B + 255) / 256, 256, 0, st>>>(A);
+    int again = 0;
+    e = cudaMemcpyAsync(&again, bs.count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return cuda_fail("large-GP Cholesky phase", e);
-    if (!fl) { info = attempt; break; }
-    if (fl & 2) { info = -1; break; }
-    info = -2;
+    if (e != cudaSuccess) return cuda_fail("staged engine, Cholesky phase", e);
+    if (!again) break;
   }
-  if (info >= 0 && want_grad) {
-    for (int i = 1; i < N; ++i) lg_inv_row<<<i, NTHREADS, LG_INV_SMEM, st>>>(A.ws, n, i);
-    lg_alpha<<<N, NTHREADS, 0, st>>>(A.ws, n);
-    k_grad<<<N * (N + 1) / 2, NTHREADS, C::SMEM_BYTES, st>>>(A);
+  if (want_grad) {
+    for (int i = 1; i < N; ++i) lg_inv_row<<<dim3(i, B), blk, LG_INV_SMEM, st>>>(A, i);
+    lg_alpha<<<dim3(N, B), blk, 0, st>>>(A);
+    k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
   }
-  lg_finish<KIND, QT, D><<<1, NTHREADS, 0, st>>>(A, info, want_grad);
+  lg_finish<KIND, QT, D><<<dim3(1, B), blk, 0, st>>>(A, want_grad);
   e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail("large-GP launch", e);
-  *info_host = info;
+  if (e != cudaSuccess) return cuda_fail("staged engine launch", e);
   return 0;
 }
 

@@ -173,40 +173,54 @@ def sm_fit(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con
     return loss_hist, raw_hist, n_iter, info
 
 
-_large_ws = {}
+_staged_ws = {}
+
+
+def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
+                       con_kind: Tensor, con_lb: Tensor, con_ub: Tensor,
+                       n_valid: Optional[Tensor], kind: int, Q: int, learn_noise: bool,
+                       want_grad: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """Same contract as :func:`sm_mll_grad`, through the staged whole-device engine
+    (``pgm_sm_mll_grad_staged_f64``): every light curve's K~ lives in HBM as 64x64 tiles and
+    the batch advances stage by stage.  Blocking."""
+    (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+        x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    if want_grad:
+        flags |= FLAG_GRAD
+    lib = _lib.load()
+    need = lib.pgm_staged_workspace_bytes(n, B)
+    key = (x.device.index,)
+    ws = _staged_ws.get(key)
+    if ws is None or ws.numel() < need:
+        _staged_ws.pop(key, None)
+        ws = None
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        _staged_ws[key] = ws
+    mll = torch.empty(B, dtype=x.dtype, device=x.device)
+    grad = torch.zeros(B, P, dtype=x.dtype, device=x.device)
+    info = torch.zeros(B, dtype=torch.int32, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    with torch.cuda.device(x.device):
+        check(lib.pgm_sm_mll_grad_staged_f64(
+            ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
+            ptr(con_ub), B, n, d, Q, kind, flags, ptr(mll), ptr(grad), ptr(info), ptr(ws),
+            ws.numel(), _stream()))
+    return mll, grad, info
 
 
 def sm_mll_grad_large(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
                       con_kind: Tensor, con_lb: Tensor, con_ub: Tensor, kind: int, Q: int,
                       learn_noise: bool, want_grad: bool = True):
-    """ONE large GP (x [n, d], y [n], raw [P]) factored by the whole device
-    (``pgm_sm_mll_grad_large_f64``).  Returns (mll 0-d tensor, grad [P], info int); blocking."""
-    import ctypes
+    """ONE large GP (x [n, d], y [n], raw [P]) factored by the whole device: the staged engine
+    with B = 1.  Returns (mll 0-d tensor, grad [P], info int); blocking."""
     if x.dim() == 1:
         x = x.unsqueeze(-1)
-    (xb, yb, fnb, rawb, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+    mll, grad, info = sm_mll_grad_staged(
         x.unsqueeze(0), y.unsqueeze(0), None if fixed_noise is None else fixed_noise.unsqueeze(0),
-        raw.reshape(1, -1), con_kind, con_lb.reshape(-1), con_ub.reshape(-1), kind, Q,
-        learn_noise)
-    if want_grad:
-        flags |= FLAG_GRAD
-    lib = _lib.load()
-    need = lib.pgm_large_workspace_bytes(n)
-    key = (x.device.index,)
-    ws = _large_ws.get(key)
-    if ws is None or ws.numel() < need:
-        _large_ws.pop(key, None)
-        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-        _large_ws[key] = ws
-    mll = torch.empty(1, dtype=x.dtype, device=x.device)
-    grad = torch.zeros(P, dtype=x.dtype, device=x.device)
-    info = ctypes.c_int32(0)
-    with torch.cuda.device(x.device):
-        check(lib.pgm_sm_mll_grad_large_f64(
-            ptr(xb), ptr(yb), ptr(fnb), ptr(rawb), ptr(con_kind), ptr(con_lb), ptr(con_ub), n, d,
-            Q, kind, flags, ptr(mll), ptr(grad), ctypes.byref(info), ptr(ws), ws.numel(),
-            _stream()))
-    return mll[0], grad, int(info.value)
+        raw.reshape(1, -1), con_kind, con_lb.reshape(-1), con_ub.reshape(-1), None, kind, Q,
+        learn_noise, want_grad)
+    return mll[0], grad[0], int(info.item())
 
 
 def peak_probe(kind: int, iters: int = 4096) -> float:
@@ -217,6 +231,6 @@ def peak_probe(kind: int, iters: int = 4096) -> float:
     return out.value
 
 
-__all__ = ["sm_mll_grad", "sm_mll_grad_large", "sm_kernel_dense", "optim_step", "sm_fit",
+__all__ = ["sm_mll_grad", "sm_mll_grad_large", "sm_mll_grad_staged", "sm_kernel_dense", "optim_step", "sm_fit",
            "peak_probe", "param_count",
            "KIND_SM1D", "KIND_SM_ARD_PRODSUM", "KIND_SM_ARD_SUMPROD"]

@@ -117,3 +117,44 @@ def test_train_routes_long_light_curves_through_the_large_path(cuda_device):
         outs.append(np.array(res["loss"], dtype=float))
         assert len(res["covar_module.mixture_means"]) == 4
     assert np.allclose(outs[0], outs[1], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_staged_batch_matches_goldens(name, cuda_device):
+    """The whole golden batch in ONE staged call (ragged n_valid, per-light-curve bounds)."""
+    from pgmuvi_b200 import ops
+    g = load_golden(name)
+    dev = cuda_device
+    mll, grad, info = ops.sm_mll_grad_staged(
+        _t(g["x"], dev), _t(g["y"], dev), _t(g["noise"], dev), _t(g["raw"], dev),
+        _t(g["kinds"], dev, torch.int32), _t(g["lb"], dev), _t(g["ub"], dev),
+        _t(g["n_valid"], dev, torch.int32), g["kind"], g["Q"], g["learn_noise"], True)
+    assert np.array_equal(info.cpu().numpy(), g["info"])
+    assert np.abs(mll.cpu().numpy() - g["mll"]).max() <= 1e-9 * np.abs(g["mll"]).max()
+    for b in range(len(g["mll"])):
+        scale = np.abs(g["grad_autograd"][b]).max()
+        assert np.abs(grad[b].cpu().numpy() - g["grad_autograd"][b]).max() <= 1e-7 * scale
+
+
+def test_staged_engine_jitter_ladder_and_bitwise_agreement_with_fused(cuda_device):
+    """Per-light-curve jitter ladder in the staged engine: the same failure codes as the fused
+    kernel (tests/test_gpu_parity.py::test_jitter_ladder_and_failure_codes) and - for healthy
+    members - the same MLL to 1e-12."""
+    from pgmuvi_b200 import ops, synthetic as S
+    bt = S.make_batch_1d(5, 96, Q=2, seed0=4242)
+    bt["x"][1, 50, 0] = bt["x"][1, 49, 0]
+    bt["noise"][1, :] = 1e-17
+    bt["noise"][2, 10] = -50.0
+    bt["x"][3, 5, 0] = float("nan")
+    dev = cuda_device
+    args = (_t(bt["x"], dev), _t(bt["y"], dev), _t(bt["noise"], dev), _t(bt["raw"], dev),
+            _t(bt["kinds"], dev, torch.int32), _t(bt["lb"], dev), _t(bt["ub"], dev), None, 0, 2,
+            False, True)
+    m0, g0, i0 = ops.sm_mll_grad(*args)
+    m1, g1, i1 = ops.sm_mll_grad_staged(*args)
+    assert i1.cpu().tolist() == i0.cpu().tolist()
+    assert i1[2] == -2 and i1[3] == -1 and i1[1] >= 1
+    for b in (0, 4):
+        assert abs(float(m1[b]) - float(m0[b])) <= 1e-12 * abs(float(m0[b]))
+        assert float((g1[b] - g0[b]).abs().max()) <= 1e-9 * float(g0[b].abs().max())
+    assert torch.isnan(m1[2]) and torch.isnan(m1[3]) and torch.isnan(g1[2]).all()
