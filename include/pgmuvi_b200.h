@@ -94,6 +94,26 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * N1 - exact posterior prediction at m test inputs per light curve:
+ *     mean*[b, s] = c_b + K*^T alpha,     var*[b, s] = k** - || L^-1 k* ||^2    (latent f)
+ * Replaces  likelihood(model(x_fine))  in eval mode (pgmuvi/lightcurve.py:9607-9640, 9862, 9937),
+ * which the reference evaluates on a 10000-point grid under gpytorch.settings.fast_pred_var
+ * (an approximate variance; this is the exact one).  The likelihood's homoskedastic noise is
+ * NOT added here (the host adds the learned noise where the reference's likelihood would).
+ * Runs the P and T phases of the staged engine, then one persistent kernel over
+ * (light curve, 64-point test tile) jobs.  Arguments as pgm_sm_mll_grad_staged_f64, plus
+ *   xstar [B, m, d] test inputs (same transformed units as x), mean / var [B, m] outputs.
+ * Failed light curves (info < 0) get NaN.  Blocking, like the staged engine.
+ */
+size_t pgm_predict_workspace_bytes(int n_max, int B, int device);
+int pgm_sm_predict_f64(const double* x, const int32_t* n_valid, const double* y,
+                       const double* fixed_noise, const double* raw, const int32_t* con_kind,
+                       const double* con_lb, const double* con_ub, int B, int n_max, int d, int Q,
+                       int kernel_kind, int flags, const double* xstar, int m, double* mean,
+                       double* var, int32_t* info, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/*
  * Staged engine: the same quantities as pgm_sm_mll_grad_f64 (same arguments), computed stage
  * by stage over the whole device: K~ of every light curve lives in HBM as the lower triangle
  * of 64x64 tile images (right-looking blocked Cholesky + inverse + gradient contraction, one

@@ -39,4 +39,5 @@ from .sm_gp import (  # noqa: F401
     psd_safe_cholesky,
     adam_step,
     train_loop,
+    predict,
 )

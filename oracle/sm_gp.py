@@ -394,6 +394,27 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
 
 
 # ---------------------------------------------------------------------------------------
+# N1: posterior prediction (GPyTorch ExactGP eval mode: ExactPredictionStrategy, exact form)
+# ---------------------------------------------------------------------------------------
+def predict(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec, xstar):
+    """Posterior mean and LATENT variance at xstar [m, d] (what ``model(x*)`` returns in eval
+    mode, pgmuvi/lightcurve.py:9862; the likelihood then adds its homoskedastic noise):
+        mean* = c + K*^T Kt^-1 (y - c),   var* = k** - K*^T Kt^-1 K*      (Cholesky solves).
+    The reference computes the variance under ``fast_pred_var`` (LOVE, approximate,
+    lightcurve.py:9607); this is the exact quantity it approximates."""
+    n = y.shape[-1]
+    theta = constrain(raw, kinds, lb, ub)
+    mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    Kt = kernel_dense(x, x, theta, spec) + torch.diag_embed(noise_diag(n, fixed_noise, noise, y.dtype))
+    L, info = psd_safe_cholesky(Kt)
+    Ks = kernel_dense(x, xstar, theta, spec)                    # [n, m]
+    alpha = torch.cholesky_solve((y - mean).unsqueeze(-1), L)
+    v = torch.linalg.solve_triangular(L, Ks, upper=False)
+    kss = torch.diagonal(kernel_dense(xstar, xstar, theta, spec))
+    return mean + (Ks.T @ alpha).squeeze(-1), kss - (v * v).sum(0), info
+
+
+# ---------------------------------------------------------------------------------------
 # batched CPU baseline (torch batch mode; same op sequence, autograd) - BASELINE.md section 3
 # ---------------------------------------------------------------------------------------
 def batched_mll_and_grad(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec):

@@ -25,6 +25,7 @@ EXPORTS = (
     "pgm_version", "pgm_last_error", "pgm_workspace_bytes", "pgm_sm_mll_grad_f64",
     "pgm_sm_kernel_dense_f64", "pgm_optim_step_f64", "pgm_sm_fit_f64", "pgm_peak_probe",
     "pgm_staged_workspace_bytes", "pgm_sm_mll_grad_staged_f64",
+    "pgm_predict_workspace_bytes", "pgm_sm_predict_f64",
 )
 
 _lib = None
@@ -67,6 +68,11 @@ def load():
     lib.pgm_staged_workspace_bytes.argtypes = [c_int, c_int]
     lib.pgm_sm_mll_grad_staged_f64.restype = c_int
     lib.pgm_sm_mll_grad_staged_f64.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
+    lib.pgm_predict_workspace_bytes.restype = c_size_t
+    lib.pgm_predict_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.pgm_sm_predict_f64.restype = c_int
+    lib.pgm_sm_predict_f64.argtypes = [dp, ip, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, dp, c_int, dp, dp, ip, vp, c_size_t, vp]
     lib.pgm_peak_probe.restype = c_int
     lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
     _lib = lib

@@ -14,7 +14,8 @@ template <int KIND, int QT, int D> int launch_eval(const EvalArgs& A0, cudaStrea
 template <int KIND, int QT, int D> int launch_fit(const FitArgs& F, cudaStream_t st);
 template <int KIND, int QT, int D> int launch_dense(const EvalArgs& A, double* K, cudaStream_t st);
 template <int KIND, int QT, int D>
-int launch_large(const LargeArgs& A, int want_grad, cudaStream_t st);
+int launch_large(const LargeArgs& A, int want_grad, cudaStream_t st, int predict_only);
+template <int KIND, int QT, int D> int launch_predict(const PredictArgs& PA, cudaStream_t st);
 
 thread_local std::string g_err;
 int fail(const std::string& m) {
@@ -55,6 +56,7 @@ using pgm::launch_dense;
 using pgm::launch_eval;
 using pgm::launch_fit;
 using pgm::launch_large;
+using pgm::launch_predict;
 
 int pad_q(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
 
@@ -174,7 +176,47 @@ int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const do
   A.ws = static_cast<double*>(workspace);
   const int want_grad = (flags & PGM_FLAG_GRAD) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PGM_DISPATCH(launch_large, A, want_grad, st);
+  PGM_DISPATCH(launch_large, A, want_grad, st, 0);
+  return 0;
+}
+
+size_t pgm_predict_workspace_bytes(int n_max, int B, int device) {
+  if (n_max < 1 || B < 1) return 0;
+  int sms = 148;
+  if (device >= 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  else sms = pgm::device_sms();
+  if (sms <= 0) sms = 148;
+  const size_t N = (n_max + pgm::TS - 1) / pgm::TS;
+  size_t staged = (pgm::large_ws_bytes(n_max, B) + 255) & ~(size_t)255;
+  return staged + (size_t)2 * sms * N * pgm::TT * sizeof(double);
+}
+
+int pgm_sm_predict_f64(const double* x, const int32_t* n_valid, const double* y,
+                       const double* fixed_noise, const double* raw, const int32_t* con_kind,
+                       const double* con_lb, const double* con_ub, int B, int n_max, int d, int Q,
+                       int kernel_kind, int flags, const double* xstar, int m, double* mean,
+                       double* var, int32_t* info, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0 || m == 0) return 0;
+  if (m < 0) return fail("m must be >= 0");
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !xstar || !mean || !var || !info ||
+      !workspace)
+    return fail("null pointer argument");
+  if (workspace_bytes < pgm_predict_workspace_bytes(n_max, B, -1))
+    return fail("workspace too small (see pgm_predict_workspace_bytes)");
+  pgm::PredictArgs PA;
+  pgm::LargeArgs& A = PA.a;
+  A.x = x; A.n_valid = n_valid; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
+  A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
+  A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags & ~PGM_FLAG_GRAD;
+  A.mll = nullptr; A.grad = nullptr; A.info = info;
+  A.ws = static_cast<double*>(workspace);
+  PA.xstar = xstar; PA.m = m; PA.mean = mean; PA.var = var;
+  const size_t staged = (pgm::large_ws_bytes(n_max, B) + 255) & ~(size_t)255;
+  PA.kscratch = reinterpret_cast<double*>(static_cast<char*>(workspace) + staged);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PGM_DISPATCH(launch_predict, PA, st);
   return 0;
 }
 

@@ -712,4 +712,172 @@ __global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int want_grad
   grad_out[tid] = gv * w.par[LG_PAR_JC + tid];
 }
 
+// ------------------------------------------------------------------------------------
+// N1: exact posterior prediction at m test inputs per light curve (the step after the fit:
+// pgmuvi/lightcurve.py:9607-9640, 9862, 9937 evaluate likelihood(model(x_fine)) on a 10000-point
+// grid; GPyTorch does it under fast_pred_var, i.e. with an approximate variance - this is the
+// exact one it approximates).   mean* = c + K*^T alpha,   var* = k** - || L^-1 k* ||^2.
+// Runs after the P and T phases (X = L^-1 and alpha in the workspace).
+// ------------------------------------------------------------------------------------
+// row-major X_ij (i > j) into tilesL: the stored X_ij^T image transposed (tilesL is dead after T)
+static __global__ void __launch_bounds__(NTHREADS) lg_transpose(LargeArgs A) {
+  const LcView v = lc_view(A);
+  if (v.st.state[v.b] != LG_FACTORED) return;
+  int i, j;
+  tri_unrank(blockIdx.x, i, j);
+  if (i >= v.N || i == j) return;
+  const double* src = lg_tile(v.w.tilesX, i, j);
+  double* dst = lg_tile(v.w.tilesL, i, j);
+  for (int idx = threadIdx.x; idx < TT / 2; idx += NTHREADS) {
+    const int r = idx >> 5, c2 = (idx & 31) * 2;   // dst[r][c2..c2+1] = src[c2..][r]
+    *reinterpret_cast<double2*>(dst + img(r, c2)) = make_double2(src[img(c2, r)], src[img(c2 + 1, r)]);
+  }
+}
+
+struct PredictArgs {
+  LargeArgs a;
+  const double* xstar;   // [B, m, D]
+  int m;
+  double* mean;          // [B, m]
+  double* var;           // [B, m]   latent variance (no likelihood noise)
+  double* kscratch;      // gridDim.x * N_max tiles: K*^T panels of the block's current job
+};
+
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+    lg_predict(PredictArgs PA) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
+  extern __shared__ __align__(16) double sm[];
+  const LargeArgs& A = PA.a;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  double* stages = sm + C::SM_STAGES;
+  double* rowv = sm + C::SM_ROW;   // test tile fields
+  double* colv = sm + C::SM_COL;   // train tile fields (+ alpha)
+  double* par = sm + C::SM_PAR;
+  double* red = par + C::PAR_RED;  // >= 8 * 15 doubles; used as [4][64] below via S region
+  double* scr = sm + C::SM_S;      // 34 KB free region: reductions
+  double* tab = par + C::PAR_TAB;
+  const unsigned bars = smem_u32(par + C::PAR_BAR);
+  (void)red;
+  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  PipeState ps;
+  pipe_init<KIND, QT, D>(sm, ps);
+  Ring r2{bars, bars + 16, stages, 0};
+  const int Nmax = (A.n_max + TS - 1) / TS;
+  const int Mt = (PA.m + TS - 1) / TS;
+  double* ks = PA.kscratch + (size_t)blockIdx.x * Nmax * TT;
+  const BatchState st = make_batch_state(A.ws, A.n_max, A.B);
+  const int Q = A.Q;
+  const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
+  (void)learn_noise;
+  for (int job = blockIdx.x; job < A.B * Mt; job += gridDim.x) {
+    const int b = job / Mt, t = job - b * Mt;
+    double* mean_out = PA.mean + (size_t)b * PA.m;
+    double* var_out = PA.var + (size_t)b * PA.m;
+    __syncthreads();
+    if (st.state[b] != LG_FACTORED) {
+      if (tid < TS && t * TS + tid < PA.m) {
+        mean_out[t * TS + tid] = nan("");
+        var_out[t * TS + tid] = nan("");
+      }
+      continue;
+    }
+    const int n = A.n_valid ? A.n_valid[b] : A.n_max;
+    const int N = (n + TS - 1) / TS, npad = N * TS;
+    const LargeWs w = make_large_ws(A.ws + large_ws_elems(A.n_max) * (size_t)b, A.n_max);
+    double wreg[QT], areg[QT * DS], lam[4];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) wreg[q] = w.par[LG_PAR_WQ + q];
+#pragma unroll
+    for (int q = 0; q < QT * DS; ++q) areg[q] = w.par[LG_PAR_AQ + q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lam[q] = w.par[LG_PAR_LM + q];
+    const double* theta = w.par + LG_PAR_TH;
+    // ---- test tile fields (centred on the light curve's first training input, as lg_setup)
+    const double* xb = A.x + (size_t)b * A.n_max * D;
+    const double* xs = PA.xstar + ((size_t)b * PA.m + (size_t)t * TS) * D;
+    if (tid < TS) {
+      const bool valid = t * TS + tid < PA.m;
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) {
+        const double xc = valid ? (xs[(size_t)tid * D + dd] - xb[dd]) : 0.0;
+        rowv[dd * TS + tid] = xc;
+        if (dd < DS) {
+#pragma unroll
+          for (int q = 0; q < QT; ++q) {
+            double sn = 0.0, cs = 1.0;
+            if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * DS + dd] * xc, &sn, &cs);
+            rowv[D * TS + ((dd * QT + q) * TS + tid) * 2] = cs;
+            rowv[D * TS + ((dd * QT + q) * TS + tid) * 2 + 1] = sn;
+          }
+        }
+      }
+    }
+    // ---- phase 1: K*^T_j tiles (rows = test points, k = training points of tile j) ----------
+    double mu[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = 0; j < N; ++j) {
+      __syncthreads();
+      lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, true);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      const double* al_c = colv + C::NFB * TS;
+      double* kt = ks + (size_t)j * TT;
+#pragma unroll 1
+      for (int p8 = 0; p8 < 8; ++p8) {
+        const int mi = p8 >> 1, ni2 = p8 & 1;
+        const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+        double kv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int gc = j * TS + c0 + e;
+          double k1 = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
+          k1 = (gc < n && t * TS + r < PA.m) ? k1 : 0.0;
+          kv[e] = k1;
+          mu[mi] += k1 * al_c[c0 + e];
+        }
+        *reinterpret_cast<double2*>(kt + img(r, c0)) = make_double2(kv[0], kv[1]);
+      }
+    }
+    fence_proxy_async();   // the K* tiles are read back by bulk copies
+    // ---- phase 2: v_i^T = sum_{j<=i} K*^T_j X_ij^T,  vsq += row sums of v_i^T squared ---------
+    double vs[4] = {0.0, 0.0, 0.0, 0.0};
+    double acc[4][2][2];
+    for (int i = 0; i < N; ++i) {
+      zero_acc(acc);
+      auto tA = [&](int kk) { return ks + (size_t)(i - kk) * TT; };
+      auto tB = [&](int kk) { return lg_tile(w.tilesL, i, i - kk); };
+      auto none = [&](int) { return (double*)nullptr; };
+      gemm_stream<M_B_LE, false, 2>(acc, r2, i + 1, tA, tB, 0, 0, none, none, []() {});
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) vs[mi] += acc[mi][ni][0] * acc[mi][ni][0] + acc[mi][ni][1] * acc[mi][ni][1];
+    }
+    // ---- reduce over the column lanes / warps; k** and outputs ------------------------------
+    __syncthreads();
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      double a1 = mu[mi], a2 = vs[mi];
+      a1 += shfl_xor_d(a1, 1); a1 += shfl_xor_d(a1, 2);
+      a2 += shfl_xor_d(a2, 1); a2 += shfl_xor_d(a2, 2);
+      if (tq == 0) {
+        scr[wn * TS + frag_row(wm, mi, g)] = a1;
+        scr[4 * TS + wn * TS + frag_row(wm, mi, g)] = a2;
+      }
+    }
+    __syncthreads();
+    if (tid < TS && t * TS + tid < PA.m) {
+      const double m1 = (scr[tid] + scr[TS + tid]) + (scr[2 * TS + tid] + scr[3 * TS + tid]);
+      const double v1 = (scr[4 * TS + tid] + scr[5 * TS + tid]) + (scr[6 * TS + tid] + scr[7 * TS + tid]);
+      const double kss = k_entry<KIND, QT, D>(rowv, rowv, tid, tid, wreg, areg, lam, tab);
+      mean_out[t * TS + tid] = theta[0] + m1;
+      var_out[t * TS + tid] = kss - v1;
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
 }  // namespace pgm

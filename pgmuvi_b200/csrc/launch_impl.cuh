@@ -13,6 +13,7 @@ namespace pgm {
 int fail(const std::string& m);
 int cuda_fail(const char* what, cudaError_t e);
 int device_sms();
+inline int predict_blocks() { return 2 * device_sms(); }   // persistent blocks of lg_predict
 
 template <int KIND, int QT, int D>
 int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
@@ -99,7 +100,7 @@ int launch_dense(const pgm::EvalArgs& A, double* K, cudaStream_t st) {
 // Host-orchestrated on `st`; synchronises once per Cholesky pass to read how many light curves
 // must repeat it with more jitter (psd_safe_cholesky's ladder) - the call is blocking.
 template <int KIND, int QT, int D>
-int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st) {
+int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int predict_only = 0) {
   using C = pgm::Cfg<KIND, QT, D>;
   using namespace pgm;
   const int n = A.n_max, N = (n + TS - 1) / TS, npad = N * TS, B = A.B;
@@ -142,14 +143,41 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_fail("staged engine, Cholesky phase", e);
     if (!again) break;
   }
-  if (want_grad) {
+  if (want_grad || predict_only) {
     for (int i = 1; i < N; ++i) lg_inv_row<<<dim3(i, B), blk, LG_INV_SMEM, st>>>(A, i);
     lg_alpha<<<dim3(N, B), blk, 0, st>>>(A);
-    k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
+    if (!predict_only) k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
   }
-  lg_finish<KIND, QT, D><<<dim3(1, B), blk, 0, st>>>(A, want_grad);
+  if (predict_only) {
+    lg_transpose<<<dim3(N * (N + 1) / 2, B), blk, 0, st>>>(A);
+  } else {
+    lg_finish<KIND, QT, D><<<dim3(1, B), blk, 0, st>>>(A, want_grad);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("staged engine launch", e);
+  return 0;
+}
+
+// N1: posterior prediction = P + T phases of the staged engine, then lg_predict (persistent
+// blocks over (light curve, test tile) jobs, each with its own K* panel scratch).
+template <int KIND, int QT, int D>
+int launch_predict(const pgm::PredictArgs& PA0, cudaStream_t st) {
+  using C = pgm::Cfg<KIND, QT, D>;
+  using namespace pgm;
+  PredictArgs PA = PA0;
+  if (int r = launch_large<KIND, QT, D>(PA.a, 0, st, 1)) return r;
+  auto kern = lg_predict<KIND, QT, D>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::SMEM_BYTES);
+  if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_predict)", e);
+  const int Mt = (PA.m + TS - 1) / TS;
+  int grid = predict_blocks();
+  const long long jobs = (long long)PA.a.B * Mt;
+  if (jobs < grid) grid = (int)jobs;
+  if (grid < 1) return 0;
+  kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(PA);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("lg_predict launch", e);
   return 0;
 }
 

@@ -290,6 +290,61 @@ class Lightcurve(torch.nn.Module):
         scales = (1 / (2 * np.pi * sg[:, 0, 0])).numpy()
         return periods, w.numpy(), scales
 
+    # ---- posterior prediction (lightcurve.py:9607-9640, 9849-9880: the body of plot()) -----
+    def predict(self, x_fine_raw=None, n_points=10000):
+        """``observed_pred = self.likelihood(self.model(x_fine_transformed))`` on the GPU (N1).
+
+        ``x_fine_raw``: raw-unit test inputs ([m] for 1-D data, [m, 2] for 2-D); default: the
+        reference's 10000-point grid across the time range (lightcurve.py:9624).  Returns
+        ``{"x", "mean", "variance", "lower", "upper"}`` (numpy; transformed-y units like
+        GPyTorch's ``observed_pred``): ``variance`` is the exact latent variance plus the learned
+        homoskedastic noise (a FixedNoise likelihood adds nothing at new inputs, as GPyTorch
+        warns), ``lower/upper = mean -/+ 2 stddev`` (``confidence_region``)."""
+        from . import ops
+        from .mll import engine_device, pack_model
+        if x_fine_raw is None:
+            if self.ndim != 1:
+                raise ValueError("pass x_fine_raw [m, 2] (time, wavelength) for 2-D data")
+            xr = self._xdata_raw
+            x_fine_raw = torch.linspace(float(xr.min()), float(xr.max()), n_points)
+        xf = torch.as_tensor(np.asarray(x_fine_raw) if not torch.is_tensor(x_fine_raw)
+                             else x_fine_raw).to(self._xdata_raw.dtype)
+        xt = xf if self.xtransform is None else self.xtransform.transform(xf)
+        pk = pack_model(self.model, self.likelihood)
+        dev = engine_device(pk.params[0])
+        f64 = lambda t: t.detach().to(device=dev, dtype=torch.float64)
+        x = self._xdata_transformed
+        x = x if x.dim() > 1 else x.unsqueeze(-1)
+        xs = xt if xt.dim() > 1 else xt.unsqueeze(-1)
+        mean, var, info = ops.sm_predict(
+            f64(x).unsqueeze(0).contiguous(), f64(self._ydata_transformed).unsqueeze(0).contiguous(),
+            None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
+            f64(pk.raw()).unsqueeze(0).contiguous(), pk.kinds.to(dev), pk.lb.to(dev),
+            pk.ub.to(dev), None, f64(xs).unsqueeze(0).contiguous(), pk.kind, pk.Q, pk.learn_noise)
+        code = int(info.item())
+        if code < 0:
+            from .gp import NanError, NotPSDError
+            raise (NanError if code == -1 else NotPSDError)(
+                "the covariance of the fitted model could not be factorised")
+        mean, var = mean[0].cpu(), var[0].cpu()
+        if pk.learn_noise:
+            # the learned noise is the slot right after the kernel parameters (pack_model order:
+            # mean, weights, means, scales, noise, wavelength-kernel parameters)
+            noise_par = pk.params[4]
+            noise_con = getattr(self._owner_of(noise_par), "raw_noise_constraint", None)
+            nv = noise_con.transform(noise_par) if noise_con is not None else noise_par
+            var = var + float(nv.detach().reshape(-1)[0])
+        std = var.clamp_min(1e-9).sqrt()      # MultivariateNormal.stddev clamps the variance
+        return {"x": xf.cpu().numpy(), "mean": mean.numpy(), "variance": var.numpy(),
+                "lower": (mean - 2 * std).numpy(), "upper": (mean + 2 * std).numpy()}
+
+    def _owner_of(self, param):
+        for mod in list(self.model.modules()) + list(self.likelihood.modules()):
+            for p in mod._parameters.values():
+                if p is param:
+                    return mod
+        return None
+
     # ---- fit (lightcurve.py:5211-5882) -------------------------------------------------
     def fit(self, model=None, likelihood=None, num_mixtures=None, guess=None, periods=None,
             constraint_set=None, cuda=False, training_iter=300, optim="AdamW", miniter=None,

@@ -209,6 +209,44 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
     return mll, grad, info
 
 
+def sm_predict(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
+               con_kind: Tensor, con_lb: Tensor, con_ub: Tensor, n_valid: Optional[Tensor],
+               xstar: Tensor, kind: int, Q: int, learn_noise: bool
+               ) -> Tuple[Tensor, Tensor, Tensor]:
+    """Exact posterior mean and latent variance at ``xstar [B, m, d]`` for B light curves
+    (``pgm_sm_predict_f64``).  Returns (mean [B, m], var [B, m], info [B]); blocking."""
+    (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+        x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    _require_cuda(xstar)
+    if xstar.dim() == 2:
+        xstar = xstar.unsqueeze(-1)
+    if xstar.shape[0] != B or xstar.shape[2] != d or xstar.dtype != torch.float64:
+        raise RuntimeError(f"xstar must be float64 [B, m, {d}]")
+    xstar = xstar.contiguous()
+    m = xstar.shape[1]
+    lib = _lib.load()
+    need = lib.pgm_predict_workspace_bytes(n, B, x.device.index if x.device.index is not None
+                                           else torch.cuda.current_device())
+    key = (x.device.index,)
+    ws = _staged_ws.get(key)
+    if ws is None or ws.numel() < need:
+        _staged_ws.pop(key, None)
+        ws = None
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        _staged_ws[key] = ws
+    mean = torch.empty(B, m, dtype=x.dtype, device=x.device)
+    var = torch.empty(B, m, dtype=x.dtype, device=x.device)
+    info = torch.zeros(B, dtype=torch.int32, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    with torch.cuda.device(x.device):
+        check(lib.pgm_sm_predict_f64(
+            ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
+            ptr(con_ub), B, n, d, Q, kind, flags, ptr(xstar), m, ptr(mean), ptr(var), ptr(info),
+            ptr(ws), ws.numel(), _stream()))
+    return mean, var, info
+
+
 def sm_mll_grad_large(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
                       con_kind: Tensor, con_lb: Tensor, con_ub: Tensor, kind: int, Q: int,
                       learn_noise: bool, want_grad: bool = True):
@@ -231,6 +269,6 @@ def peak_probe(kind: int, iters: int = 4096) -> float:
     return out.value
 
 
-__all__ = ["sm_mll_grad", "sm_mll_grad_large", "sm_mll_grad_staged", "sm_kernel_dense", "optim_step", "sm_fit",
+__all__ = ["sm_mll_grad", "sm_mll_grad_large", "sm_mll_grad_staged", "sm_predict", "sm_kernel_dense", "optim_step", "sm_fit",
            "peak_probe", "param_count",
            "KIND_SM1D", "KIND_SM_ARD_PRODSUM", "KIND_SM_ARD_SUMPROD"]

@@ -158,3 +158,55 @@ def test_staged_engine_jitter_ladder_and_bitwise_agreement_with_fused(cuda_devic
         assert abs(float(m1[b]) - float(m0[b])) <= 1e-12 * abs(float(m0[b]))
         assert float((g1[b] - g0[b]).abs().max()) <= 1e-9 * float(g0[b].abs().max())
     assert torch.isnan(m1[2]) and torch.isnan(m1[3]) and torch.isnan(g1[2]).all()
+
+
+# ---------------------------------------------------------------------------------------
+# N1: posterior prediction (pgm_sm_predict_f64)
+# ---------------------------------------------------------------------------------------
+import os
+
+PRED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_predict")
+PRED_CASES = sorted(f[:-4] for f in os.listdir(PRED_DIR) if f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", PRED_CASES)
+def test_prediction_matches_oracle_goldens(name, cuda_device):
+    """mean* and the exact latent variance at 150 test points per light curve against the
+    oracle's Cholesky-solve prediction (tests/golden_predict, oracle/make_golden_predict.py).
+    Tolerance 1e-9 of the prior variance scale (var* is a difference of O(1) quantities)."""
+    from pgmuvi_b200 import ops
+    g = load_golden(name)
+    p = np.load(os.path.join(PRED_DIR, name + ".npz"))
+    dev = cuda_device
+    mean, var, info = ops.sm_predict(
+        _t(g["x"], dev), _t(g["y"], dev), _t(g["noise"], dev), _t(g["raw"], dev),
+        _t(g["kinds"], dev, torch.int32), _t(g["lb"], dev), _t(g["ub"], dev),
+        _t(g["n_valid"], dev, torch.int32), _t(p["xstar"], dev), g["kind"], g["Q"],
+        g["learn_noise"])
+    assert info.cpu().tolist() == [0] * mean.shape[0]
+    scale = max(1.0, float(np.abs(p["var"]).max()), float(np.abs(p["mean"]).max()))
+    assert np.abs(mean.cpu().numpy() - p["mean"]).max() <= 1e-9 * scale
+    assert np.abs(var.cpu().numpy() - p["var"]).max() <= 1e-9 * scale
+
+
+def test_prediction_interpolates_and_reverts_to_the_prior(cuda_device):
+    """Properties at C2's size (n = 512): at the training inputs the latent variance is below
+    the noise level and the mean tracks y; far outside the data var* -> k(0) = sum w_q and
+    mean* -> the constant mean.  Also 10000 test points per light curve (the reference's grid)."""
+    from pgmuvi_b200 import ops, synthetic as S
+    bt = S.make_batch_1d(3, 512, Q=4, seed0=909)
+    dev = cuda_device
+    x, y, nz, raw = (_t(bt[k], dev) for k in ("x", "y", "noise", "raw"))
+    kinds, lb, ub = _t(bt["kinds"], dev, torch.int32), _t(bt["lb"], dev), _t(bt["ub"], dev)
+    xs = torch.cat([x[:, :, 0], torch.full((3, 64), 50.0, dtype=torch.float64, device=dev)], 1)
+    mean, var, info = ops.sm_predict(x, y, nz, raw, kinds, lb, ub, None, xs.unsqueeze(-1), 0, 4,
+                                     False)
+    assert info.cpu().tolist() == [0, 0, 0]
+    assert bool((var[:, :512] < nz).all()) and bool((var[:, :512] > -1e-12).all())
+    assert float((mean[:, :512] - y).abs().max()) < 0.5
+    from oracle import CON_SOFTPLUS  # noqa: F401  (constraints follow the oracle's table)
+    w = torch.nn.functional.softplus(raw[:, 1:5])
+    assert torch.allclose(var[:, 512:], w.sum(1, keepdim=True).expand(-1, 64), rtol=1e-9)
+    grid = torch.linspace(0, 1, 10000, dtype=torch.float64, device=dev).expand(3, -1).contiguous()
+    m2, v2, _ = ops.sm_predict(x, y, nz, raw, kinds, lb, ub, None, grid.unsqueeze(-1), 0, 4, False)
+    assert bool(torch.isfinite(m2).all()) and bool((v2 > -1e-10).all())

@@ -148,3 +148,27 @@ def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
     assert np.allclose(pk.raw().detach().numpy(), ref["raw"][-1], rtol=1e-8, atol=1e-10)
     res = train(lc, maxiter=40, miniter=40, stop=None, lr=0.05, optim="AdamW")
     assert res["loss"][-1] < res["loss"][0]
+
+
+def test_lightcurve_predict_after_fit(cuda_device):
+    """The body of the reference's plot(): likelihood(model(x_fine)) on the 10000-point grid
+    (lightcurve.py:9607-9640, 9862), here exact and on the GPU, against the oracle."""
+    from oracle import predict
+    torch.manual_seed(0)
+    lc = _lc(n=150).double()
+    lc.set_model("1D", likelihood="learn", num_mixtures=2)
+    lc.double()
+    lc.fit(training_iter=20, lr=0.05, periods=[57.0, 120.0])
+    out = lc.predict(n_points=1000)
+    assert out["mean"].shape == (1000,) and np.all(out["upper"] >= out["lower"])
+    args, pk = _oracle_inputs(lc)
+    xs = lc.xtransform.transform(torch.as_tensor(out["x"])).double().unsqueeze(-1)
+    mu, var, info = predict(*args[:7], args[7], xs)
+    noise = float(lc.likelihood.second_noise_covar.raw_noise_constraint.transform(
+        lc.likelihood.second_noise_covar.raw_noise))
+    assert np.abs(out["mean"] - mu.numpy()).max() <= 1e-8
+    assert np.abs(out["variance"] - (var.numpy() + noise)).max() <= 1e-8
+    # the fitted GP follows the sinusoid it was trained on
+    t = out["x"]
+    truth = np.sin(2 * np.pi * t / 57.0)
+    assert np.sqrt(np.mean((out["mean"] - truth) ** 2)) < 0.15
