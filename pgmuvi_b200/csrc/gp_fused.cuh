@@ -134,10 +134,13 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
 
 __host__ __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// exp(x) for x <= 0, branch free: x = (64 e + j) ln2/64 + r, |r| <= ln2/128,
-// exp(x) = 2^e * T[j] * (1 + r + ... + r^5/120)   (truncation 3.5e-17 relative).
-// T = correctly rounded 2^(j/64), held in shared memory.
-__constant__ double c_exp2_tab[64] = {
+// exp(x) for x <= 0 (small positive x also fine), branch free:
+//   x = (2048 e + 32 j1 + j2) ln2/2048 + r, |r| <= ln2/4096,
+//   exp(x) = 2^e * T1[j1] * T2[j2] * (1 + r + r^2/2 + r^3/6)   (truncation 3.4e-17 relative).
+// T1 = correctly rounded 2^(j/64), T2 = 2^(j/2048), 96 doubles held in shared memory.
+// One-constant argument reduction: |error| <= |x| * 8e-17 relative, <= 3e-17 absolute.
+constexpr int EXP_TAB = 96;
+__constant__ double c_exp2_tab[EXP_TAB] = {
     0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
     0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
     0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
@@ -153,7 +156,20 @@ __constant__ double c_exp2_tab[64] = {
     0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
     0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
     0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
-    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+    // 2^(j/2048), j = 0..31
+    0x1.0000000000000p+0, 0x1.00162f3904052p+0, 0x1.002c605e2e8cfp+0, 0x1.0042936faa3d8p+0,
+    0x1.0058c86da1c0ap+0, 0x1.006eff583fc3dp+0, 0x1.0085382faef83p+0, 0x1.009b72f41a12bp+0,
+    0x1.00b1afa5abcbfp+0, 0x1.00c7ee448ee02p+0, 0x1.00de2ed0ee0f5p+0, 0x1.00f4714af41d3p+0,
+    0x1.010ab5b2cbd11p+0, 0x1.0120fc089ff63p+0, 0x1.0137444c9b5b5p+0, 0x1.014d8e7ee8d2fp+0,
+    0x1.0163da9fb3335p+0, 0x1.017a28af25567p+0, 0x1.019078ad6a19fp+0, 0x1.01a6ca9aac5f3p+0,
+    0x1.01bd1e77170b4p+0, 0x1.01d37442d5070p+0, 0x1.01e9cbfe113efp+0, 0x1.020025a8f6a35p+0,
+    0x1.02168143b0281p+0, 0x1.022cdece68c4fp+0, 0x1.02433e494b755p+0, 0x1.02599fb483385p+0,
+    0x1.027003103b10ep+0, 0x1.0286685c9e059p+0, 0x1.029ccf99d720ap+0, 0x1.02b338c811703p+0};
+// cooperative copy of the table into shared memory (any block of >= 96 threads)
+__device__ __forceinline__ void load_exp_tab(double* tab) {
+  if (threadIdx.x < EXP_TAB) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+}
 
 #ifdef PGM_DEBUG_HOOKS
 // -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 and decomposition switches
@@ -177,19 +193,19 @@ __constant__ long long* c_prof = nullptr;
 #define PGM_PROF(slot) do { } while (0)
 #endif
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
-  x = fmax(x, -700.0);
-  double t = fma(x, 0x1.71547652b82fep+6, 6755399441055744.0);  // round(x * 64/ln2)
+  // clamp x >= -700 on the integer pipe (sign-magnitude: larger high word = more negative)
+  const unsigned hx = min((unsigned)__double2hiint(x), 0xC085E000u);
+  x = __hiloint2double((int)hx, __double2loint(x));
+  double t = fma(x, 0x1.71547652b82fep+11, 6755399441055744.0);  // round(x * 2048/ln2)
   const int k = __double2loint(t);
   t -= 6755399441055744.0;
-  double r = fma(t, -0x1.62e42fee00000p-7, x);   // ln2/64 hi (33 significant bits)
-  r = fma(t, -0x1.a39ef35793c76p-39, r);         // ln2/64 lo
-  double p = fma(r, 8.33333333333333333e-03, 4.16666666666666667e-02);
-  p = fma(p, r, 1.66666666666666667e-01);
-  p = fma(p, r, 0.5);
+  const double r = fma(t, -0x1.62e42fefa39efp-12, x);            // ln2/2048
+  const double tt = tab[(k >> 5) & 63] * tab[64 + (k & 31)];
+  double p = fma(r, 1.66666666666666667e-01, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  const double v = tab[k & 63] * p;
-  return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+  const double v = tt * p;
+  return __hiloint2double(__double2hiint(v) + ((k >> 11) << 20), __double2loint(v));
 }
 
 // ------------------------------------------------------------------------------------
@@ -224,8 +240,8 @@ struct Cfg {
   static constexpr int PAR_ZJ = (PAR_FIN + NV + 4 + 1) & ~1;   // z_j of the current block column [64], 16-B aligned
   static constexpr int PAR_ZI = PAR_ZJ + TS;          // z_i of the current tile row / scratch [64]
   static constexpr int PAR_DINV = PAR_ZI + TS;        // 1 / L_kk of the current diagonal block [64]
-  static constexpr int PAR_TAB = PAR_DINV + TS;       // 2^(j/64) table [64]
-  static constexpr int PAR_RAW = PAR_TAB + 64;        // raw / adam state / gradient (fit kernel)
+  static constexpr int PAR_TAB = PAR_DINV + TS;       // exp tables [EXP_TAB]
+  static constexpr int PAR_RAW = PAR_TAB + EXP_TAB;        // raw / adam state / gradient (fit kernel)
   static constexpr int PAR_BAR = PAR_RAW + 4 * PMAX;  // 11 mbarriers (8 B each)
   static constexpr int PAR_END = PAR_BAR + 12;
   static constexpr int SM_TOTAL = SM_PAR + PAR_END + 8;
@@ -891,7 +907,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     theta[tid] = th;
     jac[tid] = jc;
   }
-  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  load_exp_tab(tab);
   __syncthreads();
   if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
   if (tid < QT * DS) {
@@ -1087,7 +1103,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           zero_acc(acc);
           compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
           compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
-          // partial products L_ij z_j for the forward solve of row i (deterministic order)
+          // partial products L_ij z_j for the forward solve of row i (deterministic order);
+          // their global stores are issued after the tile has left, so that the proxy fence
+          // of the bulk store (MEMBAR.ALL.CTA) has no global store of this thread to drain
+          double pp[4];
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi) {
             double s = 0.0;
@@ -1097,9 +1116,14 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
               for (int e = 0; e < 2; ++e) s += acc[mi][ni2][e] * zj[frag_col(wn, ni2, tq, e)];
             s += shfl_xor_d(s, 1);
             s += shfl_xor_d(s, 2);
-            if (tq == 0) sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
+            pp[mi] = s;
           }
           store_tile_bulk(acc, Cst, tile(i, j), 1.0);
+          if (tq == 0) {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+              sc.fpart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = pp[mi];
+          }
           PGM_PROF(5);
         }
       }
@@ -1162,7 +1186,9 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           rwait = false;
         }
         times_resident();
-        // partial products X_ij^T z_i for alpha_j  (X_ij^T = -acc)
+        // partial products X_ij^T z_i for alpha_j  (X_ij^T = -acc); stored after the tile
+        // has left (see phase P)
+        double pp[4];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi) {
           double s = 0.0;
@@ -1172,9 +1198,14 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             for (int e = 0; e < 2; ++e) s -= acc[mi][ni2][e] * zi[frag_col(wn, ni2, tq, e)];
           s += shfl_xor_d(s, 1);
           s += shfl_xor_d(s, 2);
-          if (tq == 0) sc.apart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = s;
+          pp[mi] = s;
         }
         store_tile_bulk(acc, Cst, tile(i, j), -1.0);
+        if (tq == 0) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+            sc.apart[((size_t)tri(i, j) * 4 + wn) * TS + frag_row(wm, mi, g)] = pp[mi];
+        }
         PGM_PROF(8);
       }
     }
@@ -1343,7 +1374,7 @@ __global__ void __launch_bounds__(NTHREADS)
   constexpr int DS = C::DS;
   __shared__ __align__(16) double rowv[C::NFB * TS];
   __shared__ __align__(16) double colv[C::NFB * TS];
-  __shared__ double theta[C::PMAX], wq[QT], aq[QT * DS], lamq[4], tab[64];
+  __shared__ double theta[C::PMAX], wq[QT], aq[QT * DS], lamq[4], tab[EXP_TAB];
   const int tid = threadIdx.x;
   const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
   const int Q = A.Q;
@@ -1362,7 +1393,7 @@ __global__ void __launch_bounds__(NTHREADS)
     else if (kd == 2) th = lb + (ub - lb) * sigmoid_d(rv);
     theta[tid] = th;
   }
-  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  load_exp_tab(tab);
   __syncthreads();
   if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
   if (tid < QT * DS) {

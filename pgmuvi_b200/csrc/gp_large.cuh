@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* par = sm + C::SM_PAR;
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
-  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  load_exp_tab(tab);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
   Ring r2{bars, bars + 16, stages, 0};
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* fin = par + C::PAR_FIN;
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
-  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  load_exp_tab(tab);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
   Ring r2{bars, bars + 16, stages, 0};
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
   (void)red;
-  if (tid >= 64 && tid < 128) tab[tid - 64] = c_exp2_tab[tid - 64];
+  load_exp_tab(tab);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
   Ring r2{bars, bars + 16, stages, 0};
