@@ -180,6 +180,33 @@ int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
                    int32_t* n_iter, int32_t* info, double* opt_state, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/*
+ * fp32 entry points: the reference's DEFAULT dtype (pgmuvi casts data to torch.float32,
+ * lightcurve.py:2434-2446, 742-745; parameters and constraint bounds are fp32 unless the user
+ * calls .double()).  Same arguments as the _f64 entry points with float buffers.  Storage is
+ * fp32, arithmetic is fp64: inputs are widened into a staging area on device, the fp64 kernels
+ * run, results are rounded once to fp32 - i.e. the results are the correctly rounded fp32
+ * values of the fp64 path (north-star fp32 bar: 1e-4 relative against the fp64 oracle).
+ * The workspace is the _f64 workspace rounded up to 256 bytes, followed by
+ * pgm_f32_staging_bytes(...) bytes (maxiter = 0 / want_raw_hist = 0 for pgm_sm_mll_grad_f32).
+ * pgm_sm_fit_f32 keeps the optimiser state and the iterates in fp64 on device for the whole
+ * loop and narrows raw / loss_hist / raw_hist at the end.
+ */
+size_t pgm_f32_staging_bytes(int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                             int maxiter, int want_raw_hist);
+int pgm_sm_mll_grad_f32(const float* x, const int32_t* n_valid, const float* y,
+                        const float* fixed_noise, const float* raw, const int32_t* con_kind,
+                        const float* con_lb, const float* con_ub, int B, int n_max, int d, int Q,
+                        int kernel_kind, int flags, float* mll, float* grad_raw, int32_t* info,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
+                   const float* fixed_noise, float* raw, const int32_t* con_kind,
+                   const float* con_lb, const float* con_ub, int B, int n_max, int d, int Q,
+                   int kernel_kind, int flags, int optim_kind, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int maxiter, int miniter,
+                   double stop, int stopavg, float* loss_hist, float* raw_hist, int32_t* n_iter,
+                   int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Device yardsticks used by bench.py for the self-measured FP64 roofline: runs `iters`
  * dependent-free FP64 DMMA (kind 0), FP64 DFMA (kind 1), FP32 FFMA (kind 2) or interleaved
  * DMMA+DFMA (kind 3, equal flops each) instructions per thread on every SM and returns the

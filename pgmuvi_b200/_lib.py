@@ -26,6 +26,7 @@ EXPORTS = (
     "pgm_sm_kernel_dense_f64", "pgm_optim_step_f64", "pgm_sm_fit_f64", "pgm_peak_probe",
     "pgm_staged_workspace_bytes", "pgm_sm_mll_grad_staged_f64",
     "pgm_predict_workspace_bytes", "pgm_sm_predict_f64",
+    "pgm_f32_staging_bytes", "pgm_sm_mll_grad_f32", "pgm_sm_fit_f32",
 )
 
 _lib = None
@@ -73,6 +74,15 @@ def load():
     lib.pgm_sm_predict_f64.restype = c_int
     lib.pgm_sm_predict_f64.argtypes = [dp, ip, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int, c_int,
                                        c_int, c_int, dp, c_int, dp, dp, ip, vp, c_size_t, vp]
+    lib.pgm_f32_staging_bytes.restype = c_size_t
+    lib.pgm_f32_staging_bytes.argtypes = [c_int] * 8
+    lib.pgm_sm_mll_grad_f32.restype = c_int
+    lib.pgm_sm_mll_grad_f32.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
+    lib.pgm_sm_fit_f32.restype = c_int
+    lib.pgm_sm_fit_f32.argtypes = [dp, ip, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_int, c_double, c_double, c_double, c_double,
+                                   c_double, c_int, c_int, c_double, c_int, dp, dp, ip, ip,
+                                   vp, c_size_t, vp]
     lib.pgm_peak_probe.restype = c_int
     lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
     _lib = lib

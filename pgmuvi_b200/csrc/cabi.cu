@@ -4,6 +4,7 @@
 #include "gp_large.cuh"
 #include "../../include/pgmuvi_b200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -47,6 +48,18 @@ __global__ void optim_step_kernel(double* raw, const double* grad_mll, double* m
   if (v) v[idx] = vv;
 }
 
+
+// fp32 <-> fp64 staging of the _f32 entry points (fp32 storage, fp64 arithmetic)
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (double)src[i];
+}
+__global__ void narrow_kernel(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
 }  // namespace pgm
 
 namespace {
@@ -109,11 +122,59 @@ int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
   return 0;
 }
 
+
+// number of packed raw parameters of a model (layout in include/pgmuvi_b200.h)
+int host_param_count(int d, int Q, int kernel_kind, int flags) {
+  const bool sep = kernel_kind >= PGM_KIND_SEP_RBF;
+  const int ds = sep ? 1 : d;
+  const int nl = (kernel_kind == PGM_KIND_SEP_RBF || kernel_kind == PGM_KIND_SEP_MATERN15) ? 2
+                 : (kernel_kind == PGM_KIND_SEP_RQ) ? 3 : (kernel_kind == PGM_KIND_SEP_CONST) ? 1 : 0;
+  return 1 + Q + 2 * Q * ds + ((flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0) + nl;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// fp64 staging area of the _f32 entry points, carved from the tail of the workspace
+struct Stage32 {
+  double *x, *y, *fn, *raw, *lb, *ub, *mll, *grad, *loss, *hist;
+  size_t bytes;
+};
+Stage32 carve32(char* base, int B, int n_max, int d, int P, bool bounds_per_lc, int maxiter,
+                bool want_hist) {
+  Stage32 s;
+  size_t off = 0;
+  auto take = [&](size_t elems) {
+    double* p = base ? reinterpret_cast<double*>(base + off) : nullptr;
+    off += align256(elems * sizeof(double));
+    return p;
+  };
+  const size_t Bn = (size_t)B * n_max, BP = (size_t)B * P;
+  s.x = take(Bn * d); s.y = take(Bn); s.fn = take(Bn); s.raw = take(BP);
+  s.lb = take(bounds_per_lc ? BP : (size_t)P); s.ub = take(bounds_per_lc ? BP : (size_t)P);
+  s.mll = take((size_t)B); s.grad = take(BP);
+  s.loss = take((size_t)maxiter * B);
+  s.hist = take(want_hist ? (size_t)(maxiter + 1) * BP : 0);
+  s.bytes = off;
+  return s;
+}
+int widen(const float* src, double* dst, size_t n, cudaStream_t st) {
+  if (!n) return 0;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  pgm::widen_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+  return 0;
+}
+int narrow(const double* src, float* dst, size_t n, cudaStream_t st) {
+  if (!n) return 0;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  pgm::narrow_kernel<<<blocks, 256, 0, st>>>(src, dst, n);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
-int pgm_version(void) { return 100; }
+int pgm_version(void) { return 101; }
 const char* pgm_last_error(void) { return pgm::g_err.c_str(); }
 
 size_t pgm_workspace_bytes(int elem_size, int n_max, int d, int Q, int device) {
@@ -292,6 +353,93 @@ int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
   F.n_iter = n_iter;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGM_DISPATCH(launch_fit, F, st);
+  return 0;
+}
+
+size_t pgm_f32_staging_bytes(int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                             int maxiter, int want_raw_hist) {
+  if (B < 1 || n_max < 1) return 0;
+  const int P = host_param_count(d, Q, kernel_kind, flags);
+  return carve32(nullptr, B, n_max, d, P, (flags & PGM_FLAG_BOUNDS_PER_LC) != 0,
+                 maxiter < 0 ? 0 : maxiter, want_raw_hist != 0).bytes;
+}
+
+int pgm_sm_mll_grad_f32(const float* x, const int32_t* n_valid, const float* y,
+                        const float* fixed_noise, const float* raw, const int32_t* con_kind,
+                        const float* con_lb, const float* con_ub, int B, int n_max, int d, int Q,
+                        int kernel_kind, int flags, float* mll, float* grad_raw, int32_t* info,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
+    return fail("null pointer argument");
+  if ((flags & PGM_FLAG_GRAD) && !grad_raw) return fail("PGM_FLAG_GRAD needs grad_raw");
+  const int P = host_param_count(d, Q, kernel_kind, flags);
+  const bool per_lc = (flags & PGM_FLAG_BOUNDS_PER_LC) != 0;
+  const size_t base = align256(pgm_workspace_bytes(8, n_max, d, Q, -1));
+  const size_t need = base + pgm_f32_staging_bytes(B, n_max, d, Q, kernel_kind, flags, 0, 0);
+  if (workspace_bytes < need)
+    return fail("workspace too small (pgm_workspace_bytes rounded up to 256 + pgm_f32_staging_bytes)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Stage32 s = carve32(static_cast<char*>(workspace) + base, B, n_max, d, P, per_lc, 0, false);
+  const size_t Bn = (size_t)B * n_max, BP = (size_t)B * P;
+  widen(x, s.x, Bn * d, st); widen(y, s.y, Bn, st);
+  if (fixed_noise) widen(fixed_noise, s.fn, Bn, st);
+  widen(raw, s.raw, BP, st);
+  widen(con_lb, s.lb, per_lc ? BP : (size_t)P, st);
+  widen(con_ub, s.ub, per_lc ? BP : (size_t)P, st);
+  if (int r = pgm_sm_mll_grad_f64(s.x, n_valid, s.y, fixed_noise ? s.fn : nullptr, s.raw, con_kind,
+                                  s.lb, s.ub, B, n_max, d, Q, kernel_kind, flags, s.mll,
+                                  (flags & PGM_FLAG_GRAD) ? s.grad : nullptr, info, workspace,
+                                  base, stream))
+    return r;
+  narrow(s.mll, mll, (size_t)B, st);
+  if (flags & PGM_FLAG_GRAD) narrow(s.grad, grad_raw, BP, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("f32 staging", e);
+  return 0;
+}
+
+int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
+                   const float* fixed_noise, float* raw, const int32_t* con_kind,
+                   const float* con_lb, const float* con_ub, int B, int n_max, int d, int Q,
+                   int kernel_kind, int flags, int optim_kind, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, int maxiter, int miniter,
+                   double stop, int stopavg, float* loss_hist, float* raw_hist, int32_t* n_iter,
+                   int32_t* info, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !loss_hist || !n_iter || !info ||
+      !workspace)
+    return fail("null pointer argument");
+  if (maxiter < 1) return fail("maxiter must be >= 1");
+  const int P = host_param_count(d, Q, kernel_kind, flags);
+  const bool per_lc = (flags & PGM_FLAG_BOUNDS_PER_LC) != 0;
+  const size_t base = align256(pgm_workspace_bytes(8, n_max, d, Q, -1));
+  const size_t need = base + pgm_f32_staging_bytes(B, n_max, d, Q, kernel_kind, flags, maxiter,
+                                                   raw_hist != nullptr);
+  if (workspace_bytes < need)
+    return fail("workspace too small (pgm_workspace_bytes rounded up to 256 + pgm_f32_staging_bytes)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Stage32 s = carve32(static_cast<char*>(workspace) + base, B, n_max, d, P, per_lc, maxiter,
+                      raw_hist != nullptr);
+  const size_t Bn = (size_t)B * n_max, BP = (size_t)B * P;
+  widen(x, s.x, Bn * d, st); widen(y, s.y, Bn, st);
+  if (fixed_noise) widen(fixed_noise, s.fn, Bn, st);
+  widen(raw, s.raw, BP, st);
+  widen(con_lb, s.lb, per_lc ? BP : (size_t)P, st);
+  widen(con_ub, s.ub, per_lc ? BP : (size_t)P, st);
+  if (int r = pgm_sm_fit_f64(s.x, n_valid, s.y, fixed_noise ? s.fn : nullptr, s.raw, con_kind, s.lb,
+                             s.ub, B, n_max, d, Q, kernel_kind, flags, optim_kind, lr, beta1, beta2,
+                             eps, weight_decay, maxiter, miniter, stop, stopavg, s.loss,
+                             raw_hist ? s.hist : nullptr, n_iter, info, nullptr, workspace, base,
+                             stream))
+    return r;
+  narrow(s.raw, raw, BP, st);
+  narrow(s.loss, loss_hist, (size_t)maxiter * B, st);
+  if (raw_hist) narrow(s.hist, raw_hist, (size_t)(maxiter + 1) * BP, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("f32 staging", e);
   return 0;
 }
 

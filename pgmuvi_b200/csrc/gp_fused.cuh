@@ -173,7 +173,8 @@ __device__ __forceinline__ void load_exp_tab(double* tab) {
 
 #ifdef PGM_DEBUG_HOOKS
 // -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 and decomposition switches
-// (PGM_DEBUG_MODE: 0x100 no operand loads, 0x200 no MMAs, 0x800 ignore potrf failures) -
+// (PGM_DEBUG_MODE: 0x100 no operand loads, 0x200 no MMAs, 0x400 no exp/cos epilogue work,
+// 0x800 ignore potrf failures, 0x1000 skip the diagonal-block factorisation) -
 // timing experiments only, results are garbage
 __constant__ int c_dbg = 0;
 #define PGM_DBG(bit) (c_dbg & (bit))
@@ -1035,7 +1036,8 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int gj = j * TS + c0 + e;
-            double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
+            double kv = PGM_DBG(0x400) ? 1e-3
+                                       : k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
             kv = (gi < n && gj <= gi) ? kv : 0.0;
             if (gi == gj) kv = (gi < n) ? (kv + sc.dn[gi] + jitter) : 1.0;
             out[e] = kv - (e ? cv.y : cv.x);
@@ -1050,7 +1052,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         PGM_PROF(2);
         if (i == j) {
           __syncthreads();
-          potrf_inv_64(S, S2, dinv, s_fail);
+          if (!PGM_DBG(0x1000)) potrf_inv_64(S, S2, dinv, s_fail);
           PGM_PROF(3);
           if (*s_fail && !PGM_DBG(0x800)) { failed = true; break; }
           // X_jj -> tile(j,j) and the resident R, X_jj^T -> tilesT[j]  (tile images with
@@ -1271,7 +1273,8 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             W = (gi < n && gj <= gi) ? W : 0.0;
             if (gi == gj) trW += W;
             const double wgt = (gi == gj) ? W : 2.0 * W;
-            k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
+            if (!PGM_DBG(0x400))
+              k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
           }
         }
         PGM_PROF(11);

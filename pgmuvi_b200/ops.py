@@ -30,10 +30,12 @@ def _require_cuda(*ts):
             raise RuntimeError("pgmuvi_b200 ops need CUDA tensors (there is no CPU fallback)")
 
 
-def _workspace(device, n_max, d, Q):
+def _workspace(device, n_max, d, Q, extra=0):
     lib = _lib.load()
     need = lib.pgm_workspace_bytes(8, n_max, d, Q, device.index if device.index is not None
                                    else torch.cuda.current_device())
+    if extra:   # fp32 entry points: fp64 staging area behind the (256-aligned) base workspace
+        need = ((need + 255) & ~255) + extra
     key = (device.index, )
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
@@ -48,8 +50,12 @@ def _stream():
 
 def _prep(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise):
     _require_cuda(x, y, fixed_noise, raw, con_kind, con_lb, con_ub)
-    if x.dtype != torch.float64:
-        raise RuntimeError("only float64 is implemented in this build")
+    if x.dtype not in (torch.float64, torch.float32):
+        raise RuntimeError("pgmuvi_b200 ops take float64 or float32 tensors")
+    for t in (y, fixed_noise, raw, con_lb, con_ub):
+        if t is not None and t.dtype != x.dtype:
+            raise RuntimeError(f"all floating tensors must share one dtype ({x.dtype}), "
+                               f"got {t.dtype}")
     B, n = y.shape
     d = 1 if kind == KIND_SM1D else 2
     if x.shape != (B, n, d):
@@ -86,9 +92,13 @@ def sm_mll_grad(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor
     info = torch.zeros(B, dtype=torch.int32, device=x.device)
     if n_valid is not None:
         n_valid = n_valid.to(torch.int32).contiguous()
-    ws, nbytes = _workspace(x.device, n, d, Q)
+    lib = _lib.load()
+    f32 = x.dtype == torch.float32
+    extra = lib.pgm_f32_staging_bytes(B, n, d, Q, kind, flags, 0, 0) if f32 else 0
+    ws, nbytes = _workspace(x.device, n, d, Q, extra)
+    entry = lib.pgm_sm_mll_grad_f32 if f32 else lib.pgm_sm_mll_grad_f64
     with torch.cuda.device(x.device):
-        check(_lib.load().pgm_sm_mll_grad_f64(
+        check(entry(
             ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
             ptr(con_ub), B, n, d, Q, kind, flags, ptr(mll), ptr(grad), ptr(info), ptr(ws),
             ws.numel(), _stream()))
@@ -111,6 +121,8 @@ def sm_kernel_dense(x: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con_k
     y = x.new_empty(B, n)
     (x, _, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
         x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    if x.dtype != torch.float64:
+        raise RuntimeError("sm_kernel_dense takes float64 tensors")
     K = torch.zeros(B, n, n, dtype=x.dtype, device=x.device)
     if n_valid is not None:
         n_valid = n_valid.to(torch.int32).contiguous()
@@ -162,9 +174,21 @@ def sm_fit(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con
     info = torch.zeros(B, dtype=torch.int32, device=x.device)
     if n_valid is not None:
         n_valid = n_valid.to(torch.int32).contiguous()
+    lib = _lib.load()
+    if x.dtype == torch.float32:
+        extra = lib.pgm_f32_staging_bytes(B, n, d, Q, kind, flags, maxiter, int(keep_history))
+        ws, _ = _workspace(x.device, n, d, Q, extra)
+        with torch.cuda.device(x.device):
+            check(lib.pgm_sm_fit_f32(
+                ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind),
+                ptr(con_lb), ptr(con_ub), B, n, d, Q, kind, flags, optim_kind, lr, beta1, beta2,
+                eps, weight_decay, maxiter, miniter, stop, stopavg, ptr(loss_hist),
+                ptr(raw_hist) if keep_history else None, ptr(n_iter), ptr(info), ptr(ws),
+                ws.numel(), _stream()))
+        return loss_hist, raw_hist, n_iter, info
     ws, _ = _workspace(x.device, n, d, Q)
     with torch.cuda.device(x.device):
-        check(_lib.load().pgm_sm_fit_f64(
+        check(lib.pgm_sm_fit_f64(
             ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
             ptr(con_ub), B, n, d, Q, kind, flags, optim_kind, lr, beta1, beta2, eps, weight_decay,
             maxiter, miniter, stop, stopavg, ptr(loss_hist),
@@ -185,6 +209,8 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
     the batch advances stage by stage.  Blocking."""
     (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
         x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    if x.dtype != torch.float64:
+        raise RuntimeError("the staged engine takes float64 tensors")
     if want_grad:
         flags |= FLAG_GRAD
     lib = _lib.load()

@@ -70,6 +70,25 @@ def test_workspace_is_per_block_not_per_lightcurve():
     assert 0 < w512 < w1024 < (8 << 30)
 
 
+def test_f32_staging_size_and_validation():
+    lib = _lib.load()
+    # mll+grad: x, y, noise [B,n] + raw, grad [B,P] + lb, ub [P] + mll [B], each 256-aligned
+    s1 = lib.pgm_f32_staging_bytes(4096, 512, 1, 4, 0, 0, 0, 0)
+    assert s1 >= 8 * (3 * 4096 * 512 + 2 * 4096 * 13 + 2 * 13 + 4096)
+    assert s1 < 8 * (3 * 4096 * 512 + 2 * 4096 * 13 + 2 * 13 + 4096) + 12 * 256
+    # the fit entry adds the loss and raw histories
+    s2 = lib.pgm_f32_staging_bytes(4096, 512, 1, 4, 0, 0, 300, 1)
+    assert s2 - s1 >= 8 * (300 * 4096 + 301 * 4096 * 13)
+    one = 8
+    rc = lib.pgm_sm_mll_grad_f32(one, None, one, None, one, one, one, one, 1, 64, 1, 4, 0, 0,
+                                 one, None, one, one, 1024, None)
+    assert rc == -1 and b"workspace" in lib.pgm_last_error()
+    rc = lib.pgm_sm_fit_f32(one, None, one, None, one, one, one, one, 1, 64, 1, 4, 0, 0, 2, 0.1,
+                            0.9, 0.999, 1e-8, 0.01, 0, 0, 0.0, 9, one, None, one, one, one,
+                            1 << 30, None)
+    assert rc == -1 and b"maxiter" in lib.pgm_last_error()
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     from pgmuvi_b200 import ops

@@ -242,3 +242,66 @@ def test_c2_full_size_quadratic_form_second_difference(c2):
     q2 = F(d["y"] + 2 * r) + F(d["y"] - 2 * r) - 2 * f0
     assert (q1 > 0).all()
     assert ((q2 - 4 * q1).abs() <= 1e-8 * q2.abs()).all()
+
+
+# ---- fp32 entry points (the reference's default dtype) ---------------------------
+F32_RTOL = 1e-4   # north star: MLL and gradients within 1e-4 relative in fp32
+
+
+@pytest.mark.parametrize("name", ["sm1d_n100_q2_learn", "sm1d_n512_q4", "sm1d_ragged_q4",
+                                  "sm2d_prodsum_4x48_q4", "sep_rq_4x48_q4"])
+def test_f32_entry_matches_f64_path_on_the_same_rounded_inputs(name, cuda_device):
+    """pgm_sm_mll_grad_f32 = fp32 storage, fp64 arithmetic: on the fp32-rounded inputs it must
+    equal the fp64 entry point rounded once to fp32, and stay within the fp32 bar of the
+    oracle evaluated on those same inputs."""
+    from pgmuvi_b200 import ops
+    from oracle import ModelSpec, mll_and_grad_analytic
+    g = load_golden(name)
+    d = _dev(g, cuda_device)
+    f32 = {k: (v.to(torch.float32) if v is not None and v.dtype == torch.float64 else v)
+           for k, v in d.items()}
+    mll32, grad32, info32 = _eval(ops, g, f32)
+    assert mll32.dtype == torch.float32 and grad32.dtype == torch.float32
+    up = {k: (v.to(torch.float64) if v is not None and v.dtype == torch.float32 else v)
+          for k, v in f32.items()}
+    mll64, grad64, info64 = _eval(ops, g, up)
+    assert torch.equal(info32, info64)
+    assert torch.equal(mll32, mll64.to(torch.float32))
+    assert torch.equal(grad32, grad64.to(torch.float32))
+    # oracle on the rounded inputs (first light curve)
+    spec = ModelSpec(d=g["d"], Q=g["Q"], kind=g["kind"], learn_noise=g["learn_noise"])
+    nb = g["x"].shape[1] if g["n_valid"] is None else int(g["n_valid"][0])
+    c = lambda t: None if t is None else t[0].cpu()
+    lb, ub = up["lb"].cpu(), up["ub"].cpu()
+    if lb.dim() == 2:
+        lb, ub = lb[0], ub[0]
+    xo = c(up["x"])[:nb]
+    mo, go, _ = mll_and_grad_analytic(xo, c(up["y"])[:nb],
+                                      None if up["noise"] is None else c(up["noise"])[:nb],
+                                      c(up["raw"]), d["kinds"].cpu(), lb, ub, spec)
+    assert abs(float(mll32[0]) - float(mo)) <= F32_RTOL * abs(float(mo))
+    assert float((grad32[0].cpu().double() - go).abs().max()) <= F32_RTOL * float(go.abs().max())
+
+
+def test_f32_fit_entry_matches_f64_fit(cuda_device):
+    from pgmuvi_b200 import ops, _lib
+    g = load_golden("sm1d_n100_q2_learn")
+    d = _dev(g, cuda_device)
+    f32 = {k: (v.to(torch.float32) if v is not None and v.dtype == torch.float64 else v)
+           for k, v in d.items()}
+    args = (g["kind"], g["Q"], g["learn_noise"], _lib.OPT_ADAMW, 0.1, 0.9, 0.999, 1e-8, 0.01, 5,
+            5, 0.0, 9, True)
+    raw32 = f32["raw"].clone()
+    loss32, hist32, it32, info32 = ops.sm_fit(f32["x"], f32["y"], f32["noise"], raw32,
+                                              f32["kinds"], f32["lb"], f32["ub"], f32["n_valid"],
+                                              *args)
+    raw64 = f32["raw"].double().clone()
+    loss64, hist64, it64, info64 = ops.sm_fit(f32["x"].double(), f32["y"].double(),
+                                              f32["noise"].double(), raw64, f32["kinds"],
+                                              f32["lb"].double(), f32["ub"].double(),
+                                              f32["n_valid"], *args)
+    assert loss32.dtype == torch.float32 and hist32.dtype == torch.float32
+    assert torch.equal(it32, it64) and torch.equal(info32, info64)
+    assert torch.equal(loss32, loss64.float())
+    assert torch.equal(hist32, hist64.float())
+    assert torch.equal(raw32, raw64.float())
