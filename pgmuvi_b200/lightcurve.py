@@ -11,6 +11,8 @@ Nothing here computes the GP on the CPU.
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -84,7 +86,7 @@ class Lightcurve(torch.nn.Module):
     (``_ensure_tensor``, :2434-2446); ``.double()`` opts into float64."""
 
     def __init__(self, xdata, ydata, yerr=None, xtransform="minmax", ytransform=None, name=None,
-                 **kwargs):
+                 max_samples=1000, subsample_seed=None, sampling_kwargs=None, **kwargs):
         super().__init__()
         self.name = name
         self.xtransform = _make_transform(xtransform)
@@ -95,6 +97,22 @@ class Lightcurve(torch.nn.Module):
             x = x[:, 0]
         if torch.isnan(x).any() or torch.isnan(y).any():
             raise ValueError("The x / y values contain NaNs.")
+        # 1-D light curves longer than max_samples are sub-sampled before anything else
+        # (lightcurve.py:1733, 2150-2181; random unless subsample_seed is given)
+        if max_samples is not None and x.dim() == 1 and x.shape[0] > max_samples:
+            from .preprocess import subsample_lightcurve
+            n_total = x.shape[0]
+            idx = subsample_lightcurve(
+                x.numpy(), max_samples=max_samples, random_seed=subsample_seed,
+                max_gap_fraction=(sampling_kwargs or {}).get("max_gap_fraction", 0.3))
+            warnings.warn(
+                f"Lightcurve has {n_total} points, which exceeds max_samples={max_samples}. "
+                f"Retaining a random subsample of {len(idx)} points. "
+                "Set max_samples=None to disable subsampling.", UserWarning, stacklevel=2)
+            idx_t = torch.as_tensor(idx, dtype=torch.long)
+            x, y = x[idx_t], y[idx_t]
+            if yerr is not None:
+                yerr = self._ensure_tensor(yerr)[idx_t]
         self.register_buffer("_xdata_raw", x)
         self.register_buffer("_xdata_transformed",
                              x if self.xtransform is None else self.xtransform.transform(x))
@@ -109,6 +127,29 @@ class Lightcurve(torch.nn.Module):
                                  e if self.ytransform is None else self.ytransform.transform(e))
         self._constraints_set = False
         self._fitted = False
+
+    @classmethod
+    def from_csv(cls, path, xcol=None, ycol=None, yerrcol=None, **kwargs):
+        """1-D subset of ``Lightcurve.from_csv`` (lightcurve.py:510-760): a headed CSV with a
+        time column, a value column and an optional uncertainty column; rows with NaNs are
+        dropped with a warning, data are cast to float32 like the reference (:742-745)."""
+        data = np.genfromtxt(path, delimiter=",", names=True, dtype=None, encoding="utf-8")
+        cols = list(data.dtype.names)
+        xcol = xcol or cols[0]
+        ycol = ycol or cols[1]
+        for c in (xcol, ycol) + ((yerrcol,) if yerrcol else ()):
+            if c not in cols:
+                raise ValueError(f"Column '{c}' not found in CSV. Available columns: {cols}")
+        use = [xcol, ycol] + ([yerrcol] if yerrcol else [])
+        arr = np.stack([np.asarray(data[c], dtype=np.float64) for c in use], 1)
+        good = ~np.isnan(arr).any(1)
+        if (~good).any():
+            warnings.warn(f"Dropped {int((~good).sum())} row(s) containing NaN values.",
+                          stacklevel=2)
+        if not good.any():
+            raise ValueError("No valid data rows remain after dropping NaN-containing rows.")
+        arr = arr[good]
+        return cls(arr[:, 0], arr[:, 1], yerr=arr[:, 2] if yerrcol else None, **kwargs)
 
     @staticmethod
     def _ensure_tensor(values):

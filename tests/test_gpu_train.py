@@ -172,3 +172,32 @@ def test_lightcurve_predict_after_fit(cuda_device):
     t = out["x"]
     truth = np.sin(2 * np.pi * t / 57.0)
     assert np.sqrt(np.mean((out["mean"] - truth) ** 2)) < 0.15
+
+
+def test_c1_alfori_fit_matches_the_oracle_golden(cuda_device):
+    """BASELINE config C1: Lightcurve.fit(model='1D') SM-4 on the bundled AlfOri V-band light
+    curve (1564 -> 1000 points), Adam, 300 iterations, lr 0.1, GaussianLikelihood.  The whole
+    fit runs in ONE kernel launch; the golden trajectory is the oracle's restatement of
+    trainers.train on the CPU (oracle/make_golden_c1.py).  North star: fitted periods identical
+    to the reported precision (6 significant digits)."""
+    import os
+    from conftest import ROOT
+    from oracle.make_golden_c1 import build_lightcurve, oracle_inputs
+    z = np.load(os.path.join(ROOT, "tests", "golden_c1", "alfori_adam300.npz"))
+    lc, span = build_lightcurve()
+    args, pk = oracle_inputs(lc)
+    # the host produces exactly the inputs the golden was made from
+    assert np.array_equal(args[0].numpy(), z["x"]) and np.array_equal(args[1].numpy(), z["y"])
+    assert np.array_equal(args[3].numpy(), z["raw0"])
+    assert np.array_equal(np.asarray(pk.lb), z["lb"]) and np.array_equal(np.asarray(pk.ub), z["ub"])
+    res = lc.fit(optim="Adam", training_iter=300, lr=0.1)
+    loss = np.array(res["loss"], dtype=float)
+    assert len(loss) == 300 and np.isfinite(loss).all() and loss[-1] < loss[0]
+    # the history is float32 (the reference's dtype) of an fp64 trajectory
+    assert np.allclose(loss, z["loss"], rtol=2e-6, atol=2e-7)
+    raw_got = pk.raw().detach().double().numpy()
+    assert np.abs(raw_got - z["raw_final"]).max() <= 1e-5 * np.abs(z["raw_final"]).max()
+    periods, weights, _ = lc.get_periods()
+    got, want = np.sort(np.asarray(periods, dtype=float)), np.sort(z["periods"])
+    assert np.allclose(got, want, rtol=2e-6), (got, want)
+    print("C1 periods [d]:", ["%.6g" % p for p in got], "oracle:", ["%.6g" % p for p in want])
