@@ -207,6 +207,28 @@ int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
                    double stop, int stopavg, float* loss_hist, float* raw_hist, int32_t* n_iter,
                    int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * N2 - batched Lomb-Scargle initialisation (the step before the path).
+ * pgm_lombscargle_f64 replaces  LombScargle(t, y, dy).power(freq)  of Lightcurve.fit_LS
+ * (pgmuvi/lightcurve.py:4214-4611; astropy floating-mean periodogram, 'standard'
+ * normalisation) on the regular grid  freq[k] = f0[b] + k * df[b], k < nf[b]  that
+ * LombScargle.autofrequency(nyquist_factor) produces (host: pgmuvi_b200/lombscargle.py).
+ *   t, y, dy  [B, n_max] (dy NULL = unit errors), n_valid [B] or NULL
+ *   flags     PGM_LS_FIT_MEAN | PGM_LS_CENTER_DATA (astropy defaults: both)
+ *   power     [B, nf_max] out (entries k >= nf[b] untouched)
+ * pgm_ls_peaks_f64 replaces  find_peaks(power, distance=Nyquist_factor)  + sort by height
+ * (lightcurve.py:4531-4532): peak_idx / peak_power [B, num_peaks], highest first, padded with
+ * -1 / NaN; scratch = B * nf_max bytes.
+ */
+#define PGM_LS_FIT_MEAN 1
+#define PGM_LS_CENTER_DATA 2
+int pgm_lombscargle_f64(const double* t, const int32_t* n_valid, const double* y, const double* dy,
+                        int B, int n_max, const double* f0, const double* df, const int32_t* nf,
+                        int nf_max, int flags, double* power, void* stream);
+int pgm_ls_peaks_f64(const double* power, const int32_t* nf, int B, int nf_max, int distance,
+                     int num_peaks, int32_t* peak_idx, double* peak_power, void* scratch,
+                     size_t scratch_bytes, void* stream);
+
 /* Device yardsticks used by bench.py for the self-measured FP64 roofline: runs `iters`
  * dependent-free FP64 DMMA (kind 0), FP64 DFMA (kind 1), FP32 FFMA (kind 2) or interleaved
  * DMMA+DFMA (kind 3, equal flops each) instructions per thread on every SM and returns the

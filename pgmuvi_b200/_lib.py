@@ -27,6 +27,7 @@ EXPORTS = (
     "pgm_staged_workspace_bytes", "pgm_sm_mll_grad_staged_f64",
     "pgm_predict_workspace_bytes", "pgm_sm_predict_f64",
     "pgm_f32_staging_bytes", "pgm_sm_mll_grad_f32", "pgm_sm_fit_f32",
+    "pgm_lombscargle_f64", "pgm_ls_peaks_f64",
 )
 
 _lib = None
@@ -83,6 +84,11 @@ def load():
                                    c_int, c_int, c_int, c_double, c_double, c_double, c_double,
                                    c_double, c_int, c_int, c_double, c_int, dp, dp, ip, ip,
                                    vp, c_size_t, vp]
+    lib.pgm_lombscargle_f64.restype = c_int
+    lib.pgm_lombscargle_f64.argtypes = [dp, ip, dp, dp, c_int, c_int, dp, dp, ip, c_int, c_int,
+                                        dp, vp]
+    lib.pgm_ls_peaks_f64.restype = c_int
+    lib.pgm_ls_peaks_f64.argtypes = [dp, ip, c_int, c_int, c_int, c_int, ip, dp, vp, c_size_t, vp]
     lib.pgm_peak_probe.restype = c_int
     lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
     _lib = lib

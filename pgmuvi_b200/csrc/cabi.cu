@@ -2,6 +2,7 @@
 // code is in gp_fused.cuh.
 #include "gp_fused.cuh"
 #include "gp_large.cuh"
+#include "lombscargle.cuh"
 #include "../../include/pgmuvi_b200.h"
 
 #include <algorithm>
@@ -440,6 +441,41 @@ int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
   if (raw_hist) narrow(s.hist, raw_hist, (size_t)(maxiter + 1) * BP, st);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("f32 staging", e);
+  return 0;
+}
+
+int pgm_lombscargle_f64(const double* t, const int32_t* n_valid, const double* y, const double* dy,
+                        int B, int n_max, const double* f0, const double* df, const int32_t* nf,
+                        int nf_max, int flags, double* power, void* stream) {
+  if (B < 0 || n_max < 1 || nf_max < 1) return fail("B >= 0, n_max >= 1, nf_max >= 1 required");
+  if (B == 0) return 0;
+  if (B > 65535) return fail("B > 65535 (split the batch)");
+  if (!t || !y || !f0 || !df || !nf || !power) return fail("null pointer argument");
+  pgm::LsArgs A;
+  A.t = t; A.n_valid = n_valid; A.y = y; A.dy = dy; A.f0 = f0; A.df = df; A.nf = nf;
+  A.B = B; A.n_max = n_max; A.nf_max = nf_max; A.flags = flags; A.power = power;
+  dim3 grid((nf_max + pgm::LS_FPB - 1) / pgm::LS_FPB, B);
+  pgm::ls_power_kernel<<<grid, pgm::LS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("ls_power_kernel launch", e);
+  return 0;
+}
+
+int pgm_ls_peaks_f64(const double* power, const int32_t* nf, int B, int nf_max, int distance,
+                     int num_peaks, int32_t* peak_idx, double* peak_power, void* scratch,
+                     size_t scratch_bytes, void* stream) {
+  if (B < 0 || nf_max < 1 || num_peaks < 1) return fail("bad B / nf_max / num_peaks");
+  if (B == 0) return 0;
+  if (distance < 1) return fail("distance must be >= 1 (scipy.signal.find_peaks)");
+  if (!power || !nf || !peak_idx || !peak_power || !scratch) return fail("null pointer argument");
+  if (scratch_bytes < (size_t)B * nf_max) return fail("scratch too small (B * nf_max bytes)");
+  pgm::LsPeakArgs A;
+  A.power = power; A.nf = nf; A.B = B; A.nf_max = nf_max; A.distance = distance;
+  A.num_peaks = num_peaks; A.mask = static_cast<uint8_t*>(scratch); A.peak_idx = peak_idx;
+  A.peak_power = peak_power;
+  pgm::ls_peaks_kernel<<<B, pgm::LS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("ls_peaks_kernel launch", e);
   return 0;
 }
 

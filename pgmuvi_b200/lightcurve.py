@@ -386,29 +386,130 @@ class Lightcurve(torch.nn.Module):
                     return mod
         return None
 
+    # ---- Lomb-Scargle initialisation (lightcurve.py:4214-4611), on the GPU (N2) -----------
+    def fit_LS(self, freq_only=False, num_peaks=1, single_threshold=0.05, Nyquist_factor=5,
+               return_full=False, device=None, **kwargs):
+        """1-D ``fit_LS``: the periodogram on astropy's ``autofrequency`` grid, the
+        ``num_peaks`` highest peaks ``Nyquist_factor`` samples apart and their significance mask
+        (Davies bound on the highest peak, Benjamini-Hochberg over the single-frequency FAPs).
+        Computed by ``pgm_lombscargle_f64`` / ``pgm_ls_peaks_f64`` (exact floating-mean
+        periodogram; the reference's astropy call uses its FFT approximation beyond 200
+        frequencies).  Multiband (2-D) periodograms are outside the path."""
+        from . import lombscargle as ls
+        if self.ndim > 1:
+            raise UnsupportedModel("fit_LS: the multiband periodogram is not on the B200 path")
+        dev = torch.device(device) if device is not None else torch.device("cuda:0")
+        t = self._xdata_raw.to(dev, torch.float64).unsqueeze(0)
+        y = self._ydata_raw.to(dev, torch.float64).unsqueeze(0)
+        has_err = getattr(self, "_yerr_transformed", None) is not None
+        dy = self._yerr_raw.to(dev, torch.float64).unsqueeze(0) if has_err else None
+        out_t = lambda a, dt=None: torch.as_tensor(a, dtype=dt or self.xdata.dtype,
+                                                   device=self.xdata.device)
+        f0, df, nf, power = ls.lombscargle(t, y, dy, nyquist_factor=Nyquist_factor)
+        if freq_only or return_full:
+            freq = (f0[0] + df[0] * torch.arange(int(nf[0]), device=dev, dtype=torch.float64))
+            freq_t, power_t = out_t(freq.cpu()), out_t(power[0].cpu())
+            if freq_only:
+                return freq_t, power_t
+        freqs, sig = ls.fit_ls_batch(t, y, dy, num_peaks=num_peaks,
+                                     single_threshold=single_threshold,
+                                     nyquist_factor=Nyquist_factor)
+        keep = ~np.isnan(freqs[0])
+        pf, sm = out_t(freqs[0][keep]), out_t(sig[0][keep], torch.bool)
+        return (pf, sm, freq_t, power_t) if return_full else (pf, sm)
+
+    def _mls_initial_frequencies(self, num_mixtures, constraint_set):
+        """Choice of seed frequencies from the periodogram peaks (lightcurve.py:5475-5660,
+        1-D branch): peaks outside [1/span, constraint-set limit] are dropped; significant peaks
+        first, then the others, then evenly spaced padding."""
+        t = self._xdata_raw
+        span = float(t.max() - t.min())
+        f_lo = 1.0 / span if span > 0 else 0.0
+        d = torch.diff(torch.sort(t).values)
+        d = d[d > 0]
+        f_hi = 1.0 / (2.0 * float(d.min())) if len(d) else float("inf")
+        cs_lo, cs_hi = f_lo, float("inf")
+        if constraint_set is not None and constraint_set in CONSTRAINT_SETS:
+            pb = CONSTRAINT_SETS[constraint_set].get("period")
+            if pb is not None:
+                (pl, pl_on), (pu, pu_on) = pb["lower"], pb["upper"]
+                if pl_on and pl is not None:
+                    cs_hi = min(cs_hi, 1.0 / pl)
+                if pu_on and pu is not None:
+                    cs_lo = max(cs_lo, 1.0 / pu)
+        freqs, sig = self.fit_LS(num_peaks=max(num_mixtures or 1, 10))
+        if len(freqs) and cs_lo > 0:
+            ok = (freqs >= cs_lo) & (freqs <= cs_hi)
+            if not bool(ok.all()):
+                warnings.warn(f"{int((~ok).sum())} MLS peak(s) fell outside the allowed frequency "
+                              f"range [{cs_lo:.4g}, {cs_hi:.4g}] and were excluded from the "
+                              "initialisation.", RuntimeWarning, stacklevel=3)
+                freqs, sig = freqs[ok], sig[ok]
+        if len(freqs) == 0:
+            warnings.warn("MLS periodogram returned no peaks; falling back to "
+                          f"num_mixtures={num_mixtures or 4} with default initialisation.",
+                          RuntimeWarning, stacklevel=3)
+            return None, num_mixtures or 4
+        sig_f, insig_f = freqs[sig], freqs[~sig]
+        if num_mixtures is None:
+            init = sig_f if len(sig_f) else freqs[:1]
+            return init, len(init)
+        if num_mixtures <= len(sig_f):
+            return sig_f[:num_mixtures], num_mixtures
+        init = torch.cat([sig_f, insig_f[:num_mixtures - len(sig_f)]])
+        n_pad = num_mixtures - len(init)
+        if n_pad > 0:
+            lo, hi = f_lo, f_hi
+            if cs_lo > 0:
+                lo, hi = max(lo, cs_lo), min(hi, cs_hi)
+            if hi > lo:
+                warnings.warn(f"Only {len(init)} MLS peak(s) found but {num_mixtures} were "
+                              f"requested. Padding with {n_pad} evenly-spaced frequencies in "
+                              f"[{lo:.4g}, {hi:.4g}].", RuntimeWarning, stacklevel=3)
+                pad = torch.linspace(lo, hi, n_pad + 2, dtype=init.dtype)[1:-1]
+            else:
+                pad = init.new_full((n_pad,), float(init[-1]))
+            init = torch.cat([init, pad])
+        return init, num_mixtures
+
     # ---- fit (lightcurve.py:5211-5882) -------------------------------------------------
     def fit(self, model=None, likelihood=None, num_mixtures=None, guess=None, periods=None,
-            constraint_set=None, cuda=False, training_iter=300, optim="AdamW", miniter=None,
-            stop=1e-5, lr=0.1, stopavg=30, variance=False, **kwargs):
+            use_mls_init=False, constraint_set=None, cuda=False, training_iter=300,
+            optim="AdamW", miniter=None, stop=1e-5, lr=0.1, stopavg=30, variance=False,
+            **kwargs):
         """Same defaults as the reference: AdamW, lr 0.1, 300 iterations, stop 1e-5, stopavg 30,
-        ``miniter=None -> training_iter`` (so the early stop never fires).  The
-        Lomb-Scargle (MLS) initialisation is out of scope (astropy is absent; the reference then
-        falls back to ``num_mixtures`` 4 with a warning, lightcurve.py:5668-5688): pass
-        ``periods`` / ``guess`` for a deterministic start."""
+        ``miniter=None -> training_iter`` (so the early stop never fires).
+        ``use_mls_init=True`` (the reference's default; off here so that a fit is deterministic
+        without a device periodogram) seeds the mixture means of a 1-D model from the GPU
+        Lomb-Scargle periodogram exactly like lightcurve.py:5475-5660; ``periods`` / ``guess``
+        take precedence as in the reference."""
         if likelihood is not None or not hasattr(self, "likelihood"):
             self.set_likelihood(likelihood, variance=variance)
+        init_freqs = None
+        if periods is not None:
+            pt = torch.as_tensor(np.asarray(periods, dtype=np.float64)).flatten()
+            if pt.numel() == 0:
+                raise ValueError("When providing explicit `periods`, the sequence must be "
+                                 "non-empty.")
+            if not torch.isfinite(pt).all():
+                raise ValueError("All values in `periods` must be finite (no NaN or inf).")
+            if not (pt > 0).all():
+                raise ValueError("All values in `periods` must be strictly positive.")
+            if self.ndim == 1:
+                init_freqs = 1.0 / pt
+            if num_mixtures is None:
+                num_mixtures = len(pt)
+        elif use_mls_init and isinstance(model, str) and model in _SM_MODELS and self.ndim == 1:
+            init_freqs, num_mixtures = self._mls_initial_frequencies(num_mixtures, constraint_set)
         if model is not None or not hasattr(self, "model"):
             if model is None:
                 raise ValueError("""You must provide a model""")
-            if periods is not None and num_mixtures is None:
-                num_mixtures = len(periods)
             self.set_model(model, self.likelihood, num_mixtures=num_mixtures, **kwargs)
         if not self._constraints_set:
             self.set_default_constraints(constraint_set=constraint_set)
         hypers = {}
-        if periods is not None and self.ndim == 1:
-            hypers["covar_module.mixture_means"] = 1.0 / torch.as_tensor(
-                np.asarray(periods, dtype=np.float64))
+        if init_freqs is not None:
+            hypers["covar_module.mixture_means"] = init_freqs
         if guess is not None:
             hypers.update(guess)
         if hypers:
