@@ -36,8 +36,8 @@ LC_PER_GPU = 4096
 F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel on the C2 batch
 # (4096 light curves), from the `ncu --set full` capture summarised in
-# profiles/r01c_ncu_full_summary.txt (42.76 GB + 10.35 GB); scales with light curves per GPU
-TRAFFIC_BYTES_PER_LC = (42.764792e9 + 10.352890e9) / 4096
+# profiles/r01d_ncu_full_summary.txt (43.31 GB + 10.35 GB); scales with light curves per GPU
+TRAFFIC_BYTES_PER_LC = (43.306600e9 + 10.347435e9) / 4096
 METRIC = "MLL+grad evals/s, 4096x n=512 SM-4 lightcurves"
 UNIT = "evals/s"
 
@@ -296,7 +296,7 @@ def run_b200(args):
                     "algorithmic_flops_per_launch": B * F_EVAL,
                     "kernel_ms_avg": kern_ms_avg,
                     "traffic": TRAFFIC_BYTES_PER_LC * B,
-                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01c)",
+                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01d)",
                     "algorithmic_bytes_per_launch": B * (3 * N_POINTS + 2 * 13 + 1) * 8}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,

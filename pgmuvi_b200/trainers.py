@@ -30,7 +30,11 @@ from .mll import (B200ExactMarginalLogLikelihood, UnsupportedModelError, engine_
 
 # light curves longer than this are factored by the whole device (pgm_sm_mll_grad_large_f64)
 # instead of one thread block (the fused kernel's per-block scratch grows with n^2)
-LARGE_N = 2048
+# A single light curve longer than this is evaluated by the staged whole-device engine instead
+# of one thread block of the fused kernel: measured on B200 for BASELINE config C1 (AlfOri,
+# n = 1000, 300 Adam iterations) 1.32 ms / iteration staged vs 7.38 ms fused on ONE SM
+# (profiles/r01d_all_configs.log); one block's scratch stops fitting beyond n = 2048 anyway.
+LARGE_N = 384
 
 _X_KEYS = ("mixture_means", "mixture_scales")      # lightcurve.py:9036-9041
 _Y_KEYS = ("noise", "mean_module")
@@ -183,6 +187,7 @@ def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, sto
     raw = raw.clone().reshape(1, -1)
     m, v = torch.zeros_like(raw), torch.zeros_like(raw)
     raws, losses = [raw[0].cpu().clone()], []
+    np_dt = np.float32 if pk.params[0].dtype == torch.float32 else np.float64
     for i in range(maxiter):
         mll, grad, code = ops.sm_mll_grad_large(x, y, fixed, raw[0], kinds, lb, ub, pk.kind, pk.Q,
                                                 pk.learn_noise, True)
@@ -195,7 +200,7 @@ def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, sto
                               f"to 1.0e-06 (training iteration {i}).")
         ops.optim_step(raw, grad.reshape(1, -1), m, v, None, od["optim_kind"], lr, od["beta1"],
                        od["beta2"], od["eps"], od["weight_decay"], i + 1)
-        losses.append(np.asarray(-float(mll), dtype=np.float64))
+        losses.append(np.asarray(-float(mll), dtype=np_dt))   # history in the model's dtype
         raws.append(raw[0].cpu().clone())
         if stop and i > miniter and np.std(losses[-stopavg:]) < stop:
             print(f"""Average change in loss over the last {stopavg} iterations
