@@ -644,96 +644,133 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
 
 // ------------------------------------------------------------------------------------
 // 64x64 diagonal block:  S (lower) -> L in place,  X = L^-1 into S2,  dinv[k] = 1/L_kk.
-// Panel width 8: warp 0 factors the panel in registers (shuffles); the trailing update and
-// the next 8 rows of L^-1 (block forward substitution) run on the tensor cores (DMMA 8x8x4).
+// Panel width 8.  Warp 0 factors a panel in registers (shuffles); the trailing update and the
+// next 8 rows of L^-1 (block forward substitution) run on the tensor cores (DMMA 8x8x4).
+// The serial chain is what bounds this routine, so
+//  * inside a panel the columns stay UNSCALED (v_ik) and the updates use v_ik v_ck / d_k with a
+//    short reciprocal (MUFU.RCP64H + 2 Newton steps); the 8 rsqrt that turn v into L are
+//    independent of each other and happen after the chain;
+//  * look-ahead: after panel p only tile column p+1 of the trailing matrix is updated before
+//    warp 0 starts panel p+1; the other warps finish the trailing update and the inverse rows
+//    of panel p meanwhile (2 block barriers per panel).
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ double rcp_pos(double d) {   // 1/d for normal d > 0
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
+
+// warp 0: factor columns c0..c0+7 (rows c0..63; lane holds rows c0+lane and c0+lane+32)
+__device__ __forceinline__ void potrf_panel8(double* __restrict__ S, double* __restrict__ dinv,
+                                             int c0, int lane, int* fail) {
+  const int r0 = c0 + lane, r1 = c0 + lane + 32;
+  double a0[8], a1[8], dp[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    a0[k] = (r0 < TS) ? S[r0 * LD_S + c0 + k] : 0.0;
+    a1[k] = (r1 < TS) ? S[r1 * LD_S + c0 + k] : 0.0;
+  }
+  bool bad = false, isnan_ = false;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double dpiv = shfl_d(a0[k], k);
+    if (!(dpiv > 0.0)) { bad = true; if (dpiv != dpiv) isnan_ = true; }
+    dp[k] = bad ? 1.0 : dpiv;
+    const double rd = rcp_pos(dp[k]);
+#pragma unroll
+    for (int c = k + 1; c < 8; ++c) {
+      const double u = shfl_d(a0[k], c) * rd;      // v_ck / d_k
+      a0[c] = fma(-a0[k], u, a0[c]);
+      a1[c] = fma(-a1[k], u, a1[c]);
+    }
+  }
+  double myrs = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double rs = rsqrt(dp[k]);
+    if (lane == k) myrs = rs;
+    a0[k] *= rs;
+    a1[k] *= rs;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (r0 < TS) S[r0 * LD_S + c0 + k] = a0[k];
+    if (r1 < TS) S[r1 * LD_S + c0 + k] = a1[k];
+  }
+  if (lane < 8) dinv[c0 + lane] = myrs;
+  if (lane == 0 && bad) atomicOr(fail, isnan_ ? 2 : 1);
+}
+
+// C(ti,tj) -= P_ti P_tj^T on one 8x8 MMA tile, P = S[:, c0:c0+8]
+__device__ __forceinline__ void potrf_syrk_tile(double* __restrict__ S, int c0, int ti, int tj,
+                                                int g, int tq) {
+  double2* cp = reinterpret_cast<double2*>(S + (8 * ti + g) * LD_S + 8 * tj + 2 * tq);
+  const double2 cv = *cp;
+  double c2[2] = {cv.x, cv.y};
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    mma_f64(c2, -S[(8 * ti + g) * LD_S + c0 + 4 * s + tq], S[(8 * tj + g) * LD_S + c0 + 4 * s + tq]);
+  *cp = make_double2(c2[0], c2[1]);
+}
+
 __device__ __forceinline__ void potrf_inv_64(double* __restrict__ S, double* __restrict__ S2,
                                              double* __restrict__ dinv, int* fail) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
+  if (warp == 0) potrf_panel8(S, dinv, 0, lane, fail);
   for (int p = 0; p < 8; ++p) {
     const int c0 = p * 8;
-    if (warp == 0) {
-      const int r0 = c0 + lane, r1 = c0 + lane + 32;
-      double a0[8], a1[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a0[k] = (r0 < TS) ? S[r0 * LD_S + c0 + k] : 0.0;
-        a1[k] = (r1 < TS) ? S[r1 * LD_S + c0 + k] : 0.0;
-      }
-      bool bad = false, isnan_ = false;
-      double myrs = 0.0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const double dpiv = shfl_d(a0[k], k);
-        if (!(dpiv > 0.0)) { bad = true; if (dpiv != dpiv) isnan_ = true; }
-        const double rs = bad ? 1.0 : rsqrt(dpiv);
-        if (lane == k) myrs = rs;
-        a0[k] *= rs;
-        a1[k] *= rs;
-#pragma unroll
-        for (int c = k + 1; c < 8; ++c) {
-          const double lc = shfl_d(a0[k], c);
-          a0[c] -= a0[k] * lc;
-          a1[c] -= a1[k] * lc;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (r0 < TS) S[r0 * LD_S + c0 + k] = a0[k];
-        if (r1 < TS) S[r1 * LD_S + c0 + k] = a1[k];
-      }
-      if (lane < 8) dinv[c0 + lane] = myrs;
-      if (lane == 0 && bad) atomicOr(fail, isnan_ ? 2 : 1);
-    }
+    __syncthreads();   // panel p is factored
+    // step 1: tile column p+1 of the trailing matrix (what the next panel needs)
+    if (p < 7 && warp < 7 - p) potrf_syrk_tile(S, c0, p + 1 + warp, p + 1, g, tq);
     __syncthreads();
-    // (i) trailing SYRK on 8x8 MMA tiles (ti >= tj > p):  C -= P_ti P_tj^T,  P = S[:, c0:c0+8]
-    {
-      const int m8 = 7 - p;
-      const int cnt = m8 * (m8 + 1) / 2;
-      for (int t = warp; t < cnt; t += NTHREADS / 32) {
+    if (p < 7 && warp == 0) {
+      potrf_panel8(S, dinv, c0 + 8, lane, fail);
+    } else {
+      const int nw = (p < 7) ? 7 : 8, w = (p < 7) ? warp - 1 : warp;
+      // step 2a: the rest of the trailing update, tiles (ti >= tj >= p+2)
+      const int m8 = 6 - p;
+      const int cnt = (m8 > 0) ? m8 * (m8 + 1) / 2 : 0;
+      for (int t = w; t < cnt; t += nw) {
         int a_ = 0;
         while ((a_ + 1) * (a_ + 2) / 2 <= t) ++a_;
         const int b_ = t - a_ * (a_ + 1) / 2;
-        const int ti = p + 1 + a_, tj = p + 1 + b_;
-        double2* cp = reinterpret_cast<double2*>(S + (8 * ti + g) * LD_S + 8 * tj + 2 * tq);
-        const double2 cv = *cp;
-        double c2[2] = {cv.x, cv.y};
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-          mma_f64(c2, -S[(8 * ti + g) * LD_S + c0 + 4 * s + tq], S[(8 * tj + g) * LD_S + c0 + 4 * s + tq]);
-        *cp = make_double2(c2[0], c2[1]);
+        potrf_syrk_tile(S, c0, p + 2 + a_, p + 2 + b_, g, tq);
       }
-    }
-    // (ii) rows c0..c0+7 of T = I - L[c0.., :c0] X[:c0, :]   (column tiles 0..p)
-    for (int nt = warp; nt <= p; nt += NTHREADS / 32) {
-      double c2[2];
+      // step 2b: rows c0..c0+7 of X.  T = I - L[c0.., :c0] X[:c0, :] per column tile nt <= p,
+      // then the 8x8 triangular solve of its 8 columns (lanes 0..7 of the same warp)
+      for (int nt = w; nt <= p; nt += nw) {
+        double c2[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) c2[e] = (c0 + g == 8 * nt + 2 * tq + e) ? 1.0 : 0.0;
-      for (int kt = nt; kt < p; ++kt) {
+        for (int e = 0; e < 2; ++e) c2[e] = (c0 + g == 8 * nt + 2 * tq + e) ? 1.0 : 0.0;
+        for (int kt = nt; kt < p; ++kt) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
-          mma_f64(c2, -S[(c0 + g) * LD_S + 8 * kt + 4 * s + tq],
-                  S2[(8 * kt + 4 * s + tq) * LD_S + 8 * nt + g]);
+          for (int s = 0; s < 2; ++s)
+            mma_f64(c2, -S[(c0 + g) * LD_S + 8 * kt + 4 * s + tq],
+                    S2[(8 * kt + 4 * s + tq) * LD_S + 8 * nt + g]);
+        }
+        *reinterpret_cast<double2*>(S2 + (c0 + g) * LD_S + 8 * nt + 2 * tq) = make_double2(c2[0], c2[1]);
+        __syncwarp();
+        if (lane < 8) {
+          const int c = 8 * nt + lane;
+          double v[8];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) v[rr] = S2[(c0 + rr) * LD_S + c];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            double sacc = v[rr];
+#pragma unroll
+            for (int kk = 0; kk < rr; ++kk) sacc -= S[(c0 + rr) * LD_S + c0 + kk] * v[kk];
+            v[rr] = sacc * dinv[c0 + rr];
+          }
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) S2[(c0 + rr) * LD_S + c] = v[rr];
+        }
+        __syncwarp();
       }
-      *reinterpret_cast<double2*>(S2 + (c0 + g) * LD_S + 8 * nt + 2 * tq) = make_double2(c2[0], c2[1]);
-    }
-    __syncthreads();
-    // (iii) 8x8 triangular solve per column (threads 32.., overlaps the next panel on warp 0)
-    if (tid >= 32 && tid < 32 + c0 + 8) {
-      const int c = tid - 32;
-      double v[8];
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) v[rr] = S2[(c0 + rr) * LD_S + c];
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        double s = v[rr];
-#pragma unroll
-        for (int kk = 0; kk < rr; ++kk) s -= S[(c0 + rr) * LD_S + c0 + kk] * v[kk];
-        v[rr] = s * dinv[c0 + rr];
-      }
-#pragma unroll
-      for (int rr = 0; rr < 8; ++rr) S2[(c0 + rr) * LD_S + c] = v[rr];
     }
   }
   __syncthreads();
