@@ -105,7 +105,11 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   using namespace pgm;
   const int n = A.n_max, N = (n + TS - 1) / TS, npad = N * TS, B = A.B;
   if (B > 65535) return fail("staged engine: B > 65535 (split the batch)");
-  constexpr int NB = 8;   // tile columns per panel
+  // tile columns per panel (one right-looking trailing update every NB columns): wider panels
+  // amortise the C-tile round trip of the trailing update once there are enough tile rows to
+  // keep the in-panel launches busy (B200, C4: NB 8 -> 32 takes the P phase from 497 to 416 ms)
+  int NB = (N <= 64) ? 8 : (N <= 256) ? 16 : 32;
+  if (const char* f = getenv("PGM_STAGED_NB")) NB = std::max(1, atoi(f));
   auto k_upd = lg_update<KIND, QT, D>;
   auto k_grad = lg_grad<KIND, QT, D>;
   cudaError_t e;
