@@ -174,7 +174,8 @@ __device__ __forceinline__ void load_exp_tab(double* tab) {
 #ifdef PGM_DEBUG_HOOKS
 // -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 and decomposition switches
 // (PGM_DEBUG_MODE: 0x100 no operand loads, 0x200 no MMAs, 0x400 no exp/cos epilogue work,
-// 0x800 ignore potrf failures, 0x1000 skip the diagonal-block factorisation) -
+// 0x800 ignore potrf failures, 0x1000 skip the diagonal-block factorisation, 0x2000 no tile
+// bulk stores, 0x4000 no resident-tile products, 0x8000 no epilogue loops) -
 // timing experiments only, results are garbage
 __constant__ int c_dbg = 0;
 #define PGM_DBG(bit) (c_dbg & (bit))
@@ -477,7 +478,7 @@ __device__ __forceinline__ void store_tile_bulk(const double (&acc)[4][2][2], do
   store_acc_tile(acc, stage, sign);
   fence_proxy_async_smem();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !PGM_DBG(0x2000)) {
     bulk_s2g(gtile, smem_u32(stage), 2 * OPBUF * sizeof(double));
     bulk_commit();
   }
@@ -1022,6 +1023,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     store_acc_tile(acc, Cst, 1.0);
     __syncthreads();
     zero_acc(acc);
+    if (PGM_DBG(0x4000)) return;
     compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
     compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
   };
@@ -1062,7 +1064,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         // (padded points carry finite dummy fields); MMA tiles above the diagonal are skipped.
         store_acc_tile(acc, Cst, 1.0);
 #pragma unroll 1
-        for (int p8 = 0; p8 < 8; ++p8) {
+        for (int p8 = PGM_DBG(0x8000) ? 8 : 0; p8 < 8; ++p8) {
           const int mi = p8 >> 1, ni2 = p8 & 1;
           if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
           const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
@@ -1140,8 +1142,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
           // L_ij = C * X_jj^T  straight from shared memory (C in stage 1, X_jj resident)
           __syncthreads();
           zero_acc(acc);
-          compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
-          compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+          if (!PGM_DBG(0x4000)) {
+            compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+            compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+          }
           // partial products L_ij z_j for the forward solve of row i (deterministic order);
           // their global stores are issued after the tile has left, so that the proxy fence
           // of the bulk store (MEMBAR.ALL.CTA) has no global store of this thread to drain
@@ -1297,7 +1301,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         const double* al_r = rowv + C::NFB * TS;
         const double* al_c = colv + C::NFB * TS;
 #pragma unroll 1
-        for (int p8 = 0; p8 < 8; ++p8) {
+        for (int p8 = PGM_DBG(0x8000) ? 8 : 0; p8 < 8; ++p8) {
           const int mi = p8 >> 1, ni2 = p8 & 1;
           if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
           const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
