@@ -171,3 +171,156 @@ def gather_results(local: torch.Tensor, counts=None):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([o[:c] for o, c in zip(out, counts)], 0)
+
+
+def fit_batch(lightcurves, model="1D", likelihood=None, num_mixtures=None, periods=None,
+              use_mls_init=False, constraint_set=None, training_iter=300, optim="AdamW",
+              miniter=None, stop=1e-5, lr=0.1, stopavg=30, variance=False, keep_history=True,
+              device=None, **kwargs):
+    """``[lc.fit(model=..., ...) for lc in lightcurves]`` as ONE launch of the fused training
+    kernel per rank (the survey-scale loop pgmuvi users write today).
+
+    Every ``Lightcurve`` is set up exactly as ``Lightcurve.fit`` would (likelihood, model,
+    default constraints, Lomb-Scargle or explicit period seeds: the same host code, so the
+    packed parameters are the single-source ones), the ragged batch is padded and packed once,
+    ``pgm_sm_fit`` runs the whole optimisation for all of them, and each object gets its fitted
+    parameters and its ``results`` dict back.  Under ``torch.distributed`` (one process per
+    GPU) each rank fits ``shard_range(B, rank, world)`` and the fitted raw parameters, losses
+    and iteration counts are all-gathered once at the end (no collective inside the loop).
+
+    ``periods``: None, one sequence for all light curves, or one sequence per light curve.
+    ``use_mls_init``: seed 1-D models from the batched GPU periodogram (one launch for all).
+    Returns ``dict(loss [iters, B], raw [B, P], n_iter [B], info [B], periods [B, Q],
+    weights [B, Q])`` (host tensors / arrays, all B light curves on every rank)."""
+    import torch.distributed as dist
+    from .mll import engine_device, pack_model
+    from .trainers import history_from_raw
+
+    lcs = list(lightcurves)
+    B = len(lcs)
+    if B == 0:
+        raise ValueError("fit_batch needs at least one light curve")
+    per_lc_periods = (periods is not None and len(periods) == B
+                      and np.ndim(periods[0]) >= 1)
+    # ---- host set-up, identical to Lightcurve.fit (lightcurve.py:5211-5850) -----------------
+    seeds = [None] * B
+    nmix = [num_mixtures] * B
+    if periods is not None:
+        for b in range(B):
+            p = np.asarray(periods[b] if per_lc_periods else periods, dtype=np.float64).ravel()
+            if p.size == 0 or not np.isfinite(p).all() or not (p > 0).all():
+                raise ValueError("`periods` must be non-empty, finite and strictly positive")
+            seeds[b] = torch.as_tensor(1.0 / p)
+            if nmix[b] is None:
+                nmix[b] = p.size
+    elif use_mls_init and all(lc.ndim == 1 for lc in lcs):
+        # one periodogram + peak-search launch for all light curves (lightcurve.py:4214-4611),
+        # then the reference's per-source peak selection (lightcurve.py:5475-5660)
+        from . import lombscargle as ls
+        ldev = torch.device(device) if device is not None else torch.device("cuda:0")
+        ns = [int(lc._xdata_raw.shape[0]) for lc in lcs]
+        tt = torch.zeros(B, max(ns), dtype=torch.float64)
+        yy = torch.zeros(B, max(ns), dtype=torch.float64)
+        have_err = all(getattr(lc, "_yerr_transformed", None) is not None for lc in lcs)
+        ee = torch.ones(B, max(ns), dtype=torch.float64) if have_err else None
+        for b, lc in enumerate(lcs):
+            tt[b, :ns[b]] = lc._xdata_raw.to(torch.float64)
+            yy[b, :ns[b]] = lc._ydata_raw.to(torch.float64)
+            if have_err:
+                ee[b, :ns[b]] = lc._yerr_raw.to(torch.float64)
+        k = max(num_mixtures or 1, 10)
+        freqs, sig = ls.fit_ls_batch(tt.to(ldev), yy.to(ldev), None if ee is None else ee.to(ldev),
+                                     torch.tensor(ns, dtype=torch.int32, device=ldev), num_peaks=k)
+        for b, lc in enumerate(lcs):
+            keep = ~np.isnan(freqs[b])
+            pf = torch.as_tensor(freqs[b][keep], dtype=lc.xdata.dtype)
+            sm = torch.as_tensor(sig[b][keep], dtype=torch.bool)
+            seeds[b], nmix[b] = lc._mls_initial_frequencies(num_mixtures, constraint_set, (pf, sm))
+    packs = []
+    for b, lc in enumerate(lcs):
+        if likelihood is not None or not hasattr(lc, "likelihood"):
+            lc.set_likelihood(likelihood, variance=variance)
+        lc.set_model(model, lc.likelihood, num_mixtures=nmix[b], **kwargs)
+        lc.set_default_constraints(constraint_set=constraint_set)
+        if seeds[b] is not None and lc.ndim == 1:
+            lc.set_hypers({"covar_module.mixture_means": seeds[b]})
+        lc.model.train()
+        lc.likelihood.train()
+        packs.append(pack_model(lc.model, lc.likelihood))
+    pk0 = packs[0]
+    for pk in packs[1:]:
+        if (pk.kind, pk.Q, pk.d, pk.learn_noise, pk.P) != (pk0.kind, pk0.Q, pk0.d, pk0.learn_noise,
+                                                        pk0.P) or not torch.equal(pk.kinds,
+                                                                                  pk0.kinds):
+            raise ValueError("fit_batch: all light curves must share one model family, number "
+                             "of mixtures and likelihood type")
+    # ---- pack the (ragged) batch ----------------------------------------------------------
+    n_each = [int(lc._ydata_transformed.shape[0]) for lc in lcs]
+    n_max = max(n_each)
+    if n_max > 2048:
+        raise ValueError("fit_batch: light curves longer than 2048 points go through "
+                         "Lightcurve.fit (staged whole-device engine)")
+    d, P = pk0.d, pk0.P
+    x = torch.zeros(B, n_max, d, dtype=torch.float64)
+    y = torch.zeros(B, n_max, dtype=torch.float64)
+    has_fixed = pk0.fixed_noise is not None
+    noise = torch.ones(B, n_max, dtype=torch.float64) if has_fixed else None
+    raw = torch.zeros(B, P, dtype=torch.float64)
+    lb = torch.zeros(B, P, dtype=torch.float64)
+    ub = torch.zeros(B, P, dtype=torch.float64)
+    for b, (lc, pk) in enumerate(zip(lcs, packs)):
+        n = n_each[b]
+        xt = lc._xdata_transformed.detach().to(torch.float64)
+        x[b, :n] = xt if xt.dim() > 1 else xt.unsqueeze(-1)
+        y[b, :n] = lc._ydata_transformed.detach().to(torch.float64)
+        if has_fixed:
+            noise[b, :n] = pk.fixed_noise.detach().to(torch.float64)
+        raw[b] = pk.raw().detach().to(torch.float64)
+        lb[b], ub[b] = pk.lb, pk.ub
+    n_valid = torch.tensor(n_each, dtype=torch.int32)
+    # ---- shard, fit, gather ----------------------------------------------------------------
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world = dist.get_world_size() if distributed else 1
+    rank = dist.get_rank() if distributed else 0
+    a, z = shard_range(B, rank, world)
+    dev = torch.device(device) if device is not None else engine_device(pk0.params[0])
+    od = optimizer_defaults(optim, 1e-8)
+    miniter = training_iter if miniter is None else miniter
+    to = lambda t: None if t is None else t[a:z].contiguous().to(dev)
+    raw_dev = to(raw)
+    if z > a:
+        loss, raw_hist, n_iter, info = ops.sm_fit(
+            to(x), to(y), to(noise), raw_dev, pk0.kinds.to(dev), to(lb), to(ub), to(n_valid),
+            pk0.kind, pk0.Q, pk0.learn_noise, od["optim_kind"], float(lr), od["beta1"],
+            od["beta2"], od["eps"], od["weight_decay"], int(training_iter), int(miniter),
+            float(stop or 0.0), int(stopavg), bool(keep_history))
+    else:   # more ranks than light curves
+        loss = torch.zeros(training_iter, 0, dtype=torch.float64, device=dev)
+        raw_hist = torch.zeros(training_iter + 1, 0, P, dtype=torch.float64, device=dev)
+        n_iter = torch.zeros(0, dtype=torch.int32, device=dev)
+        info = torch.zeros(0, dtype=torch.int32, device=dev)
+    # local light curves get their history; everyone gets the fitted parameters
+    if keep_history:
+        rh = raw_hist.cpu()
+        lh = loss.cpu()
+        for b in range(a, z):
+            k = int(n_iter[b - a])
+            lc, pk = lcs[b], packs[b]
+            pdt = pk.params[0].dtype
+            ls_ = lh[:k, b - a].to(pdt).numpy()
+            res = {"loss": [ls_[i] for i in range(k)],
+                   "delta_loss": [ls_[i] - ls_[i - 1] for i in range(1, k)]}
+            res.update(history_from_raw(rh[:k + 1, b - a], pk, lc.model, lc))
+            lc.results = res
+    counts = [shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world)]
+    g = lambda t: gather_results(t.contiguous(), counts) if distributed else t
+    raw_all = g(raw_dev).cpu()
+    loss_all = g(loss.t().contiguous()).t().cpu()          # gather along the light-curve axis
+    n_iter_all, info_all = g(n_iter).cpu(), g(info).cpu()
+    for b, (lc, pk) in enumerate(zip(lcs, packs)):
+        pk.scatter_raw_(raw_all[b])
+        lc._fitted = True
+    per = np.stack([lc.get_periods()[0] for lc in lcs])
+    wts = np.stack([lc.get_periods()[1] for lc in lcs])
+    return dict(loss=loss_all, raw=raw_all, n_iter=n_iter_all, info=info_all, periods=per,
+                weights=wts)

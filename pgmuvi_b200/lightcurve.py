@@ -418,10 +418,12 @@ class Lightcurve(torch.nn.Module):
         pf, sm = out_t(freqs[0][keep]), out_t(sig[0][keep], torch.bool)
         return (pf, sm, freq_t, power_t) if return_full else (pf, sm)
 
-    def _mls_initial_frequencies(self, num_mixtures, constraint_set):
+    def _mls_initial_frequencies(self, num_mixtures, constraint_set, peaks=None):
         """Choice of seed frequencies from the periodogram peaks (lightcurve.py:5475-5660,
         1-D branch): peaks outside [1/span, constraint-set limit] are dropped; significant peaks
-        first, then the others, then evenly spaced padding."""
+        first, then the others, then evenly spaced padding.  ``peaks`` = precomputed
+        ``(peak_freqs, significance_mask)`` (``fit_batch`` runs one periodogram launch for all
+        its light curves)."""
         t = self._xdata_raw
         span = float(t.max() - t.min())
         f_lo = 1.0 / span if span > 0 else 0.0
@@ -437,7 +439,8 @@ class Lightcurve(torch.nn.Module):
                     cs_hi = min(cs_hi, 1.0 / pl)
                 if pu_on and pu is not None:
                     cs_lo = max(cs_lo, 1.0 / pu)
-        freqs, sig = self.fit_LS(num_peaks=max(num_mixtures or 1, 10))
+        freqs, sig = peaks if peaks is not None else self.fit_LS(
+            num_peaks=max(num_mixtures or 1, 10))
         if len(freqs) and cs_lo > 0:
             ok = (freqs >= cs_lo) & (freqs <= cs_hi)
             if not bool(ok.all()):

@@ -227,3 +227,52 @@ def test_fit_with_mls_init_seeds_from_the_gpu_periodogram(cuda_device):
     periods, weights, _ = lc.get_periods()
     assert abs(periods[np.argmax(weights)] - 57.0) < 1.5
 
+
+
+def test_fit_batch_matches_per_source_fits_and_mls_seeding(cuda_device):
+    """fit_batch = [lc.fit(...) for lc in ...] in one launch of the fused training kernel: ragged
+    light curves, per-source constraint bounds, same loss histories and fitted periods; with
+    use_mls_init the seeds come from ONE batched periodogram launch."""
+    import warnings
+    from pgmuvi_b200.batch import fit_batch
+    from pgmuvi_b200.mll import pack_model
+
+    def make():
+        rng = np.random.default_rng(21)
+        out = []
+        for n in (90, 200, 131, 64, 257):
+            per = rng.uniform(30, 120)
+            t = np.sort(rng.uniform(2450000.0, 2450000.0 + 7 * per, n))
+            y = np.sin(2 * np.pi * t / per) + 0.1 * rng.standard_normal(n)
+            from pgmuvi_b200.lightcurve import Lightcurve
+            out.append((Lightcurve(t, y, yerr=np.full(n, 0.1)).double(), per))
+        return out
+
+    torch.manual_seed(3)
+    single = []
+    for lc, per in make():
+        res = lc.fit(model="1D", num_mixtures=2, periods=[per, 1.9 * per], training_iter=40,
+                     optim="AdamW", lr=0.05)
+        single.append((np.array(res["loss"], dtype=float), lc.get_periods()[0]))
+    torch.manual_seed(3)
+    lcs = make()
+    out = fit_batch([lc for lc, _ in lcs], model="1D", num_mixtures=2,
+                    periods=[[per, 1.9 * per] for _, per in lcs], training_iter=40, optim="AdamW",
+                    lr=0.05)
+    assert out["info"].tolist() == [0] * 5 and out["n_iter"].tolist() == [40] * 5
+    for b, (lc, per) in enumerate(lcs):
+        assert np.allclose(out["loss"][:, b].numpy(), single[b][0], rtol=1e-6, atol=1e-7)
+        assert np.allclose(out["periods"][b], single[b][1], rtol=1e-5)
+        assert np.array_equal(np.array(lc.results["loss"], dtype=float), single[b][0])
+    # Lomb-Scargle seeding for the whole batch at once
+    lcs = make()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = fit_batch([lc for lc, _ in lcs], model="1D", num_mixtures=2, use_mls_init=True,
+                        training_iter=60, optim="AdamW", lr=0.05)
+    for b, (lc, per) in enumerate(lcs):
+        first = lc.results["covar_module.mixture_means"][0].reshape(-1)
+        assert abs(1 / float(first[0]) - per) < 0.03 * per      # seeded at the periodogram peak
+        best = out["periods"][b][np.argmax(out["weights"][b])]
+        assert abs(best - per) < 0.05 * per
+        assert out["loss"][-1, b] < out["loss"][0, b]

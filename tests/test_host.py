@@ -28,7 +28,9 @@ def fake_sm_fit(x, y, fixed_noise, raw, kinds, lb, ub, n_valid, kind, Q, learn_n
     hist = torch.zeros(maxiter + 1, B, P, dtype=torch.float64)
     n_iter = torch.zeros(B, dtype=torch.int32)
     for b in range(B):
-        res = train_loop(x[b], y[b], None if fixed_noise is None else fixed_noise[b], raw[b],
+        n = x.shape[1] if n_valid is None else int(n_valid[b])
+        res = train_loop(x[b, :n], y[b, :n], None if fixed_noise is None else fixed_noise[b, :n],
+                         raw[b],
                          kinds, lb if lb.dim() == 1 else lb[b], ub if ub.dim() == 1 else ub[b],
                          spec, maxiter=maxiter, miniter=miniter, stop=stop or None, lr=lr,
                          optim=OPT_NAMES[optim_kind], eps=eps, stopavg=stopavg)
@@ -255,3 +257,77 @@ def test_gather_results_world_size_2_gloo():
     for rank, full, even in outs:
         assert full == [float(i) for i in range(11)]
         assert even == [0.0] * 4 + [1.0] * 4
+
+
+def _ragged_lcs(ns=(50, 64, 37), seed=4, **kw):
+    rng = np.random.default_rng(seed)
+    out = []
+    for n in ns:
+        per = rng.uniform(40, 90)
+        t = np.sort(rng.uniform(2450000.0, 2450000.0 + 6 * per, n))
+        y = np.sin(2 * np.pi * t / per) + 0.1 * rng.standard_normal(n)
+        out.append((Lightcurve(t, y, yerr=np.full(n, 0.1), **kw).double(), per))
+    return out
+
+
+def test_fit_batch_equals_a_loop_over_lightcurve_fit(cpu_engine):
+    """fit_batch packs a ragged batch with the SAME host set-up as Lightcurve.fit: per light
+    curve the loss history and fitted parameters equal the single-source call."""
+    from pgmuvi_b200.batch import fit_batch
+    single = []
+    torch.manual_seed(7)                     # initialize_from_data draws from the torch RNG
+    for lc, per in _ragged_lcs():
+        res = lc.fit(model="1D", num_mixtures=2, periods=[per, 2.1 * per], training_iter=4,
+                     optim="AdamW", lr=0.05)
+        single.append((np.array(res["loss"], dtype=float), pack_model(lc.model).raw().detach()))
+    lcs = _ragged_lcs()
+    torch.manual_seed(7)
+    out = fit_batch([lc for lc, _ in lcs], model="1D", num_mixtures=2,
+                    periods=[[per, 2.1 * per] for _, per in lcs], training_iter=4, optim="AdamW",
+                    lr=0.05, device="cpu")
+    assert out["loss"].shape == (4, 3) and out["raw"].shape[0] == 3
+    assert out["n_iter"].tolist() == [4, 4, 4] and out["info"].tolist() == [0, 0, 0]
+    for b, (lc, per) in enumerate(lcs):
+        # the single-source history is in the model's dtype (fp32 here), the batch one is fp64
+        assert np.allclose(out["loss"][:, b].numpy(), single[b][0], rtol=1e-6, atol=1e-7)
+        assert np.allclose(out["raw"][b].numpy(), single[b][1].numpy(), rtol=1e-6, atol=1e-7)
+        assert np.allclose(np.array(lc.results["loss"], dtype=float), single[b][0], rtol=1e-10)
+        assert len(lc.results["covar_module.mixture_means"]) == 5
+        assert abs(out["periods"][b][0] - per) < 0.2 * per
+    with pytest.raises(ValueError):
+        fit_batch([], model="1D")
+
+
+def _gloo_fit_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from pgmuvi_b200.batch import fit_batch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    trainers.ops.sm_fit = fake_sm_fit
+    lcs = _ragged_lcs()
+    torch.manual_seed(7)
+    out = fit_batch([lc for lc, _ in lcs], model="1D", num_mixtures=2,
+                    periods=[[per, 2.1 * per] for _, per in lcs], training_iter=3, optim="Adam",
+                    lr=0.05, device="cpu")
+    has_results = [hasattr(lc, "results") for lc, _ in lcs]
+    q.put((rank, out["raw"].numpy(), out["loss"].numpy(), has_results))
+    dist.destroy_process_group()
+
+
+def test_fit_batch_shards_over_ranks_and_gathers_gloo():
+    """world_size 2: rank 0 fits light curves 0-1, rank 1 fits light curve 2; both end with all
+    fitted parameters (one all-gather at the end), equal to the single-process result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted((q.get(timeout=300) for _ in procs), key=lambda o: o[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == [True, True, False] and outs[1][3] == [False, False, True]
+    assert outs[0][1].shape[0] == 3 and np.isfinite(outs[0][2]).all()
