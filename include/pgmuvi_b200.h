@@ -94,6 +94,20 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same call, additionally returning alpha = K~^-1 (y - c)  ([B, n_max], zero beyond n_valid;
+ * needs PGM_FLAG_GRAD).  d mll / d y = -alpha / n, which is all a NON-constant mean function
+ * needs: the host evaluates any mean m(x; theta_m) (gpytorch LinearMean, pgmuvi's PowerLawMean /
+ * DustMean, pgmuvi/gps.py:31-171, 223-372, 617-780), passes y - m(x) with the constant slot
+ * frozen at 0, and chains -alpha / n through d m / d theta_m (loss.backward, trainers.py:181).
+ */
+int pgm_sm_mll_grad_alpha_f64(const double* x, const int32_t* n_valid, const double* y,
+                              const double* fixed_noise, const double* raw,
+                              const int32_t* con_kind, const double* con_lb, const double* con_ub,
+                              int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                              double* mll, double* grad_raw, double* alpha_out, int32_t* info,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * N1 - exact posterior prediction at m test inputs per light curve:
  *     mean*[b, s] = c_b + K*^T alpha,     var*[b, s] = k** - || L^-1 k* ||^2    (latent f)
  * Replaces  likelihood(model(x_fine))  in eval mode (pgmuvi/lightcurve.py:9607-9640, 9862, 9937),
@@ -135,6 +149,14 @@ int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const do
                                int kernel_kind, int flags, double* mll, double* grad_raw,
                                int32_t* info, void* workspace, size_t workspace_bytes,
                                void* stream);
+
+int pgm_sm_mll_grad_staged_alpha_f64(const double* x, const int32_t* n_valid, const double* y,
+                                     const double* fixed_noise, const double* raw,
+                                     const int32_t* con_kind, const double* con_lb,
+                                     const double* con_ub, int B, int n_max, int d, int Q,
+                                     int kernel_kind, int flags, double* mll, double* grad_raw,
+                                     double* alpha_out, int32_t* info, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 
 /*
  * Dense covariance K + D of each light curve, written to K_out [B, n_max, n_max] (rows /

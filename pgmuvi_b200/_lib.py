@@ -28,6 +28,7 @@ EXPORTS = (
     "pgm_predict_workspace_bytes", "pgm_sm_predict_f64",
     "pgm_f32_staging_bytes", "pgm_sm_mll_grad_f32", "pgm_sm_fit_f32",
     "pgm_lombscargle_f64", "pgm_ls_peaks_f64",
+    "pgm_sm_mll_grad_alpha_f64", "pgm_sm_mll_grad_staged_alpha_f64",
 )
 
 _lib = None
@@ -89,6 +90,11 @@ def load():
                                         dp, vp]
     lib.pgm_ls_peaks_f64.restype = c_int
     lib.pgm_ls_peaks_f64.argtypes = [dp, ip, c_int, c_int, c_int, c_int, ip, dp, vp, c_size_t, vp]
+    lib.pgm_sm_mll_grad_alpha_f64.restype = c_int
+    lib.pgm_sm_mll_grad_alpha_f64.argtypes = [dp, ip, dp, dp, dp, ip, dp, dp, c_int, c_int, c_int,
+                                              c_int, c_int, c_int, dp, dp, dp, ip, vp, c_size_t, vp]
+    lib.pgm_sm_mll_grad_staged_alpha_f64.restype = c_int
+    lib.pgm_sm_mll_grad_staged_alpha_f64.argtypes = lib.pgm_sm_mll_grad_alpha_f64.argtypes
     lib.pgm_peak_probe.restype = c_int
     lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
     _lib = lib

@@ -193,7 +193,19 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
                         const double* con_lb, const double* con_ub, int B, int n_max, int d,
                         int Q, int kernel_kind, int flags, double* mll, double* grad_raw,
                         int32_t* info, void* workspace, size_t workspace_bytes, void* stream) {
+  return pgm_sm_mll_grad_alpha_f64(x, n_valid, y, fixed_noise, raw, con_kind, con_lb, con_ub, B,
+                                   n_max, d, Q, kernel_kind, flags, mll, grad_raw, nullptr, info,
+                                   workspace, workspace_bytes, stream);
+}
+
+int pgm_sm_mll_grad_alpha_f64(const double* x, const int32_t* n_valid, const double* y,
+                              const double* fixed_noise, const double* raw,
+                              const int32_t* con_kind, const double* con_lb, const double* con_ub,
+                              int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                              double* mll, double* grad_raw, double* alpha_out, int32_t* info,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (alpha_out && !(flags & PGM_FLAG_GRAD)) return fail("alpha_out needs PGM_FLAG_GRAD");
   if (B == 0) return 0;
   if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
     return fail("null pointer argument");
@@ -207,6 +219,7 @@ int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y
   A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags;
   A.mll = mll; A.grad = grad_raw; A.info = info;
   A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
+  A.alpha_out = alpha_out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGM_DISPATCH(launch_eval, A, st);
   return 0;
@@ -223,7 +236,21 @@ int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const do
                                int kernel_kind, int flags, double* mll, double* grad_raw,
                                int32_t* info, void* workspace, size_t workspace_bytes,
                                void* stream) {
+  return pgm_sm_mll_grad_staged_alpha_f64(x, n_valid, y, fixed_noise, raw, con_kind, con_lb,
+                                          con_ub, B, n_max, d, Q, kernel_kind, flags, mll,
+                                          grad_raw, nullptr, info, workspace, workspace_bytes,
+                                          stream);
+}
+
+int pgm_sm_mll_grad_staged_alpha_f64(const double* x, const int32_t* n_valid, const double* y,
+                                     const double* fixed_noise, const double* raw,
+                                     const int32_t* con_kind, const double* con_lb,
+                                     const double* con_ub, int B, int n_max, int d, int Q,
+                                     int kernel_kind, int flags, double* mll, double* grad_raw,
+                                     double* alpha_out, int32_t* info, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
   if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (alpha_out && !(flags & PGM_FLAG_GRAD)) return fail("alpha_out needs PGM_FLAG_GRAD");
   if (B == 0) return 0;
   if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
     return fail("null pointer argument");
@@ -236,6 +263,7 @@ int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const do
   A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags;
   A.mll = mll; A.grad = grad_raw; A.info = info;
   A.ws = static_cast<double*>(workspace);
+  A.alpha_out = alpha_out;
   const int want_grad = (flags & PGM_FLAG_GRAD) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGM_DISPATCH(launch_large, A, want_grad, st, 0);
@@ -274,6 +302,7 @@ int pgm_sm_predict_f64(const double* x, const int32_t* n_valid, const double* y,
   A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags & ~PGM_FLAG_GRAD;
   A.mll = nullptr; A.grad = nullptr; A.info = info;
   A.ws = static_cast<double*>(workspace);
+  A.alpha_out = nullptr;
   PA.xstar = xstar; PA.m = m; PA.mean = mean; PA.var = var;
   const size_t staged = (pgm::large_ws_bytes(n_max, B) + 255) & ~(size_t)255;
   PA.kscratch = reinterpret_cast<double*>(static_cast<char*>(workspace) + staged);
@@ -348,6 +377,7 @@ int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
   A.B = B; A.n_max = n_max; A.Q = Q; A.flags = flags | PGM_FLAG_GRAD;
   A.mll = nullptr; A.grad = nullptr; A.info = info;
   A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
+  A.alpha_out = nullptr;
   F.raw_io = raw; F.optim_kind = optim_kind; F.lr = lr; F.beta1 = beta1; F.beta2 = beta2;
   F.eps = eps; F.weight_decay = weight_decay; F.stop = stop; F.maxiter = maxiter;
   F.miniter = miniter; F.stopavg = stopavg; F.loss_hist = loss_hist; F.raw_hist = raw_hist;

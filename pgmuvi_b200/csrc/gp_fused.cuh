@@ -795,6 +795,7 @@ struct EvalArgs {
   int32_t* info;
   double* ws;
   size_t ws_per_block;  // elements
+  double* alpha_out;    // [B, n_max] or null: alpha = K~^-1 (y - mean)  (d MLL / d y = -alpha / n)
 };
 
 struct FitArgs {
@@ -1332,6 +1333,9 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     double sa = 0.0;
     for (int i2 = tid; i2 < n; i2 += NTHREADS) sa += sc.alpha[i2];
     v[C::NV] = sa;
+    if (A.alpha_out)
+      for (int i2 = tid; i2 < A.n_max; i2 += NTHREADS)
+        A.alpha_out[(size_t)b * A.n_max + i2] = (i2 < n) ? sc.alpha[i2] : 0.0;
     __syncthreads();
     block_reduce<C::NV + 1>(v, red, fin);
   }

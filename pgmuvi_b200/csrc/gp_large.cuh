@@ -95,6 +95,7 @@ struct LargeArgs {
   double* grad;               // [B, P]
   int32_t* info;              // [B] (device)
   double* ws;
+  double* alpha_out;          // [B, n_max] or null
 };
 
 // the light curve of this block: its size and workspace
@@ -673,6 +674,9 @@ __global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int want_grad
 #pragma unroll
       for (int k = 0; k < C::NV; ++k) vv[k] += w.gpart[(size_t)t * LG_GP + k];
     for (int i2 = tid; i2 < n; i2 += NTHREADS) vv[C::NV] += w.alpha[i2];
+    if (A.alpha_out)
+      for (int i2 = tid; i2 < A.n_max; i2 += NTHREADS)
+        A.alpha_out[(size_t)v.b * A.n_max + i2] = (i2 < n) ? w.alpha[i2] : 0.0;
   }
   block_reduce<C::NV + 3>(vv, red, fin);
   if (tid == 0) {

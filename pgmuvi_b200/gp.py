@@ -109,6 +109,103 @@ class ConstantMean(Module):
         return self.constant.expand(x.shape[:-1])
 
 
+class LinearMean(Module):
+    """gpytorch.means.LinearMean(input_size, bias=True): m(x) = x . weights + bias; weights
+    [input_size, 1] and bias [1] are unconstrained and start from N(0, 1) draws (used by
+    pgmuvi/gps.py:255, 357)."""
+
+    def __init__(self, input_size, bias=True):
+        super().__init__()
+        self.register_parameter("weights", nn.Parameter(torch.randn(input_size, 1)))
+        self.register_parameter("bias", nn.Parameter(torch.randn(1)) if bias else None)
+
+    def forward(self, x):
+        res = x.matmul(self.weights).squeeze(-1)
+        return res if self.bias is None else res + self.bias
+
+
+class PowerLawMean(Module):
+    """pgmuvi/gps.py:31-91: m(t, lam) = offset + weight * lam ** exponent (second input column
+    = wavelength); offset 0, weight 1, exponent -2 initially, all unconstrained."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("offset", nn.Parameter(torch.zeros(1)))
+        self.register_parameter("weight", nn.Parameter(torch.ones(1)))
+        self.register_parameter("exponent", nn.Parameter(torch.full((1,), -2.0)))
+
+    def forward(self, x):
+        lam = x[..., 1]
+        return self.offset.squeeze(-1) + self.weight.squeeze(-1) * lam.pow(self.exponent.squeeze(-1))
+
+
+class DustMean(Module):
+    """pgmuvi/gps.py:93-171: m(t, lam) = offset + exp(log_amplitude) *
+    exp(-exp(log_tau) * lam ** (-exp(log_alpha))), wavelengths clamped at 1e-6; log_alpha starts
+    at log 1.7, the other parameters at 0."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("offset", nn.Parameter(torch.zeros(1)))
+        self.register_parameter("log_amplitude", nn.Parameter(torch.zeros(1)))
+        self.register_parameter("log_tau", nn.Parameter(torch.zeros(1)))
+        self.register_parameter("log_alpha", nn.Parameter(torch.full((1,), 0.5306282510621704)))
+
+    def forward(self, x):
+        lam = x[..., 1].clamp(min=1e-6)
+        amp = self.log_amplitude.squeeze(-1).exp()
+        tau = self.log_tau.squeeze(-1).exp()
+        alpha = self.log_alpha.squeeze(-1).exp()
+        return self.offset.squeeze(-1) + amp * (-(tau * lam.pow(-alpha))).exp()
+
+
+class CustomLinearConstantMean(Module):
+    """pgmuvi/gps.py:1425-1445: bias + wavelength_slope * lam (constant in time)."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("wavelength_slope", nn.Parameter(torch.tensor(0.0)))
+        self.register_parameter("bias", nn.Parameter(torch.tensor(0.0)))
+
+    def forward(self, x):
+        return self.bias + self.wavelength_slope * x[:, 1]
+
+
+class CustomQuadConstantMean(Module):
+    """pgmuvi/gps.py:1448-1473: bias + w1 lam + w2 lam^2 (constant in time)."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("weights", nn.Parameter(torch.tensor([0.0, 0.0])))
+        self.register_parameter("bias", nn.Parameter(torch.tensor(0.0)))
+
+    def forward(self, x):
+        lam = x[:, 1].unsqueeze(-1)
+        powers = torch.arange(1, self.weights.numel() + 1, device=self.weights.device,
+                              dtype=self.weights.dtype)
+        return self.bias + (self.weights * lam ** powers).sum(-1)
+
+
+def _build_mean_module(mean_module):
+    """Mean choices of WavelengthDependentGPModel (pgmuvi/gps.py:1587-1609)."""
+    if mean_module is None or mean_module in ("quad", "quadratic", "quad_constant"):
+        return CustomQuadConstantMean()
+    if mean_module in ("linear", "linear_mean"):
+        return CustomLinearConstantMean()
+    if mean_module in ("constant", "constant_mean"):
+        return ConstantMean()
+    if mean_module in ("dust", "dust_mean"):
+        return DustMean()
+    if mean_module in ("power_law", "power_law_mean"):
+        return PowerLawMean()
+    if isinstance(mean_module, nn.Module):
+        return mean_module
+    raise ValueError(f"Unsupported mean_module value {mean_module!r}. Choose from "
+                     "'quad'/'quadratic'/'quad_constant', 'linear'/'linear_mean', "
+                     "'constant'/'constant_mean', 'dust'/'dust_mean', "
+                     "'power_law'/'power_law_mean', or a mean module instance")
+
+
 class SpectralMixtureKernel(Module):
     """gpytorch.kernels.SpectralMixtureKernel parameters (values computed on the GPU)."""
 
@@ -297,6 +394,11 @@ class PriorOutput:
     def __init__(self, model, x):
         self.model, self.x = model, x
 
+    @property
+    def mean(self):
+        """Prior mean at the inputs (what MultivariateNormal.mean holds), with autograd."""
+        return self.model.mean_module(self.x)
+
 
 class ExactGP(Module):
     def __init__(self, train_inputs, train_targets, likelihood):
@@ -338,6 +440,38 @@ class TwoDSpectralMixtureGPModel(ExactGP):
 
     def forward(self, x):
         return PriorOutput(self, x)
+
+
+class SpectralMixtureLinearMeanGPModel(SpectralMixtureGPModel):
+    """pgmuvi/gps.py:223-267 ('1DLinear'): LinearMean(input_size=1) + SMK."""
+
+    def __init__(self, train_x, train_y, likelihood, num_mixtures=4):
+        super().__init__(train_x, train_y, likelihood, num_mixtures=num_mixtures)
+        self.mean_module = LinearMean(input_size=1)
+
+
+class TwoDSpectralMixtureLinearMeanGPModel(TwoDSpectralMixtureGPModel):
+    """pgmuvi/gps.py:321-372 ('2DLinear'): LinearMean(input_size=2) + SMK(ard_num_dims=2)."""
+
+    def __init__(self, train_x, train_y, likelihood, num_mixtures=4, **kwargs):
+        super().__init__(train_x, train_y, likelihood, num_mixtures=num_mixtures, **kwargs)
+        self.mean_module = LinearMean(input_size=self.train_inputs[0].shape[-1])
+
+
+class TwoDSpectralMixturePowerLawMeanGPModel(TwoDSpectralMixtureGPModel):
+    """pgmuvi/gps.py:617-664 ('2DPowerLaw'): PowerLawMean + SMK(ard_num_dims=2)."""
+
+    def __init__(self, train_x, train_y, likelihood, num_mixtures=4, **kwargs):
+        super().__init__(train_x, train_y, likelihood, num_mixtures=num_mixtures, **kwargs)
+        self.mean_module = PowerLawMean()
+
+
+class TwoDSpectralMixtureDustMeanGPModel(TwoDSpectralMixtureGPModel):
+    """pgmuvi/gps.py:729-779 ('2DDust'): DustMean + SMK(ard_num_dims=2)."""
+
+    def __init__(self, train_x, train_y, likelihood, num_mixtures=4, **kwargs):
+        super().__init__(train_x, train_y, likelihood, num_mixtures=num_mixtures, **kwargs)
+        self.mean_module = DustMean()
 
 
 def _build_time_kernel(time_kernel_type, num_mixtures):
@@ -410,8 +544,9 @@ class AchromaticGPModel(SeparableGPModel):
 
 
 class WavelengthDependentGPModel(SeparableGPModel):
-    """pgmuvi/gps.py:1476-1628 with the spectral-mixture time kernel and a ConstantMean (the
-    reference's default quadratic mean is outside the accelerated path)."""
+    """pgmuvi/gps.py:1476-1628 with the spectral-mixture time kernel.  ``mean_module`` as the
+    reference ('quad' default there; 'constant' here keeps the whole fit in one kernel launch,
+    the wavelength-dependent means run the host loop with the mean on the host)."""
 
     def __init__(self, train_x, train_y, likelihood, time_kernel_type="sm",
                  wavelength_kernel_type="rbf", period=None, wavelength_lengthscale=None,
@@ -420,9 +555,6 @@ class WavelengthDependentGPModel(SeparableGPModel):
         if wavelength_lengthscale is None:
             wl_span = float(train_x[:, 1].max() - train_x[:, 1].min())
             wavelength_lengthscale = max(wl_span / 2.0, 1.0)       # gps.py:1576-1578
-        if mean_module not in ("constant", "constant_mean") and not isinstance(mean_module,
-                                                                               ConstantMean):
-            raise NotImplementedError("only mean_module='constant' is on the accelerated path")
         if add_flicker:
             raise NotImplementedError("add_flicker is outside the accelerated path")
         super().__init__(train_x, train_y, likelihood,
@@ -430,4 +562,20 @@ class WavelengthDependentGPModel(SeparableGPModel):
                          wavelength_kernel=_build_wavelength_kernel(
                              wavelength_kernel_type, wavelength_lengthscale,
                              scaling=wavelength_scaling),
-                         mean_module=ConstantMean())
+                         mean_module=_build_mean_module(mean_module))
+
+
+class DustMeanGPModel(WavelengthDependentGPModel):
+    """pgmuvi/gps.py:1631-1697 ('2DDustMean'), with the spectral-mixture time kernel."""
+
+    def __init__(self, train_x, train_y, likelihood, **kwargs):
+        kwargs.setdefault("wavelength_kernel_type", "rbf")
+        super().__init__(train_x, train_y, likelihood, mean_module="dust", **kwargs)
+
+
+class PowerLawMeanGPModel(WavelengthDependentGPModel):
+    """pgmuvi/gps.py:1700-1767 ('2DPowerLawMean'), with the spectral-mixture time kernel."""
+
+    def __init__(self, train_x, train_y, likelihood, **kwargs):
+        kwargs.setdefault("wavelength_kernel_type", "rbf")
+        super().__init__(train_x, train_y, likelihood, mean_module="power_law", **kwargs)

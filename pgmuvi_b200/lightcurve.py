@@ -23,8 +23,13 @@ from .trainers import train
 # lightcurve.py:2901-2930 - the spectral-mixture exact models; the separable ones are built
 # with the spectral-mixture time kernel
 _SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPModel,
+              "1DLinear": gp.SpectralMixtureLinearMeanGPModel,
+              "2DLinear": gp.TwoDSpectralMixtureLinearMeanGPModel,
+              "2DPowerLaw": gp.TwoDSpectralMixturePowerLawMeanGPModel,
+              "2DDust": gp.TwoDSpectralMixtureDustMeanGPModel,
               "2DSeparable": gp.SeparableGPModel, "2DAchromatic": gp.AchromaticGPModel,
-              "2DWavelengthDependent": gp.WavelengthDependentGPModel}
+              "2DWavelengthDependent": gp.WavelengthDependentGPModel,
+              "2DDustMean": gp.DustMeanGPModel, "2DPowerLawMean": gp.PowerLawMeanGPModel}
 CONSTRAINT_SETS = {"LPV": {"period": {"lower": (20.0, True), "upper": (None, False)}}}
 
 
@@ -195,7 +200,7 @@ class Lightcurve(torch.nn.Module):
         if isinstance(model, torch.nn.Module):
             self.model = model
         elif model in _SM_MODELS:
-            if model == "1D" and self.ndim > 1:
+            if model in ("1D", "1DLinear") and self.ndim > 1:
                 raise ValueError("You have selected a 1D model but your data has more than one "
                                  "input dimension; use model='2D'.")   # tests/test_2d_integration.py:167-186
             if model.startswith("2D") and self.ndim != 2:
@@ -357,8 +362,15 @@ class Lightcurve(torch.nn.Module):
         x = self._xdata_transformed
         x = x if x.dim() > 1 else x.unsqueeze(-1)
         xs = xt if xt.dim() > 1 else xt.unsqueeze(-1)
+        y_fit = self._ydata_transformed
+        m_star = None
+        if pk.external_mean:      # non-constant mean: condition on y - m(x), add m(x*) back
+            with torch.no_grad():
+                pdt = next(self.model.mean_module.parameters()).dtype
+                y_fit = y_fit - self.model.mean_module(x.to(pdt)).to(y_fit.dtype)
+                m_star = self.model.mean_module(xs.to(pdt)).to(torch.float64).cpu()
         mean, var, info = ops.sm_predict(
-            f64(x).unsqueeze(0).contiguous(), f64(self._ydata_transformed).unsqueeze(0).contiguous(),
+            f64(x).unsqueeze(0).contiguous(), f64(y_fit).unsqueeze(0).contiguous(),
             None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
             f64(pk.raw()).unsqueeze(0).contiguous(), pk.kinds.to(dev), pk.lb.to(dev),
             pk.ub.to(dev), None, f64(xs).unsqueeze(0).contiguous(), pk.kind, pk.Q, pk.learn_noise)
@@ -368,6 +380,8 @@ class Lightcurve(torch.nn.Module):
             raise (NanError if code == -1 else NotPSDError)(
                 "the covariance of the fitted model could not be factorised")
         mean, var = mean[0].cpu(), var[0].cpu()
+        if m_star is not None:
+            mean = mean + m_star
         if pk.learn_noise:
             # the learned noise is the slot right after the kernel parameters (pack_model order:
             # mean, weights, means, scales, noise, wavelength-kernel parameters)

@@ -43,6 +43,8 @@ class PackedModel:
     d: int
     learn_noise: bool
     fixed_noise: Optional[torch.Tensor]   # [n] variance or None
+    external_mean: bool = False           # non-constant mean: slot 0 is a frozen zero and the
+                                          # host passes y - mean_module(x) (pgm_*_alpha_f64)
 
     @property
     def P(self):
@@ -56,9 +58,10 @@ class PackedModel:
         """Write a packed [P] vector back into the Parameters (no grad)."""
         o = 0
         with torch.no_grad():
-            for p in self.params:
+            for i, p in enumerate(self.params):
                 k = p.numel()
-                p.copy_(flat[o:o + k].reshape(p.shape).to(dtype=p.dtype, device=p.device))
+                if not (self.external_mean and i == 0):      # the frozen zero stays zero
+                    p.copy_(flat[o:o + k].reshape(p.shape).to(dtype=p.dtype, device=p.device))
                 o += k
 
 
@@ -74,11 +77,14 @@ def _find_name(model, param):
 
 
 def pack_model(model, likelihood=None) -> PackedModel:
-    """Recognise (ConstantMean, SpectralMixtureKernel, Gaussian | FixedNoise likelihood)."""
+    """Recognise (mean, SpectralMixtureKernel [x wavelength kernel], Gaussian | FixedNoise
+    likelihood).  ConstantMean is packed into slot 0; any other mean module (LinearMean,
+    PowerLawMean, DustMean, ...) stays on the host (``external_mean``)."""
     likelihood = likelihood if likelihood is not None else model.likelihood
     mean, cov = getattr(model, "mean_module", None), getattr(model, "covar_module", None)
-    if mean is None or not hasattr(mean, "raw_constant"):
-        raise UnsupportedModelError("only ConstantMean is on the accelerated path")
+    if mean is None or not callable(mean):
+        raise UnsupportedModelError("the model needs a mean_module")
+    external_mean = not hasattr(mean, "raw_constant")
     lam_params, lam_cons, sep_kind = [], [], None
     factors = getattr(cov, "kernels", None)
     if factors is not None:
@@ -137,10 +143,13 @@ def pack_model(model, likelihood=None) -> PackedModel:
         pri = getattr(m, "named_priors", None)
         if pri is not None and len(list(pri())) > 0:
             raise UnsupportedModelError("registered priors are not on the accelerated path")
-    params = [mean.raw_constant, cov.raw_mixture_weights, cov.raw_mixture_means,
-              cov.raw_mixture_scales]
-    cons = [_constraint(mean, "raw_constant"), _constraint(cov, "raw_mixture_weights"),
-            _constraint(cov, "raw_mixture_means"), _constraint(cov, "raw_mixture_scales")]
+    slot0 = (torch.zeros(1, dtype=cov.raw_mixture_weights.dtype,
+                         device=cov.raw_mixture_weights.device) if external_mean
+             else mean.raw_constant)
+    params = [slot0, cov.raw_mixture_weights, cov.raw_mixture_means, cov.raw_mixture_scales]
+    cons = [None if external_mean else _constraint(mean, "raw_constant"),
+            _constraint(cov, "raw_mixture_weights"), _constraint(cov, "raw_mixture_means"),
+            _constraint(cov, "raw_mixture_scales")]
     fixed, learn = None, False
     nc = getattr(likelihood, "noise_covar", None)
     snc = getattr(likelihood, "second_noise_covar", None)
@@ -168,7 +177,7 @@ def pack_model(model, likelihood=None) -> PackedModel:
                        kinds=torch.tensor(kinds, dtype=torch.int32),
                        lb=torch.tensor(lb, dtype=torch.float64),
                        ub=torch.tensor(ub, dtype=torch.float64), kind=kind, Q=Q, d=d,
-                       learn_noise=learn, fixed_noise=fixed)
+                       learn_noise=learn, fixed_noise=fixed, external_mean=external_mean)
 
 
 def engine_device(t=None):
@@ -190,6 +199,26 @@ def _sm_mll_backward(ctx, g_mll, g_grad, g_info):
 
 
 ops.sm_mll_grad.register_autograd(_sm_mll_backward, setup_context=_sm_mll_setup_context)
+
+
+def _sm_mll_alpha_setup_context(ctx, inputs, output):
+    y, n_valid = inputs[1], inputs[7]
+    n = (torch.full((y.shape[0], 1), float(y.shape[1]), dtype=y.dtype, device=y.device)
+         if n_valid is None else n_valid.to(y.dtype).unsqueeze(1))
+    ctx.save_for_backward(output[1], output[3], n)
+
+
+def _sm_mll_alpha_backward(ctx, g_mll, g_grad, g_info, g_alpha):
+    grad, alpha, n = ctx.saved_tensors
+    if g_mll is None:
+        return (None,) * 12
+    g_raw = g_mll.unsqueeze(1) * grad
+    g_y = -g_mll.unsqueeze(1) * alpha / n        # d mll / d y = -K~^-1 (y - c) / n
+    return (None, g_y, None, g_raw) + (None,) * 8
+
+
+ops.sm_mll_grad_alpha.register_autograd(_sm_mll_alpha_backward,
+                                        setup_context=_sm_mll_alpha_setup_context)
 
 
 class _LargeMLL(torch.autograd.Function):
@@ -231,6 +260,21 @@ class B200ExactMarginalLogLikelihood(torch.nn.Module):
         dev = engine_device(raw)
         f64 = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float64)
         from .trainers import LARGE_N
+        if pk.external_mean:
+            # non-constant mean: evaluated here with autograd; the engine sees y - m(x) and
+            # returns alpha, so that d mll / d theta_m = (alpha / n) . d m / d theta_m
+            m = getattr(function_dist, "mean", None)
+            if m is None:
+                m = model.mean_module(x)
+            y_eff = (target - m.to(target.dtype)).to(device=dev, dtype=torch.float64)
+            mll, grad, info, _ = ops.sm_mll_grad_alpha(
+                f64(x).unsqueeze(0).contiguous(), y_eff.unsqueeze(0).contiguous(),
+                None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
+                raw.to(device=dev, dtype=torch.float64).unsqueeze(0),
+                pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev), None, pk.kind, pk.Q,
+                pk.learn_noise, bool(x.shape[0] > LARGE_N))
+            self._raise_for(int(info.item()))
+            return mll[0].to(dtype=raw.dtype, device=raw.device)
         if x.shape[0] > LARGE_N:
             holder = []
             mll = _LargeMLL.apply(raw.to(device=dev, dtype=torch.float64), f64(x).contiguous(),

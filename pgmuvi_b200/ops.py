@@ -15,6 +15,7 @@ from ._lib import (FLAG_BOUNDS_PER_LC, FLAG_GRAD, FLAG_LEARN_NOISE, KIND_SM1D,
                    KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD, NUM_LAM, SEP_KINDS, check, ptr)
 
 _workspaces = {}
+_staged_ws = {}
 
 
 def param_count(Q: int, d: int, learn_noise: bool, kind: int = -1) -> int:
@@ -112,6 +113,53 @@ def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_
     return (y.new_empty(B), torch.empty_like(raw), y.new_empty(B, dtype=torch.int32))
 
 
+@torch.library.custom_op("pgmuvi_b200::sm_mll_grad_alpha", mutates_args=(), device_types="cuda")
+def sm_mll_grad_alpha(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
+                      con_kind: Tensor, con_lb: Tensor, con_ub: Tensor,
+                      n_valid: Optional[Tensor], kind: int, Q: int, learn_noise: bool,
+                      staged: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """As :func:`sm_mll_grad` (float64, with gradient), additionally returning
+    ``alpha = K~^-1 (y - c)`` [B, n]: ``d mll / d y = -alpha / n`` (the hook for non-constant
+    mean functions).  ``staged`` selects the whole-device engine (long light curves)."""
+    (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
+        x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
+    if x.dtype != torch.float64:
+        raise RuntimeError("sm_mll_grad_alpha takes float64 tensors")
+    flags |= FLAG_GRAD
+    mll = torch.empty(B, dtype=x.dtype, device=x.device)
+    grad = torch.zeros(B, P, dtype=x.dtype, device=x.device)
+    alpha = torch.zeros(B, n, dtype=x.dtype, device=x.device)
+    info = torch.zeros(B, dtype=torch.int32, device=x.device)
+    if n_valid is not None:
+        n_valid = n_valid.to(torch.int32).contiguous()
+    lib = _lib.load()
+    if staged:
+        need = lib.pgm_staged_workspace_bytes(n, B)
+        key = (x.device.index,)
+        ws = _staged_ws.get(key)
+        if ws is None or ws.numel() < need:
+            _staged_ws.pop(key, None)
+            ws = None
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            _staged_ws[key] = ws
+        entry = lib.pgm_sm_mll_grad_staged_alpha_f64
+    else:
+        ws, _ = _workspace(x.device, n, d, Q)
+        entry = lib.pgm_sm_mll_grad_alpha_f64
+    with torch.cuda.device(x.device):
+        check(entry(ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind),
+                    ptr(con_lb), ptr(con_ub), B, n, d, Q, kind, flags, ptr(mll), ptr(grad),
+                    ptr(alpha), ptr(info), ptr(ws), ws.numel(), _stream()))
+    return mll, grad, info, alpha
+
+
+@sm_mll_grad_alpha.register_fake
+def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_noise, staged):
+    B = y.shape[0]
+    return (y.new_empty(B), torch.empty_like(raw), y.new_empty(B, dtype=torch.int32),
+            torch.empty_like(y))
+
+
 @torch.library.custom_op("pgmuvi_b200::sm_kernel_dense", mutates_args=(), device_types="cuda")
 def sm_kernel_dense(x: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con_kind: Tensor,
                     con_lb: Tensor, con_ub: Tensor, n_valid: Optional[Tensor], kind: int, Q: int,
@@ -195,9 +243,6 @@ def sm_fit(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con
             ptr(raw_hist) if keep_history else None, ptr(n_iter), ptr(info), None, ptr(ws),
             ws.numel(), _stream()))
     return loss_hist, raw_hist, n_iter, info
-
-
-_staged_ws = {}
 
 
 def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
@@ -295,6 +340,6 @@ def peak_probe(kind: int, iters: int = 4096) -> float:
     return out.value
 
 
-__all__ = ["sm_mll_grad", "sm_mll_grad_large", "sm_mll_grad_staged", "sm_predict", "sm_kernel_dense", "optim_step", "sm_fit",
+__all__ = ["sm_mll_grad", "sm_mll_grad_alpha", "sm_mll_grad_large", "sm_mll_grad_staged", "sm_predict", "sm_kernel_dense", "optim_step", "sm_fit",
            "peak_probe", "param_count",
            "KIND_SM1D", "KIND_SM_ARD_PRODSUM", "KIND_SM_ARD_SUMPROD"]

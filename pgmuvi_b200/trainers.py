@@ -63,10 +63,12 @@ def history_from_raw(raw_hist, pk, model, lightcurve=None, transform=True):
     o = 0
     xt = getattr(lightcurve, "xtransform", None) if lightcurve is not None else None
     yt = getattr(lightcurve, "ytransform", None) if lightcurve is not None else None
-    for p, name in zip(pk.params, pk.names):
+    for i, (p, name) in enumerate(zip(pk.params, pk.names)):
         k = p.numel()
         vals = raw_hist[:, o:o + k].reshape((T,) + tuple(p.shape)).to(p.dtype)
         o += k
+        if getattr(pk, "external_mean", False) and i == 0:
+            continue                                        # frozen zero, not a model parameter
         if lightcurve is None:
             out[name] = [v.numpy() for v in vals]           # raw values under the raw name
             continue
@@ -134,6 +136,13 @@ def train(lightcurve=None, model=None, likelihood=None, train_x=None, train_y=No
                         """)
 
     pk = pack_model(model, likelihood)          # raises UnsupportedModelError outside the path
+    if pk.external_mean and not isinstance(optim, torch.optim.Optimizer):
+        # non-constant mean functions are evaluated on the host with autograd: the reference's
+        # own loop and optimiser construction (trainers.py:141-147), the MLL on the GPU
+        params = list(model.parameters())
+        optim = {"SGD": lambda: torch.optim.SGD(params, lr=lr),
+                 "Adam": lambda: torch.optim.Adam(params, lr=lr, eps=eps),
+                 "AdamW": lambda: torch.optim.AdamW(params, lr=lr, eps=eps)}[optim]()
     if isinstance(optim, torch.optim.Optimizer):
         return _train_with_torch_optimizer(lightcurve, model, likelihood, train_x, train_y, pk,
                                            optim, maxiter, miniter, stop, stopavg)
@@ -218,6 +227,21 @@ def _train_with_torch_optimizer(lightcurve, model, likelihood, train_x, train_y,
     """The reference's own loop (trainers.py:177-207) with the MLL evaluated on the GPU."""
     lossfn = B200ExactMarginalLogLikelihood(likelihood, model)
     raws = [pk.raw().detach().clone().to(torch.float64).cpu()]
+    packed = {id(p) for p in pk.params}
+    extra = [(n, p) for n, p in model.named_parameters() if id(p) not in packed]
+    yt = getattr(lightcurve, "ytransform", None) if lightcurve is not None else None
+
+    def snapshot():     # parameters outside the packed layout (mean-function parameters)
+        out = {}
+        for n, p in extra:
+            v = p.detach().clone().cpu()
+            key = _strip_raw(n) if lightcurve is not None else n
+            if yt is not None and any(s in key for s in _Y_KEYS):
+                v = yt.inverse(v)
+            out[key] = v.numpy()
+        return out
+
+    extras = [snapshot()]
     losses = []
     for i in range(maxiter):
         optimizer.zero_grad()
@@ -227,9 +251,12 @@ def _train_with_torch_optimizer(lightcurve, model, likelihood, train_x, train_y,
         optimizer.step()
         losses.append(loss.detach().cpu().numpy())
         raws.append(pk.raw().detach().clone().to(torch.float64).cpu())
+        extras.append(snapshot())
         if stop and i > miniter and np.std(losses[-stopavg:]) < stop:
             break
     results = {"loss": losses,
                "delta_loss": [losses[i] - losses[i - 1] for i in range(1, len(losses))]}
     results.update(history_from_raw(torch.stack(raws), pk, model, lightcurve))
+    for key in extras[0]:
+        results[key] = [e[key] for e in extras]
     return results

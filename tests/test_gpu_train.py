@@ -276,3 +276,107 @@ def test_fit_batch_matches_per_source_fits_and_mls_seeding(cuda_device):
         best = out["periods"][b][np.argmax(out["weights"][b])]
         assert abs(best - per) < 0.05 * per
         assert out["loss"][-1, b] < out["loss"][0, b]
+
+
+def _oracle_loss_external_mean(lc, pk):
+    """-MLL of the model through the oracle on the CPU, differentiable w.r.t. every model
+    parameter (kernel / noise parameters via the packed raw vector, mean parameters via
+    y - mean_module(x))."""
+    from oracle import ModelSpec, constrain
+    from oracle.sm_gp import _mll_from_theta
+    x = lc._xdata_transformed.double()
+    x = x if x.dim() > 1 else x.unsqueeze(-1)
+    spec = ModelSpec(d=pk.d, Q=pk.Q, kind=pk.kind, learn_noise=pk.learn_noise)
+    fn = None if pk.fixed_noise is None else pk.fixed_noise.double()
+
+    def loss():
+        raw = pk.raw().double()
+        theta = constrain(raw, pk.kinds, pk.lb, pk.ub)
+        m = lc.model.mean_module(lc.model.train_inputs[0]).double()
+        mll, info = _mll_from_theta(x, lc._ydata_transformed.double() - m, fn, theta, spec)
+        assert int(info) == 0
+        return -mll
+    return loss
+
+
+@pytest.mark.parametrize("model,two_d", [("1DLinear", False), ("2DLinear", True),
+                                         ("2DPowerLaw", True), ("2DDust", True),
+                                         ("2DDustMean", True), ("2DPowerLawMean", True),
+                                         ("2DWavelengthDependent:quad", True)])
+def test_non_constant_means_match_the_oracle(cuda_device, model, two_d):
+    """'1DLinear' / '2DLinear' / '2DPowerLaw' / '2DDust' (pgmuvi/gps.py:223-372, 617-779): the mean
+    function stays on the host, the engine gets y - m(x) and returns alpha; loss and the gradient
+    of EVERY parameter (kernel, noise, mean) equal the oracle's autograd, and train() follows the
+    same trajectory as the reference loop run on the oracle."""
+    from pgmuvi_b200.mll import B200ExactMarginalLogLikelihood, pack_model
+    from pgmuvi_b200.trainers import train
+    torch.manual_seed(5)
+    # wavelength-law means need physical (non min-max-scaled) wavelengths: 0 ** -2 = inf
+    model, _, mean_opt = model.partition(":")
+    kw = dict(xtransform=None) if "PowerLaw" in model or "Dust" in model else {}
+    lc = (_lc_2d(seed=9, **kw) if two_d else _lc(n=150, seed=9)).double()
+    lc.set_model(model, num_mixtures=2, **({"mean_module": mean_opt} if mean_opt else {}))
+    lc.double()
+    lc.set_default_constraints()
+    if not two_d:
+        lc.set_hypers({"covar_module.mixture_means": torch.tensor([1 / 57.0, 1 / 130.0])})
+    pk = pack_model(lc.model, lc.likelihood)
+    assert pk.external_mean
+    with torch.no_grad():      # gpytorch draws LinearMean's weights from N(0, 1): start near the
+        for n_, p_ in lc.model.mean_module.named_parameters():     # data instead of at loss ~ 1e2
+            if n_ in ("weights", "bias"):
+                p_.mul_(0.02)
+    # --- one evaluation: loss and all gradients
+    mll = B200ExactMarginalLogLikelihood(lc.likelihood, lc.model)
+    params = list(lc.model.parameters())
+    loss = -mll(lc.model(lc._xdata_transformed), lc._ydata_transformed)
+    g_gpu = torch.autograd.grad(loss, params, allow_unused=True)
+    oloss = _oracle_loss_external_mean(lc, pk)
+    lo = oloss()
+    g_cpu = torch.autograd.grad(lo, params, allow_unused=True)
+    assert abs(float(loss) - float(lo)) <= 1e-9 * abs(float(lo))
+    n_mean = 0
+    for (name, p), a, b in zip(lc.model.named_parameters(), g_gpu, g_cpu):
+        assert (a is None) == (b is None), name
+        if a is not None:
+            assert float((a - b).abs().max()) <= 1e-8 * max(1.0, float(b.abs().max())), name
+            n_mean += name.startswith("mean_module")
+    assert n_mean >= 2
+    # --- training: the reference loop on the oracle vs train()
+    # (a short, small-step run: Adam's g / sqrt(v) normalisation amplifies last-digit gradient
+    # differences quickly on these far-from-optimum starts)
+    lr, iters = (0.05, 5) if not two_d else (0.005, 3)
+    state = {k: v.detach().clone() for k, v in lc.model.state_dict().items()}
+    opt = torch.optim.Adam(params, lr=lr, eps=1e-8)
+    ref_losses = []
+    for _ in range(iters):
+        opt.zero_grad()
+        lo = oloss()
+        lo.backward()
+        opt.step()
+        ref_losses.append(float(lo))
+    ref_final = [p.detach().clone() for p in params]
+    lc.model.load_state_dict(state)
+    res = train(lc, maxiter=iters, miniter=iters, stop=None, lr=lr, optim="Adam")
+    assert np.allclose(np.array(res["loss"], dtype=float), ref_losses, rtol=1e-7, atol=1e-9)
+    for p, q in zip(params, ref_final):
+        assert float((p.detach() - q).abs().max()) <= 1e-6 * max(1.0, float(q.abs().max()))
+    mean_keys = [k for k in res if k.startswith("mean_module")]
+    assert mean_keys and all(len(res[k]) == iters + 1 for k in mean_keys)
+    # --- prediction conditions on y - m(x) and adds m(x*) back (oracle: Cholesky solve)
+    from oracle import ModelSpec, predict as oracle_predict
+    xq = lc._xdata_raw[::7]
+    out = lc.predict(xq)
+    xt = lc._xdata_transformed.double()
+    xt = xt if xt.dim() > 1 else xt.unsqueeze(-1)
+    xs = xq if lc.xtransform is None else lc.xtransform.transform(xq)   # as predict() maps them
+    xs = (xs if xs.dim() > 1 else xs.unsqueeze(-1)).double()
+    with torch.no_grad():
+        m_tr = lc.model.mean_module(xt)
+        m_q = lc.model.mean_module(xs)
+    spec = ModelSpec(d=pk.d, Q=pk.Q, kind=pk.kind, learn_noise=pk.learn_noise)
+    mo, vo, _ = oracle_predict(xt, lc._ydata_transformed.double() - m_tr,
+                               None if pk.fixed_noise is None else pk.fixed_noise.double(),
+                               pk.raw().detach().double(), pk.kinds, pk.lb, pk.ub, spec, xs)
+    assert np.allclose(out["mean"], (mo + m_q).numpy(), rtol=1e-8, atol=1e-8)
+    assert np.allclose(out["variance"], vo.numpy(), rtol=1e-6, atol=1e-9)

@@ -158,7 +158,11 @@ def test_2d_constraints_and_dimension_checks():
     pk = pack_model(lc.model)
     assert (pk.kind, pk.Q, pk.d, pk.P) == (1, 3, 2, 1 + 3 + 12)
     with pytest.raises(UnsupportedModel):
-        lc.set_model("2DLinear")
+        lc.set_model("1DQuasiPeriodic")          # time kernels other than the SM: outside the path
+    lc.set_model("2DLinear", num_mixtures=3)     # non-constant means stay on the host
+    pk = pack_model(lc.model)
+    assert pk.external_mean and pk.P == 1 + 3 + 12 and int(pk.kinds[0]) == 0
+    assert float(pk.raw()[0]) == 0.0 and pk.names[1] == "covar_module.raw_mixture_weights"
 
 
 def test_separable_models_pack_onto_the_separable_kinds():
@@ -211,9 +215,7 @@ def test_pack_model_rejects_models_outside_the_path():
                         "covar_module.raw_mixture_means", "covar_module.raw_mixture_scales"]
     assert pk.fixed_noise is not None and not pk.learn_noise
 
-    class Linear(torch.nn.Module):
-        pass
-    lc.model.mean_module = Linear()
+    lc.model.mean_module = None
     with pytest.raises(UnsupportedModelError):
         pack_model(lc.model)
 
