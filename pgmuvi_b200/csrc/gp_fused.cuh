@@ -381,11 +381,13 @@ constexpr unsigned CHUNK_BYTES = OPBUF * sizeof(double);
 // acc += sum over this job's nk k-tiles.  `pre` chunks of the job are already in flight
 // (issued by the previous call); the first chunks of the next job (next_nk k-tiles, 0 = no
 // look-ahead) are issued from here.  Returns the number of next-job chunks issued.
+// `ready(kt)` is called by the producer thread before it issues the loads of k-tile kt of THIS
+// job (a hook for operands another block of the same launch is still producing).
 template <int MODE0, bool LOWER, int NST, typename FA, typename FB, typename FNA, typename FNB,
-          typename FX>
-__device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int nk, FA tileA,
-                                           FB tileB, int pre, int next_nk, FNA nextA, FNB nextB,
-                                           FX extra_prefetch) {
+          typename FX, typename FR>
+__device__ __forceinline__ int gemm_stream_r(double (&acc)[4][2][2], Ring& rg, int nk, FA tileA,
+                                             FB tileB, int pre, int next_nk, FNA nextA, FNB nextB,
+                                             FX extra_prefetch, FR ready) {
   constexpr int LA = NST - 1;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -396,6 +398,7 @@ __device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int
   auto issue = [&](int t) {  // chunk t counted from this job's first chunk; thread 0 only
     const double *ga, *gb;
     if (t < n) {
+      if (!(t & 1)) ready(t >> 1);
       ga = tileA(t >> 1) + (t & 1) * OPBUF;
       gb = tileB(t >> 1) + (t & 1) * OPBUF;
     } else {
@@ -444,6 +447,15 @@ __device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int
   rg.gq += n;
   cp_async_wait<0>();
   return nn < LA ? nn : LA;
+}
+
+template <int MODE0, bool LOWER, int NST, typename FA, typename FB, typename FNA, typename FNB,
+          typename FX>
+__device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int nk, FA tileA,
+                                           FB tileB, int pre, int next_nk, FNA nextA, FNB nextB,
+                                           FX extra_prefetch) {
+  return gemm_stream_r<MODE0, LOWER, NST>(acc, rg, nk, tileA, tileB, pre, next_nk, nextA, nextB,
+                                          extra_prefetch, [](int) {});
 }
 
 __device__ __forceinline__ void zero_acc(double (&acc)[4][2][2]) {

@@ -44,6 +44,7 @@ struct BatchState {
   int *attempt;   // jitter rung 0..3
   int *fail;      // potrf failure bits of the current pass
   int *count;     // light curves that must repeat the P phase
+  int *tflag;     // [B, ntri(n_max)] "X tile is final" flags of the one-launch T phase
 };
 enum { LG_ACTIVE = 0, LG_FACTORED = 1, LG_FAILED = 2 };
 
@@ -52,8 +53,13 @@ __host__ __device__ inline size_t large_ws_elems(int n) {
   return 2 * ntri * TT + N * TT + (size_t)(LG_NFB_MAX + 4) * npad + LG_PAR + 2 * N +
          ntri * LG_GP + 16;
 }
+__host__ __device__ inline size_t large_ntri(int n_max) {
+  const size_t N = (n_max + TS - 1) / TS;
+  return N * (N + 1) / 2;
+}
 __host__ __device__ inline size_t large_ws_bytes(int n_max, int B) {
-  return large_ws_elems(n_max) * sizeof(double) * (size_t)B + (size_t)(3 * B + 4) * sizeof(int);
+  return large_ws_elems(n_max) * sizeof(double) * (size_t)B +
+         ((size_t)(3 * B + 4) + (size_t)B * large_ntri(n_max)) * sizeof(int);
 }
 __host__ __device__ inline BatchState make_batch_state(double* base, int n_max, int B) {
   BatchState st;
@@ -61,6 +67,7 @@ __host__ __device__ inline BatchState make_batch_state(double* base, int n_max, 
   st.attempt = st.state + B;
   st.fail = st.attempt + B;
   st.count = st.fail + B;
+  st.tflag = st.count + 4;
   return st;
 }
 __host__ __device__ inline LargeWs make_large_ws(double* base, int n) {
@@ -104,9 +111,9 @@ struct LcView {
   LargeWs w;
   BatchState st;
 };
-__device__ __forceinline__ LcView lc_view(const LargeArgs& A) {
+__device__ __forceinline__ LcView lc_view(const LargeArgs& A, int b = -1) {
   LcView v;
-  v.b = blockIdx.y;
+  v.b = b >= 0 ? b : (int)blockIdx.y;
   v.n = A.n_valid ? A.n_valid[v.b] : A.n_max;
   v.N = (v.n + TS - 1) / TS;
   v.npad = v.N * TS;
@@ -522,6 +529,83 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(LargeArgs A, in
   compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
   store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);
   if (tid == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------
+// The whole T phase in ONE launch: block t <-> tile (i, j), i > j, in row-major order.  Tile
+// (i, j) needs the X tiles (k, j), j < k < i - all of lower block index.  Blocks are
+// dispatched in index order, so every producer a block waits for is running or done: the
+// producer thread spins on the "tile is final" flag of an operand just before it issues that
+// operand's bulk copies, and each block publishes its tile (bulk store complete -> proxy fence
+// -> release store of the flag) at the end.  Rows overlap: the dependency depth drops from one
+// launch per tile row (N^2 / 2 tile products along column 0) to about two products per row.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void lg_wait_flag(const int* f) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+    if (!v) __nanosleep(40);
+  } while (!v);
+  fence_proxy_async();   // the tile was written, and will be read, through the async proxy
+}
+__device__ __forceinline__ void lg_set_flag(int* f) {
+  fence_proxy_async();
+  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(1) : "memory");
+}
+
+static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_all(LargeArgs A) {
+  extern __shared__ __align__(16) double sm[];
+  double* stages = sm;
+  double* Cst = stages + 2 * OPBUF;
+  double* R = sm + 4 * OPBUF;
+  const unsigned bars = smem_u32(sm + 6 * OPBUF);
+  const unsigned rbar = bars + 8 * 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  // tile-major block order (all light curves' tile t before any tile t + 1): in a batch the
+  // blocks adjacent in dispatch order are independent, a single GP gets plain row-major order
+  const unsigned tix = blockIdx.x / (unsigned)A.B;
+  const LcView v = lc_view(A, (int)(blockIdx.x - tix * (unsigned)A.B));
+  int i, j;
+  tri_unrank((int)tix, i, j);   // (a, b), a >= b  ->  tile (a + 1, b)
+  i += 1;
+  if (v.st.state[v.b] != LG_FACTORED || i >= v.N) return;
+  const LargeWs& w = v.w;
+  int* flags = v.st.tflag + (size_t)v.b * large_ntri(A.n_max);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (2 + s), NTHREADS / 32); }
+    mbar_init(rbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(rbar, 2 * CHUNK_BYTES);
+    bulk_g2s(smem_u32(R), lg_tile(w.tilesX, i, i), 2 * CHUNK_BYTES, rbar);
+  }
+  Ring r2{bars, bars + 16, stages, 0};
+  double acc[4][2][2];
+  zero_acc(acc);
+  auto tA = [&](int kk) { return kk == 0 ? w.tilesT + (size_t)j * TT : lg_tile(w.tilesX, j + kk, j); };
+  auto tB = [&](int kk) { return lg_tile(w.tilesL, i, j + kk); };
+  auto none = [&](int) { return (double*)nullptr; };
+  auto ready = [&](int kk) {   // producer thread only: X_{j+kk, j} must be final
+    if (kk > 0) lg_wait_flag(flags + ((size_t)(j + kk) * (j + kk + 1) / 2 + j));
+  };
+  gemm_stream_r<M_A_GE, false, 2>(acc, r2, i - j, tA, tB, 0, 0, none, none, []() {}, ready);
+  __syncthreads();
+  store_acc_tile(acc, Cst, 1.0);
+  __syncthreads();
+  mbar_wait(rbar, 0);
+  zero_acc(acc);
+  compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+  compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+  store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);
+  if (tid == 0) {
+    bulk_wait_all();
+    lg_set_flag(flags + ((size_t)i * (i + 1) / 2 + j));
+  }
 }
 
 // alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i   (tilesX holds X_jj and the X_ij^T tiles)

@@ -120,6 +120,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   cudaFuncSetAttribute(lg_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_DIAG_SMEM);
   cudaFuncSetAttribute(lg_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_TRSM_SMEM);
   cudaFuncSetAttribute(lg_inv_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_INV_SMEM);
+  cudaFuncSetAttribute(lg_inv_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_INV_SMEM);
   BatchState bs = make_batch_state(A.ws, n, B);
   cudaMemsetAsync(bs.state, 0, (size_t)(3 * B + 4) * sizeof(int), st);
   const dim3 blk(NTHREADS);
@@ -148,7 +149,14 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
     if (!again) break;
   }
   if (want_grad || predict_only) {
-    for (int i = 1; i < N; ++i) lg_inv_row<<<dim3(i, B), blk, LG_INV_SMEM, st>>>(A, i);
+    if (getenv("PGM_STAGED_ROWWISE")) {        // one launch per tile row (the r01c schedule)
+      for (int i = 1; i < N; ++i) lg_inv_row<<<dim3(i, B), blk, LG_INV_SMEM, st>>>(A, i);
+    } else if (N > 1) {                        // whole T phase in one launch, flag-ordered
+      cudaMemsetAsync(bs.tflag, 0, (size_t)B * large_ntri(n) * sizeof(int), st);
+      const long long nblk = (long long)(N * (N - 1) / 2) * B;
+      if (nblk > 2147483647LL) return fail("staged engine: too many tiles x light curves");
+      lg_inv_all<<<dim3((unsigned)nblk), blk, LG_INV_SMEM, st>>>(A);
+    }
     lg_alpha<<<dim3(N, B), blk, 0, st>>>(A);
     if (!predict_only) k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
   }
