@@ -37,6 +37,7 @@ constexpr int LG_PAR_TH = 0, LG_PAR_JC = 64, LG_PAR_WQ = 128, LG_PAR_AQ = 136, L
 struct LargeWs {
   double *tilesL, *tilesX, *tilesT;
   double *fx, *fcs, *alpha, *rhs, *z, *dn, *par, *ldz, *gpart;
+  double *fpart;   // [ntri][64]: L_ij z_j per tile (forward solve of the one-launch P phase)
 };
 // batch state behind the B per-light-curve workspaces
 struct BatchState {
@@ -51,7 +52,7 @@ enum { LG_ACTIVE = 0, LG_FACTORED = 1, LG_FAILED = 2 };
 __host__ __device__ inline size_t large_ws_elems(int n) {
   const size_t N = (n + TS - 1) / TS, npad = N * TS, ntri = N * (N + 1) / 2;
   return 2 * ntri * TT + N * TT + (size_t)(LG_NFB_MAX + 4) * npad + LG_PAR + 2 * N +
-         ntri * LG_GP + 16;
+         ntri * LG_GP + ntri * TS + 16;
 }
 __host__ __device__ inline size_t large_ntri(int n_max) {
   const size_t N = (n_max + TS - 1) / TS;
@@ -85,6 +86,7 @@ __host__ __device__ inline LargeWs make_large_ws(double* base, int n) {
   w.par = w.dn + npad;
   w.ldz = w.par + LG_PAR;
   w.gpart = w.ldz + 2 * N;
+  w.fpart = w.gpart + ntri * LG_GP;
   return w;
 }
 
@@ -232,6 +234,21 @@ __device__ __forceinline__ void lg_prefetch_side(double* vec, const LargeWs& w, 
       cp_async16(vec + C::NFB * TS + o, w.alpha + I * TS + o);
     }
   }
+}
+
+// per-tile "final" flags of the one-launch phases (lg_chol_all, lg_inv_all)
+__device__ __forceinline__ void lg_wait_flag(const int* f) {
+  int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+    if (!v) __nanosleep(40);
+  } while (!v);
+  fence_proxy_async();   // the tile was written, and will be read, through the async proxy
+}
+__device__ __forceinline__ void lg_set_flag(int* f) {
+  fence_proxy_async();
+  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(1) : "memory");
 }
 
 // ------------------------------------------------------------------------------------
@@ -461,6 +478,212 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(LargeArgs A, int j
   if (tid == 0) bulk_wait_all();
 }
 
+// ------------------------------------------------------------------------------------
+// The whole P phase (blocked Cholesky + forward solve) of one pass in ONE launch: block t <->
+// tile (i, j), i >= j, in COLUMN-major order (tile-major over a batch).  Left-looking: the
+// block accumulates sum_{k<j} L_ik L_jk^T, waiting on the "final" flag of each operand tile
+// right before its bulk copies are issued, generates K~_ij in the epilogue, then
+//   i == j: 64x64 potrf + inverse, z_j = X_jj (rhs_j - sum_k L_jk z_k), log-det partials;
+//   i >  j: waits for the diagonal tile, L_ij = C X_jj^T, partial product L_ij z_j -> fpart.
+// Every dependency has a lower block index (earlier column, or the head of the same column),
+// and blocks are dispatched in index order, so waiting cannot deadlock.  A failed diagonal
+// block records its failure BEFORE it raises its flag; blocks that come later see it, skip
+// their factorisation (so that garbage never turns a "not p.d." into a NaN report) and still
+// raise their flags.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void col_unrank(int t, int N, int& i, int& j) {
+  // column j holds tiles (j..N-1, j); offset(j) = j N - j (j - 1) / 2
+  const double b = 2.0 * N + 1.0;
+  j = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+  if (j < 0) j = 0;
+  if (j > N - 1) j = N - 1;
+  while (j > 0 && j * N - j * (j - 1) / 2 > t) --j;
+  while (j < N - 1 && (j + 1) * N - (j + 1) * j / 2 <= t) ++j;
+  i = j + (t - (j * N - j * (j - 1) / 2));
+}
+
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+    lg_chol_all(LargeArgs A) {
+  using C = Cfg<KIND, QT, D>;
+  constexpr int DS = C::DS;
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
+  const unsigned tix = blockIdx.x / (unsigned)A.B;
+  const LcView v = lc_view(A, (int)(blockIdx.x - tix * (unsigned)A.B));
+  const int Nmax = (A.n_max + TS - 1) / TS;
+  int i, j;
+  col_unrank((int)tix, Nmax, i, j);
+  if (v.st.state[v.b] != LG_ACTIVE || i >= v.N) return;
+  const LargeWs& w = v.w;
+  const int n = v.n, npad = v.npad;
+  int* flags = v.st.tflag + (size_t)v.b * large_ntri(A.n_max);
+  auto flag_of = [&](int a, int b2) { return flags + ((size_t)a * (a + 1) / 2 + b2); };
+  volatile int* failp = v.st.fail + v.b;
+  const double jitter = lg_jitter(v.st.attempt[v.b]);
+  double* stages = sm + C::SM_STAGES;
+  double* S2 = stages;                  // diagonal job: X = L^-1 (the stages are idle then)
+  double* Cst = stages + 2 * OPBUF;
+  double* red = stages;                 // off-diagonal job: [4][64] partial products
+  double* S = sm + C::SM_S;
+  double* R = S;
+  double* rowv = sm + C::SM_ROW;
+  double* colv = sm + C::SM_COL;
+  double* par = sm + C::SM_PAR;
+  double* tab = par + C::PAR_TAB;
+  double* zj = par + C::PAR_ZJ;
+  double* zi = par + C::PAR_ZI;
+  double* dinv = par + C::PAR_DINV;
+  double* red2 = stages + S_ELEMS;      // [2][64] small reductions of the diagonal job (behind S2)
+  int* s_fail = reinterpret_cast<int*>(sm + C::SM_PAR + C::PAR_END);
+  const unsigned bars = smem_u32(par + C::PAR_BAR);
+  const unsigned rbar = bars + 8 * 10;
+  load_exp_tab(tab);
+  PipeState ps;
+  pipe_init<KIND, QT, D>(sm, ps);
+  if (tid == 0) *s_fail = 0;
+  Ring r2{bars, bars + 16, stages, 0};
+  double acc[4][2][2];
+  zero_acc(acc);
+  auto tA = [&](int kk) { return lg_tile(w.tilesL, i, kk); };
+  auto tB = [&](int kk) { return lg_tile(w.tilesL, j, kk); };
+  auto none = [&](int) { return (double*)nullptr; };
+  auto pf = [&]() {
+    lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
+    lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, false);
+  };
+  auto ready = [&](int kk) {            // producer thread only
+    lg_wait_flag(flag_of(j, kk));
+    if (i != j) lg_wait_flag(flag_of(i, kk));
+  };
+  if (i == j) gemm_stream_r<M_FULL, true, 2>(acc, r2, j, tA, tB, 0, 0, none, none, pf, ready);
+  else gemm_stream_r<M_FULL, false, 2>(acc, r2, j, tA, tB, 0, 0, none, none, pf, ready);
+  __syncthreads();
+  // epilogue: C = K~_ij - acc  (off-diagonal: image in stage 1; diagonal: S, lower MMA tiles)
+  {
+    double wreg[QT], areg[QT * DS], lam[4];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) wreg[q] = w.par[LG_PAR_WQ + q];
+#pragma unroll
+    for (int q = 0; q < QT * DS; ++q) areg[q] = w.par[LG_PAR_AQ + q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lam[q] = w.par[LG_PAR_LM + q];
+    store_acc_tile(acc, Cst, 1.0);
+#pragma unroll 1
+    for (int p8 = 0; p8 < 8; ++p8) {
+      const int mi = p8 >> 1, ni2 = p8 & 1;
+      if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+      const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+      const int gi = i * TS + r;
+      double2* cp = reinterpret_cast<double2*>(Cst + img(r, c0));
+      const double2 cv = *cp;
+      double o2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = j * TS + c0 + e;
+        double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
+        kv = (gi < n && gj <= gi) ? kv : 0.0;
+        if (gi == gj) kv = (gi < n) ? (kv + w.dn[gi] + jitter) : 1.0;
+        o2[e] = kv - (e ? cv.y : cv.x);
+      }
+      if (i == j) {
+        S[r * LD_S + c0] = o2[0];
+        S[r * LD_S + c0 + 1] = o2[1];
+      } else {
+        *cp = make_double2(o2[0], o2[1]);
+      }
+    }
+  }
+  if (i == j) {
+    // ---- diagonal tile: all operands (j, k < j) were awaited in the k-loop
+    if (tid < TS) {
+      double u = 0.0;
+      for (int k = 0; k < j; ++k) u += __ldcg(w.fpart + ((size_t)j * (j + 1) / 2 + k) * TS + tid);
+      zi[tid] = w.rhs[j * TS + tid] - u;
+    }
+    __syncthreads();
+    const bool earlier_failure = (*failp != 0);
+    if (!earlier_failure) potrf_inv_64(S, S2, dinv, s_fail);
+    const bool ok = !earlier_failure && (*s_fail == 0);
+    if (!earlier_failure && *s_fail && tid == 0) atomicOr(v.st.fail + v.b, *s_fail);
+    if (ok) {
+      double* tl = lg_tile(w.tilesL, j, j);
+      double* tx = lg_tile(w.tilesX, j, j);
+      double* tt = w.tilesT + (size_t)j * TT;
+      for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
+        const int r = idx >> 5, c2 = (idx & 31) * 2;
+        double2 vv, vt;
+        vv.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
+        vv.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
+        vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
+        vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
+        const int o = img(r, c2);
+        *reinterpret_cast<double2*>(tl + o) = vv;
+        *reinterpret_cast<double2*>(tx + o) = vv;
+        *reinterpret_cast<double2*>(tt + o) = vt;
+      }
+      {
+        const int r = tid >> 2, l4 = tid & 3;
+        double zz = 0.0;
+        for (int c = l4; c <= r; c += 4) zz += S2[r * LD_S + c] * zi[c];
+        zz += shfl_xor_d(zz, 1);
+        zz += shfl_xor_d(zz, 2);
+        if (l4 == 0) {
+          w.z[j * TS + r] = zz;
+          red2[r] = zz * zz;
+          red2[TS + r] = -log(dinv[r]);
+        }
+      }
+      __syncthreads();
+      if (tid < 2) {
+        double s = 0.0;
+        for (int r = 0; r < TS; ++r) s += red2[tid * TS + r];
+        w.ldz[2 * j + (tid ? 0 : 1)] = s;   // ldz[2j] = sum log L_kk, ldz[2j+1] = z_j^T z_j
+      }
+    }
+    fence_proxy_async();   // the tiles written above are read by bulk copies of other blocks
+    __syncthreads();
+    if (tid == 0) lg_set_flag(flag_of(j, j));
+    return;
+  }
+  // ---- off-diagonal tile: L_ij = C X_jj^T once the diagonal tile is final
+  __syncthreads();         // C image complete in stage 1; stage 0 free for `red`
+  if (tid == 0) {
+    lg_wait_flag(flag_of(j, j));
+    mbar_expect_tx(rbar, 2 * CHUNK_BYTES);
+    bulk_g2s(smem_u32(R), lg_tile(w.tilesL, j, j), 2 * CHUNK_BYTES, rbar);
+  }
+  __syncthreads();         // the acquire of thread 0 is ordered before everyone's loads below
+  if (tid < TS) zj[tid] = __ldcg(w.z + j * TS + tid);
+  const bool failed = (*failp != 0);
+  mbar_wait(rbar, 0);
+  __syncthreads();
+  zero_acc(acc);
+  compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
+  compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    double s = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) s += acc[mi][ni][e] * zj[frag_col(wn, ni, tq, e)];
+    s += shfl_xor_d(s, 1);
+    s += shfl_xor_d(s, 2);
+    if (tq == 0) red[wn * TS + frag_row(wm, mi, g)] = s;
+  }
+  store_tile_bulk(acc, Cst, lg_tile(w.tilesL, i, j), 1.0);   // its barriers also publish `red`
+  if (tid < TS && !failed)
+    w.fpart[((size_t)i * (i + 1) / 2 + j) * TS + tid] =
+        (red[tid] + red[TS + tid]) + (red[2 * TS + tid] + red[3 * TS + tid]);
+  __syncthreads();
+  if (tid == 0) {
+    bulk_wait_all();
+    lg_set_flag(flag_of(i, j));
+  }
+}
+
 // per-light-curve jitter ladder (psd_safe_cholesky, A.5) after a P pass
 static __global__ void lg_ladder(LargeArgs A) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,20 +763,6 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(LargeArgs A, in
 // -> release store of the flag) at the end.  Rows overlap: the dependency depth drops from one
 // launch per tile row (N^2 / 2 tile products along column 0) to about two products per row.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void lg_wait_flag(const int* f) {
-  int v;
-  do {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
-    if (!v) __nanosleep(40);
-  } while (!v);
-  fence_proxy_async();   // the tile was written, and will be read, through the async proxy
-}
-__device__ __forceinline__ void lg_set_flag(int* f) {
-  fence_proxy_async();
-  __threadfence();
-  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(1) : "memory");
-}
-
 static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_all(LargeArgs A) {
   extern __shared__ __align__(16) double sm[];
   double* stages = sm;

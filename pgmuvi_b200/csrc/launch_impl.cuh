@@ -112,9 +112,11 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   if (const char* f = getenv("PGM_STAGED_NB")) NB = std::max(1, atoi(f));
   auto k_upd = lg_update<KIND, QT, D>;
   auto k_grad = lg_grad<KIND, QT, D>;
+  auto k_chol = lg_chol_all<KIND, QT, D>;
   cudaError_t e;
   e = cudaFuncSetAttribute(k_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_update)", e);
+  cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
   e = cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_grad)", e);
   cudaFuncSetAttribute(lg_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_DIAG_SMEM);
@@ -127,7 +129,18 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   for (int pass = 0; pass <= 3; ++pass) {
     cudaMemsetAsync(bs.count, 0, sizeof(int), st);
     lg_setup<KIND, QT, D><<<dim3((npad + NTHREADS - 1) / NTHREADS, B), blk, 0, st>>>(A);
-    for (int J0 = 0; J0 < N; J0 += NB) {
+    const long long ncb = (long long)(N * (N + 1) / 2) * B;
+    // up to PGM_STAGED_CHOL_ALL_N tile rows (default 256) the left-looking one-launch schedule
+    // wins (no launch latencies, potrf overlapped: C3 11.8 -> 8.6 ms); beyond, the panel scheme's
+    // operand reuse in L2 does (C4)
+    int all_n = 256;
+    if (const char* f = getenv("PGM_STAGED_CHOL_ALL_N")) all_n = atoi(f);
+    const bool one_launch = !getenv("PGM_STAGED_ROWWISE") && N <= all_n && ncb <= 2147483647LL;
+    if (one_launch) {   // dataflow Cholesky: the whole pass in one flag-ordered launch
+      cudaMemsetAsync(bs.tflag, 0, (size_t)B * large_ntri(n) * sizeof(int), st);
+      k_chol<<<dim3((unsigned)ncb), blk, C::SMEM_BYTES, st>>>(A);
+    }
+    for (int J0 = 0; J0 < N && !one_launch; J0 += NB) {
       const int J1 = std::min(J0 + NB, N);
       const int build = (J0 == 0) ? 1 : 0;
       for (int j = J0; j < J1; ++j) {
