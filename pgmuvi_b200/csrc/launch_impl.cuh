@@ -130,10 +130,11 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
     cudaMemsetAsync(bs.count, 0, sizeof(int), st);
     lg_setup<KIND, QT, D><<<dim3((npad + NTHREADS - 1) / NTHREADS, B), blk, 0, st>>>(A);
     const long long ncb = (long long)(N * (N + 1) / 2) * B;
-    // up to PGM_STAGED_CHOL_ALL_N tile rows (default 256) the left-looking one-launch schedule
-    // wins (no launch latencies, potrf overlapped: C3 11.8 -> 8.6 ms); beyond, the panel scheme's
-    // operand reuse in L2 does (C4)
-    int all_n = 256;
+    // up to PGM_STAGED_CHOL_ALL_N tile rows (default 200) the left-looking one-launch schedule
+    // wins (no launch latencies, potrf overlapped: n=2048 1.62 -> 1.16 ms, C3 11.8 -> 8.6 ms); the
+    // two meet at N = 256 (63.1 vs 64.4 ms) and beyond the panel scheme's operand reuse in L2
+    // wins (C4: 425 vs 500 ms)
+    int all_n = 200;
     if (const char* f = getenv("PGM_STAGED_CHOL_ALL_N")) all_n = atoi(f);
     const bool one_launch = !getenv("PGM_STAGED_ROWWISE") && N <= all_n && ncb <= 2147483647LL;
     if (one_launch) {   // dataflow Cholesky: the whole pass in one flag-ordered launch

@@ -32,7 +32,7 @@ from .mll import (B200ExactMarginalLogLikelihood, UnsupportedModelError, engine_
 # instead of one thread block (the fused kernel's per-block scratch grows with n^2)
 # A single light curve longer than this is evaluated by the staged whole-device engine instead
 # of one thread block of the fused kernel: measured on B200 for BASELINE config C1 (AlfOri,
-# n = 1000, 300 Adam iterations) 1.32 ms / iteration staged vs 7.38 ms fused on ONE SM
+# n = 1000, 300 Adam iterations) 0.78 ms / iteration staged vs 7.38 ms fused on ONE SM
 # (profiles/r01d_all_configs.log); one block's scratch stops fitting beyond n = 2048 anyway.
 LARGE_N = 384
 
