@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--lightcurves", type=int, default=LC_PER_GPU, help="light curves per GPU")
     ap.add_argument("--cpu-sample", type=int, default=32, help="light curves in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short C1 / C3 / C4 / C5 timings appended to the N=1 line")
     return ap.parse_args()
 
 
@@ -182,6 +184,79 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------
+def other_configs(dev, dmma_peak):
+    """Short CUDA-event timings of the other BASELINE.json configs on one GPU (not part of the
+    headline metric; DESIGN.md section 4 quotes them): C1 = 300-iteration Adam fit of the bundled
+    AlfOri light curve, C3 = one MLL+grad of the n = 8000 2-D GP, C4 = n = 32768 SM-8,
+    C5 = the per-GPU share (2048 sources) of the 4 x 256 2-D survey batch."""
+    import warnings
+    import torch
+    from pgmuvi_b200 import ops, synthetic as S
+    T = lambda a, dt=torch.float64: torch.tensor(np.asarray(a), dtype=dt, device=dev)
+    out = {}
+
+    def ev_ms(fn, reps):
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    def single(bt, kind, Q, reps):
+        x, y, nz, raw = (T(bt[k][0]) for k in ("x", "y", "noise", "raw"))
+        kk, lo, hi = T(bt["kinds"], torch.int32), T(bt["lb"][0]), T(bt["ub"][0])
+        n = x.shape[0]
+        ms = ev_ms(lambda: ops.sm_mll_grad_large(x, y, nz, raw, kk, lo, hi, kind, Q, False, True),
+                   reps)
+        tf = (n ** 3 + 4 * n ** 2) / (ms * 1e-3) / 1e12
+        return {"n": n, "ms_per_eval": ms, "tflops": tf, "frac_of_dmma_peak": tf / dmma_peak}
+
+    try:
+        from pgmuvi_b200.lightcurve import Lightcurve
+        csv = os.path.join(ROOT, "tests", "data", "AlfOriAAVSO_Vband.csv")
+        best = 1e30
+        for _ in range(2):
+            torch.manual_seed(0)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                lc = Lightcurve.from_csv(csv, xtransform="minmax", subsample_seed=0)
+            lc.set_model("1D", num_mixtures=4)
+            lc.set_default_constraints()
+            lc.set_hypers({"covar_module.mixture_means":
+                           torch.tensor([1 / 2100.0, 1 / 400.0, 1 / 1000.0, 1 / 200.0]),
+                           "covar_module.mixture_scales":
+                           torch.tensor([1.0e-4, 5.0e-4, 2.0e-4, 1.0e-3])})
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = lc.fit(optim="Adam", training_iter=300, lr=0.1)
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        out["C1_alfori_fit"] = {"n": 1000, "iterations": 300, "seconds": best,
+                                "final_loss": float(res["loss"][-1])}
+        out["C3_2d_n8000"] = single(S.make_batch_2d(1, 8, 1000, Q=4), 1, 4, 3)
+        out["C4_1d_n32768_sm8"] = single(S.make_batch_1d(1, 32768, Q=8), 0, 8, 2)
+        bt5 = S.make_batch_2d(32, 4, 256, Q=4)
+        B5 = 2048
+        t5 = lambda a: T(np.concatenate([a] * (B5 // 32), 0)[:B5])
+        x5, y5, nz5, raw5, lb5, ub5 = (t5(bt5[k]) for k in ("x", "y", "noise", "raw", "lb", "ub"))
+        k5 = T(bt5["kinds"], torch.int32)
+        ms = ev_ms(lambda: ops.sm_mll_grad(x5, y5, nz5, raw5, k5, lb5, ub5, None, 1, 4, False,
+                                           True), 2)
+        tf = B5 * (1024 ** 3 + 4 * 1024 ** 2) / (ms * 1e-3) / 1e12
+        out["C5_2d_2048x1024_per_gpu"] = {"ms_per_eval_batch": ms, "evals_per_s": B5 / ms * 1e3,
+                                          "tflops": tf, "frac_of_dmma_peak": tf / dmma_peak}
+    except Exception as exc:   # never let the side measurements break the headline line
+        out["error"] = repr(exc)
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -312,6 +387,10 @@ def run_b200(args):
                 "value": val, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_sample} of the C2 light curves x 2 steps, fp64, torch CPU "
                           f"{cores} threads, best of {both}", "mode": mode}
+        if world == 1 and not args.no_other_configs:
+            del d, flush
+            torch.cuda.empty_cache()
+            line["other_configs"] = other_configs(dev, dmma)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
