@@ -188,20 +188,26 @@ def train(lightcurve=None, model=None, likelihood=None, train_x=None, train_y=No
 def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, stop, stopavg, dev):
     """trainers.py:177-207 for ONE large GP: each iteration is a whole-device MLL+gradient
     (``ops.sm_mll_grad_large``) followed by the batched optimiser kernel on the [1, P] raw
-    vector; the loss is read back once per iteration (the early-stop rule needs it)."""
+    vector.  Loss and parameter histories stay on the device until the end; the loss is read
+    back per iteration only when the early-stop rule can fire."""
     from .gp import NanError, NotPSDError
     fixed = None if pk.fixed_noise is None else pk.fixed_noise.detach().to(device=dev,
                                                                            dtype=torch.float64)
     kinds, lb, ub = pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev)
     raw = raw.clone().reshape(1, -1)
     m, v = torch.zeros_like(raw), torch.zeros_like(raw)
-    raws, losses = [raw[0].cpu().clone()], []
     np_dt = np.float32 if pk.params[0].dtype == torch.float32 else np.float64
+    # the history stays on the device; the loss is read back every iteration only when the
+    # early-stop rule can fire (it cannot with fit()'s default miniter = maxiter, SURVEY F10)
+    raw_dev = [raw[0].clone()]
+    mll_dev = []
+    need_loss = bool(stop) and miniter < maxiter - 1
+    host_losses = []
     for i in range(maxiter):
         mll, grad, code = ops.sm_mll_grad_large(x, y, fixed, raw[0], kinds, lb, ub, pk.kind, pk.Q,
                                                 pk.learn_noise, True)
         if code < 0:
-            pk.scatter_raw_(raws[-1])
+            pk.scatter_raw_(raw_dev[-1].cpu())
             if code == -1:
                 raise NanError("cholesky_cpu: NaN values found in the covariance matrix "
                                f"at training iteration {i}")
@@ -209,12 +215,17 @@ def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, sto
                               f"to 1.0e-06 (training iteration {i}).")
         ops.optim_step(raw, grad.reshape(1, -1), m, v, None, od["optim_kind"], lr, od["beta1"],
                        od["beta2"], od["eps"], od["weight_decay"], i + 1)
-        losses.append(np.asarray(-float(mll), dtype=np_dt))   # history in the model's dtype
-        raws.append(raw[0].cpu().clone())
-        if stop and i > miniter and np.std(losses[-stopavg:]) < stop:
-            print(f"""Average change in loss over the last {stopavg} iterations
-                    was {np.std(losses[-stopavg:])}.\n This is < {stop}, so we will end training here.""")
-            break
+        mll_dev.append(mll.reshape(()))
+        raw_dev.append(raw[0].clone())
+        if need_loss:
+            host_losses.append(np_dt(-float(mll)))
+            if i > miniter and np.std(host_losses[-stopavg:]) < stop:
+                print(f"""Average change in loss over the last {stopavg} iterations
+                    was {np.std(host_losses[-stopavg:])}.\n This is < {stop}, so we will end training here.""")
+                break
+    lh = (-torch.stack(mll_dev)).cpu().numpy()
+    losses = [np.asarray(val, dtype=np_dt) for val in lh]      # history in the model's dtype
+    raws = list(torch.stack(raw_dev).cpu())
     pk.scatter_raw_(raws[-1])
     results = {"loss": losses,
                "delta_loss": [losses[i] - losses[i - 1] for i in range(1, len(losses))]}
