@@ -491,15 +491,24 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_trsm(LargeArgs A, int j
 // their factorisation (so that garbage never turns a "not p.d." into a NaN report) and still
 // raise their flags.
 // ------------------------------------------------------------------------------------
+// Block order: column-major with look-ahead on the critical path.  t = 0 is tile (0, 0); then,
+// per column j: (j+1, j), the NEXT diagonal tile (j+1, j+1), and the rest of column j
+// (j+2.., j).  The two tiles that gate the next column are dispatched first and run while the
+// bulk of column j is still being processed; every dependency keeps a lower index.
 __device__ __forceinline__ void col_unrank(int t, int N, int& i, int& j) {
-  // column j holds tiles (j..N-1, j); offset(j) = j N - j (j - 1) / 2
+  if (t == 0) { i = 0; j = 0; return; }
+  t -= 1;
+  // group j starts at offset(j) = j N - j (j - 1) / 2 and holds N - j tiles
   const double b = 2.0 * N + 1.0;
   j = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
   if (j < 0) j = 0;
-  if (j > N - 1) j = N - 1;
+  if (j > N - 2) j = N - 2;
   while (j > 0 && j * N - j * (j - 1) / 2 > t) --j;
-  while (j < N - 1 && (j + 1) * N - (j + 1) * j / 2 <= t) ++j;
-  i = j + (t - (j * N - j * (j - 1) / 2));
+  while (j < N - 2 && (j + 1) * N - (j + 1) * j / 2 <= t) ++j;
+  const int r = t - (j * N - j * (j - 1) / 2);
+  if (r == 0) { i = j + 1; }
+  else if (r == 1) { i = j + 1; j = j + 1; }
+  else { i = j + r; }
 }
 
 template <int KIND, int QT, int D>
