@@ -511,10 +511,23 @@ __device__ __forceinline__ void col_unrank(int t, int N, int& i, int& j) {
   else { i = j + r; }
 }
 
+// shared memory: [stages 64 KB | S 34 KB | par]; the per-point fields of the epilogue are fetched
+// AFTER the k-loop into idle buffers (rows: stage 0; columns: the S region, which an
+// off-diagonal job needs only later for X_jj - a diagonal job's columns ARE its rows), so that
+// two blocks fit on an SM for every kind
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
-    lg_chol_all(LargeArgs A) {
+struct CholAllSmem {
   using C = Cfg<KIND, QT, D>;
+  static_assert(C::NFB * TS <= 2 * OPBUF, "row fields must fit in stage 0");
+  static constexpr int S_OFF = STAGE_ELEMS;
+  static constexpr int PAR_OFF = S_OFF + S_ELEMS;
+  static constexpr size_t BYTES = (size_t)(PAR_OFF + C::PAR_END + 8) * sizeof(double);
+};
+
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
+  using C = Cfg<KIND, QT, D>;
+  using L = CholAllSmem<KIND, QT, D>;
   constexpr int DS = C::DS;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -531,43 +544,50 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   auto flag_of = [&](int a, int b2) { return flags + ((size_t)a * (a + 1) / 2 + b2); };
   volatile int* failp = v.st.fail + v.b;
   const double jitter = lg_jitter(v.st.attempt[v.b]);
-  double* stages = sm + C::SM_STAGES;
+  double* stages = sm;
   double* S2 = stages;                  // diagonal job: X = L^-1 (the stages are idle then)
   double* Cst = stages + 2 * OPBUF;
   double* red = stages;                 // off-diagonal job: [4][64] partial products
-  double* S = sm + C::SM_S;
+  double* S = sm + L::S_OFF;
   double* R = S;
-  double* rowv = sm + C::SM_ROW;
-  double* colv = sm + C::SM_COL;
-  double* par = sm + C::SM_PAR;
+  double* rowv = stages;                // epilogue only: stage 0 is idle after the k-loop
+  double* colv = (i == j) ? rowv : S;   // S is idle until the off-diagonal job loads X_jj
+  double* par = sm + L::PAR_OFF;
   double* tab = par + C::PAR_TAB;
   double* zj = par + C::PAR_ZJ;
   double* zi = par + C::PAR_ZI;
   double* dinv = par + C::PAR_DINV;
   double* red2 = stages + S_ELEMS;      // [2][64] small reductions of the diagonal job (behind S2)
-  int* s_fail = reinterpret_cast<int*>(sm + C::SM_PAR + C::PAR_END);
+  int* s_fail = reinterpret_cast<int*>(par + C::PAR_END);
   const unsigned bars = smem_u32(par + C::PAR_BAR);
   const unsigned rbar = bars + 8 * 10;
   load_exp_tab(tab);
-  PipeState ps;
-  pipe_init<KIND, QT, D>(sm, ps);
-  if (tid == 0) *s_fail = 0;
+  if (tid == 0) {   // mbarriers: 2-stage ring (full / empty) + the resident-tile barrier
+    for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (2 + s), NTHREADS / 32); }
+    mbar_init(rbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+    *s_fail = 0;
+  }
+  __syncthreads();
   Ring r2{bars, bars + 16, stages, 0};
   double acc[4][2][2];
   zero_acc(acc);
   auto tA = [&](int kk) { return lg_tile(w.tilesL, i, kk); };
   auto tB = [&](int kk) { return lg_tile(w.tilesL, j, kk); };
   auto none = [&](int) { return (double*)nullptr; };
-  auto pf = [&]() {
-    lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
-    lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, false);
-  };
   auto ready = [&](int kk) {            // producer thread only
     lg_wait_flag(flag_of(j, kk));
     if (i != j) lg_wait_flag(flag_of(i, kk));
   };
-  if (i == j) gemm_stream_r<M_FULL, true, 2>(acc, r2, j, tA, tB, 0, 0, none, none, pf, ready);
-  else gemm_stream_r<M_FULL, false, 2>(acc, r2, j, tA, tB, 0, 0, none, none, pf, ready);
+  if (i == j) gemm_stream_r<M_FULL, true, 2>(acc, r2, j, tA, tB, 0, 0, none, none, []() {}, ready);
+  else gemm_stream_r<M_FULL, false, 2>(acc, r2, j, tA, tB, 0, 0, none, none, []() {}, ready);
+  __syncthreads();
+  // the stages are idle now: per-point fields of tile row i / column j into stage 0
+  lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
+  if (i != j) lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, false);
+  cp_async_commit();
+  cp_async_wait<0>();
   __syncthreads();
   // epilogue: C = K~_ij - acc  (off-diagonal: image in stage 1; diagonal: S, lower MMA tiles)
   {

@@ -116,7 +116,8 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   cudaError_t e;
   e = cudaFuncSetAttribute(k_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_update)", e);
-  cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+  constexpr size_t CHOL_SMEM = CholAllSmem<KIND, QT, D>::BYTES;
+  cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM);
   e = cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_grad)", e);
   cudaFuncSetAttribute(lg_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_DIAG_SMEM);
@@ -142,7 +143,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
     const bool one_launch = !getenv("PGM_STAGED_ROWWISE") && few && N <= all_n && ncb <= 2147483647LL;
     if (one_launch) {   // dataflow Cholesky: the whole pass in one flag-ordered launch
       cudaMemsetAsync(bs.tflag, 0, (size_t)B * large_ntri(n) * sizeof(int), st);
-      k_chol<<<dim3((unsigned)ncb), blk, C::SMEM_BYTES, st>>>(A);
+      k_chol<<<dim3((unsigned)ncb), blk, CHOL_SMEM, st>>>(A);
     }
     for (int J0 = 0; J0 < N && !one_launch; J0 += NB) {
       const int J1 = std::min(J0 + NB, N);
