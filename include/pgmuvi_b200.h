@@ -48,6 +48,16 @@ extern "C" {
 #define PGM_KIND_SEP_RQ 5       /* ScaleKernel(RQKernel):         os (1+tau^2/2 a l^2)^-a      NL=3 */
 #define PGM_KIND_SEP_CONST 6    /* ConstantKernel (AchromaticGPModel, gps.py:1414-1415)        NL=1 */
 
+/* N3 - stationary time kernels instead of the spectral mixture (pgmuvi/gps.py:985-990: the
+ * reference's DEFAULT time kernel of the separable models is ScaleKernel(MaternKernel(1.5));
+ * MaternGPModel gps.py:1131-1184).  kernel_kind = PGM_KIND_STAT(tk, wk):
+ *   tk 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(nu=1.5))            (time)
+ *   wk 0 none (d = 1), 1 ScaleKernel(RBF), 2 ScaleKernel(Matern-1.5), 3 ScaleKernel(RQ),
+ *      4 ConstantKernel                                                          (wavelength)
+ * Pass Q = 0; packed layout [ mean | (noise) | os_t, l_t | wavelength parameters as above ]. */
+#define PGM_KIND_STAT_BASE 8
+#define PGM_KIND_STAT(tk, wk) (PGM_KIND_STAT_BASE + 5 * (tk) + (wk))
+
 /* constraint kinds: gpytorch.constraints chosen at pgmuvi/lightcurve.py:3817-4008 */
 #define PGM_CON_NONE 0     /* value = raw                                         */
 #define PGM_CON_SOFTPLUS 1 /* Positive / GreaterThan(lb): softplus(raw) + lb      */

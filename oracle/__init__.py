@@ -23,6 +23,9 @@ from .sm_gp import (  # noqa: F401
     KIND_SEP_RQ,
     KIND_SEP_CONST,
     SEP_KINDS,
+    KIND_STAT_BASE,
+    stat_kind,
+    stat_atoms,
     kernel_dense,
     wavelength_kernel_dense,
     unpack_lam,

@@ -44,6 +44,13 @@ CASES = [
     ("sep_rq_4x48_q4", dict(dim=2, kind=5, B=2, bands=4, per=48, Q=4, learn_noise=False)),
     ("sep_const_3x40_q3_learn", dict(dim=2, kind=6, B=2, bands=3, per=40, Q=3, learn_noise=True)),
     ("sep_rbf_4x128_q8", dict(dim=2, kind=3, B=1, bands=4, per=128, Q=8, learn_noise=False)),
+    # N3: stationary time kernels, kind = 8 + 5 * TK + WK (Q = 0)
+    ("stat_rbf_1d_n100_learn", dict(dim=1, kind=8, B=2, n=100, Q=0, learn_noise=True)),
+    ("stat_matern_1d_n150", dict(dim=1, kind=13, B=2, n=150, Q=0, learn_noise=False)),
+    ("stat_matern_rbf_4x48", dict(dim=2, kind=14, B=2, bands=4, per=48, Q=0, learn_noise=False)),  # reference default 2DSeparable
+    ("stat_rbf_rq_3x40_learn", dict(dim=2, kind=11, B=2, bands=3, per=40, Q=0, learn_noise=True)),
+    ("stat_matern_const_4x32", dict(dim=2, kind=17, B=2, bands=4, per=32, Q=0, learn_noise=False)),
+    ("stat_matern_matern_4x40", dict(dim=2, kind=15, B=1, bands=4, per=40, Q=0, learn_noise=False)),
 ]
 
 
@@ -52,7 +59,10 @@ def make_case(name, kw):
     dim = kw.pop("dim")
     kind = kw.pop("kind", 0)
     n_valid = kw.pop("n_valid", None)
-    if dim == 1:
+    if kind >= 8:
+        bt = S.make_batch_stat(kw["B"], kind, n=kw.get("n"), n_bands=kw.get("bands"),
+                               n_per_band=kw.get("per"), learn_noise=kw["learn_noise"])
+    elif dim == 1:
         bt = S.make_batch_1d(kw["B"], kw["n"], Q=kw["Q"], learn_noise=kw["learn_noise"],
                              fixed_noise=kw.get("fixed_noise", True))
     elif kind >= 3:

@@ -40,6 +40,21 @@ KIND_SEP_RQ = 5            # x ScaleKernel(RQKernel())           gps.py:1053-105
 KIND_SEP_CONST = 6         # x ConstantKernel()                  gps.py:1414-1415 (Achromatic)
 SEP_KINDS = (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)
 NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST: 1}
+# N3: stationary time kernels instead of the spectral mixture (gps.py:985-990, 1131-1184,
+# 1316-1319): kind = 8 + 5 * TK + WK, TK 0 ScaleKernel(RBF) / 1 ScaleKernel(Matern-1.5) in time,
+# WK 0 none (1-D) / 1 RBF / 2 Matern-1.5 / 3 RQ / 4 Constant in wavelength; Q = 0.
+KIND_STAT_BASE = 8
+
+
+def stat_kind(tk: int, wk: int) -> int:
+    return KIND_STAT_BASE + 5 * tk + wk
+
+
+def stat_atoms(kind: int):
+    """(time atom, wavelength atom or None) as separable-kind codes."""
+    tk, wk = divmod(kind - KIND_STAT_BASE, 5)
+    return ((KIND_SEP_RBF, KIND_SEP_MATERN15)[tk],
+            None if wk == 0 else (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)[wk - 1])
 
 # constraint kinds (A.2) ---------------------------------------------------------------
 CON_NONE = 0       # value = raw
@@ -62,11 +77,15 @@ class ModelSpec:
     @property
     def ds(self) -> int:
         """dims the spectral mixture acts on (separable kinds: time only)."""
-        return 1 if self.kind in SEP_KINDS else self.d
+        return 1 if (self.kind in SEP_KINDS or self.kind >= KIND_STAT_BASE) else self.d
 
     @property
     def NL(self) -> int:
-        """wavelength-kernel parameters of the separable kinds."""
+        """parameters behind the mixture: wavelength kernel of the separable kinds; time +
+        wavelength kernel of the stationary kinds."""
+        if self.kind >= KIND_STAT_BASE:
+            wl = stat_atoms(self.kind)[1]
+            return 2 + (0 if wl is None else NUM_LAM[wl])
         return NUM_LAM.get(self.kind, 0)
 
     @property
@@ -195,6 +214,15 @@ def kernel_dense(x1, x2, theta, spec: ModelSpec):
     Separable kinds: ProductKernel restricted by active_dims (gps.py:1319-1336), i.e. the
     elementwise product K_t(x[:, 0]) * K_l(x[:, 1])  (tests/test_kernels.py:130-139)."""
     mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    if spec.kind >= KIND_STAT_BASE:
+        # ScaleKernel(time atom)(x[:, 0]) [* wavelength kernel (x[:, 1])]: the same GPyTorch
+        # kernels as the wavelength factors, acting on the time column
+        lam = unpack_lam(theta, spec)
+        ta, wa = stat_atoms(spec.kind)
+        K = wavelength_kernel_dense(x1[..., 0], x2[..., 0], lam[..., :2], ta)
+        if wa is not None:
+            K = K * wavelength_kernel_dense(x1[..., 1], x2[..., 1], lam[..., 2:], wa)
+        return K
     if spec.kind in SEP_KINDS:
         Kt = sm_kernel_dense(x1[..., :1], x2[..., :1], w, mu, sigma, KIND_SM1D)
         Kl = wavelength_kernel_dense(x1[..., 1], x2[..., 1], unpack_lam(theta, spec), spec.kind)
@@ -304,6 +332,10 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
     dt = y.dtype
     n = y.shape[-1]
     Q, d = spec.Q, spec.ds
+    if spec.kind >= KIND_STAT_BASE:
+        # stationary kinds: the closed form is d K / d theta by autograd of the dense kernel,
+        # contracted with W (the Cholesky part is still the explicit one below)
+        return _mll_and_grad_stat(x, y, fixed_noise, raw, kinds, lb, ub, spec)
     theta = constrain(raw, kinds, lb, ub)
     mean, w, mu, sigma, noise = unpack_params(theta, spec)
     K = kernel_dense(x, x, theta, spec)
@@ -391,6 +423,33 @@ def mll_and_grad_analytic(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec
         g[spec.o_noise] = half * torch.diagonal(W).sum()
     g = g * constraint_jacobian(raw, kinds, lb, ub)
     return mll, g, info
+
+
+def _mll_and_grad_stat(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec):
+    """mll_and_grad_analytic for the stationary kinds: W from the explicit Cholesky, then
+    g_theta = (1/2n) sum_ij W_ij dK_ij/dtheta with dK/dtheta from autograd of kernel_dense."""
+    dt = y.dtype
+    n = y.shape[-1]
+    rawg = raw.detach().clone().requires_grad_(True)
+    theta = constrain(rawg, kinds, lb, ub)
+    mean, w, mu, sigma, noise = unpack_params(theta, spec)
+    K = kernel_dense(x, x, theta, spec)
+    Kt = K + torch.diag_embed(noise_diag(n, fixed_noise, noise, dt))
+    L, info = psd_safe_cholesky(Kt.detach())
+    if int(info) < 0:
+        nanv = torch.full((), float("nan"), dtype=dt)
+        return nanv, torch.full_like(raw, float("nan")), info
+    if int(info) > 0:
+        Kt = Kt + 1e-8 * 10 ** (int(info) - 1) * torch.eye(n, dtype=dt)
+    r = (y - mean.detach()).unsqueeze(-1)
+    alpha = torch.cholesky_solve(r, L)
+    Kinv = torch.cholesky_inverse(L)
+    mll = -0.5 * ((r * alpha).sum() + 2.0 * torch.log(torch.diagonal(L)).sum()
+                  + n * math.log(TWO_PI)) / n
+    W = (alpha @ alpha.T - Kinv).detach()
+    surrogate = (0.5 / n) * (W * Kt).sum() + (alpha.detach().sum() / n) * mean
+    (g,) = torch.autograd.grad(surrogate, rawg)
+    return mll.detach(), g.detach(), info
 
 
 # ---------------------------------------------------------------------------------------

@@ -75,7 +75,7 @@ using pgm::launch_predict;
 int pad_q(int Q) { return Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8; }
 
 // NF of the instantiated config serving (d, Q): sizes the workspace (upper bound over kinds)
-int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q <= 4 ? 4 : Q) + 1; }
+int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q <= 4 ? 4 : Q) + 1; }  // Q = 0 -> QT = 4
 
 #define PGM_DISPATCH_Q(KIND, D, FN, ...)                     \
   switch (pad_q(Q)) {                                        \
@@ -103,13 +103,32 @@ int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q <= 4 ? 4 : Q) + 1; }
       PGM_DISPATCH_Q48(PGM_KIND_SEP_MATERN15, 2, FN, __VA_ARGS__)                    \
     } else if (kernel_kind == PGM_KIND_SEP_RQ) {                                     \
       PGM_DISPATCH_Q48(PGM_KIND_SEP_RQ, 2, FN, __VA_ARGS__)                          \
-    } else {                                                                         \
+    } else if (kernel_kind == PGM_KIND_SEP_CONST) {                                  \
       PGM_DISPATCH_Q48(PGM_KIND_SEP_CONST, 2, FN, __VA_ARGS__)                       \
+    } else {                                                                         \
+      switch (kernel_kind) {                                                         \
+        case PGM_KIND_STAT(0, 0): return FN<PGM_KIND_STAT(0, 0), 4, 1>(__VA_ARGS__); \
+        case PGM_KIND_STAT(0, 1): return FN<PGM_KIND_STAT(0, 1), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(0, 2): return FN<PGM_KIND_STAT(0, 2), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(0, 3): return FN<PGM_KIND_STAT(0, 3), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(0, 4): return FN<PGM_KIND_STAT(0, 4), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(1, 0): return FN<PGM_KIND_STAT(1, 0), 4, 1>(__VA_ARGS__); \
+        case PGM_KIND_STAT(1, 1): return FN<PGM_KIND_STAT(1, 1), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(1, 2): return FN<PGM_KIND_STAT(1, 2), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(1, 3): return FN<PGM_KIND_STAT(1, 3), 4, 2>(__VA_ARGS__); \
+        default: return FN<PGM_KIND_STAT(1, 4), 4, 2>(__VA_ARGS__);                  \
+      }                                                                              \
     }                                                                                \
   } while (0)
 
 int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
   if (B < 0 || n_max < 1) return fail("B must be >= 0 and n_max >= 1");
+  if (kernel_kind >= PGM_KIND_STAT_BASE && kernel_kind <= PGM_KIND_STAT(1, 4)) {
+    if (Q != 0) return fail("stationary kinds have no mixtures: pass Q == 0");
+    const int wk = (kernel_kind - PGM_KIND_STAT_BASE) % 5;
+    if (d != (wk == 0 ? 1 : 2)) return fail("stationary kind / d mismatch (d = 1 without, 2 with a wavelength kernel)");
+    return 0;
+  }
   if (Q < 1 || Q > 8) return fail("Q (num_mixtures) must be in 1..8");
   if (kernel_kind == PGM_KIND_SM1D) {
     if (d != 1) return fail("PGM_KIND_SM1D needs d == 1");
@@ -128,8 +147,9 @@ int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
 int host_param_count(int d, int Q, int kernel_kind, int flags) {
   const bool sep = kernel_kind >= PGM_KIND_SEP_RBF;
   const int ds = sep ? 1 : d;
-  const int nl = (kernel_kind == PGM_KIND_SEP_RBF || kernel_kind == PGM_KIND_SEP_MATERN15) ? 2
-                 : (kernel_kind == PGM_KIND_SEP_RQ) ? 3 : (kernel_kind == PGM_KIND_SEP_CONST) ? 1 : 0;
+  const int nl = (kernel_kind >= PGM_KIND_STAT_BASE)
+                     ? 2 + pgm::sep_num_lam(pgm::stat_wave_atom(kernel_kind))
+                     : pgm::sep_num_lam(kernel_kind);
   return 1 + Q + 2 * Q * ds + ((flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0) + nl;
 }
 

@@ -43,6 +43,12 @@ constexpr int S_ELEMS = TS * LD_S;                 // 4352
 #define PGM_KIND_SEP_MATERN15 4   // ScaleKernel(MaternKernel(1.5))   gps.py:1049-1052
 #define PGM_KIND_SEP_RQ 5         // ScaleKernel(RQKernel)            gps.py:1053-1056
 #define PGM_KIND_SEP_CONST 6      // ConstantKernel (achromatic)      gps.py:1414-1415
+// stationary (non-spectral-mixture) time kernels, N3: kind = 8 + 5 * TK + WK,
+//   TK: 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(1.5))      gps.py:985-990
+//   WK: 0 none (1-D model), 1 RBF, 2 Matern-1.5, 3 RQ, 4 Constant       gps.py:1045-1072
+// K = os_t f_T(tau_t) [x os_w f_W(tau_lambda)]; no mixtures (Q = 0 in the packed layout).
+#define PGM_KIND_STAT_BASE 8
+#define PGM_KIND_STAT(tk, wk) (PGM_KIND_STAT_BASE + 5 * (tk) + (wk))
 #define PGM_FLAG_GRAD 1
 #define PGM_FLAG_LEARN_NOISE 2
 #define PGM_FLAG_BOUNDS_PER_LC 4
@@ -213,13 +219,29 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
 // ------------------------------------------------------------------------------------
 // static configuration per (kernel kind, padded mixture count, input dims)
 // ------------------------------------------------------------------------------------
+// the separable-kind code whose lam_factor implements an atom of the stationary kinds
+__host__ __device__ constexpr int stat_time_atom(int kind) {
+  return ((kind - PGM_KIND_STAT_BASE) / 5 == 0) ? PGM_KIND_SEP_RBF : PGM_KIND_SEP_MATERN15;
+}
+__host__ __device__ constexpr int stat_wave_atom(int kind) {   // 0 = no wavelength factor
+  return ((kind - PGM_KIND_STAT_BASE) % 5 == 0) ? 0
+         : (PGM_KIND_SEP_RBF + (kind - PGM_KIND_STAT_BASE) % 5 - 1);
+}
+__host__ __device__ constexpr int sep_num_lam(int sep_kind) {
+  return (sep_kind == PGM_KIND_SEP_RBF || sep_kind == PGM_KIND_SEP_MATERN15) ? 2
+         : (sep_kind == PGM_KIND_SEP_RQ) ? 3 : (sep_kind == PGM_KIND_SEP_CONST) ? 1 : 0;
+}
+
 template <int KIND, int QT, int D>
 struct Cfg {
-  static constexpr bool SEP = KIND >= PGM_KIND_SEP_RBF;
-  static constexpr int DS = SEP ? 1 : D;      // dims the spectral mixture acts on
-  // wavelength-kernel parameters: (outputscale, lengthscale[, alpha]) or (constant)
-  static constexpr int NL = (KIND == PGM_KIND_SEP_RBF || KIND == PGM_KIND_SEP_MATERN15) ? 2
-                            : (KIND == PGM_KIND_SEP_RQ) ? 3 : (KIND == PGM_KIND_SEP_CONST) ? 1 : 0;
+  static constexpr bool STAT = KIND >= PGM_KIND_STAT_BASE;
+  static constexpr bool SEP = KIND >= PGM_KIND_SEP_RBF && !STAT;
+  static constexpr int DS = (SEP || STAT) ? 1 : D;      // dims the spectral mixture acts on
+  // kernel parameters behind the mixture: wavelength kernel (outputscale, lengthscale[, alpha])
+  // or (constant); stationary kinds: time kernel (outputscale, lengthscale) + wavelength kernel
+  static constexpr int NLT = STAT ? 2 : 0;
+  static constexpr int NL = STAT ? NLT + sep_num_lam(stat_wave_atom(KIND)) : sep_num_lam(KIND);
+  static_assert(!STAT || QT == 4, "stationary kinds carry the time-kernel constants in w[4]");
   static constexpr int NCS = DS * QT;         // (cos, sin) pairs per point
   static constexpr int NFB = D + 2 * NCS;     // per-point doubles: x[D], (cos,sin)[DS][QT]
   static constexpr int NF = NFB + 1;          // + alpha
@@ -546,6 +568,14 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
                                           const double (&lam)[4],
                                           const double* __restrict__ tab) {
   constexpr int DS = Cfg<KIND, QT, D>::DS;
+  if constexpr (Cfg<KIND, QT, D>::STAT) {
+    // K = os_t f_T(tau_t) [x os_w f_W(tau_lambda)]; time-kernel constants travel in w[4]
+    double gl, ga_;
+    double k = w[0] * lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, gl, ga_);
+    if constexpr (stat_wave_atom(KIND) != 0)
+      k *= lam[0] * lam_factor<stat_wave_atom(KIND)>(rowv[TS + r] - colv[TS + c], lam, tab, gl, ga_);
+    return k;
+  }
   const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
   const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
   double tau2[DS];
@@ -600,6 +630,28 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
                                              double (&ga)[Cfg<KIND, QT, D>::NG]) {
   using C = Cfg<KIND, QT, D>;
   constexpr int DS = C::DS;
+  if constexpr (C::STAT) {
+    // raw carriers in the slots behind the (unused) mixture accumulators; constant factors
+    // (outputscales, d c1 / d lengthscale) are applied once per light curve at the end
+    constexpr int G0 = QT + 2 * QT * DS;
+    double glt, gat, glw = 0.0, gaw = 0.0;
+    const double ft = lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, glt, gat);
+    double fw = 1.0, kw = 1.0;
+    if constexpr (stat_wave_atom(KIND) != 0) {
+      fw = lam_factor<stat_wave_atom(KIND)>(rowv[TS + r] - colv[TS + c], lam, tab, glw, gaw);
+      kw = lam[0] * fw;
+    }
+    const double wk = wgt * kw;
+    ga[G0] += wk * ft;            // d / d outputscale_t
+    ga[G0 + 1] += wk * glt;       // d / d lengthscale_t   (x os_t x const)
+    if constexpr (stat_wave_atom(KIND) != 0) {
+      const double wkt = wgt * (w[0] * ft);
+      ga[G0 + 2] += wkt * fw;                               // d / d outputscale_w | constant
+      if constexpr (C::NL >= 4) ga[G0 + 3] += wkt * glw;    // d / d lengthscale_w
+      if constexpr (C::NL >= 5) ga[G0 + 4] += wkt * gaw;    // d / d alpha_w
+    }
+    return;
+  }
   const double2* rcs = reinterpret_cast<const double2*>(rowv + D * TS);
   const double2* ccs = reinterpret_cast<const double2*>(colv + D * TS);
   double tau[DS], EC[DS][QT], ES[DS][QT], Ssum[DS];
@@ -869,6 +921,35 @@ __device__ __forceinline__ void lam_setup(const double* th /* NL constrained val
   }
 }
 
+// stationary kinds: time-kernel constants into wq[4] (same {scale, c1, alpha, lengthscale}
+// layout), wavelength-kernel constants into lamq[4]
+template <int KIND>
+__device__ __forceinline__ void stat_setup(const double* th, double* wq, double* lamq) {
+  lam_setup<stat_time_atom(KIND)>(th, wq);
+  lamq[0] = 1.0; lamq[1] = 0.0; lamq[2] = 1.0; lamq[3] = 1.0;
+  if constexpr (stat_wave_atom(KIND) != 0) lam_setup<stat_wave_atom(KIND)>(th + 2, lamq);
+}
+
+// d K / d theta constant factor of slot t of the parameters behind the mixture (carriers of
+// lam_factor): 1 for scales / constants, scale x d c1-term for lengthscales, scale for alpha
+template <int KIND>
+__device__ __forceinline__ double lam_grad_factor(int t, const double* wq, const double* lamq) {
+  auto ell_factor = [](int atom, const double* lm) {
+    return (atom == PGM_KIND_SEP_RBF) ? lm[0] / (lm[3] * lm[3] * lm[3])
+           : (atom == PGM_KIND_SEP_MATERN15) ? lm[0] / lm[3] : lm[0] * 2.0 * lm[2] / lm[3];
+  };
+  if constexpr (KIND >= PGM_KIND_STAT_BASE) {
+    if (t == 0 || t == 2) return 1.0;
+    if (t == 1) return ell_factor(stat_time_atom(KIND), wq);
+    if (t == 3) return ell_factor(stat_wave_atom(KIND), lamq);
+    return lamq[0];
+  } else {
+    if (t == 1) return ell_factor(KIND, lamq);
+    if (t == 2) return lamq[0];
+    return 1.0;
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // pipeline state carried by a block across light curves (mbarrier phases keep running)
 // ------------------------------------------------------------------------------------
@@ -961,13 +1042,16 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   }
   load_exp_tab(tab);
   __syncthreads();
-  if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
+  if (!C::STAT && tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
   if (tid < QT * DS) {
     const int q = tid / DS, dd = tid - q * DS;
     const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
     aq[q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
-  if (tid == 32) lam_setup<KIND>(theta + o_lam, lamq);
+  if (tid == 32) {
+    if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, lamq);
+    else lam_setup<KIND>(theta + o_lam, lamq);
+  }
   const double mean = theta[0];
   const double lnoise = learn_noise ? theta[o_noise] : 0.0;
   // ---- per-point fields into the block's scratch ------------------------------------
@@ -1367,17 +1451,9 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
     } else if (tid < o_lam) {
       gv = half * fin[C::NG];   // learned noise: tr W
     } else {
-      // wavelength kernel: constant factors of lam_factor's derivative carriers
+      // parameters behind the mixture: constant factors of lam_factor's derivative carriers
       const int t = tid - o_lam;
-      double cf = 1.0;
-      if (t == 1) {
-        if (KIND == PGM_KIND_SEP_RBF) cf = lamq[0] / (lamq[3] * lamq[3] * lamq[3]);
-        else if (KIND == PGM_KIND_SEP_MATERN15) cf = lamq[0] / lamq[3];
-        else cf = lamq[0] * 2.0 * lamq[2] / lamq[3];
-      } else if (t == 2) {
-        cf = lamq[0];
-      }
-      gv = half * cf * fin[QT + 2 * QT * DS + t];
+      gv = half * lam_grad_factor<KIND>(t, wq, lamq) * fin[QT + 2 * QT * DS + t];
     }
     grad_out[tid] = gv * jac[tid];
   }
@@ -1455,13 +1531,16 @@ __global__ void __launch_bounds__(NTHREADS)
   }
   load_exp_tab(tab);
   __syncthreads();
-  if (tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
+  if (!C::STAT && tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
   if (tid < QT * DS) {
     const int q = tid / DS, dd = tid - q * DS;
     const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
     aq[q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
-  if (tid == 32) lam_setup<KIND>(theta + o_lam, lamq);
+  if (tid == 32) {
+    if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, lamq);
+    else lam_setup<KIND>(theta + o_lam, lamq);
+  }
   const double* xb = A.x + (size_t)b * A.n_max * D;
   for (int idx = tid; idx < 2 * TS; idx += NTHREADS) {
     const int side = idx >> 6, r = idx & 63;

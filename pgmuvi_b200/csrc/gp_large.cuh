@@ -182,13 +182,16 @@ __global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
       w.par[LG_PAR_TH + tid] = theta[tid];
       w.par[LG_PAR_JC + tid] = jac[tid];
     }
-    if (tid < QT) w.par[LG_PAR_WQ + tid] = (tid < Q) ? theta[1 + tid] : 0.0;
+    if (!C::STAT && tid < QT) w.par[LG_PAR_WQ + tid] = (tid < Q) ? theta[1 + tid] : 0.0;
     if (tid < QT * DS) {
       const int q = tid / DS, dd = tid - q * DS;
       const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
       w.par[LG_PAR_AQ + q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
     }
-    if (tid == 32) lam_setup<KIND>(theta + o_lam, w.par + LG_PAR_LM);
+    if (tid == 32) {
+      if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, w.par + LG_PAR_WQ, w.par + LG_PAR_LM);
+      else lam_setup<KIND>(theta + o_lam, w.par + LG_PAR_LM);
+    }
   }
   const double mean = theta[0];
   const double lnoise = learn_noise ? theta[o_noise] : 0.0;
@@ -1025,15 +1028,7 @@ __global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int want_grad
     gv = half * fin[C::NG];
   } else {
     const int t = tid - o_lam;
-    double cf = 1.0;
-    if (t == 1) {
-      if (KIND == PGM_KIND_SEP_RBF) cf = lamq[0] / (lamq[3] * lamq[3] * lamq[3]);
-      else if (KIND == PGM_KIND_SEP_MATERN15) cf = lamq[0] / lamq[3];
-      else cf = lamq[0] * 2.0 * lamq[2] / lamq[3];
-    } else if (t == 2) {
-      cf = lamq[0];
-    }
-    gv = half * cf * fin[QT + 2 * QT * DS + t];
+    gv = half * lam_grad_factor<KIND>(t, wq, lamq) * fin[QT + 2 * QT * DS + t];
   }
   grad_out[tid] = gv * w.par[LG_PAR_JC + tid];
 }

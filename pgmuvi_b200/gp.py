@@ -475,14 +475,22 @@ class TwoDSpectralMixtureDustMeanGPModel(TwoDSpectralMixtureGPModel):
 
 
 def _build_time_kernel(time_kernel_type, num_mixtures):
-    """pgmuvi/gps.py:938-1007; only the spectral-mixture time kernel is on the path."""
+    """pgmuvi/gps.py:938-1007: 'matern' (the reference's default), 'rbf', 'spectral_mixture' /
+    'sm'; 'quasi_periodic' and the flicker term are outside the accelerated path."""
     if isinstance(time_kernel_type, nn.Module):
         return time_kernel_type
     if time_kernel_type in ("spectral_mixture", "sm"):
         return SpectralMixtureKernel(num_mixtures=num_mixtures, ard_num_dims=1)
-    raise NotImplementedError(
-        f"time_kernel_type {time_kernel_type!r} is outside the accelerated path "
-        "(SURVEY.md section 8a row a4: only 'spectral_mixture' / 'sm')")
+    if time_kernel_type == "matern":
+        return ScaleKernel(MaternKernel(nu=1.5))
+    if time_kernel_type == "rbf":
+        return ScaleKernel(RBFKernel())
+    if time_kernel_type == "quasi_periodic":
+        raise NotImplementedError("time_kernel_type 'quasi_periodic' is outside the accelerated "
+                                  "path (no periodic kernel kind yet)")
+    raise ValueError(
+        f"Unknown time_kernel_type '{time_kernel_type}'. Choose from 'quasi_periodic', 'matern', "
+        "'rbf', 'spectral_mixture'/'sm', or supply a kernel instance.")
 
 
 def _build_wavelength_kernel(wavelength_kernel_type, wavelength_lengthscale,
@@ -519,13 +527,31 @@ class SeparableGPModel(ExactGP):
                  mean_module=None, num_mixtures=4, **kwargs):
         super().__init__(train_x, train_y, likelihood)
         self.mean_module = ConstantMean() if mean_module is None else mean_module
-        if time_kernel is None:      # the reference defaults to Matern here (gps.py:1316-1317)
-            time_kernel = SpectralMixtureKernel(num_mixtures=num_mixtures, ard_num_dims=1)
+        if time_kernel is None:      # gps.py:1316-1317
+            time_kernel = ScaleKernel(MaternKernel(nu=1.5))
         if wavelength_kernel is None:
             wavelength_kernel = ScaleKernel(RBFKernel())
         time_kernel.register_buffer("active_dims", torch.tensor([0], dtype=torch.long))
         wavelength_kernel.register_buffer("active_dims", torch.tensor([1], dtype=torch.long))
         self.covar_module = time_kernel * wavelength_kernel
+        self.sci_kernel = self.covar_module
+
+    def forward(self, x):
+        return PriorOutput(self, x)
+
+
+class MaternGPModel(ExactGP):
+    """pgmuvi/gps.py:1131-1184 ('1DMatern'): ConstantMean + ScaleKernel(MaternKernel(nu)),
+    lengthscale initialised to span / 4.  nu = 1.5 is on the accelerated path."""
+
+    def __init__(self, train_x, train_y, likelihood, nu=1.5, lengthscale=None, **kwargs):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean()
+        if lengthscale is None:
+            lengthscale = float(train_x.max() - train_x.min()) / 4.0
+        k = MaternKernel(nu=nu)
+        k.lengthscale = lengthscale
+        self.covar_module = ScaleKernel(k)
         self.sci_kernel = self.covar_module
 
     def forward(self, x):

@@ -29,7 +29,9 @@ _SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPMod
               "2DDust": gp.TwoDSpectralMixtureDustMeanGPModel,
               "2DSeparable": gp.SeparableGPModel, "2DAchromatic": gp.AchromaticGPModel,
               "2DWavelengthDependent": gp.WavelengthDependentGPModel,
-              "2DDustMean": gp.DustMeanGPModel, "2DPowerLawMean": gp.PowerLawMeanGPModel}
+              "2DDustMean": gp.DustMeanGPModel, "2DPowerLawMean": gp.PowerLawMeanGPModel,
+              "1DMatern": gp.MaternGPModel}
+_NO_MIXTURE_MODELS = ("1DMatern",)
 CONSTRAINT_SETS = {"LPV": {"period": {"lower": (20.0, True), "upper": (None, False)}}}
 
 
@@ -200,14 +202,14 @@ class Lightcurve(torch.nn.Module):
         if isinstance(model, torch.nn.Module):
             self.model = model
         elif model in _SM_MODELS:
-            if model in ("1D", "1DLinear") and self.ndim > 1:
+            if model in ("1D", "1DLinear", "1DMatern") and self.ndim > 1:
                 raise ValueError("You have selected a 1D model but your data has more than one "
                                  "input dimension; use model='2D'.")   # tests/test_2d_integration.py:167-186
             if model.startswith("2D") and self.ndim != 2:
                 raise ValueError(f"model={model!r} needs xdata of shape [n, 2] (time, wavelength)")
+            mk = {} if model in _NO_MIXTURE_MODELS else {"num_mixtures": num_mixtures or 4}
             self.model = _SM_MODELS[model](self._xdata_transformed, self._ydata_transformed,
-                                           self.likelihood, num_mixtures=num_mixtures or 4,
-                                           **kwargs)
+                                           self.likelihood, **mk, **kwargs)
         else:
             raise UnsupportedModel(
                 f"model {model!r} is outside the accelerated path (SURVEY section 8a): "

@@ -20,7 +20,7 @@ from typing import List, Optional
 import torch
 
 from . import ops
-from ._lib import (KIND_SEP_CONST, KIND_SEP_MATERN15, KIND_SEP_RBF, KIND_SEP_RQ, KIND_SM1D,
+from ._lib import (KIND_STAT_BASE, stat_kind, KIND_SEP_CONST, KIND_SEP_MATERN15, KIND_SEP_RBF, KIND_SEP_RQ, KIND_SM1D,
                    KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD)
 from .constraints import describe
 
@@ -76,6 +76,84 @@ def _find_name(model, param):
     return "?"
 
 
+def _scaled_atom(k):
+    """(atom code, params, constraints) of ScaleKernel(RBF | Matern-1.5 | RQ) or ConstantKernel;
+    atom codes: 1 RBF, 2 Matern-1.5, 3 RQ, 4 Constant (the WK numbering of the stationary
+    kinds).  None if ``k`` is something else."""
+    if hasattr(k, "raw_constant") and not hasattr(k, "base_kernel"):
+        return 4, [k.raw_constant], [_constraint(k, "raw_constant")]
+    if not (hasattr(k, "raw_outputscale") and hasattr(k, "base_kernel")):
+        return None
+    base = k.base_kernel
+    bname = type(base).__name__
+    if not hasattr(base, "raw_lengthscale") or hasattr(base, "raw_period_length"):
+        return None
+    params = [k.raw_outputscale, base.raw_lengthscale]
+    cons = [_constraint(k, "raw_outputscale"), _constraint(base, "raw_lengthscale")]
+    if hasattr(base, "raw_alpha"):
+        return 3, params + [base.raw_alpha], cons + [_constraint(base, "raw_alpha")]
+    if "Matern" in bname:
+        if float(getattr(base, "nu", 1.5)) != 1.5:
+            raise UnsupportedModelError("only MaternKernel(nu=1.5) is supported")
+        return 2, params, cons
+    if "RBF" in bname:
+        return 1, params, cons
+    return None
+
+
+def _pack_stationary(model, likelihood, mean, cov, external_mean):
+    """N3: covar_module = ScaleKernel(RBF | Matern-1.5) [* wavelength kernel] (gps.py:985-990,
+    1131-1184, 1316-1336) -> kinds 8 + 5 TK + WK, layout [mean | (noise) | os_t, l_t | wavelength]."""
+    factors = getattr(cov, "kernels", None)
+    tk = cov if factors is None else factors[0]
+    ta = _scaled_atom(tk)
+    if ta is None or ta[0] not in (1, 2):
+        return None
+    wk_code, wparams, wcons = 0, [], []
+    if factors is not None:
+        if len(factors) != 2:
+            return None
+        wa = _scaled_atom(factors[1])
+        if wa is None:
+            return None
+        wk_code, wparams, wcons = wa
+    kind = stat_kind(ta[0] - 1, wk_code)
+    d = 1 if wk_code == 0 else 2
+    ref = ta[1][0]
+    slot0 = (torch.zeros(1, dtype=ref.dtype, device=ref.device) if external_mean
+             else mean.raw_constant)
+    params = [slot0]
+    cons = [None if external_mean else _constraint(mean, "raw_constant")]
+    fixed, learn = None, False
+    nc = getattr(likelihood, "noise_covar", None)
+    snc = getattr(likelihood, "second_noise_covar", None)
+    if nc is not None and hasattr(nc, "raw_noise"):
+        learn = True
+        params.append(nc.raw_noise)
+        cons.append(_constraint(nc, "raw_noise"))
+    elif nc is not None and hasattr(nc, "noise"):
+        fixed = nc.noise
+        if snc is not None and hasattr(snc, "raw_noise"):
+            learn = True
+            params.append(snc.raw_noise)
+            cons.append(_constraint(snc, "raw_noise"))
+    else:
+        raise UnsupportedModelError("likelihood must be Gaussian or FixedNoiseGaussian")
+    params += ta[1] + wparams
+    cons += ta[2] + wcons
+    kinds, lb, ub = [], [], []
+    for p, c in zip(params, cons):
+        k, lo, hi = describe(c)
+        kinds += [k] * p.numel()
+        lb += [lo] * p.numel()
+        ub += [hi] * p.numel()
+    return PackedModel(params=params, names=[_find_name(model, p) for p in params],
+                       kinds=torch.tensor(kinds, dtype=torch.int32),
+                       lb=torch.tensor(lb, dtype=torch.float64),
+                       ub=torch.tensor(ub, dtype=torch.float64), kind=kind, Q=0, d=d,
+                       learn_noise=learn, fixed_noise=fixed, external_mean=external_mean)
+
+
 def pack_model(model, likelihood=None) -> PackedModel:
     """Recognise (mean, SpectralMixtureKernel [x wavelength kernel], Gaussian | FixedNoise
     likelihood).  ConstantMean is packed into slot 0; any other mean module (LinearMean,
@@ -85,6 +163,13 @@ def pack_model(model, likelihood=None) -> PackedModel:
     if mean is None or not callable(mean):
         raise UnsupportedModelError("the model needs a mean_module")
     external_mean = not hasattr(mean, "raw_constant")
+    for m in (model, likelihood):
+        pri = getattr(m, "named_priors", None)
+        if pri is not None and len(list(pri())) > 0:
+            raise UnsupportedModelError("registered priors are not on the accelerated path")
+    stat = _pack_stationary(model, likelihood, mean, cov, external_mean) if cov is not None else None
+    if stat is not None:
+        return stat
     lam_params, lam_cons, sep_kind = [], [], None
     factors = getattr(cov, "kernels", None)
     if factors is not None:

@@ -12,7 +12,8 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import (FLAG_BOUNDS_PER_LC, FLAG_GRAD, FLAG_LEARN_NOISE, KIND_SM1D,
-                   KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD, NUM_LAM, SEP_KINDS, check, ptr)
+                   KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD, KIND_STAT_BASE, NUM_LAM, SEP_KINDS,
+                   check, is_stat, ptr, stat_num_lam)
 
 _workspaces = {}
 _staged_ws = {}
@@ -20,6 +21,8 @@ _staged_ws = {}
 
 def param_count(Q: int, d: int, learn_noise: bool, kind: int = -1) -> int:
     """P of the packed layout ``[mean | w | mu | sigma | (noise) | lam]`` (pgmuvi_b200.h)."""
+    if is_stat(kind):            # stationary time kernels: no mixtures (Q = 0)
+        return 1 + (1 if learn_noise else 0) + stat_num_lam(kind)
     if kind in SEP_KINDS:
         return 1 + 3 * Q + (1 if learn_noise else 0) + NUM_LAM[kind]
     return 1 + Q + 2 * Q * d + (1 if learn_noise else 0)
@@ -58,7 +61,9 @@ def _prep(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise
             raise RuntimeError(f"all floating tensors must share one dtype ({x.dtype}), "
                                f"got {t.dtype}")
     B, n = y.shape
-    d = 1 if kind == KIND_SM1D else 2
+    d = 1 if (kind == KIND_SM1D or (is_stat(kind) and (kind - KIND_STAT_BASE) % 5 == 0)) else 2
+    if is_stat(kind) and Q != 0:
+        raise RuntimeError("stationary kinds have no mixtures: pass Q = 0")
     if x.shape != (B, n, d):
         raise RuntimeError(f"x must be [B, n, {d}], got {tuple(x.shape)}")
     P = param_count(Q, d, learn_noise, kind)

@@ -258,3 +258,52 @@ def make_batch_sep(B, n_bands, n_per_band, Q=4, kind=3, learn_noise=False, seed0
         raw[b, o_lam:o_lam + NL] = inv_softplus(np.array(lamv))
     return dict(x=x, y=y, noise=noise, raw=raw, kinds=kinds, lb=lb, ub=ub, Q=Q, d=2,
                 kind=kind, learn_noise=learn_noise)
+
+
+def make_batch_stat(B, kind, n=None, n_bands=None, n_per_band=None, learn_noise=False, seed0=9000):
+    """N3: stationary time kernels (ScaleKernel(RBF | Matern-1.5) in time, optionally x a
+    wavelength kernel; pgmuvi/gps.py:985-990, 1131-1184, 1316-1319) on the 1-D / 2-D synthetic
+    light curves.  kind = 8 + 5 * TK + WK, Q = 0; packed [mean | (noise) | os_t, l_t | wavelength
+    parameters]; GPyTorch's default Positive constraints, mean / learned noise Interval."""
+    from ._lib import KIND_STAT_BASE, stat_num_lam
+    wk = (kind - KIND_STAT_BASE) % 5
+    d = 1 if wk == 0 else 2
+    NL = stat_num_lam(kind)
+    P = 1 + (1 if learn_noise else 0) + NL
+    o_noise = 1
+    o_lam = 1 + (1 if learn_noise else 0)
+    npts = n if d == 1 else n_bands * n_per_band
+    x = np.zeros((B, npts, d))
+    y = np.zeros((B, npts))
+    noise = np.zeros((B, npts))
+    raw = np.zeros((B, P))
+    lb = np.zeros((B, P))
+    ub = np.zeros((B, P))
+    kinds = np.full(P, CON_SOFTPLUS, dtype=np.int32)
+    kinds[0] = CON_INTERVAL
+    if learn_noise:
+        kinds[o_noise] = CON_INTERVAL
+    for b in range(B):
+        rng = np.random.default_rng(40_000_000 + seed0 + b)
+        if d == 1:
+            bt = make_batch_1d(1, npts, Q=1, seed0=seed0 + b)
+            x[b], yy, noise[b] = bt["x"][0], bt["y"][0], bt["noise"][0]
+            yerr = np.sqrt(bt["noise"][0])
+        else:
+            x01, yy, yerr, _ = make_lightcurve_2d(seed0 + b, n_bands, n_per_band)
+            x[b] = x01
+            noise[b] = fixed_noise_variance(yerr)
+        y[b] = yy
+        lb[b, 0], ub[b, 0] = float(yy.min()), float(yy.max())
+        if learn_noise:
+            lb[b, o_noise], ub[b, o_noise] = min(1e-4, float(yerr.min()) / 10.0), float(np.std(yy, ddof=1))
+        lamv = [rng.uniform(0.5, 1.5), rng.uniform(0.03, 0.2)]       # os_t, l_t (x in [0, 1])
+        if wk in (1, 2, 3):
+            lamv += [rng.uniform(0.6, 1.5), rng.uniform(0.3, 1.2)]   # os_w, l_w
+        if wk == 3:
+            lamv.append(rng.uniform(0.5, 3.0))                       # RQ alpha
+        if wk == 4:
+            lamv.append(rng.uniform(0.6, 1.5))                       # constant
+        raw[b, o_lam:o_lam + NL] = inv_softplus(np.array(lamv))
+    return dict(x=x, y=y, noise=noise, raw=raw, kinds=kinds, lb=lb, ub=ub, Q=0, d=d,
+                kind=kind, learn_noise=learn_noise)

@@ -125,20 +125,37 @@ def _lc_2d(seed=5, n_per=40, **kw):
 @pytest.mark.parametrize("model,kw", [("2DWavelengthDependent", dict(wavelength_kernel_type="rbf")),
                                       ("2DWavelengthDependent", dict(wavelength_kernel_type="matern")),
                                       ("2DWavelengthDependent", dict(wavelength_kernel_type="rq")),
-                                      ("2DAchromatic", {}), ("2DSeparable", {})])
+                                      ("2DAchromatic", {}), ("2DSeparable", dict(time_kernel="sm")),
+                                      # stationary time kernels (N3); "2DSeparable" with no
+                                      # arguments is the reference's default Matern x RBF
+                                      ("2DSeparable", {}),
+                                      ("2DAchromatic", dict(time_kernel_type="matern")),
+                                      ("2DWavelengthDependent", dict(time_kernel_type="rbf",
+                                                                     wavelength_kernel_type="rq")),
+                                      ("1DMatern", {})])
 def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
-    """SM(time) x wavelength kernel through Lightcurve -> train (seam #1) against the oracle's
+    """time kernel x wavelength kernel through Lightcurve -> train (seam #1) against the oracle's
     restatement of the same loop, and the loss goes down (tests/test_2d_integration.py:112-135)."""
     from oracle import train_loop
     from pgmuvi_b200.trainers import train
     torch.manual_seed(0)
-    lc = _lc_2d().double()
-    lc.set_model(model, num_mixtures=2, **kw)
+    kw = dict(kw)
+    if kw.pop("time_kernel", None) == "sm":
+        from pgmuvi_b200 import gp
+        kw["time_kernel"] = gp.SpectralMixtureKernel(num_mixtures=2, ard_num_dims=1)
+    lc = (_lc(n=140, seed=4) if model.startswith("1D") else _lc_2d()).double()
+    lc.set_model(model, **({} if model == "1DMatern" else {"num_mixtures": 2}), **kw)
     lc.double()
     lc.set_default_constraints()
-    # hypers in the min-max-scaled units of the time axis (span ~400 d)
-    lc.model.initialize(**{"covar_module.kernels.0.mixture_means": torch.tensor([4.8, 9.7]),
-                           "covar_module.kernels.0.mixture_scales": torch.tensor([1.5, 1.0])})
+    tk = lc.model.covar_module.kernels[0] if hasattr(lc.model.covar_module, "kernels") else None
+    if tk is not None and hasattr(tk, "raw_mixture_means"):
+        # hypers in the min-max-scaled units of the time axis (span ~400 d)
+        lc.model.initialize(**{"covar_module.kernels.0.mixture_means": torch.tensor([4.8, 9.7]),
+                               "covar_module.kernels.0.mixture_scales": torch.tensor([1.5, 1.0])})
+    elif tk is not None:
+        tk.base_kernel.lengthscale = 0.08        # min-max-scaled time, period ~0.2
+    else:
+        lc.model.covar_module.base_kernel.lengthscale = 0.05
     args, pk = _oracle_inputs(lc)
     assert pk.kind >= 3
     ref = train_loop(*args, maxiter=5, miniter=5, stop=None, lr=0.05, optim="AdamW")

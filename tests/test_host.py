@@ -202,7 +202,19 @@ def test_separable_models_pack_onto_the_separable_kinds():
     assert pk.names[-2:] == ["likelihood.noise_covar.raw_noise",
                              "covar_module.kernels.1.raw_constant"]
     with pytest.raises(NotImplementedError):
-        lc.set_model("2DAchromatic", time_kernel_type="matern")
+        lc.set_model("2DAchromatic", time_kernel_type="quasi_periodic")
+    # stationary time kernels (N3): the reference's default Matern time kernel packs onto the
+    # kinds 8 + 5 TK + WK with no mixtures
+    lc.set_model("2DAchromatic", time_kernel_type="matern")
+    pk = pack_model(lc.model)
+    assert (pk.kind, pk.Q, pk.d, pk.P) == (8 + 5 * 1 + 4, 0, 2, 1 + 1 + 2 + 1)
+    lc.set_model("2DSeparable")                              # gps.py:1316-1319: Matern x RBF
+    pk = pack_model(lc.model)
+    assert (pk.kind, pk.P) == (8 + 5 * 1 + 1, 1 + 1 + 4)
+    assert pk.names[2:] == ["covar_module.kernels.0.raw_outputscale",
+                            "covar_module.kernels.0.base_kernel.raw_lengthscale",
+                            "covar_module.kernels.1.raw_outputscale",
+                            "covar_module.kernels.1.base_kernel.raw_lengthscale"]
     with pytest.raises(ValueError):
         Lightcurve(x[:, 0], y).set_model("2DSeparable")
 
