@@ -51,10 +51,13 @@ extern "C" {
 /* N3 - stationary time kernels instead of the spectral mixture (pgmuvi/gps.py:985-990: the
  * reference's DEFAULT time kernel of the separable models is ScaleKernel(MaternKernel(1.5));
  * MaternGPModel gps.py:1131-1184).  kernel_kind = PGM_KIND_STAT(tk, wk):
- *   tk 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(nu=1.5))            (time)
+ *   tk 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(nu=1.5)),           (time)
+ *      2 quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935:
+ *        os exp(-2 sin^2(pi tau / p) / lambda) exp(-tau^2 / (2 l^2)), slots os, lambda, p, l
  *   wk 0 none (d = 1), 1 ScaleKernel(RBF), 2 ScaleKernel(Matern-1.5), 3 ScaleKernel(RQ),
  *      4 ConstantKernel                                                          (wavelength)
- * Pass Q = 0; packed layout [ mean | (noise) | os_t, l_t | wavelength parameters as above ]. */
+ * Pass Q = 0; packed layout [ mean | (noise) | time-kernel parameters (os_t, l_t | os, lambda,
+ * p, l) | wavelength parameters as above ]. */
 #define PGM_KIND_STAT_BASE 8
 #define PGM_KIND_STAT(tk, wk) (PGM_KIND_STAT_BASE + 5 * (tk) + (wk))
 

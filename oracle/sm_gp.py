@@ -44,6 +44,7 @@ NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST
 # 1316-1319): kind = 8 + 5 * TK + WK, TK 0 ScaleKernel(RBF) / 1 ScaleKernel(Matern-1.5) in time,
 # WK 0 none (1-D) / 1 RBF / 2 Matern-1.5 / 3 RQ / 4 Constant in wavelength; Q = 0.
 KIND_STAT_BASE = 8
+ATOM_QP = 100      # time atom 2: quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
 
 
 def stat_kind(tk: int, wk: int) -> int:
@@ -53,7 +54,7 @@ def stat_kind(tk: int, wk: int) -> int:
 def stat_atoms(kind: int):
     """(time atom, wavelength atom or None) as separable-kind codes."""
     tk, wk = divmod(kind - KIND_STAT_BASE, 5)
-    return ((KIND_SEP_RBF, KIND_SEP_MATERN15)[tk],
+    return ((KIND_SEP_RBF, KIND_SEP_MATERN15, ATOM_QP)[tk],
             None if wk == 0 else (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)[wk - 1])
 
 # constraint kinds (A.2) ---------------------------------------------------------------
@@ -84,8 +85,8 @@ class ModelSpec:
         """parameters behind the mixture: wavelength kernel of the separable kinds; time +
         wavelength kernel of the stationary kinds."""
         if self.kind >= KIND_STAT_BASE:
-            wl = stat_atoms(self.kind)[1]
-            return 2 + (0 if wl is None else NUM_LAM[wl])
+            ta, wl = stat_atoms(self.kind)
+            return (4 if ta == ATOM_QP else 2) + (0 if wl is None else NUM_LAM[wl])
         return NUM_LAM.get(self.kind, 0)
 
     @property
@@ -219,9 +220,20 @@ def kernel_dense(x1, x2, theta, spec: ModelSpec):
         # kernels as the wavelength factors, acting on the time column
         lam = unpack_lam(theta, spec)
         ta, wa = stat_atoms(spec.kind)
-        K = wavelength_kernel_dense(x1[..., 0], x2[..., 0], lam[..., :2], ta)
+        if ta == ATOM_QP:
+            # GPyTorch PeriodicKernel: exp(-2 sin^2(pi tau / p) / lengthscale) (the lengthscale
+            # is NOT squared in gpytorch >= 1.x), times RBFKernel, inside one ScaleKernel
+            nt = 4
+            ex = lambda t: t.unsqueeze(-1).unsqueeze(-1)
+            tau = x1[..., 0].unsqueeze(-1) - x2[..., 0].unsqueeze(-2)
+            os_, lmb, per, ell = (ex(lam[..., k]) for k in range(4))
+            K = os_ * torch.exp(-2.0 * torch.sin(math.pi * tau / per) ** 2 / lmb) \
+                * torch.exp(-0.5 * (tau / ell) ** 2)
+        else:
+            nt = 2
+            K = wavelength_kernel_dense(x1[..., 0], x2[..., 0], lam[..., :2], ta)
         if wa is not None:
-            K = K * wavelength_kernel_dense(x1[..., 1], x2[..., 1], lam[..., 2:], wa)
+            K = K * wavelength_kernel_dense(x1[..., 1], x2[..., 1], lam[..., nt:], wa)
         return K
     if spec.kind in SEP_KINDS:
         Kt = sm_kernel_dense(x1[..., :1], x2[..., :1], w, mu, sigma, KIND_SM1D)

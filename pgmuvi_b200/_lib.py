@@ -17,7 +17,7 @@ KIND_SM1D, KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD = 0, 1, 2
 KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST = 3, 4, 5, 6
 SEP_KINDS = (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)
 NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST: 1}
-# N3 stationary time kernels: kind = 8 + 5 * TK + WK (TK 0 RBF / 1 Matern-1.5; WK 0 none,
+# N3 stationary time kernels: kind = 8 + 5 * TK + WK (TK 0 RBF / 1 Matern-1.5 / 2 QP; WK 0 none,
 # 1 RBF, 2 Matern-1.5, 3 RQ, 4 Constant), no mixtures (Q = 0)
 KIND_STAT_BASE = 8
 
@@ -27,12 +27,12 @@ def stat_kind(tk, wk):
 
 
 def is_stat(kind):
-    return KIND_STAT_BASE <= kind <= stat_kind(1, 4)
+    return KIND_STAT_BASE <= kind <= stat_kind(2, 4)
 
 
 def stat_num_lam(kind):
-    wk = (kind - KIND_STAT_BASE) % 5
-    return 2 + (0, 2, 2, 3, 1)[wk]
+    tk, wk = divmod(kind - KIND_STAT_BASE, 5)
+    return (2, 2, 4)[tk] + (0, 2, 2, 3, 1)[wk]
 
 
 CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2

@@ -116,14 +116,19 @@ int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q <= 4 ? 4 : Q) + 1; }  // Q
         case PGM_KIND_STAT(1, 1): return FN<PGM_KIND_STAT(1, 1), 4, 2>(__VA_ARGS__); \
         case PGM_KIND_STAT(1, 2): return FN<PGM_KIND_STAT(1, 2), 4, 2>(__VA_ARGS__); \
         case PGM_KIND_STAT(1, 3): return FN<PGM_KIND_STAT(1, 3), 4, 2>(__VA_ARGS__); \
-        default: return FN<PGM_KIND_STAT(1, 4), 4, 2>(__VA_ARGS__);                  \
+        case PGM_KIND_STAT(1, 4): return FN<PGM_KIND_STAT(1, 4), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(2, 0): return FN<PGM_KIND_STAT(2, 0), 4, 1>(__VA_ARGS__); \
+        case PGM_KIND_STAT(2, 1): return FN<PGM_KIND_STAT(2, 1), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(2, 2): return FN<PGM_KIND_STAT(2, 2), 4, 2>(__VA_ARGS__); \
+        case PGM_KIND_STAT(2, 3): return FN<PGM_KIND_STAT(2, 3), 4, 2>(__VA_ARGS__); \
+        default: return FN<PGM_KIND_STAT(2, 4), 4, 2>(__VA_ARGS__);                  \
       }                                                                              \
     }                                                                                \
   } while (0)
 
 int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
   if (B < 0 || n_max < 1) return fail("B must be >= 0 and n_max >= 1");
-  if (kernel_kind >= PGM_KIND_STAT_BASE && kernel_kind <= PGM_KIND_STAT(1, 4)) {
+  if (kernel_kind >= PGM_KIND_STAT_BASE && kernel_kind <= PGM_KIND_STAT(2, 4)) {
     if (Q != 0) return fail("stationary kinds have no mixtures: pass Q == 0");
     const int wk = (kernel_kind - PGM_KIND_STAT_BASE) % 5;
     if (d != (wk == 0 ? 1 : 2)) return fail("stationary kind / d mismatch (d = 1 without, 2 with a wavelength kernel)");
@@ -148,7 +153,7 @@ int host_param_count(int d, int Q, int kernel_kind, int flags) {
   const bool sep = kernel_kind >= PGM_KIND_SEP_RBF;
   const int ds = sep ? 1 : d;
   const int nl = (kernel_kind >= PGM_KIND_STAT_BASE)
-                     ? 2 + pgm::sep_num_lam(pgm::stat_wave_atom(kernel_kind))
+                     ? pgm::stat_num_time(kernel_kind) + pgm::sep_num_lam(pgm::stat_wave_atom(kernel_kind))
                      : pgm::sep_num_lam(kernel_kind);
   return 1 + Q + 2 * Q * ds + ((flags & PGM_FLAG_LEARN_NOISE) ? 1 : 0) + nl;
 }

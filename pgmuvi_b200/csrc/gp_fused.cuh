@@ -45,6 +45,7 @@ constexpr int S_ELEMS = TS * LD_S;                 // 4352
 #define PGM_KIND_SEP_CONST 6      // ConstantKernel (achromatic)      gps.py:1414-1415
 // stationary (non-spectral-mixture) time kernels, N3: kind = 8 + 5 * TK + WK,
 //   TK: 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(1.5))      gps.py:985-990
+//       2 quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel)         gps.py:915-935
 //   WK: 0 none (1-D model), 1 RBF, 2 Matern-1.5, 3 RQ, 4 Constant       gps.py:1045-1072
 // K = os_t f_T(tau_t) [x os_w f_W(tau_lambda)]; no mixtures (Q = 0 in the packed layout).
 #define PGM_KIND_STAT_BASE 8
@@ -220,8 +221,13 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
 // static configuration per (kernel kind, padded mixture count, input dims)
 // ------------------------------------------------------------------------------------
 // the separable-kind code whose lam_factor implements an atom of the stationary kinds
+#define PGM_ATOM_QP 100   // ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
 __host__ __device__ constexpr int stat_time_atom(int kind) {
-  return ((kind - PGM_KIND_STAT_BASE) / 5 == 0) ? PGM_KIND_SEP_RBF : PGM_KIND_SEP_MATERN15;
+  return ((kind - PGM_KIND_STAT_BASE) / 5 == 0) ? PGM_KIND_SEP_RBF
+         : ((kind - PGM_KIND_STAT_BASE) / 5 == 1) ? PGM_KIND_SEP_MATERN15 : PGM_ATOM_QP;
+}
+__host__ __device__ constexpr int stat_num_time(int kind) {   // time-kernel parameters
+  return stat_time_atom(kind) == PGM_ATOM_QP ? 4 : 2;
 }
 __host__ __device__ constexpr int stat_wave_atom(int kind) {   // 0 = no wavelength factor
   return ((kind - PGM_KIND_STAT_BASE) % 5 == 0) ? 0
@@ -239,7 +245,7 @@ struct Cfg {
   static constexpr int DS = (SEP || STAT) ? 1 : D;      // dims the spectral mixture acts on
   // kernel parameters behind the mixture: wavelength kernel (outputscale, lengthscale[, alpha])
   // or (constant); stationary kinds: time kernel (outputscale, lengthscale) + wavelength kernel
-  static constexpr int NLT = STAT ? 2 : 0;
+  static constexpr int NLT = STAT ? stat_num_time(KIND) : 0;
   static constexpr int NL = STAT ? NLT + sep_num_lam(stat_wave_atom(KIND)) : sep_num_lam(KIND);
   static_assert(!STAT || QT == 4, "stationary kinds carry the time-kernel constants in w[4]");
   static constexpr int NCS = DS * QT;         // (cos, sin) pairs per point
@@ -560,6 +566,22 @@ __device__ __forceinline__ double lam_factor(double tl, const double (&lam)[4],
   return 1.0;
 }
 
+// quasi-periodic time factor (GPyTorch PeriodicKernel x RBFKernel):
+//   f = exp(-2 sin^2(pi tau / p) / lambda) * exp(-tau^2 / (2 l_r^2))
+// w = {outputscale, lambda, p, l_r}, a = {2 / lambda, 1 / p, 1 / (2 l_r^2)}; g[] returns the
+// derivative carriers f s^2, f sin(2 theta) tau, f tau^2 (constants applied at the end).
+__device__ __forceinline__ double qp_factor(double tau, const double (&a)[4],
+                                            const double* __restrict__ tab, double (&g)[3]) {
+  double sn, cs;
+  sincospi(tau * a[1], &sn, &cs);
+  const double s2 = sn * sn, t2 = tau * tau;
+  const double f = exp_neg(-(a[0] * s2 + a[2] * t2), tab);
+  g[0] = f * s2;
+  g[1] = f * (2.0 * sn * cs) * tau;
+  g[2] = f * t2;
+  return f;
+}
+
 template <int KIND, int QT, int D>
 __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
                                           const double* __restrict__ colv, int r, int c,
@@ -570,8 +592,13 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
   constexpr int DS = Cfg<KIND, QT, D>::DS;
   if constexpr (Cfg<KIND, QT, D>::STAT) {
     // K = os_t f_T(tau_t) [x os_w f_W(tau_lambda)]; time-kernel constants travel in w[4]
-    double gl, ga_;
-    double k = w[0] * lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, gl, ga_);
+    double gl, ga_, k;
+    if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP) {
+      double g3[3];
+      k = w[0] * qp_factor(rowv[r] - colv[c], a, tab, g3);
+    } else {
+      k = w[0] * lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, gl, ga_);
+    }
     if constexpr (stat_wave_atom(KIND) != 0)
       k *= lam[0] * lam_factor<stat_wave_atom(KIND)>(rowv[TS + r] - colv[TS + c], lam, tab, gl, ga_);
     return k;
@@ -634,8 +661,11 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
     // raw carriers in the slots behind the (unused) mixture accumulators; constant factors
     // (outputscales, d c1 / d lengthscale) are applied once per light curve at the end
     constexpr int G0 = QT + 2 * QT * DS;
-    double glt, gat, glw = 0.0, gaw = 0.0;
-    const double ft = lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, glt, gat);
+    constexpr int GW = G0 + C::NLT;        // first wavelength-kernel slot
+    constexpr bool QP = stat_time_atom(KIND) == PGM_ATOM_QP;
+    double glt = 0.0, gat = 0.0, glw = 0.0, gaw = 0.0, g3[3] = {0.0, 0.0, 0.0}, ft;
+    if constexpr (QP) ft = qp_factor(rowv[r] - colv[c], a, tab, g3);
+    else ft = lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, glt, gat);
     double fw = 1.0, kw = 1.0;
     if constexpr (stat_wave_atom(KIND) != 0) {
       fw = lam_factor<stat_wave_atom(KIND)>(rowv[TS + r] - colv[TS + c], lam, tab, glw, gaw);
@@ -643,12 +673,18 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
     }
     const double wk = wgt * kw;
     ga[G0] += wk * ft;            // d / d outputscale_t
-    ga[G0 + 1] += wk * glt;       // d / d lengthscale_t   (x os_t x const)
+    if constexpr (QP) {
+      ga[G0 + 1] += wk * g3[0];   // d / d lambda   (x os_t x const)
+      ga[G0 + 2] += wk * g3[1];   // d / d period
+      ga[G0 + 3] += wk * g3[2];   // d / d l_rbf
+    } else {
+      ga[G0 + 1] += wk * glt;     // d / d lengthscale_t   (x os_t x const)
+    }
     if constexpr (stat_wave_atom(KIND) != 0) {
       const double wkt = wgt * (w[0] * ft);
-      ga[G0 + 2] += wkt * fw;                               // d / d outputscale_w | constant
-      if constexpr (C::NL >= 4) ga[G0 + 3] += wkt * glw;    // d / d lengthscale_w
-      if constexpr (C::NL >= 5) ga[G0 + 4] += wkt * gaw;    // d / d alpha_w
+      ga[GW] += wkt * fw;                                          // d / d outputscale_w | constant
+      if constexpr (C::NL - C::NLT >= 2) ga[GW + 1] += wkt * glw;  // d / d lengthscale_w
+      if constexpr (C::NL - C::NLT >= 3) ga[GW + 2] += wkt * gaw;  // d / d alpha_w
     }
     return;
   }
@@ -924,10 +960,18 @@ __device__ __forceinline__ void lam_setup(const double* th /* NL constrained val
 // stationary kinds: time-kernel constants into wq[4] (same {scale, c1, alpha, lengthscale}
 // layout), wavelength-kernel constants into lamq[4]
 template <int KIND>
-__device__ __forceinline__ void stat_setup(const double* th, double* wq, double* lamq) {
-  lam_setup<stat_time_atom(KIND)>(th, wq);
+__device__ __forceinline__ void stat_setup(const double* th, double* wq, double* aq, double* lamq) {
+  if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP) {
+    // th = {outputscale, lambda (periodic lengthscale), period, l_rbf}
+    wq[0] = th[0]; wq[1] = th[1]; wq[2] = th[2]; wq[3] = th[3];
+    aq[0] = 2.0 / th[1]; aq[1] = 1.0 / th[2]; aq[2] = 0.5 / (th[3] * th[3]); aq[3] = 0.0;
+  } else {
+    lam_setup<stat_time_atom(KIND)>(th, wq);
+    aq[0] = aq[1] = aq[2] = aq[3] = 0.0;
+  }
   lamq[0] = 1.0; lamq[1] = 0.0; lamq[2] = 1.0; lamq[3] = 1.0;
-  if constexpr (stat_wave_atom(KIND) != 0) lam_setup<stat_wave_atom(KIND)>(th + 2, lamq);
+  if constexpr (stat_wave_atom(KIND) != 0)
+    lam_setup<stat_wave_atom(KIND)>(th + stat_num_time(KIND), lamq);
 }
 
 // d K / d theta constant factor of slot t of the parameters behind the mixture (carriers of
@@ -939,9 +983,18 @@ __device__ __forceinline__ double lam_grad_factor(int t, const double* wq, const
            : (atom == PGM_KIND_SEP_MATERN15) ? lm[0] / lm[3] : lm[0] * 2.0 * lm[2] / lm[3];
   };
   if constexpr (KIND >= PGM_KIND_STAT_BASE) {
-    if (t == 0 || t == 2) return 1.0;
-    if (t == 1) return ell_factor(stat_time_atom(KIND), wq);
-    if (t == 3) return ell_factor(stat_wave_atom(KIND), lamq);
+    constexpr int NT = stat_num_time(KIND);
+    if (t == 0 || t == NT) return 1.0;
+    if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP) {
+      // wq = {os, lambda, p, l_r}: d f / d lambda = f s^2 2 / lambda^2,
+      // d f / d p = f sin(2 theta) tau (2 / lambda) pi / p^2,  d f / d l_r = f tau^2 / l_r^3
+      if (t == 1) return wq[0] * 2.0 / (wq[1] * wq[1]);
+      if (t == 2) return wq[0] * (2.0 / wq[1]) * M_PI / (wq[2] * wq[2]);
+      if (t == 3) return wq[0] / (wq[3] * wq[3] * wq[3]);
+    } else {
+      if (t == 1) return ell_factor(stat_time_atom(KIND), wq);
+    }
+    if (t == NT + 1) return ell_factor(stat_wave_atom(KIND), lamq);
     return lamq[0];
   } else {
     if (t == 1) return ell_factor(KIND, lamq);
@@ -1043,13 +1096,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   load_exp_tab(tab);
   __syncthreads();
   if (!C::STAT && tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
-  if (tid < QT * DS) {
+  if (!C::STAT && tid < QT * DS) {
     const int q = tid / DS, dd = tid - q * DS;
     const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
     aq[q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
   if (tid == 32) {
-    if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, lamq);
+    if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, aq, lamq);
     else lam_setup<KIND>(theta + o_lam, lamq);
   }
   const double mean = theta[0];
@@ -1532,13 +1585,13 @@ __global__ void __launch_bounds__(NTHREADS)
   load_exp_tab(tab);
   __syncthreads();
   if (!C::STAT && tid < QT) wq[tid] = (tid < Q) ? theta[1 + tid] : 0.0;
-  if (tid < QT * DS) {
+  if (!C::STAT && tid < QT * DS) {
     const int q = tid / DS, dd = tid - q * DS;
     const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
     aq[q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
   }
   if (tid == 32) {
-    if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, lamq);
+    if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, aq, lamq);
     else lam_setup<KIND>(theta + o_lam, lamq);
   }
   const double* xb = A.x + (size_t)b * A.n_max * D;

@@ -183,13 +183,14 @@ __global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
       w.par[LG_PAR_JC + tid] = jac[tid];
     }
     if (!C::STAT && tid < QT) w.par[LG_PAR_WQ + tid] = (tid < Q) ? theta[1 + tid] : 0.0;
-    if (tid < QT * DS) {
+    if (!C::STAT && tid < QT * DS) {
       const int q = tid / DS, dd = tid - q * DS;
       const double sg = (q < Q) ? theta[1 + Q + Q * DS + q * DS + dd] : 0.0;
       w.par[LG_PAR_AQ + q * DS + dd] = 2.0 * M_PI * M_PI * sg * sg;
     }
     if (tid == 32) {
-      if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, w.par + LG_PAR_WQ, w.par + LG_PAR_LM);
+      if constexpr (C::STAT)
+        stat_setup<KIND>(theta + o_lam, w.par + LG_PAR_WQ, w.par + LG_PAR_AQ, w.par + LG_PAR_LM);
       else lam_setup<KIND>(theta + o_lam, w.par + LG_PAR_LM);
     }
   }

@@ -281,6 +281,20 @@ class RBFKernel(_ParamKernel):
                            lambda self, v: self.initialize(lengthscale=v))
 
 
+class PeriodicKernel(RBFKernel):
+    """gpytorch.kernels.PeriodicKernel: exp(-2 sin^2(pi tau / p) / lengthscale);
+    raw_lengthscale [1, 1] and raw_period_length [1, 1], both Positive."""
+    lam_kind = "periodic"
+
+    def __init__(self):
+        super().__init__()
+        self.register_parameter("raw_period_length", nn.Parameter(torch.zeros(1, 1)))
+        self.register_constraint("raw_period_length", Positive())
+
+    period_length = property(lambda self: self._constrained("raw_period_length"),
+                             lambda self, v: self.initialize(period_length=v))
+
+
 class MaternKernel(RBFKernel):
     """gpytorch.kernels.MaternKernel; only nu = 1.5 is on the accelerated path."""
     lam_kind = "matern"
@@ -474,9 +488,19 @@ class TwoDSpectralMixtureDustMeanGPModel(TwoDSpectralMixtureGPModel):
         self.mean_module = DustMean()
 
 
-def _build_time_kernel(time_kernel_type, num_mixtures):
-    """pgmuvi/gps.py:938-1007: 'matern' (the reference's default), 'rbf', 'spectral_mixture' /
-    'sm'; 'quasi_periodic' and the flicker term are outside the accelerated path."""
+def _make_qp_kernel(period):
+    """pgmuvi/gps.py:915-935: ScaleKernel(PeriodicKernel * RBFKernel), period_length = period,
+    RBF lengthscale = 5 x period (long-term decay)."""
+    periodic_k = PeriodicKernel()
+    periodic_k.period_length = period
+    rbf_k = RBFKernel()
+    rbf_k.lengthscale = period * 5.0
+    return ScaleKernel(ProductKernel(periodic_k, rbf_k))
+
+
+def _build_time_kernel(time_kernel_type, num_mixtures, period=None):
+    """pgmuvi/gps.py:938-1007: 'matern' (the reference's default), 'rbf', 'quasi_periodic',
+    'spectral_mixture' / 'sm'; the flicker term is outside the accelerated path."""
     if isinstance(time_kernel_type, nn.Module):
         return time_kernel_type
     if time_kernel_type in ("spectral_mixture", "sm"):
@@ -486,8 +510,7 @@ def _build_time_kernel(time_kernel_type, num_mixtures):
     if time_kernel_type == "rbf":
         return ScaleKernel(RBFKernel())
     if time_kernel_type == "quasi_periodic":
-        raise NotImplementedError("time_kernel_type 'quasi_periodic' is outside the accelerated "
-                                  "path (no periodic kernel kind yet)")
+        return _make_qp_kernel(period)
     raise ValueError(
         f"Unknown time_kernel_type '{time_kernel_type}'. Choose from 'quasi_periodic', 'matern', "
         "'rbf', 'spectral_mixture'/'sm', or supply a kernel instance.")
@@ -558,14 +581,40 @@ class MaternGPModel(ExactGP):
         return PriorOutput(self, x)
 
 
+class QuasiPeriodicGPModel(ExactGP):
+    """pgmuvi/gps.py:1075-1129 ('1DQuasiPeriodic'): ConstantMean + ScaleKernel(Periodic * RBF),
+    period defaults to span / 2."""
+
+    def __init__(self, train_x, train_y, likelihood, period=None, **kwargs):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean()
+        if period is None:
+            period = float(train_x.max() - train_x.min()) / 2.0
+        self.covar_module = _make_qp_kernel(period)
+        self.sci_kernel = self.covar_module
+
+    def forward(self, x):
+        return PriorOutput(self, x)
+
+
+class LinearMeanQuasiPeriodicGPModel(QuasiPeriodicGPModel):
+    """pgmuvi/gps.py:1239-1271 ('1DLinearQuasiPeriodic'): LinearMean(1) + the same kernel."""
+
+    def __init__(self, train_x, train_y, likelihood, period=None, **kwargs):
+        super().__init__(train_x, train_y, likelihood, period=period, **kwargs)
+        self.mean_module = LinearMean(input_size=1)
+
+
 class AchromaticGPModel(SeparableGPModel):
     """pgmuvi/gps.py:1345-1423: ConstantKernel in wavelength (all bands share the temporal
     variability)."""
 
     def __init__(self, train_x, train_y, likelihood, time_kernel_type="sm", period=None,
                  num_mixtures=4, mean_module=None, **kwargs):
+        if period is None:      # gps.py:1410-1412
+            period = float(train_x[:, 0].max() - train_x[:, 0].min()) / 2.0
         super().__init__(train_x, train_y, likelihood,
-                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures),
+                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures, period),
                          wavelength_kernel=ConstantKernel())
 
 
@@ -583,8 +632,10 @@ class WavelengthDependentGPModel(SeparableGPModel):
             wavelength_lengthscale = max(wl_span / 2.0, 1.0)       # gps.py:1576-1578
         if add_flicker:
             raise NotImplementedError("add_flicker is outside the accelerated path")
+        if period is None:      # gps.py:1581-1583
+            period = float(train_x[:, 0].max() - train_x[:, 0].min()) / 2.0
         super().__init__(train_x, train_y, likelihood,
-                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures),
+                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures, period),
                          wavelength_kernel=_build_wavelength_kernel(
                              wavelength_kernel_type, wavelength_lengthscale,
                              scaling=wavelength_scaling),

@@ -30,8 +30,9 @@ _SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPMod
               "2DSeparable": gp.SeparableGPModel, "2DAchromatic": gp.AchromaticGPModel,
               "2DWavelengthDependent": gp.WavelengthDependentGPModel,
               "2DDustMean": gp.DustMeanGPModel, "2DPowerLawMean": gp.PowerLawMeanGPModel,
-              "1DMatern": gp.MaternGPModel}
-_NO_MIXTURE_MODELS = ("1DMatern",)
+              "1DMatern": gp.MaternGPModel, "1DQuasiPeriodic": gp.QuasiPeriodicGPModel,
+              "1DLinearQuasiPeriodic": gp.LinearMeanQuasiPeriodicGPModel}
+_NO_MIXTURE_MODELS = ("1DMatern", "1DQuasiPeriodic", "1DLinearQuasiPeriodic")
 CONSTRAINT_SETS = {"LPV": {"period": {"lower": (20.0, True), "upper": (None, False)}}}
 
 
@@ -202,7 +203,7 @@ class Lightcurve(torch.nn.Module):
         if isinstance(model, torch.nn.Module):
             self.model = model
         elif model in _SM_MODELS:
-            if model in ("1D", "1DLinear", "1DMatern") and self.ndim > 1:
+            if model.startswith("1D") and self.ndim > 1:
                 raise ValueError("You have selected a 1D model but your data has more than one "
                                  "input dimension; use model='2D'.")   # tests/test_2d_integration.py:167-186
             if model.startswith("2D") and self.ndim != 2:

@@ -86,6 +86,17 @@ def _scaled_atom(k):
         return None
     base = k.base_kernel
     bname = type(base).__name__
+    sub = getattr(base, "kernels", None)
+    if sub is not None:
+        # quasi-periodic: ScaleKernel(ProductKernel(PeriodicKernel, RBFKernel)), gps.py:915-935
+        if (len(sub) == 2 and hasattr(sub[0], "raw_period_length")
+                and hasattr(sub[1], "raw_lengthscale") and "RBF" in type(sub[1]).__name__):
+            return (5, [k.raw_outputscale, sub[0].raw_lengthscale, sub[0].raw_period_length,
+                        sub[1].raw_lengthscale],
+                    [_constraint(k, "raw_outputscale"), _constraint(sub[0], "raw_lengthscale"),
+                     _constraint(sub[0], "raw_period_length"),
+                     _constraint(sub[1], "raw_lengthscale")])
+        return None
     if not hasattr(base, "raw_lengthscale") or hasattr(base, "raw_period_length"):
         return None
     params = [k.raw_outputscale, base.raw_lengthscale]
@@ -107,17 +118,17 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
     factors = getattr(cov, "kernels", None)
     tk = cov if factors is None else factors[0]
     ta = _scaled_atom(tk)
-    if ta is None or ta[0] not in (1, 2):
+    if ta is None or ta[0] not in (1, 2, 5):
         return None
     wk_code, wparams, wcons = 0, [], []
     if factors is not None:
         if len(factors) != 2:
             return None
         wa = _scaled_atom(factors[1])
-        if wa is None:
+        if wa is None or wa[0] == 5:
             return None
         wk_code, wparams, wcons = wa
-    kind = stat_kind(ta[0] - 1, wk_code)
+    kind = stat_kind({1: 0, 2: 1, 5: 2}[ta[0]], wk_code)
     d = 1 if wk_code == 0 else 2
     ref = ta[1][0]
     slot0 = (torch.zeros(1, dtype=ref.dtype, device=ref.device) if external_mean

@@ -266,7 +266,7 @@ def make_batch_stat(B, kind, n=None, n_bands=None, n_per_band=None, learn_noise=
     light curves.  kind = 8 + 5 * TK + WK, Q = 0; packed [mean | (noise) | os_t, l_t | wavelength
     parameters]; GPyTorch's default Positive constraints, mean / learned noise Interval."""
     from ._lib import KIND_STAT_BASE, stat_num_lam
-    wk = (kind - KIND_STAT_BASE) % 5
+    tk, wk = divmod(kind - KIND_STAT_BASE, 5)
     d = 1 if wk == 0 else 2
     NL = stat_num_lam(kind)
     P = 1 + (1 if learn_noise else 0) + NL
@@ -297,7 +297,11 @@ def make_batch_stat(B, kind, n=None, n_bands=None, n_per_band=None, learn_noise=
         lb[b, 0], ub[b, 0] = float(yy.min()), float(yy.max())
         if learn_noise:
             lb[b, o_noise], ub[b, o_noise] = min(1e-4, float(yerr.min()) / 10.0), float(np.std(yy, ddof=1))
-        lamv = [rng.uniform(0.5, 1.5), rng.uniform(0.03, 0.2)]       # os_t, l_t (x in [0, 1])
+        if tk == 2:    # quasi-periodic: os, lambda (periodic lengthscale), period, l_rbf
+            lamv = [rng.uniform(0.5, 1.5), rng.uniform(0.5, 2.0), rng.uniform(0.08, 0.3),
+                    rng.uniform(0.3, 1.0)]
+        else:
+            lamv = [rng.uniform(0.5, 1.5), rng.uniform(0.03, 0.2)]   # os_t, l_t (x in [0, 1])
         if wk in (1, 2, 3):
             lamv += [rng.uniform(0.6, 1.5), rng.uniform(0.3, 1.2)]   # os_w, l_w
         if wk == 3:

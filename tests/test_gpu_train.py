@@ -132,7 +132,9 @@ def _lc_2d(seed=5, n_per=40, **kw):
                                       ("2DAchromatic", dict(time_kernel_type="matern")),
                                       ("2DWavelengthDependent", dict(time_kernel_type="rbf",
                                                                      wavelength_kernel_type="rq")),
-                                      ("1DMatern", {})])
+                                      ("1DMatern", {}), ("1DQuasiPeriodic", dict(period=57.0)),
+                                      ("2DAchromatic", dict(time_kernel_type="quasi_periodic",
+                                                            period=83.0))])
 def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
     """time kernel x wavelength kernel through Lightcurve -> train (seam #1) against the oracle's
     restatement of the same loop, and the loss goes down (tests/test_2d_integration.py:112-135)."""
@@ -144,7 +146,8 @@ def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
         from pgmuvi_b200 import gp
         kw["time_kernel"] = gp.SpectralMixtureKernel(num_mixtures=2, ard_num_dims=1)
     lc = (_lc(n=140, seed=4) if model.startswith("1D") else _lc_2d()).double()
-    lc.set_model(model, **({} if model == "1DMatern" else {"num_mixtures": 2}), **kw)
+    lc.set_model(model, **({} if model in ("1DMatern", "1DQuasiPeriodic")
+                           else {"num_mixtures": 2}), **kw)
     lc.double()
     lc.set_default_constraints()
     tk = lc.model.covar_module.kernels[0] if hasattr(lc.model.covar_module, "kernels") else None
@@ -152,10 +155,16 @@ def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
         # hypers in the min-max-scaled units of the time axis (span ~400 d)
         lc.model.initialize(**{"covar_module.kernels.0.mixture_means": torch.tensor([4.8, 9.7]),
                                "covar_module.kernels.0.mixture_scales": torch.tensor([1.5, 1.0])})
-    elif tk is not None:
-        tk.base_kernel.lengthscale = 0.08        # min-max-scaled time, period ~0.2
     else:
-        lc.model.covar_module.base_kernel.lengthscale = 0.05
+        tk = tk if tk is not None else lc.model.covar_module
+        if hasattr(tk.base_kernel, "kernels"):   # quasi-periodic: period given in raw days
+            span = float(lc._xdata_raw.reshape(len(lc._ydata_raw), -1)[:, 0].max()
+                         - lc._xdata_raw.reshape(len(lc._ydata_raw), -1)[:, 0].min())
+            per = float(tk.base_kernel.kernels[0].period_length) / span
+            tk.base_kernel.kernels[0].period_length = per       # min-max-scaled time axis
+            tk.base_kernel.kernels[1].lengthscale = 5.0 * per
+        else:
+            tk.base_kernel.lengthscale = 0.08    # min-max-scaled time, period ~0.2
     args, pk = _oracle_inputs(lc)
     assert pk.kind >= 3
     ref = train_loop(*args, maxiter=5, miniter=5, stop=None, lr=0.05, optim="AdamW")

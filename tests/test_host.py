@@ -158,7 +158,7 @@ def test_2d_constraints_and_dimension_checks():
     pk = pack_model(lc.model)
     assert (pk.kind, pk.Q, pk.d, pk.P) == (1, 3, 2, 1 + 3 + 12)
     with pytest.raises(UnsupportedModel):
-        lc.set_model("1DQuasiPeriodic")          # time kernels other than the SM: outside the path
+        lc.set_model("1DPeriodicStochastic")     # additive kernels: outside the path
     lc.set_model("2DLinear", num_mixtures=3)     # non-constant means stay on the host
     pk = pack_model(lc.model)
     assert pk.external_mean and pk.P == 1 + 3 + 12 and int(pk.kinds[0]) == 0
@@ -201,8 +201,15 @@ def test_separable_models_pack_onto_the_separable_kinds():
     assert (pk.kind, pk.P, pk.learn_noise) == (6, 1 + 6 + 1 + 1, True)
     assert pk.names[-2:] == ["likelihood.noise_covar.raw_noise",
                              "covar_module.kernels.1.raw_constant"]
-    with pytest.raises(NotImplementedError):
-        lc.set_model("2DAchromatic", time_kernel_type="quasi_periodic")
+    with pytest.raises(ValueError):
+        lc.set_model("2DAchromatic", time_kernel_type="nonsense")
+    lc.set_model("2DAchromatic", time_kernel_type="quasi_periodic")   # gps.py:915-935
+    pk = pack_model(lc.model)
+    assert (pk.kind, pk.Q, pk.P) == (8 + 5 * 2 + 4, 0, 1 + 1 + 4 + 1)
+    assert pk.names[2:6] == ["covar_module.kernels.0.raw_outputscale",
+                             "covar_module.kernels.0.base_kernel.kernels.0.raw_lengthscale",
+                             "covar_module.kernels.0.base_kernel.kernels.0.raw_period_length",
+                             "covar_module.kernels.0.base_kernel.kernels.1.raw_lengthscale"]
     # stationary time kernels (N3): the reference's default Matern time kernel packs onto the
     # kinds 8 + 5 TK + WK with no mixtures
     lc.set_model("2DAchromatic", time_kernel_type="matern")
