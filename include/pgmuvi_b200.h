@@ -54,6 +54,8 @@ extern "C" {
  *   tk 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(nu=1.5)),           (time)
  *      2 quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935:
  *        os exp(-2 sin^2(pi tau / p) / lambda) exp(-tau^2 / (2 l^2)), slots os, lambda, p, l
+ *      3 quasi-periodic + ScaleKernel(RBFKernel) (PeriodicPlusStochasticGPModel,
+ *        gps.py:1187-1236; wk = 0 only), slots os, lambda, p, l, os2, l2
  *   wk 0 none (d = 1), 1 ScaleKernel(RBF), 2 ScaleKernel(Matern-1.5), 3 ScaleKernel(RQ),
  *      4 ConstantKernel                                                          (wavelength)
  * Pass Q = 0; packed layout [ mean | (noise) | time-kernel parameters (os_t, l_t | os, lambda,

@@ -45,6 +45,7 @@ NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST
 # WK 0 none (1-D) / 1 RBF / 2 Matern-1.5 / 3 RQ / 4 Constant in wavelength; Q = 0.
 KIND_STAT_BASE = 8
 ATOM_QP = 100      # time atom 2: quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
+ATOM_QP_RBF = 101  # time atom 3: AdditiveKernel(QP, ScaleKernel(RBFKernel)), gps.py:1187-1236 (1-D only)
 
 
 def stat_kind(tk: int, wk: int) -> int:
@@ -54,7 +55,7 @@ def stat_kind(tk: int, wk: int) -> int:
 def stat_atoms(kind: int):
     """(time atom, wavelength atom or None) as separable-kind codes."""
     tk, wk = divmod(kind - KIND_STAT_BASE, 5)
-    return ((KIND_SEP_RBF, KIND_SEP_MATERN15, ATOM_QP)[tk],
+    return ((KIND_SEP_RBF, KIND_SEP_MATERN15, ATOM_QP, ATOM_QP_RBF)[tk],
             None if wk == 0 else (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)[wk - 1])
 
 # constraint kinds (A.2) ---------------------------------------------------------------
@@ -86,7 +87,7 @@ class ModelSpec:
         wavelength kernel of the stationary kinds."""
         if self.kind >= KIND_STAT_BASE:
             ta, wl = stat_atoms(self.kind)
-            return (4 if ta == ATOM_QP else 2) + (0 if wl is None else NUM_LAM[wl])
+            return {ATOM_QP: 4, ATOM_QP_RBF: 6}.get(ta, 2) + (0 if wl is None else NUM_LAM[wl])
         return NUM_LAM.get(self.kind, 0)
 
     @property
@@ -220,7 +221,7 @@ def kernel_dense(x1, x2, theta, spec: ModelSpec):
         # kernels as the wavelength factors, acting on the time column
         lam = unpack_lam(theta, spec)
         ta, wa = stat_atoms(spec.kind)
-        if ta == ATOM_QP:
+        if ta in (ATOM_QP, ATOM_QP_RBF):
             # GPyTorch PeriodicKernel: exp(-2 sin^2(pi tau / p) / lengthscale) (the lengthscale
             # is NOT squared in gpytorch >= 1.x), times RBFKernel, inside one ScaleKernel
             nt = 4
@@ -229,6 +230,9 @@ def kernel_dense(x1, x2, theta, spec: ModelSpec):
             os_, lmb, per, ell = (ex(lam[..., k]) for k in range(4))
             K = os_ * torch.exp(-2.0 * torch.sin(math.pi * tau / per) ** 2 / lmb) \
                 * torch.exp(-0.5 * (tau / ell) ** 2)
+            if ta == ATOM_QP_RBF:       # + stochastic ScaleKernel(RBFKernel)
+                nt = 6
+                K = K + wavelength_kernel_dense(x1[..., 0], x2[..., 0], lam[..., 4:6], KIND_SEP_RBF)
         else:
             nt = 2
             K = wavelength_kernel_dense(x1[..., 0], x2[..., 0], lam[..., :2], ta)

@@ -30,6 +30,7 @@ CONFIGS = [(k, q, d) for (k, d) in ((0, 1), (1, 2), (2, 2)) for q in (1, 2, 4, 8
 CONFIGS += [(k, q, 2) for k in (3, 4, 5, 6) for q in (4, 8)]
 # stationary time kernels (N3): kind = 8 + 5 * TK + WK, TK in {RBF, Matern-1.5, quasi-periodic}, WK = 0 -> 1-D
 CONFIGS += [(8 + 5 * tk + wk, 4, 1 if wk == 0 else 2) for tk in (0, 1, 2) for wk in range(5)]
+CONFIGS += [(23, 4, 1)]   # quasi-periodic + RBF (PeriodicPlusStochasticGPModel), 1-D only
 
 
 def _nvcc():

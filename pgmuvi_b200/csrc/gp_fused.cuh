@@ -46,6 +46,7 @@ constexpr int S_ELEMS = TS * LD_S;                 // 4352
 // stationary (non-spectral-mixture) time kernels, N3: kind = 8 + 5 * TK + WK,
 //   TK: 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(1.5))      gps.py:985-990
 //       2 quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel)         gps.py:915-935
+//       3 quasi-periodic + ScaleKernel(RBFKernel) (WK = 0 only)          gps.py:1187-1236
 //   WK: 0 none (1-D model), 1 RBF, 2 Matern-1.5, 3 RQ, 4 Constant       gps.py:1045-1072
 // K = os_t f_T(tau_t) [x os_w f_W(tau_lambda)]; no mixtures (Q = 0 in the packed layout).
 #define PGM_KIND_STAT_BASE 8
@@ -221,13 +222,15 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
 // static configuration per (kernel kind, padded mixture count, input dims)
 // ------------------------------------------------------------------------------------
 // the separable-kind code whose lam_factor implements an atom of the stationary kinds
-#define PGM_ATOM_QP 100   // ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
+#define PGM_ATOM_QP 100      // ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
+#define PGM_ATOM_QP_RBF 101  // AdditiveKernel(QP, ScaleKernel(RBFKernel)), gps.py:1187-1236 (1-D)
 __host__ __device__ constexpr int stat_time_atom(int kind) {
   return ((kind - PGM_KIND_STAT_BASE) / 5 == 0) ? PGM_KIND_SEP_RBF
-         : ((kind - PGM_KIND_STAT_BASE) / 5 == 1) ? PGM_KIND_SEP_MATERN15 : PGM_ATOM_QP;
+         : ((kind - PGM_KIND_STAT_BASE) / 5 == 1) ? PGM_KIND_SEP_MATERN15
+         : ((kind - PGM_KIND_STAT_BASE) / 5 == 2) ? PGM_ATOM_QP : PGM_ATOM_QP_RBF;
 }
 __host__ __device__ constexpr int stat_num_time(int kind) {   // time-kernel parameters
-  return stat_time_atom(kind) == PGM_ATOM_QP ? 4 : 2;
+  return stat_time_atom(kind) == PGM_ATOM_QP ? 4 : stat_time_atom(kind) == PGM_ATOM_QP_RBF ? 6 : 2;
 }
 __host__ __device__ constexpr int stat_wave_atom(int kind) {   // 0 = no wavelength factor
   return ((kind - PGM_KIND_STAT_BASE) % 5 == 0) ? 0
@@ -596,6 +599,12 @@ __device__ __forceinline__ double k_entry(const double* __restrict__ rowv,
     if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP) {
       double g3[3];
       k = w[0] * qp_factor(rowv[r] - colv[c], a, tab, g3);
+    } else if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP_RBF) {
+      // additive: the stochastic ScaleKernel(RBF) term travels in lam[] (no wavelength kernel)
+      double g3[3];
+      const double tt = rowv[r] - colv[c];
+      k = w[0] * qp_factor(tt, a, tab, g3)
+          + lam[0] * lam_factor<PGM_KIND_SEP_RBF>(tt, lam, tab, gl, ga_);
     } else {
       k = w[0] * lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, gl, ga_);
     }
@@ -662,8 +671,22 @@ __device__ __forceinline__ void k_grad_entry(const double* __restrict__ rowv,
     // (outputscales, d c1 / d lengthscale) are applied once per light curve at the end
     constexpr int G0 = QT + 2 * QT * DS;
     constexpr int GW = G0 + C::NLT;        // first wavelength-kernel slot
-    constexpr bool QP = stat_time_atom(KIND) == PGM_ATOM_QP;
+    constexpr bool QP = stat_time_atom(KIND) == PGM_ATOM_QP ||
+                        stat_time_atom(KIND) == PGM_ATOM_QP_RBF;
     double glt = 0.0, gat = 0.0, glw = 0.0, gaw = 0.0, g3[3] = {0.0, 0.0, 0.0}, ft;
+    if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP_RBF) {
+      // K = os qp + os2 rbf: six independent slots, nothing else multiplies them
+      const double tt = rowv[r] - colv[c];
+      ft = qp_factor(tt, a, tab, g3);
+      const double fr = lam_factor<PGM_KIND_SEP_RBF>(tt, lam, tab, glt, gat);
+      ga[G0] += wgt * ft;
+      ga[G0 + 1] += wgt * g3[0];
+      ga[G0 + 2] += wgt * g3[1];
+      ga[G0 + 3] += wgt * g3[2];
+      ga[G0 + 4] += wgt * fr;       // d / d outputscale_2
+      ga[G0 + 5] += wgt * glt;      // d / d lengthscale_2  (x os_2 / l^3)
+      return;
+    }
     if constexpr (QP) ft = qp_factor(rowv[r] - colv[c], a, tab, g3);
     else ft = lam_factor<stat_time_atom(KIND)>(rowv[r] - colv[c], w, tab, glt, gat);
     double fw = 1.0, kw = 1.0;
@@ -961,7 +984,7 @@ __device__ __forceinline__ void lam_setup(const double* th /* NL constrained val
 // layout), wavelength-kernel constants into lamq[4]
 template <int KIND>
 __device__ __forceinline__ void stat_setup(const double* th, double* wq, double* aq, double* lamq) {
-  if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP) {
+  if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP || stat_time_atom(KIND) == PGM_ATOM_QP_RBF) {
     // th = {outputscale, lambda (periodic lengthscale), period, l_rbf}
     wq[0] = th[0]; wq[1] = th[1]; wq[2] = th[2]; wq[3] = th[3];
     aq[0] = 2.0 / th[1]; aq[1] = 1.0 / th[2]; aq[2] = 0.5 / (th[3] * th[3]); aq[3] = 0.0;
@@ -970,6 +993,7 @@ __device__ __forceinline__ void stat_setup(const double* th, double* wq, double*
     aq[0] = aq[1] = aq[2] = aq[3] = 0.0;
   }
   lamq[0] = 1.0; lamq[1] = 0.0; lamq[2] = 1.0; lamq[3] = 1.0;
+  if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP_RBF) lam_setup<PGM_KIND_SEP_RBF>(th + 4, lamq);
   if constexpr (stat_wave_atom(KIND) != 0)
     lam_setup<stat_wave_atom(KIND)>(th + stat_num_time(KIND), lamq);
 }
@@ -985,7 +1009,11 @@ __device__ __forceinline__ double lam_grad_factor(int t, const double* wq, const
   if constexpr (KIND >= PGM_KIND_STAT_BASE) {
     constexpr int NT = stat_num_time(KIND);
     if (t == 0 || t == NT) return 1.0;
-    if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP) {
+    if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP_RBF) {
+      if (t == 4) return 1.0;
+      if (t == 5) return ell_factor(PGM_KIND_SEP_RBF, lamq);
+    }
+    if constexpr (stat_time_atom(KIND) == PGM_ATOM_QP || stat_time_atom(KIND) == PGM_ATOM_QP_RBF) {
       // wq = {os, lambda, p, l_r}: d f / d lambda = f s^2 2 / lambda^2,
       // d f / d p = f sin(2 theta) tau (2 / lambda) pi / p^2,  d f / d l_r = f tau^2 / l_r^3
       if (t == 1) return wq[0] * 2.0 / (wq[1] * wq[1]);

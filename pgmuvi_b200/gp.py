@@ -347,6 +347,14 @@ class ProductKernel(_ParamKernel):
         self.kernels = nn.ModuleList(kernels)
 
 
+class AdditiveKernel(_ParamKernel):
+    """gpytorch.kernels.AdditiveKernel: parameters live under ``kernels.0`` / ``kernels.1``."""
+
+    def __init__(self, *kernels):
+        super().__init__()
+        self.kernels = nn.ModuleList(kernels)
+
+
 SpectralMixtureKernel.__mul__ = lambda self, other: ProductKernel(self, other)
 
 
@@ -591,6 +599,24 @@ class QuasiPeriodicGPModel(ExactGP):
         if period is None:
             period = float(train_x.max() - train_x.min()) / 2.0
         self.covar_module = _make_qp_kernel(period)
+        self.sci_kernel = self.covar_module
+
+    def forward(self, x):
+        return PriorOutput(self, x)
+
+
+class PeriodicPlusStochasticGPModel(ExactGP):
+    """pgmuvi/gps.py:1187-1236 ('1DPeriodicStochastic'): ConstantMean + AdditiveKernel(quasi-
+    periodic, ScaleKernel(RBFKernel)) with the stochastic lengthscale initialised to the period."""
+
+    def __init__(self, train_x, train_y, likelihood, period=None, **kwargs):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean()
+        if period is None:
+            period = float(train_x.max() - train_x.min()) / 2.0
+        rbf_stochastic = ScaleKernel(RBFKernel())
+        rbf_stochastic.base_kernel.lengthscale = period
+        self.covar_module = AdditiveKernel(_make_qp_kernel(period), rbf_stochastic)
         self.sci_kernel = self.covar_module
 
     def forward(self, x):

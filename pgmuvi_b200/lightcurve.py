@@ -31,8 +31,10 @@ _SM_MODELS = {"1D": gp.SpectralMixtureGPModel, "2D": gp.TwoDSpectralMixtureGPMod
               "2DWavelengthDependent": gp.WavelengthDependentGPModel,
               "2DDustMean": gp.DustMeanGPModel, "2DPowerLawMean": gp.PowerLawMeanGPModel,
               "1DMatern": gp.MaternGPModel, "1DQuasiPeriodic": gp.QuasiPeriodicGPModel,
-              "1DLinearQuasiPeriodic": gp.LinearMeanQuasiPeriodicGPModel}
-_NO_MIXTURE_MODELS = ("1DMatern", "1DQuasiPeriodic", "1DLinearQuasiPeriodic")
+              "1DLinearQuasiPeriodic": gp.LinearMeanQuasiPeriodicGPModel,
+              "1DPeriodicStochastic": gp.PeriodicPlusStochasticGPModel}
+_NO_MIXTURE_MODELS = ("1DMatern", "1DQuasiPeriodic", "1DLinearQuasiPeriodic",
+                      "1DPeriodicStochastic")
 CONSTRAINT_SETS = {"LPV": {"period": {"lower": (20.0, True), "upper": (None, False)}}}
 
 

@@ -116,9 +116,19 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
     """N3: covar_module = ScaleKernel(RBF | Matern-1.5) [* wavelength kernel] (gps.py:985-990,
     1131-1184, 1316-1336) -> kinds 8 + 5 TK + WK, layout [mean | (noise) | os_t, l_t | wavelength]."""
     factors = getattr(cov, "kernels", None)
-    tk = cov if factors is None else factors[0]
-    ta = _scaled_atom(tk)
-    if ta is None or ta[0] not in (1, 2, 5):
+    if factors is not None and "Additive" in type(cov).__name__:
+        # AdditiveKernel(quasi-periodic, ScaleKernel(RBF)): PeriodicPlusStochasticGPModel
+        if len(factors) != 2:
+            return None
+        qa, ra = _scaled_atom(factors[0]), _scaled_atom(factors[1])
+        if qa is None or ra is None or qa[0] != 5 or ra[0] != 1:
+            return None
+        ta = (6, qa[1] + ra[1], qa[2] + ra[2])
+        factors = None
+    else:
+        tk = cov if factors is None else factors[0]
+        ta = _scaled_atom(tk)
+    if ta is None or ta[0] not in (1, 2, 5, 6):
         return None
     wk_code, wparams, wcons = 0, [], []
     if factors is not None:
@@ -128,7 +138,7 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
         if wa is None or wa[0] == 5:
             return None
         wk_code, wparams, wcons = wa
-    kind = stat_kind({1: 0, 2: 1, 5: 2}[ta[0]], wk_code)
+    kind = stat_kind({1: 0, 2: 1, 5: 2, 6: 3}[ta[0]], wk_code)
     d = 1 if wk_code == 0 else 2
     ref = ta[1][0]
     slot0 = (torch.zeros(1, dtype=ref.dtype, device=ref.device) if external_mean

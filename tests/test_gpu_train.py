@@ -133,6 +133,7 @@ def _lc_2d(seed=5, n_per=40, **kw):
                                       ("2DWavelengthDependent", dict(time_kernel_type="rbf",
                                                                      wavelength_kernel_type="rq")),
                                       ("1DMatern", {}), ("1DQuasiPeriodic", dict(period=57.0)),
+                                      ("1DPeriodicStochastic", dict(period=57.0)),
                                       ("2DAchromatic", dict(time_kernel_type="quasi_periodic",
                                                             period=83.0))])
 def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
@@ -146,25 +147,30 @@ def test_separable_models_train_like_the_oracle(cuda_device, model, kw):
         from pgmuvi_b200 import gp
         kw["time_kernel"] = gp.SpectralMixtureKernel(num_mixtures=2, ard_num_dims=1)
     lc = (_lc(n=140, seed=4) if model.startswith("1D") else _lc_2d()).double()
-    lc.set_model(model, **({} if model in ("1DMatern", "1DQuasiPeriodic")
-                           else {"num_mixtures": 2}), **kw)
+    lc.set_model(model, **({} if model.startswith("1D") else {"num_mixtures": 2}), **kw)
     lc.double()
     lc.set_default_constraints()
-    tk = lc.model.covar_module.kernels[0] if hasattr(lc.model.covar_module, "kernels") else None
-    if tk is not None and hasattr(tk, "raw_mixture_means"):
+    cm = lc.model.covar_module
+    extra = None
+    if "Additive" in type(cm).__name__:          # quasi-periodic + stochastic RBF (1-D)
+        tk, extra = cm.kernels[0], cm.kernels[1]
+    elif hasattr(cm, "kernels"):
+        tk = cm.kernels[0]
+    else:
+        tk = cm
+    if hasattr(tk, "raw_mixture_means"):
         # hypers in the min-max-scaled units of the time axis (span ~400 d)
         lc.model.initialize(**{"covar_module.kernels.0.mixture_means": torch.tensor([4.8, 9.7]),
                                "covar_module.kernels.0.mixture_scales": torch.tensor([1.5, 1.0])})
+    elif hasattr(tk.base_kernel, "kernels"):     # quasi-periodic: period given in raw days
+        xr = lc._xdata_raw.reshape(len(lc._ydata_raw), -1)[:, 0]
+        per = float(tk.base_kernel.kernels[0].period_length.detach()) / float(xr.max() - xr.min())
+        tk.base_kernel.kernels[0].period_length = per       # min-max-scaled time axis
+        tk.base_kernel.kernels[1].lengthscale = 5.0 * per
+        if extra is not None:
+            extra.base_kernel.lengthscale = 0.04
     else:
-        tk = tk if tk is not None else lc.model.covar_module
-        if hasattr(tk.base_kernel, "kernels"):   # quasi-periodic: period given in raw days
-            span = float(lc._xdata_raw.reshape(len(lc._ydata_raw), -1)[:, 0].max()
-                         - lc._xdata_raw.reshape(len(lc._ydata_raw), -1)[:, 0].min())
-            per = float(tk.base_kernel.kernels[0].period_length) / span
-            tk.base_kernel.kernels[0].period_length = per       # min-max-scaled time axis
-            tk.base_kernel.kernels[1].lengthscale = 5.0 * per
-        else:
-            tk.base_kernel.lengthscale = 0.08    # min-max-scaled time, period ~0.2
+        tk.base_kernel.lengthscale = 0.08        # min-max-scaled time, period ~0.2
     args, pk = _oracle_inputs(lc)
     assert pk.kind >= 3
     ref = train_loop(*args, maxiter=5, miniter=5, stop=None, lr=0.05, optim="AdamW")

@@ -158,7 +158,7 @@ def test_2d_constraints_and_dimension_checks():
     pk = pack_model(lc.model)
     assert (pk.kind, pk.Q, pk.d, pk.P) == (1, 3, 2, 1 + 3 + 12)
     with pytest.raises(UnsupportedModel):
-        lc.set_model("1DPeriodicStochastic")     # additive kernels: outside the path
+        lc.set_model("1DSKI")                    # approximate (KISS-GP) models: outside the path
     lc.set_model("2DLinear", num_mixtures=3)     # non-constant means stay on the host
     pk = pack_model(lc.model)
     assert pk.external_mean and pk.P == 1 + 3 + 12 and int(pk.kinds[0]) == 0
