@@ -266,6 +266,22 @@ int pgm_ls_peaks_f64(const double* power, const int32_t* nf, int B, int nf_max, 
                      int num_peaks, int32_t* peak_idx, double* peak_power, void* scratch,
                      size_t scratch_bytes, void* stream);
 
+/*
+ * N4 (first stage) - PSD period summary for whole batches: the summed spectral-mixture PSD
+ *   PSD(f) = sum_q w_q exp(-0.5 ((f - mu_q) / sigma_q)^2)   on   logspace(log10 fmin, log10 fmax, n_grid)
+ * and its dominant peak = highest local maximum, else the arg-max (the first stage of
+ * Lightcurve.get_period_summary, pgmuvi/lightcurve.py:6537-6578, 7474-7482, 7900-7940; the
+ * grid expansion, basin-mass intervals and LSP flags that follow are host post-processing and
+ * not part of this call).  freq / fscale / weight [B, Q] are the component frequencies, scales
+ * and weights in raw data units (Lightcurve._extract_sm_params, :6397-6535).
+ *   grid [B, n_grid] or NULL, psd [B, n_grid] (required), dom_idx / dom_freq / dom_height /
+ *   n_peaks [B] outputs.
+ */
+int pgm_sm_psd_peak_f64(const double* freq, const double* fscale, const double* weight,
+                        const double* fmin, const double* fmax, int B, int Q, int n_grid,
+                        double* grid, double* psd, int32_t* dom_idx, double* dom_freq,
+                        double* dom_height, int32_t* n_peaks, void* stream);
+
 /* Device yardsticks used by bench.py for the self-measured FP64 roofline: runs `iters`
  * dependent-free FP64 DMMA (kind 0), FP64 DFMA (kind 1), FP32 FFMA (kind 2) or interleaved
  * DMMA+DFMA (kind 3, equal flops each) instructions per thread on every SM and returns the

@@ -47,6 +47,7 @@ EXPORTS = (
     "pgm_f32_staging_bytes", "pgm_sm_mll_grad_f32", "pgm_sm_fit_f32",
     "pgm_lombscargle_f64", "pgm_ls_peaks_f64",
     "pgm_sm_mll_grad_alpha_f64", "pgm_sm_mll_grad_staged_alpha_f64",
+    "pgm_sm_psd_peak_f64",
 )
 
 _lib = None
@@ -113,6 +114,9 @@ def load():
                                               c_int, c_int, c_int, dp, dp, dp, ip, vp, c_size_t, vp]
     lib.pgm_sm_mll_grad_staged_alpha_f64.restype = c_int
     lib.pgm_sm_mll_grad_staged_alpha_f64.argtypes = lib.pgm_sm_mll_grad_alpha_f64.argtypes
+    lib.pgm_sm_psd_peak_f64.restype = c_int
+    lib.pgm_sm_psd_peak_f64.argtypes = [dp, dp, dp, dp, dp, c_int, c_int, c_int, dp, dp, ip, dp, dp,
+                                        ip, vp]
     lib.pgm_peak_probe.restype = c_int
     lib.pgm_peak_probe.argtypes = [c_int, c_int, POINTER(c_double), vp]
     _lib = lib

@@ -190,8 +190,10 @@ def fit_batch(lightcurves, model="1D", likelihood=None, num_mixtures=None, perio
 
     ``periods``: None, one sequence for all light curves, or one sequence per light curve.
     ``use_mls_init``: seed 1-D models from the batched GPU periodogram (one launch for all).
-    Returns ``dict(loss [iters, B], raw [B, P], n_iter [B], info [B], periods [B, Q],
-    weights [B, Q])`` (host tensors / arrays, all B light curves on every rank)."""
+    Returns ``dict(loss [iters, B], raw [B, P], n_iter [B], info [B])`` plus, for spectral-
+    mixture models, ``periods`` / ``weights`` [B, Q] (component values, ``get_periods``) and
+    ``dominant_period`` [B] (highest peak of the summed PSD, ``get_period_summary``'s first
+    stage, one launch for the batch) - host tensors / arrays, all B light curves on every rank."""
     import torch.distributed as dist
     from .mll import engine_device, pack_model
     from .trainers import history_from_raw
@@ -320,7 +322,21 @@ def fit_batch(lightcurves, model="1D", likelihood=None, num_mixtures=None, perio
     for b, (lc, pk) in enumerate(zip(lcs, packs)):
         pk.scatter_raw_(raw_all[b])
         lc._fitted = True
-    per = np.stack([lc.get_periods()[0] for lc in lcs])
-    wts = np.stack([lc.get_periods()[1] for lc in lcs])
-    return dict(loss=loss_all, raw=raw_all, n_iter=n_iter_all, info=info_all, periods=per,
-                weights=wts)
+    out = dict(loss=loss_all, raw=raw_all, n_iter=n_iter_all, info=info_all)
+    if packs[0].Q > 0:      # spectral-mixture models: component periods + the PSD period summary
+        from .period_summary import period_summary_batch, sm_components
+        out["periods"] = np.stack([lc.get_periods()[0] for lc in lcs])
+        out["weights"] = np.stack([lc.get_periods()[1] for lc in lcs])
+        comps = [sm_components(lc) for lc in lcs]
+        spans = []
+        for lc in lcs:
+            xr = lc._xdata_raw[:, 0] if lc.ndim > 1 else lc._xdata_raw
+            spans.append(float(xr.max() - xr.min()))
+        summ = period_summary_batch(torch.stack([c[0] for c in comps]),
+                                    torch.stack([c[1] for c in comps]),
+                                    torch.stack([c[2] for c in comps]),
+                                    t_span=torch.tensor(spans, dtype=torch.float64)) \
+            if dev.type == "cuda" else None
+        if summ is not None:
+            out["dominant_period"] = summ["dominant_period"]
+    return out

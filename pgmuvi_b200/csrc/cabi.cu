@@ -535,6 +535,25 @@ int pgm_ls_peaks_f64(const double* power, const int32_t* nf, int B, int nf_max, 
   return 0;
 }
 
+int pgm_sm_psd_peak_f64(const double* freq, const double* fscale, const double* weight,
+                        const double* fmin, const double* fmax, int B, int Q, int n_grid,
+                        double* grid, double* psd, int32_t* dom_idx, double* dom_freq,
+                        double* dom_height, int32_t* n_peaks, void* stream) {
+  if (B < 0 || Q < 1 || Q > 8 || n_grid < 3) return fail("bad B / Q (1..8) / n_grid (>= 3)");
+  if (B == 0) return 0;
+  if (!freq || !fscale || !weight || !fmin || !fmax || !psd || !dom_idx || !dom_freq ||
+      !dom_height || !n_peaks)
+    return fail("null pointer argument");
+  pgm::PsdArgs A;
+  A.freq = freq; A.fscale = fscale; A.weight = weight; A.fmin = fmin; A.fmax = fmax;
+  A.B = B; A.Q = Q; A.n_grid = n_grid; A.grid = grid; A.psd = psd; A.dom_idx = dom_idx;
+  A.dom_freq = dom_freq; A.dom_height = dom_height; A.n_peaks = n_peaks;
+  pgm::sm_psd_peak_kernel<<<B, pgm::LS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(A);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("sm_psd_peak_kernel launch", e);
+  return 0;
+}
+
 }  // extern "C"
 
 // ---- FP64 yardsticks ---------------------------------------------------------------------

@@ -250,3 +250,99 @@ __global__ void __launch_bounds__(LS_THREADS) ls_peaks_kernel(LsPeakArgs A) {
 }
 
 }  // namespace pgm
+
+// ------------------------------------------------------------------------------------
+// N4 (first stage): spectral-mixture PSD of every fitted light curve on the reference's
+// log-spaced frequency grid and its dominant peak
+//   PSD(f) = sum_q w_q exp(-0.5 ((f - mu_q) / sigma_q)^2)          (lightcurve.py:6537-6578)
+//   grid   = logspace(log10 fmin, log10 fmax, n_grid)              (:7474-7482)
+//   dominant = highest local maximum (scipy.signal.find_peaks), or the arg-max when the PSD
+//   has no interior peak                                           (:7931-7940)
+// One block per light curve; the PSD row is optional output.
+// ------------------------------------------------------------------------------------
+namespace pgm {
+struct PsdArgs {
+  const double* freq;    // [B, Q] component frequencies (raw units)
+  const double* fscale;  // [B, Q] component frequency scales
+  const double* weight;  // [B, Q]
+  const double* fmin;    // [B]
+  const double* fmax;    // [B]
+  int B, Q, n_grid;
+  double* grid;          // [B, n_grid] or null
+  double* psd;           // [B, n_grid] (required: scratch + output)
+  int32_t* dom_idx;      // [B]
+  double* dom_freq;      // [B]
+  double* dom_height;    // [B]
+  int32_t* n_peaks;      // [B] number of local maxima
+};
+
+__global__ void __launch_bounds__(LS_THREADS) sm_psd_peak_kernel(PsdArgs A) {
+  __shared__ double s_mu[8], s_is[8], s_w[8];
+  __shared__ double s_val[LS_THREADS / 32];
+  __shared__ int s_idx[LS_THREADS / 32], s_cnt[LS_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < A.Q) {
+    s_mu[tid] = A.freq[(size_t)b * A.Q + tid];
+    s_is[tid] = 1.0 / A.fscale[(size_t)b * A.Q + tid];
+    s_w[tid] = A.weight[(size_t)b * A.Q + tid];
+  }
+  __syncthreads();
+  const double l0 = log10(A.fmin[b]), l1 = log10(A.fmax[b]);
+  const double step = (A.n_grid > 1) ? (l1 - l0) / (double)(A.n_grid - 1) : 0.0;
+  double* p = A.psd + (size_t)b * A.n_grid;
+  for (int k = tid; k < A.n_grid; k += LS_THREADS) {
+    // numpy.logspace: 10 ** (start + k * step), last sample pinned to the end point
+    const double f = (k == A.n_grid - 1 && A.n_grid > 1) ? pow(10.0, l1) : pow(10.0, l0 + k * step);
+    double s = 0.0;
+    for (int q = 0; q < A.Q; ++q) {
+      const double z = (f - s_mu[q]) * s_is[q];
+      s += s_w[q] * exp(-0.5 * z * z);
+    }
+    p[k] = s;
+    if (A.grid) A.grid[(size_t)b * A.n_grid + k] = f;
+  }
+  __syncthreads();
+  // highest strict local maximum (plateaus: left-edge rule is enough for a smooth PSD), the
+  // global arg-max as fall-back, and the number of local maxima
+  double best = -INFINITY, gbest = -INFINITY;
+  int bi = -1, gi = -1, cnt = 0;
+  for (int k = tid; k < A.n_grid; k += LS_THREADS) {
+    const double v = p[k];
+    if (v > gbest || (v == gbest && k < gi)) { gbest = v; gi = k; }
+    if (k > 0 && k < A.n_grid - 1 && p[k - 1] < v && v > p[k + 1]) {
+      ++cnt;
+      if (v > best || (v == best && k < bi)) { best = v; bi = k; }
+    }
+  }
+  auto merge = [](double& v, int& i, double ov, int oi) {
+    if (oi >= 0 && (i < 0 || ov > v || (ov == v && oi < i))) { v = ov; i = oi; }
+  };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    merge(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+    merge(gbest, gi, __shfl_xor_sync(0xffffffffu, gbest, o), __shfl_xor_sync(0xffffffffu, gi, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  // two rounds through shared memory: peaks first, then the global maximum
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; s_cnt[warp] = cnt; }
+  __syncthreads();
+  double fb = -INFINITY;
+  int fi = -1, fc = 0;
+  if (tid == 0)
+    for (int w8 = 0; w8 < LS_THREADS / 32; ++w8) { merge(fb, fi, s_val[w8], s_idx[w8]); fc += s_cnt[w8]; }
+  __syncthreads();
+  if (lane == 0) { s_val[warp] = gbest; s_idx[warp] = gi; }
+  __syncthreads();
+  if (tid == 0) {
+    double gb = -INFINITY;
+    int gj = -1;
+    for (int w8 = 0; w8 < LS_THREADS / 32; ++w8) merge(gb, gj, s_val[w8], s_idx[w8]);
+    const int d = fi >= 0 ? fi : gj;
+    A.dom_idx[b] = d;
+    A.dom_height[b] = p[d];
+    const double f = (d == A.n_grid - 1 && A.n_grid > 1) ? pow(10.0, l1) : pow(10.0, l0 + d * step);
+    A.dom_freq[b] = f;
+    A.n_peaks[b] = fc;
+  }
+}
+}  // namespace pgm

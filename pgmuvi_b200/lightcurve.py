@@ -341,6 +341,27 @@ class Lightcurve(torch.nn.Module):
         scales = (1 / (2 * np.pi * sg[:, 0, 0])).numpy()
         return periods, w.numpy(), scales
 
+    def get_period_summary(self, n_grid=5000, min_freq=None, max_freq=None, **kwargs):
+        """First stage of ``get_period_summary`` (lightcurve.py:7860-7950, 8134-8305) on the GPU:
+        the summed spectral-mixture PSD on the log-spaced grid and its dominant peak.  Returns a
+        dict with ``dominant_period``, ``dominant_frequency``, ``peak_height``, ``n_peaks``,
+        ``freq_grid``, ``psd`` and the ``component_*`` diagnostics; the reference's basin-mass
+        interval and LSP flags are not computed."""
+        from .period_summary import period_summary_batch, sm_components
+        mu, sg, w = sm_components(self)
+        xr = self._xdata_raw[:, 0] if self.ndim > 1 else self._xdata_raw
+        span = torch.tensor([float(xr.max() - xr.min())])
+        f = lambda v: None if v is None else torch.tensor([float(v)])
+        out = period_summary_batch(mu[None], sg[None], w[None], t_span=span, fmin=f(min_freq),
+                                   fmax=f(max_freq), n_grid=n_grid, return_psd=True)
+        return dict(method="spectral_mixture_psd_peak", backend="spectral_mixture",
+                    dominant_period=float(out["dominant_period"][0]),
+                    dominant_frequency=float(out["dominant_frequency"][0]),
+                    peak_height=float(out["peak_height"][0]), n_peaks=int(out["n_peaks"][0]),
+                    freq_grid=out["freq_grid"][0], psd=out["psd"][0],
+                    component_frequencies=mu.numpy(), component_periods=(1.0 / mu).numpy(),
+                    component_frequency_scales=sg.numpy(), component_weights=w.numpy())
+
     # ---- posterior prediction (lightcurve.py:9607-9640, 9849-9880: the body of plot()) -----
     def predict(self, x_fine_raw=None, n_points=10000):
         """``observed_pred = self.likelihood(self.model(x_fine_transformed))`` on the GPU (N1).

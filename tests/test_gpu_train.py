@@ -307,6 +307,7 @@ def test_fit_batch_matches_per_source_fits_and_mls_seeding(cuda_device):
         assert abs(1 / float(first[0]) - per) < 0.03 * per      # seeded at the periodogram peak
         best = out["periods"][b][np.argmax(out["weights"][b])]
         assert abs(best - per) < 0.05 * per
+        assert abs(out["dominant_period"][b] - per) < 0.05 * per     # PSD period summary (N4)
         assert out["loss"][-1, b] < out["loss"][0, b]
 
 
