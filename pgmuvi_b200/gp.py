@@ -635,7 +635,7 @@ class AchromaticGPModel(SeparableGPModel):
     """pgmuvi/gps.py:1345-1423: ConstantKernel in wavelength (all bands share the temporal
     variability)."""
 
-    def __init__(self, train_x, train_y, likelihood, time_kernel_type="sm", period=None,
+    def __init__(self, train_x, train_y, likelihood, time_kernel_type="matern", period=None,
                  num_mixtures=4, mean_module=None, **kwargs):
         if period is None:      # gps.py:1410-1412
             period = float(train_x[:, 0].max() - train_x[:, 0].min()) / 2.0
@@ -645,13 +645,13 @@ class AchromaticGPModel(SeparableGPModel):
 
 
 class WavelengthDependentGPModel(SeparableGPModel):
-    """pgmuvi/gps.py:1476-1628 with the spectral-mixture time kernel.  ``mean_module`` as the
-    reference ('quad' default there; 'constant' here keeps the whole fit in one kernel launch,
-    the wavelength-dependent means run the host loop with the mean on the host)."""
+    """pgmuvi/gps.py:1476-1628, same defaults (Matern-1.5 time kernel, RBF wavelength kernel,
+    quadratic-in-wavelength mean).  ``mean_module='constant'`` keeps the whole fit in one kernel
+    launch; the wavelength-dependent means run the host loop with the mean on the host."""
 
-    def __init__(self, train_x, train_y, likelihood, time_kernel_type="sm",
+    def __init__(self, train_x, train_y, likelihood, time_kernel_type="matern",
                  wavelength_kernel_type="rbf", period=None, wavelength_lengthscale=None,
-                 num_mixtures=4, mean_module="constant", add_flicker=False,
+                 num_mixtures=4, mean_module=None, add_flicker=False,
                  wavelength_scaling="constant", **kwargs):
         if wavelength_lengthscale is None:
             wl_span = float(train_x[:, 1].max() - train_x[:, 1].min())
@@ -669,16 +669,18 @@ class WavelengthDependentGPModel(SeparableGPModel):
 
 
 class DustMeanGPModel(WavelengthDependentGPModel):
-    """pgmuvi/gps.py:1631-1697 ('2DDustMean'), with the spectral-mixture time kernel."""
+    """pgmuvi/gps.py:1631-1697 ('2DDustMean'): Matern time kernel, RBF wavelength kernel."""
 
     def __init__(self, train_x, train_y, likelihood, **kwargs):
+        kwargs.setdefault("time_kernel_type", "matern")
         kwargs.setdefault("wavelength_kernel_type", "rbf")
         super().__init__(train_x, train_y, likelihood, mean_module="dust", **kwargs)
 
 
 class PowerLawMeanGPModel(WavelengthDependentGPModel):
-    """pgmuvi/gps.py:1700-1767 ('2DPowerLawMean'), with the spectral-mixture time kernel."""
+    """pgmuvi/gps.py:1700-1767 ('2DPowerLawMean'): Matern time kernel, RBF wavelength kernel."""
 
     def __init__(self, train_x, train_y, likelihood, **kwargs):
+        kwargs.setdefault("time_kernel_type", "matern")
         kwargs.setdefault("wavelength_kernel_type", "rbf")
         super().__init__(train_x, train_y, likelihood, mean_module="power_law", **kwargs)

@@ -122,16 +122,21 @@ def _lc_2d(seed=5, n_per=40, **kw):
     return Lightcurve(x, y, yerr=np.full(len(y), 0.05), **kw)
 
 
-@pytest.mark.parametrize("model,kw", [("2DWavelengthDependent", dict(wavelength_kernel_type="rbf")),
-                                      ("2DWavelengthDependent", dict(wavelength_kernel_type="matern")),
-                                      ("2DWavelengthDependent", dict(wavelength_kernel_type="rq")),
-                                      ("2DAchromatic", {}), ("2DSeparable", dict(time_kernel="sm")),
+_SMC = dict(time_kernel_type="sm", mean_module="constant")   # the one-launch SM configuration
+
+
+@pytest.mark.parametrize("model,kw", [("2DWavelengthDependent", dict(wavelength_kernel_type="rbf", **_SMC)),
+                                      ("2DWavelengthDependent", dict(wavelength_kernel_type="matern", **_SMC)),
+                                      ("2DWavelengthDependent", dict(wavelength_kernel_type="rq", **_SMC)),
+                                      ("2DAchromatic", dict(time_kernel_type="sm")),
+                                      ("2DSeparable", dict(time_kernel="sm")),
                                       # stationary time kernels (N3); "2DSeparable" with no
                                       # arguments is the reference's default Matern x RBF
                                       ("2DSeparable", {}),
                                       ("2DAchromatic", dict(time_kernel_type="matern")),
                                       ("2DWavelengthDependent", dict(time_kernel_type="rbf",
-                                                                     wavelength_kernel_type="rq")),
+                                                                     wavelength_kernel_type="rq",
+                                                                     mean_module="constant")),
                                       ("1DMatern", {}), ("1DQuasiPeriodic", dict(period=57.0)),
                                       ("1DPeriodicStochastic", dict(period=57.0)),
                                       ("2DAchromatic", dict(time_kernel_type="quasi_periodic",

@@ -176,7 +176,8 @@ def test_separable_models_pack_onto_the_separable_kinds():
     expect = {"rbf": (3, 2), "matern": (4, 2), "rq": (5, 3)}
     for wk, (kind, nl) in expect.items():
         lc = Lightcurve(x, y, yerr=np.full(75, 0.05))
-        lc.set_model("2DWavelengthDependent", num_mixtures=3, wavelength_kernel_type=wk)
+        lc.set_model("2DWavelengthDependent", num_mixtures=3, wavelength_kernel_type=wk,
+                     time_kernel_type="sm", mean_module="constant")
         lc.set_default_constraints()
         pk = pack_model(lc.model)
         assert (pk.kind, pk.Q, pk.d, pk.P) == (kind, 3, 2, 1 + 9 + nl)
@@ -196,7 +197,11 @@ def test_separable_models_pack_onto_the_separable_kinds():
         if wk == "rq":       # the reference's str.lstrip("raw_") quirk
             assert "covar_module.kernels.1.base_kernel.lpha" in keys
     lc = Lightcurve(x, y)                                   # Gaussian likelihood: learned noise
-    lc.set_model("2DAchromatic", num_mixtures=2)
+    lc.set_model("2DWavelengthDependent")                   # the reference's defaults, gps.py:1566-1609
+    pk = pack_model(lc.model)
+    assert (pk.kind, pk.Q, pk.external_mean) == (8 + 5 * 1 + 1, 0, True)   # Matern x RBF, quad mean
+    assert type(lc.model.mean_module).__name__ == "CustomQuadConstantMean"
+    lc.set_model("2DAchromatic", num_mixtures=2, time_kernel_type="sm")
     pk = pack_model(lc.model)
     assert (pk.kind, pk.P, pk.learn_noise) == (6, 1 + 6 + 1 + 1, True)
     assert pk.names[-2:] == ["likelihood.noise_covar.raw_noise",
