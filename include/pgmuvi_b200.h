@@ -56,6 +56,8 @@ extern "C" {
  *        os exp(-2 sin^2(pi tau / p) / lambda) exp(-tau^2 / (2 l^2)), slots os, lambda, p, l
  *      3 quasi-periodic + ScaleKernel(RBFKernel) (PeriodicPlusStochasticGPModel,
  *        gps.py:1187-1236; wk = 0 only), slots os, lambda, p, l, os2, l2
+ *      4 / 5 ScaleKernel(MaternKernel(nu = 0.5 | 2.5)) (MaternGPModel nu, gps.py:1166-1179;
+ *        wk = 0 only), slots os, l
  *   wk 0 none (d = 1), 1 ScaleKernel(RBF), 2 ScaleKernel(Matern-1.5), 3 ScaleKernel(RQ),
  *      4 ConstantKernel                                                          (wavelength)
  * Pass Q = 0; packed layout [ mean | (noise) | time-kernel parameters (os_t, l_t | os, lambda,

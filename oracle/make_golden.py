@@ -55,6 +55,8 @@ CASES = [
     ("stat_qp_rbf_4x40", dict(dim=2, kind=19, B=2, bands=4, per=40, Q=0, learn_noise=False)),
     ("stat_qp_const_3x48_learn", dict(dim=2, kind=22, B=1, bands=3, per=48, Q=0, learn_noise=True)),
     ("stat_qp_plus_rbf_1d_n130", dict(dim=1, kind=23, B=2, n=130, Q=0, learn_noise=False)),  # 1DPeriodicStochastic
+    ("stat_matern12_1d_n110_learn", dict(dim=1, kind=28, B=2, n=110, Q=0, learn_noise=True)),
+    ("stat_matern25_1d_n140", dict(dim=1, kind=33, B=2, n=140, Q=0, learn_noise=False)),
 ]
 
 

@@ -46,6 +46,7 @@ NUM_LAM = {KIND_SEP_RBF: 2, KIND_SEP_MATERN15: 2, KIND_SEP_RQ: 3, KIND_SEP_CONST
 KIND_STAT_BASE = 8
 ATOM_QP = 100      # time atom 2: quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
 ATOM_QP_RBF = 101  # time atom 3: AdditiveKernel(QP, ScaleKernel(RBFKernel)), gps.py:1187-1236 (1-D only)
+ATOM_M12, ATOM_M25 = 102, 103   # time atoms 4 / 5: ScaleKernel(MaternKernel(0.5 | 2.5)), gps.py:1166-1179
 
 
 def stat_kind(tk: int, wk: int) -> int:
@@ -55,7 +56,7 @@ def stat_kind(tk: int, wk: int) -> int:
 def stat_atoms(kind: int):
     """(time atom, wavelength atom or None) as separable-kind codes."""
     tk, wk = divmod(kind - KIND_STAT_BASE, 5)
-    return ((KIND_SEP_RBF, KIND_SEP_MATERN15, ATOM_QP, ATOM_QP_RBF)[tk],
+    return ((KIND_SEP_RBF, KIND_SEP_MATERN15, ATOM_QP, ATOM_QP_RBF, ATOM_M12, ATOM_M25)[tk],
             None if wk == 0 else (KIND_SEP_RBF, KIND_SEP_MATERN15, KIND_SEP_RQ, KIND_SEP_CONST)[wk - 1])
 
 # constraint kinds (A.2) ---------------------------------------------------------------
@@ -205,6 +206,11 @@ def wavelength_kernel_dense(l1, l2, lam, kind):
     if kind == KIND_SEP_MATERN15:
         r = math.sqrt(3.0) * (tau / ell).abs()
         return os_ * (1.0 + r) * torch.exp(-r)
+    if kind == ATOM_M12:      # MaternKernel(nu=0.5): exp(-|tau| / l)
+        return os_ * torch.exp(-(tau / ell).abs())
+    if kind == ATOM_M25:      # MaternKernel(nu=2.5): (1 + sqrt5 d + 5/3 d^2) exp(-sqrt5 d)
+        r = math.sqrt(5.0) * (tau / ell).abs()
+        return os_ * (1.0 + r + r * r / 3.0) * torch.exp(-r)
     if kind == KIND_SEP_RQ:
         al = ex(lam[..., 2])
         return os_ * (1.0 + (tau / ell) ** 2 / (2.0 * al)) ** (-al)

@@ -27,12 +27,12 @@ def stat_kind(tk, wk):
 
 
 def is_stat(kind):
-    return KIND_STAT_BASE <= kind <= stat_kind(3, 0)
+    return KIND_STAT_BASE <= kind <= stat_kind(5, 0)
 
 
 def stat_num_lam(kind):
     tk, wk = divmod(kind - KIND_STAT_BASE, 5)
-    return (2, 2, 4, 6)[tk] + (0, 2, 2, 3, 1)[wk]
+    return (2, 2, 4, 6, 2, 2)[tk] + (0, 2, 2, 3, 1)[wk]
 
 
 CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2

@@ -31,6 +31,7 @@ CONFIGS += [(k, q, 2) for k in (3, 4, 5, 6) for q in (4, 8)]
 # stationary time kernels (N3): kind = 8 + 5 * TK + WK, TK in {RBF, Matern-1.5, quasi-periodic}, WK = 0 -> 1-D
 CONFIGS += [(8 + 5 * tk + wk, 4, 1 if wk == 0 else 2) for tk in (0, 1, 2) for wk in range(5)]
 CONFIGS += [(23, 4, 1)]   # quasi-periodic + RBF (PeriodicPlusStochasticGPModel), 1-D only
+CONFIGS += [(28, 4, 1), (33, 4, 1)]   # Matern-0.5 / Matern-2.5 (MaternGPModel nu), 1-D only
 
 
 def _nvcc():

@@ -122,16 +122,20 @@ int nf_for(int d, int Q) { return d + 2 * d * pad_q(Q <= 4 ? 4 : Q) + 1; }  // Q
         case PGM_KIND_STAT(2, 2): return FN<PGM_KIND_STAT(2, 2), 4, 2>(__VA_ARGS__); \
         case PGM_KIND_STAT(2, 3): return FN<PGM_KIND_STAT(2, 3), 4, 2>(__VA_ARGS__); \
         case PGM_KIND_STAT(2, 4): return FN<PGM_KIND_STAT(2, 4), 4, 2>(__VA_ARGS__); \
-        default: return FN<PGM_KIND_STAT(3, 0), 4, 1>(__VA_ARGS__);                  \
+        case PGM_KIND_STAT(3, 0): return FN<PGM_KIND_STAT(3, 0), 4, 1>(__VA_ARGS__); \
+        case PGM_KIND_STAT(4, 0): return FN<PGM_KIND_STAT(4, 0), 4, 1>(__VA_ARGS__); \
+        default: return FN<PGM_KIND_STAT(5, 0), 4, 1>(__VA_ARGS__);                  \
       }                                                                              \
     }                                                                                \
   } while (0)
 
 int check_common(int B, int n_max, int d, int Q, int kernel_kind) {
   if (B < 0 || n_max < 1) return fail("B must be >= 0 and n_max >= 1");
-  if (kernel_kind >= PGM_KIND_STAT_BASE && kernel_kind <= PGM_KIND_STAT(3, 0)) {
+  if (kernel_kind >= PGM_KIND_STAT_BASE && kernel_kind <= PGM_KIND_STAT(5, 0)) {
     if (Q != 0) return fail("stationary kinds have no mixtures: pass Q == 0");
     const int wk = (kernel_kind - PGM_KIND_STAT_BASE) % 5;
+    if ((kernel_kind - PGM_KIND_STAT_BASE) / 5 >= 3 && wk != 0)
+      return fail("time kernels 3..5 exist for 1-D models only (wk = 0)");
     if (d != (wk == 0 ? 1 : 2)) return fail("stationary kind / d mismatch (d = 1 without, 2 with a wavelength kernel)");
     return 0;
   }

@@ -47,6 +47,7 @@ constexpr int S_ELEMS = TS * LD_S;                 // 4352
 //   TK: 0 ScaleKernel(RBFKernel), 1 ScaleKernel(MaternKernel(1.5))      gps.py:985-990
 //       2 quasi-periodic ScaleKernel(PeriodicKernel * RBFKernel)         gps.py:915-935
 //       3 quasi-periodic + ScaleKernel(RBFKernel) (WK = 0 only)          gps.py:1187-1236
+//       4 / 5 ScaleKernel(MaternKernel(0.5 | 2.5)) (WK = 0 only)         gps.py:1166-1179
 //   WK: 0 none (1-D model), 1 RBF, 2 Matern-1.5, 3 RQ, 4 Constant       gps.py:1045-1072
 // K = os_t f_T(tau_t) [x os_w f_W(tau_lambda)]; no mixtures (Q = 0 in the packed layout).
 #define PGM_KIND_STAT_BASE 8
@@ -224,10 +225,14 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
 // the separable-kind code whose lam_factor implements an atom of the stationary kinds
 #define PGM_ATOM_QP 100      // ScaleKernel(PeriodicKernel * RBFKernel), gps.py:915-935
 #define PGM_ATOM_QP_RBF 101  // AdditiveKernel(QP, ScaleKernel(RBFKernel)), gps.py:1187-1236 (1-D)
+#define PGM_ATOM_M12 102     // MaternKernel(nu=0.5): exp(-r), r = |tau| / l        (MaternGPModel nu)
+#define PGM_ATOM_M25 103     // MaternKernel(nu=2.5): (1 + u + u^2/3) e^-u, u = sqrt5 |tau| / l
 __host__ __device__ constexpr int stat_time_atom(int kind) {
   return ((kind - PGM_KIND_STAT_BASE) / 5 == 0) ? PGM_KIND_SEP_RBF
          : ((kind - PGM_KIND_STAT_BASE) / 5 == 1) ? PGM_KIND_SEP_MATERN15
-         : ((kind - PGM_KIND_STAT_BASE) / 5 == 2) ? PGM_ATOM_QP : PGM_ATOM_QP_RBF;
+         : ((kind - PGM_KIND_STAT_BASE) / 5 == 2) ? PGM_ATOM_QP
+         : ((kind - PGM_KIND_STAT_BASE) / 5 == 3) ? PGM_ATOM_QP_RBF
+         : ((kind - PGM_KIND_STAT_BASE) / 5 == 4) ? PGM_ATOM_M12 : PGM_ATOM_M25;
 }
 __host__ __device__ constexpr int stat_num_time(int kind) {   // time-kernel parameters
   return stat_time_atom(kind) == PGM_ATOM_QP ? 4 : stat_time_atom(kind) == PGM_ATOM_QP_RBF ? 6 : 2;
@@ -565,6 +570,17 @@ __device__ __forceinline__ double lam_factor(double tl, const double (&lam)[4],
     gl = f * uu;
     ga_ = f * (uu - l1);
     return f;
+  } else if (KIND == PGM_ATOM_M12) {
+    const double u = lam[1] * fabs(tl);
+    const double e = exp_neg(-u, tab);
+    gl = u * e;                       // df/dl = u e^-u / l
+    return e;
+  } else if (KIND == PGM_ATOM_M25) {
+    const double u = lam[1] * fabs(tl);
+    const double e = exp_neg(-u, tab);
+    const double u23 = u * u * (1.0 / 3.0);
+    gl = u23 * (1.0 + u) * e;         // df/dl = (u^2 / 3)(1 + u) e^-u / l
+    return (1.0 + u + u23) * e;
   }
   return 1.0;
 }
@@ -977,6 +993,10 @@ __device__ __forceinline__ void lam_setup(const double* th /* NL constrained val
     lam[0] = th[0]; lam[3] = th[1]; lam[2] = th[2]; lam[1] = 0.5 / (th[2] * th[1] * th[1]);
   } else if (KIND == PGM_KIND_SEP_CONST) {
     lam[0] = th[0];
+  } else if (KIND == PGM_ATOM_M12) {
+    lam[0] = th[0]; lam[3] = th[1]; lam[1] = 1.0 / th[1];
+  } else if (KIND == PGM_ATOM_M25) {
+    lam[0] = th[0]; lam[3] = th[1]; lam[1] = 2.2360679774997896964 / th[1];
   }
 }
 
@@ -1004,7 +1024,8 @@ template <int KIND>
 __device__ __forceinline__ double lam_grad_factor(int t, const double* wq, const double* lamq) {
   auto ell_factor = [](int atom, const double* lm) {
     return (atom == PGM_KIND_SEP_RBF) ? lm[0] / (lm[3] * lm[3] * lm[3])
-           : (atom == PGM_KIND_SEP_MATERN15) ? lm[0] / lm[3] : lm[0] * 2.0 * lm[2] / lm[3];
+           : (atom == PGM_KIND_SEP_MATERN15 || atom == PGM_ATOM_M12 || atom == PGM_ATOM_M25)
+               ? lm[0] / lm[3] : lm[0] * 2.0 * lm[2] / lm[3];
   };
   if constexpr (KIND >= PGM_KIND_STAT_BASE) {
     constexpr int NT = stat_num_time(KIND);

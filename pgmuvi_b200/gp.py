@@ -296,7 +296,7 @@ class PeriodicKernel(RBFKernel):
 
 
 class MaternKernel(RBFKernel):
-    """gpytorch.kernels.MaternKernel; only nu = 1.5 is on the accelerated path."""
+    """gpytorch.kernels.MaternKernel (nu in 0.5, 1.5, 2.5; 0.5 / 2.5 as 1-D time kernels)."""
     lam_kind = "matern"
 
     def __init__(self, nu=1.5):
@@ -573,7 +573,7 @@ class SeparableGPModel(ExactGP):
 
 class MaternGPModel(ExactGP):
     """pgmuvi/gps.py:1131-1184 ('1DMatern'): ConstantMean + ScaleKernel(MaternKernel(nu)),
-    lengthscale initialised to span / 4.  nu = 1.5 is on the accelerated path."""
+    lengthscale initialised to span / 4; nu in {0.5, 1.5, 2.5}."""
 
     def __init__(self, train_x, train_y, likelihood, nu=1.5, lengthscale=None, **kwargs):
         super().__init__(train_x, train_y, likelihood)

@@ -104,9 +104,12 @@ def _scaled_atom(k):
     if hasattr(base, "raw_alpha"):
         return 3, params + [base.raw_alpha], cons + [_constraint(base, "raw_alpha")]
     if "Matern" in bname:
-        if float(getattr(base, "nu", 1.5)) != 1.5:
-            raise UnsupportedModelError("only MaternKernel(nu=1.5) is supported")
-        return 2, params, cons
+        nu = float(getattr(base, "nu", 1.5))
+        if nu == 1.5:
+            return 2, params, cons
+        if nu in (0.5, 2.5):          # MaternGPModel(nu=...): 1-D time kernels only
+            return (7 if nu == 0.5 else 8), params, cons
+        raise UnsupportedModelError("MaternKernel: nu must be 0.5, 1.5 or 2.5")
     if "RBF" in bname:
         return 1, params, cons
     return None
@@ -128,17 +131,19 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
     else:
         tk = cov if factors is None else factors[0]
         ta = _scaled_atom(tk)
-    if ta is None or ta[0] not in (1, 2, 5, 6):
+    if ta is None or ta[0] not in (1, 2, 5, 6, 7, 8):
         return None
+    if ta[0] in (7, 8) and factors is not None:
+        raise UnsupportedModelError("Matern nu = 0.5 / 2.5 time kernels are 1-D only")
     wk_code, wparams, wcons = 0, [], []
     if factors is not None:
         if len(factors) != 2:
             return None
         wa = _scaled_atom(factors[1])
-        if wa is None or wa[0] == 5:
+        if wa is None or wa[0] in (5, 7, 8):
             return None
         wk_code, wparams, wcons = wa
-    kind = stat_kind({1: 0, 2: 1, 5: 2, 6: 3}[ta[0]], wk_code)
+    kind = stat_kind({1: 0, 2: 1, 5: 2, 6: 3, 7: 4, 8: 5}[ta[0]], wk_code)
     d = 1 if wk_code == 0 else 2
     ref = ta[1][0]
     slot0 = (torch.zeros(1, dtype=ref.dtype, device=ref.device) if external_mean

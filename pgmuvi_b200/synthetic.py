@@ -297,7 +297,7 @@ def make_batch_stat(B, kind, n=None, n_bands=None, n_per_band=None, learn_noise=
         lb[b, 0], ub[b, 0] = float(yy.min()), float(yy.max())
         if learn_noise:
             lb[b, o_noise], ub[b, o_noise] = min(1e-4, float(yerr.min()) / 10.0), float(np.std(yy, ddof=1))
-        if tk >= 2:    # quasi-periodic: os, lambda (periodic lengthscale), period, l_rbf
+        if tk in (2, 3):    # quasi-periodic: os, lambda (periodic lengthscale), period, l_rbf
             lamv = [rng.uniform(0.5, 1.5), rng.uniform(0.5, 2.0), rng.uniform(0.08, 0.3),
                     rng.uniform(0.3, 1.0)]
             if tk == 3:                                              # + os_2, l_2 (stochastic RBF)

@@ -137,7 +137,9 @@ _SMC = dict(time_kernel_type="sm", mean_module="constant")   # the one-launch SM
                                       ("2DWavelengthDependent", dict(time_kernel_type="rbf",
                                                                      wavelength_kernel_type="rq",
                                                                      mean_module="constant")),
-                                      ("1DMatern", {}), ("1DQuasiPeriodic", dict(period=57.0)),
+                                      ("1DMatern", {}), ("1DMatern", dict(nu=0.5)),
+                                      ("1DMatern", dict(nu=2.5)),
+                                      ("1DQuasiPeriodic", dict(period=57.0)),
                                       ("1DPeriodicStochastic", dict(period=57.0)),
                                       ("2DAchromatic", dict(time_kernel_type="quasi_periodic",
                                                             period=83.0))])
