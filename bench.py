@@ -38,6 +38,7 @@ F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval (
 # (4096 light curves), from the `ncu --set full` capture summarised in
 # profiles/r01d_ncu_full_summary.txt (43.31 GB + 10.35 GB); scales with light curves per GPU
 TRAFFIC_BYTES_PER_LC = (43.306600e9 + 10.347435e9) / 4096
+PREWARM_STEPS = 30
 METRIC = "MLL+grad evals/s, 4096x n=512 SM-4 lightcurves"
 UNIT = "evals/s"
 
@@ -63,7 +64,8 @@ def workload_config(args, world):
             "n": N_POINTS, "num_mixtures": Q_MIX, "params_per_lightcurve": 13,
             "parallelism": f"independent light curves sharded over {world} GPU(s), "
                            "no collective inside the step",
-            "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)"}
+            "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)",
+            "prewarm_steps": PREWARM_STEPS}
 
 
 # ---------------------------------------------------------------------------------------
@@ -300,6 +302,12 @@ def run_b200(args):
         return mll
 
     # ---- device-resident throughput ("value") -------------------------------------------
+    # a fresh box starts with cold clocks / power state: about one second of untimed pre-warm
+    # steps before the W warm-up steps (config.prewarm_steps), so that the K timed steps are not
+    # the ones that absorb the ramp (one r01f run measured 38 ms instead of 31 ms per step
+    # right after start-up)
+    for _ in range(PREWARM_STEPS):
+        step_device()
     for _ in range(args.warmup):
         step_device()
     barrier()
