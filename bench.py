@@ -39,6 +39,7 @@ F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval (
 # profiles/r01d_ncu_full_summary.txt (43.31 GB + 10.35 GB); scales with light curves per GPU
 TRAFFIC_BYTES_PER_LC = (43.306600e9 + 10.347435e9) / 4096
 PREWARM_STEPS = 30
+_OUT = sys.stdout      # replaced in main() by a private handle to the real stdout
 METRIC = "MLL+grad evals/s, 4096x n=512 SM-4 lightcurves"
 UNIT = "evals/s"
 
@@ -180,7 +181,7 @@ def run_reference(args):
                              "sample": sample, "mode": mode},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------
@@ -399,12 +400,17 @@ def run_b200(args):
             del d, flush
             torch.cuda.empty_cache()
             line["other_configs"] = other_configs(dev, dmma)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # the contract is ONE JSON line on stdout: keep a private handle to the real stdout for it and
+    # send everything libraries print to fd 1 (NCCL's version banner, warnings) to stderr
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
