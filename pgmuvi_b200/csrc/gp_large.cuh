@@ -243,10 +243,22 @@ __device__ __forceinline__ void lg_prefetch_side(double* vec, const LargeWs& w, 
 // per-tile "final" flags of the one-launch phases (lg_chol_all, lg_inv_all)
 __device__ __forceinline__ void lg_wait_flag(const int* f) {
   int v;
-  do {
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
-    if (!v) __nanosleep(40);
-  } while (!v);
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+  if (!v) {
+    // Watchdog: the schedule relies on blocks being dispatched in index order (every awaited
+    // producer is then running or done).  Should that ever not hold, fail the launch after 20 s
+    // of waiting instead of hanging the device.
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+    do {
+      __nanosleep(40);
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+      if (!v) {
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) __trap();
+      }
+    } while (!v);
+  }
   fence_proxy_async();   // the tile was written, and will be read, through the async proxy
 }
 __device__ __forceinline__ void lg_set_flag(int* f) {
