@@ -220,8 +220,9 @@ def other_configs(dev, dmma_peak):
         return {"n": n, "ms_per_eval": ms, "tflops": tf, "frac_of_dmma_peak": tf / dmma_peak}
 
     try:
+        import tempfile
         from pgmuvi_b200.lightcurve import Lightcurve
-        csv = os.path.join(ROOT, "tests", "data", "AlfOriAAVSO_Vband.csv")
+        csv = S.alfori_csv(os.path.join(tempfile.gettempdir(), f"alfori_vband_{os.getpid()}.csv"))
         best = 1e30
         for _ in range(2):
             torch.manual_seed(0)
@@ -389,7 +390,8 @@ def run_b200(args):
                 "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": d2h},
                 "gpu_launches": args.steps, "roofline": roofline, "clocks": clocks,
-                "cholesky_info_nonzero": bad, "wall_s_timed_loop": t_wall}
+                "cholesky_info_nonzero": bad, "wall_s_timed_loop": t_wall,
+                "step_ms": [round(v, 3) for v in step_ms]}
         if world == 1 and not args.no_cpu_baseline:
             val, mode, both, cores = cpu_reference(args.cpu_sample, 2, 1)
             line["cpu_baseline"] = {

@@ -1,5 +1,5 @@
 """Golden trajectory for BASELINE config C1 (TEST INFRASTRUCTURE ONLY):
-Lightcurve.fit(model='1D') SM-4 on the bundled AlfOriAAVSO_Vband.csv (1564 -> 1000 points,
+Lightcurve.fit(model='1D') SM-4 on the reference's bundled AlfOri V-band light curve (1564 -> 1000 points,
 subsample_seed 0, minmax x-transform, GaussianLikelihood), Adam, 300 iterations, lr 0.1, run by
 the oracle's restatement of pgmuvi/trainers.py:105-209 on the CPU in fp64.
 
@@ -23,7 +23,10 @@ def build_lightcurve():
     torch.manual_seed(0)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        lc = Lightcurve.from_csv(os.path.join(ROOT, "tests", "data", "AlfOriAAVSO_Vband.csv"),
+        import tempfile
+        from pgmuvi_b200.synthetic import alfori_csv
+        csv = alfori_csv(os.path.join(tempfile.gettempdir(), f"alfori_vband_{os.getpid()}.csv"))
+        lc = Lightcurve.from_csv(csv,
                                  xtransform="minmax", subsample_seed=0)
     lc.set_model("1D", num_mixtures=4)
     lc.set_default_constraints()

@@ -16,8 +16,7 @@ REF = "/root/reference/pgmuvi/preprocess/quality.py"
 
 
 def cases():
-    d = np.genfromtxt(os.path.join(ROOT, "tests", "data", "AlfOriAAVSO_Vband.csv"),
-                      delimiter=",", names=True)
+    d = np.load(os.path.join(ROOT, "tests", "data", "alfori_vband.npz"))
     t = d["JD"].astype(np.float32).astype(float)     # the Lightcurve stores float32
     yield "alfori_seed0", t, 1000, 0.3, 0
     yield "alfori_seed42_500", t, 500, 0.3, 42

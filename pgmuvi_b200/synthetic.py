@@ -313,3 +313,17 @@ def make_batch_stat(B, kind, n=None, n_bands=None, n_per_band=None, learn_noise=
         raw[b, o_lam:o_lam + NL] = inv_softplus(np.array(lamv))
     return dict(x=x, y=y, noise=noise, raw=raw, kinds=kinds, lb=lb, ub=ub, Q=0, d=d,
                 kind=kind, learn_noise=learn_noise)
+
+
+def alfori_csv(path):
+    """Write the AlfOri V-band light curve of BASELINE config C1 (tests/data/alfori_vband.npz:
+    the 1564 (JD, Magnitude) rows of the reference's bundled pgmuvi/AlfOriAAVSO_Vband.csv) as a
+    CSV with the reference's column names, for ``Lightcurve.from_csv``.  Returns ``path``."""
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(here, "tests", "data", "alfori_vband.npz"))
+    with open(path, "w") as f:
+        f.write("JD,Magnitude\n")
+        for jd, mag in zip(z["JD"], z["Magnitude"]):
+            f.write(f"{float(jd)!r},{float(mag)!r}\n")
+    return path

@@ -9,7 +9,10 @@ import pytest
 
 from conftest import ROOT
 
-CSV = os.path.join(ROOT, "tests", "data", "AlfOriAAVSO_Vband.csv")
+@pytest.fixture(scope="module")
+def CSV(tmp_path_factory):
+    from pgmuvi_b200.synthetic import alfori_csv
+    return alfori_csv(str(tmp_path_factory.mktemp("alfori") / "AlfOri_Vband.csv"))
 
 
 def test_subsample_matches_the_reference_indices():
@@ -35,7 +38,7 @@ def test_subsample_edge_cases():
         subsample_lightcurve(t, max_samples=1)
 
 
-def test_from_csv_alfori_is_subsampled_to_1000_float32():
+def test_from_csv_alfori_is_subsampled_to_1000_float32(CSV):
     """BASELINE config C1: bundled AlfOriAAVSO_Vband.csv has 1564 rows -> 1000 after the default
     max_samples; no uncertainty column -> GaussianLikelihood."""
     import torch
