@@ -36,8 +36,8 @@ LC_PER_GPU = 4096
 F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel on the C2 batch
 # (4096 light curves), from the `ncu --set full` capture summarised in
-# profiles/r01d_ncu_full_summary.txt (43.31 GB + 10.35 GB); scales with light curves per GPU
-TRAFFIC_BYTES_PER_LC = (43.306600e9 + 10.347435e9) / 4096
+# profiles/r01g_fused_ncu_summary.txt (43.57 GB + 10.35 GB); scales with light curves per GPU
+TRAFFIC_BYTES_PER_LC = (43.565392e9 + 10.345462e9) / 4096
 PREWARM_STEPS = 30
 _OUT = sys.stdout      # replaced in main() by a private handle to the real stdout
 METRIC = "MLL+grad evals/s, 4096x n=512 SM-4 lightcurves"
@@ -381,7 +381,7 @@ def run_b200(args):
                     "algorithmic_flops_per_launch": B * F_EVAL,
                     "kernel_ms_avg": kern_ms_avg,
                     "traffic": TRAFFIC_BYTES_PER_LC * B,
-                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01d)",
+                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01g_fused_ncu_summary.txt)",
                     "algorithmic_bytes_per_launch": B * (3 * N_POINTS + 2 * 13 + 1) * 8}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
