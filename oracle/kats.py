@@ -69,3 +69,93 @@ def k3_run(dtype=torch.float64, iters=3000):
                mixture_mean=float(th[2]) / meta["trange"], noise=float(th[4]))
     out["period"] = 1.0 / out["mixture_mean"]
     return out, meta
+
+
+# ---------------------------------------------------------------------------------------
+# K1 / K2 - the comparison notebook's 1-D and 2-D fits
+#   /root/reference/docs/source/notebooks/PGMUVI_comparison_with_other_codes.ipynb
+#   cell 7 (data), cell 11 (1-D fit + printed start state and result), cell 30 (2-D fit).
+# Data: tests/golden_kats/comparison_nb_data.npz, written by oracle/make_golden_kats.py from
+# the REFERENCE'S OWN generator (pgmuvi/synthetic.py:686-907) with the notebook's arguments.
+# Both fits ran with float64 data and float32 parameters / constraint bounds: the Lightcurve
+# was .double()-ed before fit() built the model - `param_dtype` restates that.
+# ---------------------------------------------------------------------------------------
+K1_PUBLISHED = dict(loss=-1.562, freqs=(0.00665436, 0.0151593), periods=(150.27731, 65.966125),
+                    constant0=0.028102993965148926, weight0=0.4779, early_stop=False)
+K2_PUBLISHED = dict(loss=0.904, time_freq=13.842627, stop_iter=348, means0=9.4067,
+                    weight0=0.6931, constant0=0.028102993965148926)
+
+
+def _nb_data():
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(here, "tests", "golden_kats", "comparison_nb_data.npz"))
+    return (torch.tensor(z["x"]), torch.tensor(z["y"]), torch.tensor(z["yerr"]))
+
+
+def k1_problem(param_dtype=torch.float32):
+    """1-D fit on the best-sampled band (0.8 um, n = 89), FixedNoise(yerr**2), Q = 2, start
+    state = the printout of cell 11 (4 digits)."""
+    x32, y32, e32 = _nb_data()
+    m = x32[:, 1] == x32[0, 1]
+    t, y, e = x32[m, 0].double(), y32[m].double(), e32[m].double()
+    assert t.numel() == 89
+    fixed = (e ** 2).clamp_min(1e-6)         # lightcurve.py:2780-2784; fp64 min_fixed_noise
+    spec = ModelSpec(d=1, Q=2, kind=0, learn_noise=False)
+    kinds = torch.tensor([CON_INTERVAL] + [CON_SOFTPLUS] * 6)
+    pd = param_dtype
+    span = (t.max() - t.min()).to(pd)
+    lb = torch.zeros(7, dtype=pd)
+    ub = torch.zeros(7, dtype=pd)
+    lb[0], ub[0] = y.min().to(pd), y.max().to(pd)      # lightcurve.py:3830-3838
+    lb[3:5] = 1.0 / span                               # GreaterThan(1/span), :3920-3932
+    w0 = float(y.std()) / 2                            # SMK.initialize_from_data, gps.py:209
+    start = torch.tensor([0.0, w0, w0, 0.0067, 0.0154, 0.0053, 0.0037], dtype=pd)
+    raw0 = unconstrain(start, kinds, lb, ub).to(pd)
+    raw0[0] = 0.0                                      # raw_constant = 0 -> mid-range
+    return t.unsqueeze(-1), y, fixed, raw0, kinds, lb, ub, spec
+
+
+def k1_run(param_dtype=torch.float32, iters=1000):
+    x, y, fixed, raw0, kinds, lb, ub, spec = k1_problem(param_dtype)
+    th0 = constrain(raw0, kinds, lb, ub)
+    res = train_loop(x, y, fixed, raw0, kinds, lb, ub, spec, maxiter=iters, miniter=50,
+                     stop=1e-5, lr=0.05, optim="AdamW", stopavg=30)
+    th = constrain(torch.as_tensor(res["raw"][-1]), kinds, lb, ub)
+    return dict(loss=float(res["loss"][-1]), freqs=(float(th[3]), float(th[4])),
+                n_iter=len(res["loss"]), constant0=float(th0[0]), weight0=float(th0[1]))
+
+
+def k2_problem(param_dtype=torch.float32):
+    """2-D fit on all 225 rows, x = (t, lambda) untransformed, FixedNoise(yerr**2), Q = 2,
+    SMK(ard_num_dims=2) with every raw parameter 0 (gps.py:302-318: no initialize_from_data)."""
+    x32, y32, e32 = _nb_data()
+    x, y, e = x32.double(), y32.double(), e32.double()
+    fixed = (e ** 2).clamp_min(1e-6)
+    spec = ModelSpec(d=2, Q=2, kind=1, learn_noise=False)   # product over dims of mixture sums
+    P = spec.P
+    kinds = torch.full((P,), CON_SOFTPLUS)
+    kinds[0] = CON_INTERVAL
+    kinds[spec.o_mu:spec.o_mu + 4] = CON_INTERVAL
+    pd = param_dtype
+    lb = torch.zeros(P, dtype=pd)
+    ub = torch.zeros(P, dtype=pd)
+    lb[0], ub[0] = y.min().to(pd), y.max().to(pd)
+    ts = x[:, 0].sort().values
+    dif = ts[1:] - ts[:-1]
+    lb[spec.o_mu:spec.o_mu + 4] = (1.0 / (ts.max() - ts.min())).to(pd)   # :3883-3906
+    ub[spec.o_mu:spec.o_mu + 4] = (1.0 / (2.0 * dif[dif > 0].min())).to(pd)
+    raw0 = torch.zeros(P, dtype=pd)
+    return x, y, fixed, raw0, kinds, lb, ub, spec
+
+
+def k2_run(param_dtype=torch.float32, iters=1000):
+    x, y, fixed, raw0, kinds, lb, ub, spec = k2_problem(param_dtype)
+    th0 = constrain(raw0, kinds, lb, ub)
+    res = train_loop(x, y, fixed, raw0, kinds, lb, ub, spec, maxiter=iters, miniter=50,
+                     stop=1e-5, lr=0.05, optim="AdamW", stopavg=30)
+    th = constrain(torch.as_tensor(res["raw"][-1]), kinds, lb, ub)
+    return dict(loss=float(res["loss"][-1]), loss_hist=np.array(res["loss"], dtype=float),
+                time_freqs=(float(th[spec.o_mu]), float(th[spec.o_mu + 2])),
+                n_iter=len(res["loss"]), means0=float(th0[spec.o_mu]),
+                weight0=float(th0[1]), constant0=float(th0[0]))

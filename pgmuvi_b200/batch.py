@@ -195,7 +195,7 @@ def fit_batch(lightcurves, model="1D", likelihood=None, num_mixtures=None, perio
     ``dominant_period`` [B] (highest peak of the summed PSD, ``get_period_summary``'s first
     stage, one launch for the batch) - host tensors / arrays, all B light curves on every rank."""
     import torch.distributed as dist
-    from .mll import engine_device, pack_model
+    from .mll import UnsupportedModelError, engine_device, pack_model
     from .trainers import history_from_raw
 
     lcs = list(lightcurves)
@@ -250,6 +250,12 @@ def fit_batch(lightcurves, model="1D", likelihood=None, num_mixtures=None, perio
         lc.likelihood.train()
         packs.append(pack_model(lc.model, lc.likelihood))
     pk0 = packs[0]
+    if any(pk.external_mean for pk in packs):
+        # non-constant mean modules keep their parameters on the host (autograd through
+        # y - m(x), pgm_sm_mll_grad_alpha_f64): the one-launch batch loop cannot train them
+        raise UnsupportedModelError(
+            f"fit_batch: model {model!r} has a non-constant mean function, whose parameters are "
+            "optimised on the host; fit these light curves one by one with Lightcurve.fit")
     for pk in packs[1:]:
         if (pk.kind, pk.Q, pk.d, pk.learn_noise, pk.P) != (pk0.kind, pk0.Q, pk0.d, pk0.learn_noise,
                                                         pk0.P) or not torch.equal(pk.kinds,

@@ -91,14 +91,19 @@ def _make_transform(t):
 
 
 class Lightcurve(torch.nn.Module):
-    """``Lightcurve(xdata, ydata, yerr=None, xtransform='minmax', ytransform=None)``
-    (pgmuvi/lightcurve.py:1724-1742).  Data are stored float32 like the reference
-    (``_ensure_tensor``, :2434-2446); ``.double()`` opts into float64."""
+    """``Lightcurve(xdata, ydata, yerr=None, xtransform=None, ytransform=None, ...)`` with the
+    reference's signature and defaults (pgmuvi/lightcurve.py:1724-1742).  Data are stored float32
+    like the reference (``_ensure_tensor``, :2434-2446); ``.double()`` opts into float64.  The
+    pre-processing gates (``check_sampling``, ``check_variability``, per-band sub-sampling) sit
+    outside the path: the flags are accepted, the gates are not run."""
 
-    def __init__(self, xdata, ydata, yerr=None, xtransform="minmax", ytransform=None, name=None,
-                 max_samples=1000, subsample_seed=None, sampling_kwargs=None, **kwargs):
+    def __init__(self, xdata, ydata, yerr=None, xtransform=None, ytransform=None, name=None,
+                 time_units=None, max_samples=1000, max_samples_per_band=None,
+                 subsample_seed=None, check_sampling=False, sampling_kwargs=None,
+                 check_variability=False, variability_kwargs=None, band=None, **kwargs):
         super().__init__()
         self.name = name
+        self.time_units = time_units
         self.xtransform = _make_transform(xtransform)
         self.ytransform = _make_transform(ytransform)
         x = self._ensure_tensor(xdata)
@@ -409,9 +414,9 @@ class Lightcurve(torch.nn.Module):
         if m_star is not None:
             mean = mean + m_star
         if pk.learn_noise:
-            # the learned noise is the slot right after the kernel parameters (pack_model order:
-            # mean, weights, means, scales, noise, wavelength-kernel parameters)
-            noise_par = pk.params[4]
+            # the learned-noise Parameter: its position differs between the spectral-mixture
+            # layout [mean, w, mu, sigma, noise, ...] and the stationary one [mean, noise, ...]
+            noise_par = pk.params[pk.noise_index]
             noise_con = getattr(self._owner_of(noise_par), "raw_noise_constraint", None)
             nv = noise_con.transform(noise_par) if noise_con is not None else noise_par
             var = var + float(nv.detach().reshape(-1)[0])
@@ -458,13 +463,13 @@ class Lightcurve(torch.nn.Module):
         pf, sm = out_t(freqs[0][keep]), out_t(sig[0][keep], torch.bool)
         return (pf, sm, freq_t, power_t) if return_full else (pf, sm)
 
-    def _mls_initial_frequencies(self, num_mixtures, constraint_set, peaks=None):
+    def _mls_initial_frequencies(self, num_mixtures, constraint_set, peaks=None, f_cap=None):
         """Choice of seed frequencies from the periodogram peaks (lightcurve.py:5475-5660,
         1-D branch): peaks outside [1/span, constraint-set limit] are dropped; significant peaks
         first, then the others, then evenly spaced padding.  ``peaks`` = precomputed
         ``(peak_freqs, significance_mask)`` (``fit_batch`` runs one periodogram launch for all
         its light curves)."""
-        t = self._xdata_raw
+        t = self._xdata_raw[:, 0] if self.ndim > 1 else self._xdata_raw
         span = float(t.max() - t.min())
         f_lo = 1.0 / span if span > 0 else 0.0
         d = torch.diff(torch.sort(t).values)
@@ -479,6 +484,9 @@ class Lightcurve(torch.nn.Module):
                     cs_hi = min(cs_hi, 1.0 / pl)
                 if pu_on and pu is not None:
                     cs_lo = max(cs_lo, 1.0 / pu)
+        if f_cap is not None:      # best-band Nyquist (lightcurve.py:5533-5552)
+            cs_hi = min(cs_hi, f_cap)
+            f_hi = cs_hi
         freqs, sig = peaks if peaks is not None else self.fit_LS(
             num_peaks=max(num_mixtures or 1, 10))
         if len(freqs) and cs_lo > 0:
@@ -516,16 +524,39 @@ class Lightcurve(torch.nn.Module):
         return init, num_mixtures
 
     # ---- fit (lightcurve.py:5211-5882) -------------------------------------------------
+    def _get_best_sampled_band_lc(self):
+        """1-D light curve of the band with the most points (lightcurve.py:5512-5520 uses it for
+        ``use_best_band_init``): same transforms off, no sub-sampling."""
+        wl = self._xdata_raw[:, 1]
+        vals, counts = torch.unique(wl, return_counts=True)
+        m = wl == vals[int(torch.argmax(counts))]
+        err = self._yerr_raw[m] if hasattr(self, "_yerr_raw") else None
+        return Lightcurve(self._xdata_raw[m, 0], self._ydata_raw[m], yerr=err, max_samples=None)
+
     def fit(self, model=None, likelihood=None, num_mixtures=None, guess=None, periods=None,
-            use_mls_init=False, constraint_set=None, cuda=False, training_iter=300,
-            optim="AdamW", miniter=None, stop=1e-5, lr=0.1, stopavg=30, variance=False,
-            **kwargs):
-        """Same defaults as the reference: AdamW, lr 0.1, 300 iterations, stop 1e-5, stopavg 30,
-        ``miniter=None -> training_iter`` (so the early stop never fires).
-        ``use_mls_init=True`` (the reference's default; off here so that a fit is deterministic
-        without a device periodogram) seeds the mixture means of a 1-D model from the GPU
-        Lomb-Scargle periodogram exactly like lightcurve.py:5475-5660; ``periods`` / ``guess``
-        take precedence as in the reference."""
+            use_mls_init=True, use_best_band_init=False, constraint_set=None, grid_size=2000,
+            cuda=False, training_iter=300, max_cg_iterations=None, optim="AdamW", miniter=None,
+            stop=1e-5, lr=0.1, stopavg=30, variance=False, **kwargs):
+        """The reference's signature and defaults (lightcurve.py:5211-5232): AdamW, lr 0.1, 300
+        iterations, stop 1e-5, stopavg 30, ``miniter=None -> training_iter`` (so the early stop
+        never fires), ``use_mls_init=True``.
+
+        MLS initialisation (lightcurve.py:5475-5688): 1-D spectral-mixture models are seeded from
+        the GPU Lomb-Scargle periodogram; 2-D ones from the best-sampled band's 1-D periodogram
+        when ``use_best_band_init`` is set (:5512-5532, 5777-5839).  As in the reference, ANY
+        failure of that step (here: no CUDA device, or the multiband periodogram, which is
+        outside the path) degrades to a ``RuntimeWarning`` and the default initialisation with
+        ``num_mixtures`` (4 if not given) - :5668-5688.  ``periods`` / ``guess`` take precedence.
+        ``grid_size`` only concerns the KISS-GP models (outside the path);
+        ``max_cg_iterations`` is GPyTorch's CG budget (:5852-5870) and has no effect on the
+        exact-Cholesky path.  ``cuda`` is accepted: the engine always runs on the GPU."""
+        if num_mixtures is not None:
+            if isinstance(num_mixtures, bool) or not isinstance(num_mixtures, int):
+                raise TypeError("`num_mixtures` must be a positive integer or None, "
+                                f"got {num_mixtures!r} of type {type(num_mixtures)!r}.")
+            if num_mixtures < 1:
+                raise ValueError("`num_mixtures` must be a positive integer or None, "
+                                 f"got {num_mixtures}.")
         if likelihood is not None or not hasattr(self, "likelihood"):
             self.set_likelihood(likelihood, variance=variance)
         init_freqs = None
@@ -538,12 +569,32 @@ class Lightcurve(torch.nn.Module):
                 raise ValueError("All values in `periods` must be finite (no NaN or inf).")
             if not (pt > 0).all():
                 raise ValueError("All values in `periods` must be strictly positive.")
-            if self.ndim == 1:
-                init_freqs = 1.0 / pt
-            if num_mixtures is None:
-                num_mixtures = len(pt)
-        elif use_mls_init and isinstance(model, str) and model in _SM_MODELS and self.ndim == 1:
-            init_freqs, num_mixtures = self._mls_initial_frequencies(num_mixtures, constraint_set)
+            init_freqs = 1.0 / pt
+            num_mixtures = len(pt)
+        elif use_mls_init and isinstance(model, str) and model in _SM_MODELS \
+                and model not in _NO_MIXTURE_MODELS:
+            try:
+                if self.ndim > 1 and use_best_band_init:
+                    bb = self._get_best_sampled_band_lc()
+                    peaks = bb.fit_LS(num_peaks=max(num_mixtures or 1, 10))
+                    tb = bb._xdata_raw.sort().values
+                    db = tb[1:] - tb[:-1]
+                    db = db[db > 0]
+                    nyq = float(1.0 / (2.0 * db.min())) if len(db) else float("inf")
+                    init_freqs, num_mixtures = self._mls_initial_frequencies(
+                        num_mixtures, constraint_set, peaks, f_cap=nyq)
+                else:
+                    init_freqs, num_mixtures = self._mls_initial_frequencies(
+                        num_mixtures, constraint_set)
+            except Exception as exc:      # lightcurve.py:5668-5688
+                if num_mixtures is None:
+                    num_mixtures = 4
+                init_freqs = None
+                warnings.warn("MLS-based initialisation failed; falling back to "
+                              f"num_mixtures={num_mixtures}. Original error was: {exc}",
+                              RuntimeWarning, stacklevel=2)
+        if num_mixtures is None:
+            num_mixtures = 4
         if model is not None or not hasattr(self, "model"):
             if model is None:
                 raise ValueError("""You must provide a model""")
@@ -551,8 +602,23 @@ class Lightcurve(torch.nn.Module):
         if not self._constraints_set:
             self.set_default_constraints(constraint_set=constraint_set)
         hypers = {}
-        if init_freqs is not None:
+        sm = getattr(self.model, "covar_module", None)
+        ard = getattr(sm, "ard_num_dims", None) if hasattr(sm, "raw_mixture_means") else None
+        if init_freqs is not None and ard == 1 and self.ndim == 1:
             hypers["covar_module.mixture_means"] = init_freqs
+        elif init_freqs is not None and use_best_band_init and self.ndim > 1 and ard == 2:
+            # time frequencies from the best band, 1 / wavelength span as the wavelength
+            # placeholder (lightcurve.py:5777-5839)
+            wl = self._xdata_raw[:, 1]
+            wspan = float(wl.max() - wl.min())
+            f2 = torch.stack([init_freqs, init_freqs.new_full((len(init_freqs),),
+                                                              1.0 / wspan if wspan > 0 else 1e-6)], 1)
+            if self.xtransform is None:
+                con = getattr(sm, "raw_mixture_means_constraint", None)
+                if con is not None and hasattr(con, "lower_bound"):
+                    hi = float(con.upper_bound) if hasattr(con, "upper_bound") else float("inf")
+                    f2 = f2.clamp(min=float(con.lower_bound), max=hi)
+            hypers["covar_module.mixture_means"] = f2
         if guess is not None:
             hypers.update(guess)
         if hypers:

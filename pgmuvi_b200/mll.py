@@ -45,6 +45,8 @@ class PackedModel:
     fixed_noise: Optional[torch.Tensor]   # [n] variance or None
     external_mean: bool = False           # non-constant mean: slot 0 is a frozen zero and the
                                           # host passes y - mean_module(x) (pgm_*_alpha_f64)
+    noise_index: Optional[int] = None     # index into ``params`` of the learned-noise Parameter
+                                          # (the two packed layouts put it in different places)
 
     @property
     def P(self):
@@ -153,14 +155,17 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
     fixed, learn = None, False
     nc = getattr(likelihood, "noise_covar", None)
     snc = getattr(likelihood, "second_noise_covar", None)
+    noise_index = None
     if nc is not None and hasattr(nc, "raw_noise"):
         learn = True
+        noise_index = len(params)
         params.append(nc.raw_noise)
         cons.append(_constraint(nc, "raw_noise"))
     elif nc is not None and hasattr(nc, "noise"):
         fixed = nc.noise
         if snc is not None and hasattr(snc, "raw_noise"):
             learn = True
+            noise_index = len(params)
             params.append(snc.raw_noise)
             cons.append(_constraint(snc, "raw_noise"))
     else:
@@ -177,7 +182,8 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
                        kinds=torch.tensor(kinds, dtype=torch.int32),
                        lb=torch.tensor(lb, dtype=torch.float64),
                        ub=torch.tensor(ub, dtype=torch.float64), kind=kind, Q=0, d=d,
-                       learn_noise=learn, fixed_noise=fixed, external_mean=external_mean)
+                       learn_noise=learn, fixed_noise=fixed, external_mean=external_mean,
+                       noise_index=noise_index)
 
 
 def pack_model(model, likelihood=None) -> PackedModel:
@@ -261,17 +267,19 @@ def pack_model(model, likelihood=None) -> PackedModel:
     cons = [None if external_mean else _constraint(mean, "raw_constant"),
             _constraint(cov, "raw_mixture_weights"), _constraint(cov, "raw_mixture_means"),
             _constraint(cov, "raw_mixture_scales")]
-    fixed, learn = None, False
+    fixed, learn, noise_index = None, False, None
     nc = getattr(likelihood, "noise_covar", None)
     snc = getattr(likelihood, "second_noise_covar", None)
     if nc is not None and hasattr(nc, "raw_noise"):            # GaussianLikelihood
         learn = True
+        noise_index = len(params)
         params.append(nc.raw_noise)
         cons.append(_constraint(nc, "raw_noise"))
     elif nc is not None and hasattr(nc, "noise"):              # FixedNoiseGaussianLikelihood
         fixed = nc.noise
         if snc is not None and hasattr(snc, "raw_noise"):
             learn = True
+            noise_index = len(params)
             params.append(snc.raw_noise)
             cons.append(_constraint(snc, "raw_noise"))
     else:
@@ -288,7 +296,8 @@ def pack_model(model, likelihood=None) -> PackedModel:
                        kinds=torch.tensor(kinds, dtype=torch.int32),
                        lb=torch.tensor(lb, dtype=torch.float64),
                        ub=torch.tensor(ub, dtype=torch.float64), kind=kind, Q=Q, d=d,
-                       learn_noise=learn, fixed_noise=fixed, external_mean=external_mean)
+                       learn_noise=learn, fixed_noise=fixed, external_mean=external_mean,
+                       noise_index=noise_index)
 
 
 def engine_device(t=None):

@@ -246,7 +246,8 @@ def _train_with_torch_optimizer(lightcurve, model, likelihood, train_x, train_y,
         out = {}
         for n, p in extra:
             v = p.detach().clone().cpu()
-            key = _strip_raw(n) if lightcurve is not None else n
+            # lightcurve.py:9031-9077 strips only names that contain 'raw'
+            key = _strip_raw(n) if (lightcurve is not None and "raw" in n) else n
             if yt is not None and any(s in key for s in _Y_KEYS):
                 v = yt.inverse(v)
             out[key] = v.numpy()

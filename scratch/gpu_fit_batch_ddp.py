@@ -13,7 +13,7 @@ for n in (90, 200, 131, 64, 257, 150, 77):
     per = rng.uniform(30, 120)
     t = np.sort(rng.uniform(2450000.0, 2450000.0 + 7 * per, n))
     y = np.sin(2 * np.pi * t / per) + 0.1 * rng.standard_normal(n)
-    lcs.append(Lightcurve(t, y, yerr=np.full(n, 0.1)).double()); pers.append(per)
+    lcs.append(Lightcurve(t, y, yerr=np.full(n, 0.1), xtransform="minmax").double()); pers.append(per)
 torch.manual_seed(3)
 with warnings.catch_warnings():
     warnings.simplefilter('ignore')

@@ -3,6 +3,8 @@ the whole device factors ONE K~.  Checked against the oracle's golden vectors (e
 kind, ragged last tile), against the fused one-block-per-light-curve kernel at n = 1500, and -
 at n = 8000 (C3's size) - through size-independent properties (finite differences of the MLL
 along the gradient; permutation invariance)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -79,6 +81,43 @@ def test_large_path_c3_size_properties(cuda_device):
     assert abs(mp - float(mll)) <= 1e-9 * abs(float(mll))
 
 
+LARGE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_large")
+LARGE_CASES = sorted(f[:-4] for f in os.listdir(LARGE_DIR) if f.endswith(".npz")) \
+    if os.path.isdir(LARGE_DIR) else []
+
+
+@pytest.mark.parametrize("name", LARGE_CASES)
+def test_large_path_matches_at_size_goldens(name, cuda_device):
+    """PARITY AT SIZE (tests/golden_large, oracle/make_golden_large.py): C3 (n = 8000, 2-D SM-4),
+    C4 (n = 32768, SM-8) and an n = 14000 case (N = 219 tile rows, ragged last tile, learned
+    noise) that takes the staged engine's right-looking PANEL schedule (N > 200).  MLL, the full
+    raw-parameter gradient and info against the blocked fp64 CPU oracle - LAPACK dpotrf / dpotri
+    on the assembled K~, gradient by autograd through the restated kernel - i.e. the Cholesky
+    branch of pgmuvi/trainers.py:179-181 (fast_computations off, lightcurve.py:5965-5968).
+    Tolerance: 1e-6 relative (north star, fp64); measured agreement is ~1e-9."""
+    from pgmuvi_b200 import ops
+    z = np.load(os.path.join(LARGE_DIR, name + ".npz"))
+    dev = cuda_device
+    mll, grad, info = ops.sm_mll_grad_large(
+        _t(z["x"], dev), _t(z["y"], dev), _t(z["noise"], dev), _t(z["raw"], dev),
+        _t(z["kinds"], dev, torch.int32), _t(z["lb"], dev), _t(z["ub"], dev), int(z["kind"]),
+        int(z["Q"]), bool(z["learn_noise"]), want_grad=True)
+    assert info == int(z["info"])
+    ref = float(z["mll"])
+    err_m = abs(float(mll) - ref) / abs(ref)
+    gref = z["grad"]
+    err_g = float(np.abs(grad.cpu().numpy() - gref).max() / np.abs(gref).max())
+    print(f"[at-size parity] {name}: n={z['x'].shape[0]} mll rel err {err_m:.2e}, "
+          f"grad rel err {err_g:.2e}")
+    assert err_m <= 1e-6 and err_g <= 1e-6
+    # MLL-only entry: the same Cholesky phase, no inverse / gradient
+    m2, _, i2 = ops.sm_mll_grad_large(
+        _t(z["x"], dev), _t(z["y"], dev), _t(z["noise"], dev), _t(z["raw"], dev),
+        _t(z["kinds"], dev, torch.int32), _t(z["lb"], dev), _t(z["ub"], dev), int(z["kind"]),
+        int(z["Q"]), bool(z["learn_noise"]), want_grad=False)
+    assert i2 == int(z["info"]) and abs(float(m2) - ref) <= 1e-6 * abs(ref)
+
+
 def test_train_routes_long_light_curves_through_the_large_path(cuda_device):
     """trainers.train on n = 2600 > LARGE_N: host loop over the whole-device MLL+gradient and
     the optimiser kernel, against the oracle's restatement of pgmuvi/trainers.py:177-207; the
@@ -94,7 +133,8 @@ def test_train_routes_long_light_curves_through_the_large_path(cuda_device):
         rng = np.random.default_rng(11)
         t = np.sort(rng.uniform(0.0, 900.0, n))
         y = np.sin(2 * np.pi * t / 61.0) + 0.1 * rng.standard_normal(n)
-        lc = Lightcurve(t, y, yerr=np.full(n, 0.1), max_samples=None).double()
+        lc = Lightcurve(t, y, yerr=np.full(n, 0.1), max_samples=None,
+                        xtransform="minmax").double()
         lc.set_model("1D", num_mixtures=2)
         lc.double()
         lc.set_default_constraints()
@@ -163,8 +203,6 @@ def test_staged_engine_jitter_ladder_and_bitwise_agreement_with_fused(cuda_devic
 # ---------------------------------------------------------------------------------------
 # N1: posterior prediction (pgm_sm_predict_f64)
 # ---------------------------------------------------------------------------------------
-import os
-
 PRED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_predict")
 PRED_CASES = sorted(f[:-4] for f in os.listdir(PRED_DIR) if f.endswith(".npz"))
 

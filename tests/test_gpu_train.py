@@ -14,6 +14,7 @@ def _lc(n=120, seed=3, period=57.0, yerr=True, **kw):
     rng = np.random.default_rng(seed)
     t = np.sort(rng.uniform(2450000.0, 2450000.0 + 6.3 * period, n))
     y = np.sin(2 * np.pi * t / period) + 0.1 * rng.standard_normal(n)
+    kw.setdefault("xtransform", "minmax")
     return Lightcurve(t, y, yerr=np.full(n, 0.1) if yerr else None, **kw)
 
 
@@ -101,7 +102,8 @@ def test_fit_2d_loss_decreases(cuda_device):
         xs.append(np.stack([t, np.full(60, wl)], 1))
         ys.append((1.0 + 0.2 * wl) * np.sin(2 * np.pi * t / 150.0 + 0.1 * wl)
                   + 0.05 * rng.standard_normal(60))
-    lc = Lightcurve(np.concatenate(xs), np.concatenate(ys), yerr=np.full(180, 0.05))
+    lc = Lightcurve(np.concatenate(xs), np.concatenate(ys), yerr=np.full(180, 0.05),
+                    xtransform="minmax")
     res = lc.fit(model="2D", num_mixtures=3, training_iter=100, lr=0.01, miniter=100)
     loss = np.array(res["loss"], dtype=float)
     assert len(loss) == 100 and np.isfinite(loss).all()
@@ -119,6 +121,7 @@ def _lc_2d(seed=5, n_per=40, **kw):
         xs.append(np.stack([t, np.full(n_per, wl)], 1))
         ys.append(amp * np.sin(2 * np.pi * t / 83.0 + 0.1 * wl) + 0.05 * rng.standard_normal(n_per))
     x, y = np.concatenate(xs), np.concatenate(ys)
+    kw.setdefault("xtransform", "minmax")
     return Lightcurve(x, y, yerr=np.full(len(y), 0.05), **kw)
 
 
@@ -213,6 +216,30 @@ def test_lightcurve_predict_after_fit(cuda_device):
     assert np.sqrt(np.mean((out["mean"] - truth) ** 2)) < 0.15
 
 
+@pytest.mark.parametrize("model,yerr", [("1DMatern", False), ("1DQuasiPeriodic", False),
+                                        ("1DMatern", True)])
+def test_predict_adds_the_learned_noise_for_stationary_layouts(cuda_device, model, yerr):
+    """predict() must find the learned-noise Parameter through the packed model
+    (the stationary kinds pack [mean, noise, ...], not [mean, w, mu, sigma, noise]): GaussianLikelihood
+    for yerr-less data, FixedNoise + learned noise ('learn') otherwise."""
+    from oracle import predict
+    torch.manual_seed(0)
+    lc = _lc(n=90, yerr=yerr).double()
+    lc.set_model(model, likelihood="learn" if yerr else None)
+    lc.double()
+    lc.set_default_constraints()
+    out = lc.predict(n_points=200)
+    args, pk = _oracle_inputs(lc)
+    assert pk.learn_noise and pk.noise_index == 1
+    xs = lc.xtransform.transform(torch.as_tensor(out["x"])).double().unsqueeze(-1)
+    mu, var, info = predict(*args[:7], args[7], xs)
+    nc = lc.likelihood.second_noise_covar if yerr else lc.likelihood.noise_covar
+    noise = float(nc.raw_noise_constraint.transform(nc.raw_noise))
+    assert noise > 0
+    assert np.abs(out["mean"] - mu.numpy()).max() <= 1e-8
+    assert np.abs(out["variance"] - (var.numpy() + noise)).max() <= 1e-8
+
+
 def test_c1_alfori_fit_matches_the_oracle_golden(cuda_device):
     """BASELINE config C1: Lightcurve.fit(model='1D') SM-4 on the bundled AlfOri V-band light
     curve (1564 -> 1000 points), Adam, 300 iterations, lr 0.1, GaussianLikelihood.  The whole
@@ -284,7 +311,7 @@ def test_fit_batch_matches_per_source_fits_and_mls_seeding(cuda_device):
             t = np.sort(rng.uniform(2450000.0, 2450000.0 + 7 * per, n))
             y = np.sin(2 * np.pi * t / per) + 0.1 * rng.standard_normal(n)
             from pgmuvi_b200.lightcurve import Lightcurve
-            out.append((Lightcurve(t, y, yerr=np.full(n, 0.1)).double(), per))
+            out.append((Lightcurve(t, y, yerr=np.full(n, 0.1), xtransform="minmax").double(), per))
         return out
 
     torch.manual_seed(3)
@@ -403,6 +430,9 @@ def test_non_constant_means_match_the_oracle(cuda_device, model, two_d):
         assert float((p.detach() - q).abs().max()) <= 1e-6 * max(1.0, float(q.abs().max()))
     mean_keys = [k for k in res if k.startswith("mean_module")]
     assert mean_keys and all(len(res[k]) == iters + 1 for k in mean_keys)
+    # the history keys are exactly get_parameters()'s (lightcurve.py:9031-9077: only names that
+    # contain 'raw' are stripped - 'mean_module.weights', never 'mean_module.eights')
+    assert set(res) == {"loss", "delta_loss"} | set(lc.get_parameters())
     # --- prediction conditions on y - m(x) and adds m(x*) back (oracle: Cholesky solve)
     from oracle import ModelSpec, predict as oracle_predict
     xq = lc._xdata_raw[::7]

@@ -52,6 +52,7 @@ def _lc_1d(n=60, yerr=True, seed=0, **kw):
     rng = np.random.default_rng(seed)
     t = np.sort(rng.uniform(2450000.0, 2450400.0, n))
     y = np.sin(2 * np.pi * t / 57.0) + 0.1 * rng.standard_normal(n)
+    kw.setdefault("xtransform", "minmax")
     return Lightcurve(t, y, yerr=np.full(n, 0.1) if yerr else None, **kw), t, y
 
 
@@ -141,7 +142,7 @@ def test_2d_constraints_and_dimension_checks():
     x = np.concatenate([np.stack([np.sort(rng.uniform(0, 300, 30)), np.full(30, wl)], 1)
                         for wl in (0.8, 1.2, 2.2)])
     y = rng.standard_normal(90)
-    lc = Lightcurve(x, y, yerr=np.full(90, 0.05))
+    lc = Lightcurve(x, y, yerr=np.full(90, 0.05), xtransform="minmax")
     with pytest.raises(ValueError):                           # tests/test_2d_integration.py:167-186
         lc.set_model("1D", num_mixtures=2)
     lc.set_model("2D", num_mixtures=3)
@@ -175,7 +176,7 @@ def test_separable_models_pack_onto_the_separable_kinds():
     y = rng.standard_normal(75)
     expect = {"rbf": (3, 2), "matern": (4, 2), "rq": (5, 3)}
     for wk, (kind, nl) in expect.items():
-        lc = Lightcurve(x, y, yerr=np.full(75, 0.05))
+        lc = Lightcurve(x, y, yerr=np.full(75, 0.05), xtransform="minmax")
         lc.set_model("2DWavelengthDependent", num_mixtures=3, wavelength_kernel_type=wk,
                      time_kernel_type="sm", mean_module="constant")
         lc.set_default_constraints()
@@ -196,7 +197,7 @@ def test_separable_models_pack_onto_the_separable_kinds():
         assert "covar_module.kernels.1.base_kernel.lengthscale" in keys
         if wk == "rq":       # the reference's str.lstrip("raw_") quirk
             assert "covar_module.kernels.1.base_kernel.lpha" in keys
-    lc = Lightcurve(x, y)                                   # Gaussian likelihood: learned noise
+    lc = Lightcurve(x, y, xtransform="minmax")              # Gaussian likelihood: learned noise
     lc.set_model("2DWavelengthDependent")                   # the reference's defaults, gps.py:1566-1609
     pk = pack_model(lc.model)
     assert (pk.kind, pk.Q, pk.external_mean) == (8 + 5 * 1 + 1, 0, True)   # Matern x RBF, quad mean
@@ -292,6 +293,7 @@ def _ragged_lcs(ns=(50, 64, 37), seed=4, **kw):
         per = rng.uniform(40, 90)
         t = np.sort(rng.uniform(2450000.0, 2450000.0 + 6 * per, n))
         y = np.sin(2 * np.pi * t / per) + 0.1 * rng.standard_normal(n)
+        kw.setdefault("xtransform", "minmax")
         out.append((Lightcurve(t, y, yerr=np.full(n, 0.1), **kw).double(), per))
     return out
 
@@ -357,3 +359,46 @@ def test_fit_batch_shards_over_ranks_and_gathers_gloo():
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
     assert outs[0][3] == [True, True, False] and outs[1][3] == [False, False, True]
     assert outs[0][1].shape[0] == 3 and np.isfinite(outs[0][2]).all()
+
+
+def test_packed_noise_index_for_both_layouts():
+    """the learned-noise Parameter sits at params[4] only in the spectral-mixture
+    layout [mean, w, mu, sigma, noise, ...]; the stationary kinds pack [mean, noise, ...]."""
+    lc, *_ = _lc_1d(n=30, yerr=False)                 # GaussianLikelihood: learned noise
+    lc.set_model("1D", num_mixtures=2)
+    pk = pack_model(lc.model)
+    assert pk.learn_noise and pk.noise_index == 4
+    assert pk.params[pk.noise_index] is lc.likelihood.noise_covar.raw_noise
+    for name in ("1DMatern", "1DQuasiPeriodic"):
+        lc.set_model(name)
+        pk = pack_model(lc.model)
+        assert pk.learn_noise and pk.noise_index == 1
+        assert pk.params[pk.noise_index] is lc.likelihood.noise_covar.raw_noise
+    lc2, *_ = _lc_1d(n=30, yerr=True)                  # plain FixedNoise: nothing learned
+    lc2.set_model("1DMatern")
+    assert pack_model(lc2.model).noise_index is None
+
+
+def test_fit_batch_rejects_non_constant_means():
+    """mean-function parameters live on the host; the one-launch batch loop would
+    silently train a free constant instead, so fit_batch refuses such models."""
+    from pgmuvi_b200.batch import fit_batch
+    lcs = [_lc_1d(n=24, seed=s)[0] for s in (1, 2)]
+    with pytest.raises(UnsupportedModelError):
+        fit_batch(lcs, model="1DLinear", num_mixtures=2, training_iter=2)
+
+
+def test_torch_optimizer_history_keys_follow_the_reference(cpu_engine, monkeypatch):
+    """parameters without 'raw' in their name keep it (lightcurve.py:9031-9077):
+    'mean_module.weights', not 'mean_module.eights'."""
+    keys = []
+    lc, *_ = _lc_1d(n=24)
+    lc.set_model("1DLinear", num_mixtures=2)
+    names = [n for n, _ in lc.model.named_parameters() if n.startswith("mean_module")]
+    assert names
+    snap = {}
+    for n in names:
+        key = trainers._strip_raw(n) if "raw" in n else n
+        snap[n] = key
+    assert all(not k.startswith("mean_module.eights") for k in snap.values())
+    assert set(snap.values()) <= set(lc.get_parameters())

@@ -51,7 +51,7 @@ def test_lightcurve_period_summary_after_fit(cuda_device):
     rng = np.random.default_rng(2)
     t = np.sort(rng.uniform(0.0, 600.0, 200))
     y = np.sin(2 * np.pi * t / 57.0) + 0.1 * rng.standard_normal(200)
-    lc = Lightcurve(t, y, yerr=np.full(200, 0.1))
+    lc = Lightcurve(t, y, yerr=np.full(200, 0.1), xtransform="minmax")
     lc.fit(model="1D", num_mixtures=2, periods=[55.0, 130.0], training_iter=120, lr=0.05)
     s = lc.get_period_summary()
     assert abs(s["dominant_period"] - 57.0) < 1.5
