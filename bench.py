@@ -7,9 +7,12 @@
 
 A "step" is one pass of the hot path over one batch: K(x,x') build + Cholesky + solve +
 log-det + full raw-parameter gradient for every light curve of the batch (one "eval" per
-light curve).  Under torchrun every rank owns its own 4096-light-curve shard (independent
-light curves: no collective inside the step; weak scaling) and the only exchange is the
-result all-gather after the step.  Rank 0 prints ONE JSON line.
+light curve).  Under torchrun the 4096 light curves of BASELINE config 2 are SPLIT over the
+ranks (``batch.shard_range``: 512 per GPU at N = 8; strong scaling - SURVEY.md section 8e);
+light curves are independent, so there is no collective inside the evaluation and the only
+exchange is the all-gather of the [B/G, 1+P] results, which is inside both timed regions.
+``--scaling weak`` gives every rank its own 4096 instead.  Rank 0 prints ONE JSON line, which
+also carries the C5 survey batch (16384 sources x (4 bands x 256 epochs), sharded the same way).
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, torch CPU with
 all host threads: GPyTorch itself is not installable in this image - SURVEY.md F3) on a
@@ -38,6 +41,8 @@ F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval (
 # (4096 light curves), from the `ncu --set full` capture summarised in
 # profiles/r01g_fused_ncu_summary.txt (43.57 GB + 10.35 GB); scales with light curves per GPU
 TRAFFIC_BYTES_PER_LC = (43.565392e9 + 10.345462e9) / 4096
+TRAFFIC_SOURCE = "profiles/r01g_fused_ncu_summary.txt"
+KERNEL_NAME = "pgm::sm_mll_grad_kernel<0,4,1>"
 PREWARM_STEPS = 30
 _OUT = sys.stdout      # replaced in main() by a private handle to the real stdout
 METRIC = "MLL+grad evals/s, 4096x n=512 SM-4 lightcurves"
@@ -50,7 +55,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--lightcurves", type=int, default=LC_PER_GPU, help="light curves per GPU")
+    ap.add_argument("--lightcurves", type=int, default=LC_PER_GPU,
+                    help="light curves: the global batch (strong scaling) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the batch is split over the ranks; weak: per rank")
+    ap.add_argument("--c5-sources", type=int, default=16384, help="global sources of the C5 line")
     ap.add_argument("--cpu-sample", type=int, default=32, help="light curves in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
@@ -59,12 +68,20 @@ def parse():
 
 
 def workload_config(args, world):
-    return {"workload": "C2: batch of synthetic 1-D light curves n=512, SM-4 kernel, "
+    strong = getattr(args, "scaling", "strong") == "strong"
+    glob = args.lightcurves if strong else args.lightcurves * world
+    return {"workload": "C2: batch of 4096 synthetic 1-D light curves n=512, SM-4 kernel, "
                         "FixedNoise likelihood, batched exact MLL+grad",
-            "lightcurves_per_gpu": args.lightcurves, "global_lightcurves": args.lightcurves * world,
+            "global_lightcurves": glob,
+            "lightcurves_per_gpu": (glob + world - 1) // world,
             "n": N_POINTS, "num_mixtures": Q_MIX, "params_per_lightcurve": 13,
-            "parallelism": f"independent light curves sharded over {world} GPU(s), "
-                           "no collective inside the step",
+            "parallelism": (f"the {glob} independent light curves split contiguously over "
+                            f"{world} GPU(s) (batch.shard_range)" if strong else
+                            f"{args.lightcurves} independent light curves per GPU x {world}")
+                           + "; no collective inside the evaluation, one all-gather of the "
+                             "[B/G, 1+P] results per step inside the timed region",
+            "data_note": "512 distinct seeded light curves, global index g uses seed 1000 + g % 512 "
+                         "(the work per light curve does not depend on the data)",
             "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)",
             "prewarm_steps": PREWARM_STEPS}
 
@@ -190,8 +207,8 @@ def run_reference(args):
 def other_configs(dev, dmma_peak):
     """Short CUDA-event timings of the other BASELINE.json configs on one GPU (not part of the
     headline metric; DESIGN.md section 4 quotes them): C1 = 300-iteration Adam fit of the bundled
-    AlfOri light curve, C3 = one MLL+grad of the n = 8000 2-D GP, C4 = n = 32768 SM-8,
-    C5 = the per-GPU share (2048 sources) of the 4 x 256 2-D survey batch."""
+    AlfOri light curve, C3 = one MLL+grad of the n = 8000 2-D GP, C4 = n = 32768 SM-8 (C5 has its
+    own sharded line, :func:`c5_line`)."""
     import warnings
     import torch
     from pgmuvi_b200 import ops, synthetic as S
@@ -246,26 +263,75 @@ def other_configs(dev, dmma_peak):
                                 "final_loss": float(res["loss"][-1])}
         out["C3_2d_n8000"] = single(S.make_batch_2d(1, 8, 1000, Q=4), 1, 4, 3)
         out["C4_1d_n32768_sm8"] = single(S.make_batch_1d(1, 32768, Q=8), 0, 8, 2)
-        bt5 = S.make_batch_2d(32, 4, 256, Q=4)
-        B5 = 2048
-        t5 = lambda a: T(np.concatenate([a] * (B5 // 32), 0)[:B5])
-        x5, y5, nz5, raw5, lb5, ub5 = (t5(bt5[k]) for k in ("x", "y", "noise", "raw", "lb", "ub"))
-        k5 = T(bt5["kinds"], torch.int32)
-        ms = ev_ms(lambda: ops.sm_mll_grad(x5, y5, nz5, raw5, k5, lb5, ub5, None, 1, 4, False,
-                                           True), 2)
-        tf = B5 * (1024 ** 3 + 4 * 1024 ** 2) / (ms * 1e-3) / 1e12
-        out["C5_2d_2048x1024_per_gpu"] = {"ms_per_eval_batch": ms, "evals_per_s": B5 / ms * 1e3,
-                                          "tflops": tf, "frac_of_dmma_peak": tf / dmma_peak}
     except Exception as exc:   # never let the side measurements break the headline line
         out["error"] = repr(exc)
     return out
+
+
+def c5_line(args, dev, rank, world, dmma_peak):
+    """BASELINE config 5: 16384 sources x (4 bands x 256 epochs = 1024 rows), 2-D SM-4, split
+    over the ranks (2048 per GPU at N = 8) through BatchEngine with host buffers; the all-gather
+    of the results is inside both timed regions.  32 distinct seeded sources are replicated."""
+    import torch
+    import torch.distributed as dist
+    from pgmuvi_b200 import synthetic as S
+    from pgmuvi_b200.batch import BatchEngine, HostBatch, gather_results, shard_range
+    G5 = args.c5_sources
+    a, z = shard_range(G5, rank, world)
+    B5 = z - a
+    bt = S.make_batch_2d(32, 4, 256, Q=4)
+    idx = np.arange(a, z) % 32
+    for k in ("x", "y", "noise", "raw", "lb", "ub"):
+        bt[k] = bt[k][idx]
+    hb = HostBatch.from_numpy(bt, pin=True)
+    eng = BatchEngine(kind=1, Q=4, learn_noise=False, device=dev)
+    counts = [shard_range(G5, r, world)[1] - shard_range(G5, r, world)[0] for r in range(world)]
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    d = eng.upload(hb)
+    reps = 2
+    for _ in range(1):
+        gather_results(torch.cat([t.unsqueeze(1) if t.dim() == 1 else t
+                                  for t in eng.evaluate_device(d, True)[:2]], 1), counts)
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        mll, grad, info = eng.evaluate_device(d, True)
+        gather_results(torch.cat([mll.unsqueeze(1), grad], 1), counts)
+    e1.record()
+    sync()
+    dev_ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d = eng.upload(hb)
+        mll, grad, info = eng.evaluate_device(d, True)
+        allr = gather_results(torch.cat([mll.unsqueeze(1), grad], 1), counts)
+        host = allr.cpu()
+    sync()
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    tm = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = (float(v) for v in tm.tolist())
+    tf = G5 * (1024 ** 3 + 4 * 1024 ** 2) / (dev_ms * 1e-3) / 1e12
+    return {"workload": f"C5: {G5} sources x (4 bands x 256 epochs), 2-D SM-4, fp64, "
+                        f"{B5} per GPU", "global_sources": G5, "ms_per_eval_batch": dev_ms,
+            "evals_per_s": G5 / dev_ms * 1e3, "e2e_evals_per_s": G5 / e2e_ms * 1e3,
+            "tflops_all_gpus": tf, "frac_of_dmma_peak": tf / (dmma_peak * world),
+            "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": host.numel() * 8,
+            "info_nonzero": int((info != 0).sum().item())}
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
     from pgmuvi_b200 import ops, synthetic as S
-    from pgmuvi_b200.batch import BatchEngine, HostBatch, gather_results
+    from pgmuvi_b200.batch import BatchEngine, HostBatch, gather_results, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -278,13 +344,19 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.lightcurves
-    # distinct synthetic light curves per rank (seeded), C2 shape
-    distinct = min(B, 512)
-    bt = S.make_batch_1d(distinct, N_POINTS, Q=Q_MIX, seed0=1000 + rank * 100000)
-    rep = (B + distinct - 1) // distinct
+    strong = args.scaling == "strong"
+    G = args.lightcurves if strong else args.lightcurves * world      # global batch
+    a, z = shard_range(G, rank, world) if strong else (rank * args.lightcurves,
+                                                       (rank + 1) * args.lightcurves)
+    B = z - a                                                          # this rank's shard
+    counts = [shard_range(G, r, world)[1] - shard_range(G, r, world)[0] for r in range(world)] \
+        if strong else [args.lightcurves] * world
+    # 512 distinct seeded light curves of the C2 shape; global index g -> seed 1000 + g % 512
+    distinct = min(G, 512)
+    bt = S.make_batch_1d(distinct, N_POINTS, Q=Q_MIX, seed0=1000)
+    idx = np.arange(a, z) % distinct
     for k in ("x", "y", "noise", "raw", "lb", "ub"):
-        bt[k] = np.concatenate([bt[k]] * rep, 0)[:B]
+        bt[k] = bt[k][idx]
     hb = HostBatch.from_numpy(bt, pin=True)
     eng = BatchEngine(kind=ops.KIND_SM1D, Q=Q_MIX, learn_noise=False, device=dev)
     d = eng.upload(hb)
@@ -298,10 +370,7 @@ def run_b200(args):
 
     def step_device():
         mll, grad, info = eng.evaluate_device(d, want_grad=True)
-        if world > 1:
-            res = gather_results(torch.cat([mll.unsqueeze(1), grad], 1))
-            return res
-        return mll
+        return gather_results(torch.cat([mll.unsqueeze(1), grad], 1), counts), info
 
     # ---- device-resident throughput ("value") -------------------------------------------
     # a fresh box starts with cold clocks / power state: about one second of untimed pre-warm
@@ -328,23 +397,31 @@ def run_b200(args):
         kev[i][0].record()
         mll, grad, info = eng.evaluate_device(d, want_grad=True)
         kev[i][1].record()
-        if world > 1:
-            gather_results(torch.cat([mll.unsqueeze(1), grad], 1))
+        gather_results(torch.cat([mll.unsqueeze(1), grad], 1), counts)
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    kern_ms = [a.elapsed_time(b) for a, b in kev]
+    step_ms = [a_.elapsed_time(b_) for a_, b_ in ev]
+    kern_ms = [a_.elapsed_time(b_) for a_, b_ in kev]
     total_ms = float(sum(step_ms))
     bad = int((info != 0).sum().item())
 
     # ---- end to end through the public host API ("e2e") -----------------------------------
+    # pinned host inputs -> H2D -> kernel -> all-gather of the results -> D2H of all of them
+    def step_e2e():
+        dd = eng.upload(hb)
+        m_, g_, i_ = eng.evaluate_device(dd, want_grad=True)
+        allr = gather_results(torch.cat([m_.unsqueeze(1), g_], 1), counts)
+        out = (eng._host_out("all", allr), eng._host_out("info", i_))
+        torch.cuda.current_stream().synchronize()
+        return out
+
     for _ in range(2):
-        eng.evaluate(hb)
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = eng.evaluate(hb)                         # H2D inputs, kernel, D2H results, sync
+        out = step_e2e()
     if world > 1:
         dist.barrier()
     e2e_s = time.perf_counter() - t0
@@ -357,8 +434,19 @@ def run_b200(args):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, kern_ms_avg = (float(v) for v in tm.tolist())
 
+    dmma = ops.peak_probe(0, 8192)
+    dfma = ops.peak_probe(1, 8192)
+    del d, flush
+    torch.cuda.empty_cache()
+    c5 = None
+    if not args.no_other_configs:
+        try:
+            c5 = c5_line(args, dev, rank, world, dmma)
+        except Exception as exc:       # never let a side measurement break the headline line
+            c5 = {"error": repr(exc)}
+
     if rank == 0:
-        evals = B * world * args.steps
+        evals = G * args.steps
         value = evals / (total_ms * 1e-3)
         peaks = {}
         try:
@@ -366,10 +454,8 @@ def run_b200(args):
                 peaks = json.load(f)
         except Exception:
             pass
-        dmma = ops.peak_probe(0, 8192)
-        dfma = ops.peak_probe(1, 8192)
         achieved = B * F_EVAL / (kern_ms_avg * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "pgm::sm_mll_grad_kernel<0,4,1>",
+        roofline = {"bound": "tensor", "kernel": KERNEL_NAME,
                     "achieved": achieved, "peak": dmma, "unit": "TFLOP/s",
                     "frac": achieved / dmma,
                     "peak_source": "self-measured FP64 DMMA (mma.sync.m8n8k4.f64) probe in this "
@@ -378,20 +464,23 @@ def run_b200(args):
                                    f"{peaks.get('hbm_gbs')} GB/s do not bound an fp64 kernel); "
                                    "nominal B200 FP64 37 TFLOP/s",
                     "dfma_probe_tflops": dfma,
+                    "lightcurves_per_launch": B,
                     "algorithmic_flops_per_launch": B * F_EVAL,
                     "kernel_ms_avg": kern_ms_avg,
                     "traffic": TRAFFIC_BYTES_PER_LC * B,
-                    "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01g_fused_ncu_summary.txt)",
+                    "traffic_unit": "bytes per launch (ncu dram read+write, " + TRAFFIC_SOURCE + ")",
                     "algorithmic_bytes_per_launch": B * (3 * N_POINTS + 2 * 13 + 1) * 8}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(args, world),
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": d2h},
+                        "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": d2h,
+                        "includes": "H2D of the shard, kernel, all-gather of the results over the "
+                                    "ranks, D2H of all gathered results"},
                 "gpu_launches": args.steps, "roofline": roofline, "clocks": clocks,
                 "cholesky_info_nonzero": bad, "wall_s_timed_loop": t_wall,
-                "step_ms": [round(v, 3) for v in step_ms]}
+                "step_ms": [round(v, 3) for v in step_ms], "c5": c5}
         if world == 1 and not args.no_cpu_baseline:
             val, mode, both, cores = cpu_reference(args.cpu_sample, 2, 1)
             line["cpu_baseline"] = {
@@ -399,8 +488,6 @@ def run_b200(args):
                 "sample": f"{args.cpu_sample} of the C2 light curves x 2 steps, fp64, torch CPU "
                           f"{cores} threads, best of {both}", "mode": mode}
         if world == 1 and not args.no_other_configs:
-            del d, flush
-            torch.cuda.empty_cache()
             line["other_configs"] = other_configs(dev, dmma)
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
