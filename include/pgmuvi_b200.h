@@ -74,6 +74,9 @@ extern "C" {
 #define PGM_FLAG_GRAD 1          /* also compute d MLL / d raw (loss.backward, trainers.py:181) */
 #define PGM_FLAG_LEARN_NOISE 2   /* last slot is a learnable homoskedastic noise variance       */
 #define PGM_FLAG_BOUNDS_PER_LC 4 /* con_lb / con_ub are [B,P] (else [P], shared)                */
+#define PGM_FLAG_JITTER_F32 8    /* jitter ladder 1e-6, 1e-5, 1e-4 (GPyTorch's float32 cholesky_jitter)
+                                    instead of 1e-8, 1e-7, 1e-6; set by the *_f32 entry points, and
+                                    by f64 callers whose MODEL is float32                          */
 
 /* optimiser kinds: torch.optim.* as selected at pgmuvi/trainers.py:141-147 */
 #define PGM_OPT_SGD 0

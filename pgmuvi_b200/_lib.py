@@ -36,7 +36,7 @@ def stat_num_lam(kind):
 
 
 CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2
-FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC = 1, 2, 4
+FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC, FLAG_JITTER_F32 = 1, 2, 4, 8
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 
 EXPORTS = (

@@ -450,7 +450,8 @@ int pgm_sm_mll_grad_f32(const float* x, const int32_t* n_valid, const float* y,
   widen(con_lb, s.lb, per_lc ? BP : (size_t)P, st);
   widen(con_ub, s.ub, per_lc ? BP : (size_t)P, st);
   if (int r = pgm_sm_mll_grad_f64(s.x, n_valid, s.y, fixed_noise ? s.fn : nullptr, s.raw, con_kind,
-                                  s.lb, s.ub, B, n_max, d, Q, kernel_kind, flags, s.mll,
+                                  s.lb, s.ub, B, n_max, d, Q, kernel_kind,
+                                  flags | PGM_FLAG_JITTER_F32, s.mll,
                                   (flags & PGM_FLAG_GRAD) ? s.grad : nullptr, info, workspace,
                                   base, stream))
     return r;
@@ -491,7 +492,8 @@ int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
   widen(con_lb, s.lb, per_lc ? BP : (size_t)P, st);
   widen(con_ub, s.ub, per_lc ? BP : (size_t)P, st);
   if (int r = pgm_sm_fit_f64(s.x, n_valid, s.y, fixed_noise ? s.fn : nullptr, s.raw, con_kind, s.lb,
-                             s.ub, B, n_max, d, Q, kernel_kind, flags, optim_kind, lr, beta1, beta2,
+                             s.ub, B, n_max, d, Q, kernel_kind, flags | PGM_FLAG_JITTER_F32,
+                             optim_kind, lr, beta1, beta2,
                              eps, weight_decay, maxiter, miniter, stop, stopavg, s.loss,
                              raw_hist ? s.hist : nullptr, n_iter, info, nullptr, workspace, base,
                              stream))

@@ -123,9 +123,9 @@ __device__ __forceinline__ LcView lc_view(const LargeArgs& A, int b = -1) {
   v.st = make_batch_state(A.ws, A.n_max, A.B);
   return v;
 }
-__device__ __forceinline__ double lg_jitter(int attempt) {
+__device__ __forceinline__ double lg_jitter(int attempt, int flags) {
   if (attempt <= 0) return 0.0;
-  double j = 1e-8;
+  double j = (flags & PGM_FLAG_JITTER_F32) ? 1e-6 : 1e-8;
   for (int t = 1; t < attempt; ++t) j *= 10.0;
   return j;
 }
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   }
   if (i >= N || j >= N) return;
   if (v.st.fail[v.b]) return;
-  const double jitter = lg_jitter(v.st.attempt[v.b]);
+  const double jitter = lg_jitter(v.st.attempt[v.b], A.flags);
   double* stages = sm + C::SM_STAGES;
   double* Cst = stages + 2 * OPBUF;
   double* rowv = sm + C::SM_ROW;
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
   int* flags = v.st.tflag + (size_t)v.b * large_ntri(A.n_max);
   auto flag_of = [&](int a, int b2) { return flags + ((size_t)a * (a + 1) / 2 + b2); };
   volatile int* failp = v.st.fail + v.b;
-  const double jitter = lg_jitter(v.st.attempt[v.b]);
+  const double jitter = lg_jitter(v.st.attempt[v.b], A.flags);
   double* stages = sm;
   double* S2 = stages;                  // diagonal job: X = L^-1 (the stages are idle then)
   double* Cst = stages + 2 * OPBUF;

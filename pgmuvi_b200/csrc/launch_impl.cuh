@@ -31,6 +31,11 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
   if (grid > A.B) grid = A.B;
+  {
+    int ns = 0;
+    if (const char* f = getenv("PGM_PHASE_NS")) ns = atoi(f);
+    cudaMemcpyToSymbolAsync(pgm::c_phase_ns, &ns, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+  }
 #ifdef PGM_DEBUG_HOOKS
   {
     int dbg = 0;

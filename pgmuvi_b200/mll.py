@@ -404,25 +404,29 @@ class B200ExactMarginalLogLikelihood(torch.nn.Module):
                                   pk.learn_noise, holder)
             self._raise_for(holder[0])
             return mll.to(dtype=raw.dtype, device=raw.device)
+        # float32 models go through the *_f32 entry point (fp32 storage, fp64 arithmetic, and
+        # GPyTorch's float32 jitter ladder 1e-6..1e-4); everything else is float64
+        dt = torch.float32 if raw.dtype == torch.float32 else torch.float64
+        cv = lambda t: None if t is None else t.detach().to(device=dev, dtype=dt)
         mll, grad, info = ops.sm_mll_grad(
-            f64(x).unsqueeze(0).contiguous(), f64(target).unsqueeze(0).contiguous(),
-            None if pk.fixed_noise is None else f64(pk.fixed_noise).unsqueeze(0).contiguous(),
-            raw.to(device=dev, dtype=torch.float64).unsqueeze(0),
-            pk.kinds.to(dev), pk.lb.to(dev), pk.ub.to(dev), None, pk.kind, pk.Q, pk.learn_noise,
-            True)
-        self._raise_for(int(info.item()))
+            cv(x).unsqueeze(0).contiguous(), cv(target).unsqueeze(0).contiguous(),
+            None if pk.fixed_noise is None else cv(pk.fixed_noise).unsqueeze(0).contiguous(),
+            raw.to(device=dev, dtype=dt).unsqueeze(0),
+            pk.kinds.to(dev), pk.lb.to(device=dev, dtype=dt), pk.ub.to(device=dev, dtype=dt), None,
+            pk.kind, pk.Q, pk.learn_noise, True)
+        self._raise_for(int(info.item()), 1e-6 if dt == torch.float32 else 1e-8)
         return mll[0].to(dtype=raw.dtype, device=raw.device)
 
-    def _raise_for(self, code):
+    def _raise_for(self, code, jitter_base=1e-8):
         from .gp import NanError, NotPSDError
         self.last_info = code
         if code == -1:
             raise NanError("cholesky_cpu: NaN values found in the covariance matrix")
         if code == -2:
             raise NotPSDError("Matrix not positive definite after repeatedly adding jitter "
-                              "up to 1.0e-06.")
+                              f"up to {jitter_base * 100:.1e}.")
         if code > 0:
             import warnings
             from .gp import NumericalWarning
-            warnings.warn(f"A not p.d., added jitter of {1e-8 * 10 ** (code - 1):.1e} to the "
+            warnings.warn(f"A not p.d., added jitter of {jitter_base * 10 ** (code - 1):.1e} to the "
                           "diagonal", NumericalWarning)

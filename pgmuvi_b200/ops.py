@@ -208,6 +208,12 @@ def optim_step(raw: Tensor, grad_mll: Tensor, exp_avg: Tensor, exp_avg_sq: Tenso
             lr, beta1, beta2, eps, weight_decay, step, _stream()))
 
 
+@optim_step.register_fake
+def _(raw, grad_mll, exp_avg, exp_avg_sq, active, optim_kind, lr, beta1, beta2, eps, weight_decay,
+      step):
+    return None
+
+
 @torch.library.custom_op("pgmuvi_b200::sm_fit", mutates_args=("raw",), device_types="cuda")
 def sm_fit(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con_kind: Tensor,
            con_lb: Tensor, con_ub: Tensor, n_valid: Optional[Tensor], kind: int, Q: int,
@@ -248,6 +254,15 @@ def sm_fit(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor, con
             ptr(raw_hist) if keep_history else None, ptr(n_iter), ptr(info), None, ptr(ws),
             ws.numel(), _stream()))
     return loss_hist, raw_hist, n_iter, info
+
+
+@sm_fit.register_fake
+def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_noise, optim_kind,
+      lr, beta1, beta2, eps, weight_decay, maxiter, miniter, stop, stopavg, keep_history):
+    B, P = raw.shape
+    return (y.new_empty(maxiter, B),
+            y.new_empty((maxiter + 1, B, P) if keep_history else (0,)),
+            y.new_empty(B, dtype=torch.int32), y.new_empty(B, dtype=torch.int32))
 
 
 def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
