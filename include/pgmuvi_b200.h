@@ -74,6 +74,9 @@ extern "C" {
 #define PGM_FLAG_GRAD 1          /* also compute d MLL / d raw (loss.backward, trainers.py:181) */
 #define PGM_FLAG_LEARN_NOISE 2   /* last slot is a learnable homoskedastic noise variance       */
 #define PGM_FLAG_BOUNDS_PER_LC 4 /* con_lb / con_ub are [B,P] (else [P], shared)                */
+#define PGM_FLAG_TF32X3 16       /* staged engine: the K~^-1 = X^T X products of the gradient run on
+                                    the Blackwell tensor cores (tcgen05, 3xTF32, FP32 accumulators in
+                                    tensor memory); needs pgm_staged_tf32x3_workspace_bytes          */
 #define PGM_FLAG_JITTER_F32 8    /* jitter ladder 1e-6, 1e-5, 1e-4 (GPyTorch's float32 cholesky_jitter)
                                     instead of 1e-8, 1e-7, 1e-6; set by the *_f32 entry points, and
                                     by f64 callers whose MODEL is float32                          */
@@ -248,6 +251,37 @@ int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
                    double beta2, double eps, double weight_decay, int maxiter, int miniter,
                    double stop, int stopavg, float* loss_hist, float* raw_hist, int32_t* n_iter,
                    int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * fp32 models on the Blackwell tensor cores ("TF32-refined", north star kernel 2/3).  The staged
+ * engine with the third of the flops that only feeds the gradient - K~^-1 = X^T X (lauum), contracted
+ * with W = alpha alpha^T - K~^-1 and dK/dtheta - as 3xTF32 tcgen05.mma products: X^T is split into
+ * TF32 hi / lo operand images (hi hi + hi lo + lo hi, FP32 accumulation in tensor memory, about
+ * 2^-21 relative per product), one CTA per 128x128 tile of K~^-1, contraction in FP64 straight out of
+ * tensor memory (K~^-1 is never written anywhere).  The MLL value, the Cholesky factor, the solves and
+ * the inverse factor stay on the FP64 path, so `mll` is the same number the _f64 entry returns; the
+ * gradient meets the north star's fp32 bar (1e-4 relative against the fp64 oracle).
+ *   pgm_sm_mll_grad_staged_tf32x3_f64  double buffers, = pgm_sm_mll_grad_staged_f64 | PGM_FLAG_TF32X3
+ *   pgm_sm_mll_grad_tf32x3_f32         float buffers (the reference's default dtype,
+ *                                      pgmuvi/lightcurve.py:2434-2446); workspace =
+ *                                      pgm_staged_tf32x3_workspace_bytes rounded up to 256 +
+ *                                      pgm_f32_staging_bytes(..., 0, 0); float32 jitter ladder
+ * Both replace loss = -mll(output, y); loss.backward() of pgmuvi/trainers.py:179-181.  Blocking.
+ */
+size_t pgm_staged_tf32x3_workspace_bytes(int n_max, int B);
+int pgm_sm_mll_grad_staged_tf32x3_f64(const double* x, const int32_t* n_valid, const double* y,
+                                      const double* fixed_noise, const double* raw,
+                                      const int32_t* con_kind, const double* con_lb,
+                                      const double* con_ub, int B, int n_max, int d, int Q,
+                                      int kernel_kind, int flags, double* mll, double* grad_raw,
+                                      int32_t* info, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+int pgm_sm_mll_grad_tf32x3_f32(const float* x, const int32_t* n_valid, const float* y,
+                               const float* fixed_noise, const float* raw,
+                               const int32_t* con_kind, const float* con_lb, const float* con_ub,
+                               int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                               float* mll, float* grad_raw, int32_t* info, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 /*
  * N2 - batched Lomb-Scargle initialisation (the step before the path).

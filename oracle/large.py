@@ -32,14 +32,14 @@ def _row_block(n, spec: ModelSpec, budget_bytes=192 << 20):
 
 
 def assemble_kt(x, fixed_noise, theta, spec: ModelSpec, jitter=0.0, out=None):
-    """Dense K~ = K + D (+ jitter I), [n, n] fp64, built by row blocks."""
+    """Dense K~ = K + D (+ jitter I), [n, n] (dtype of x), built by row blocks."""
     n = x.shape[0]
-    K = out if out is not None else torch.empty(n, n, dtype=torch.float64)
+    K = out if out is not None else torch.empty(n, n, dtype=x.dtype)
     rb = _row_block(n, spec)
     for i0 in range(0, n, rb):
         K[i0:i0 + rb] = kernel_dense(x[i0:i0 + rb], x, theta, spec)
     noise = unpack_params(theta, spec)[4]
-    d = torch.zeros(n, dtype=torch.float64)
+    d = torch.zeros(n, dtype=x.dtype)
     if fixed_noise is not None:
         d = d + fixed_noise
     if noise is not None:
@@ -50,7 +50,9 @@ def assemble_kt(x, fixed_noise, theta, spec: ModelSpec, jitter=0.0, out=None):
 
 def mll_and_grad_blocked(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec,
                          want_grad=True, verbose=False):
-    """x [n, d], y [n], fixed_noise [n] or None, raw / lb / ub [P] (fp64 torch tensors).
+    """x [n, d], y [n], fixed_noise [n] or None, raw / lb / ub [P] (torch tensors of ONE dtype:
+    float64 = the oracle; float32 = the "fp32 torch restatement" whose error against the fp64
+    values is the yardstick of the fp32 tensor-core path).
     Returns (mll, dMLL/draw [P] or None, info) with the info codes of psd_safe_cholesky."""
     import time
     t0 = time.time()
@@ -61,8 +63,9 @@ def mll_and_grad_blocked(x, y, fixed_noise, raw, kinds, lb, ub, spec: ModelSpec,
     mean = theta[0]
     info = 0
     K = None
-    for attempt in range(4):        # A.5: plain, then jitter 1e-8 * 10^i, i = 0..2 (fp64)
-        jitter = 0.0 if attempt == 0 else 1e-8 * 10 ** (attempt - 1)
+    jbase = 1e-6 if y.dtype == torch.float32 else 1e-8
+    for attempt in range(4):        # A.5: plain, then jitter 1e-8 * 10^i, i = 0..2 (fp32: 1e-6 ..)
+        jitter = 0.0 if attempt == 0 else jbase * 10 ** (attempt - 1)
         K = assemble_kt(x, fixed_noise, theta, spec, jitter, out=K)
         if bool(torch.isnan(K).any()):
             return torch.tensor(float("nan")), None, -1

@@ -36,7 +36,7 @@ def stat_num_lam(kind):
 
 
 CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2
-FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC, FLAG_JITTER_F32 = 1, 2, 4, 8
+FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC, FLAG_JITTER_F32, FLAG_TF32X3 = 1, 2, 4, 8, 16
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 
 EXPORTS = (
@@ -48,6 +48,8 @@ EXPORTS = (
     "pgm_lombscargle_f64", "pgm_ls_peaks_f64",
     "pgm_sm_mll_grad_alpha_f64", "pgm_sm_mll_grad_staged_alpha_f64",
     "pgm_sm_psd_peak_f64",
+    "pgm_staged_tf32x3_workspace_bytes", "pgm_sm_mll_grad_staged_tf32x3_f64",
+    "pgm_sm_mll_grad_tf32x3_f32",
 )
 
 _lib = None
@@ -90,6 +92,12 @@ def load():
     lib.pgm_staged_workspace_bytes.argtypes = [c_int, c_int]
     lib.pgm_sm_mll_grad_staged_f64.restype = c_int
     lib.pgm_sm_mll_grad_staged_f64.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
+    lib.pgm_staged_tf32x3_workspace_bytes.restype = c_size_t
+    lib.pgm_staged_tf32x3_workspace_bytes.argtypes = [c_int, c_int]
+    lib.pgm_sm_mll_grad_staged_tf32x3_f64.restype = c_int
+    lib.pgm_sm_mll_grad_staged_tf32x3_f64.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
+    lib.pgm_sm_mll_grad_tf32x3_f32.restype = c_int
+    lib.pgm_sm_mll_grad_tf32x3_f32.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
     lib.pgm_predict_workspace_bytes.restype = c_size_t
     lib.pgm_predict_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.pgm_sm_predict_f64.restype = c_int

@@ -2,6 +2,7 @@
 // code is in gp_fused.cuh.
 #include "gp_fused.cuh"
 #include "gp_large.cuh"
+#include "gp_large_tc.cuh"
 #include "lombscargle.cuh"
 #include "../../include/pgmuvi_b200.h"
 
@@ -285,8 +286,9 @@ int pgm_sm_mll_grad_staged_alpha_f64(const double* x, const int32_t* n_valid, co
   if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
     return fail("null pointer argument");
   if ((flags & PGM_FLAG_GRAD) && !grad_raw) return fail("PGM_FLAG_GRAD needs grad_raw");
-  if (workspace_bytes < pgm_staged_workspace_bytes(n_max, B))
-    return fail("workspace too small (see pgm_staged_workspace_bytes)");
+  if (workspace_bytes < ((flags & PGM_FLAG_TF32X3) ? pgm_staged_tf32x3_workspace_bytes(n_max, B)
+                                                   : pgm_staged_workspace_bytes(n_max, B)))
+    return fail("workspace too small (see pgm_staged_workspace_bytes / pgm_staged_tf32x3_workspace_bytes)");
   pgm::LargeArgs A;
   A.x = x; A.n_valid = n_valid; A.y = y; A.fixed_noise = fixed_noise; A.raw = raw;
   A.con_kind = con_kind; A.con_lb = con_lb; A.con_ub = con_ub;
@@ -297,6 +299,61 @@ int pgm_sm_mll_grad_staged_alpha_f64(const double* x, const int32_t* n_valid, co
   const int want_grad = (flags & PGM_FLAG_GRAD) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGM_DISPATCH(launch_large, A, want_grad, st, 0);
+  return 0;
+}
+
+size_t pgm_staged_tf32x3_workspace_bytes(int n_max, int B) {
+  return (n_max < 1 || B < 1) ? 0 : pgm::large_ws_bytes_tc(n_max, B);
+}
+
+int pgm_sm_mll_grad_staged_tf32x3_f64(const double* x, const int32_t* n_valid, const double* y,
+                                      const double* fixed_noise, const double* raw,
+                                      const int32_t* con_kind, const double* con_lb,
+                                      const double* con_ub, int B, int n_max, int d, int Q,
+                                      int kernel_kind, int flags, double* mll, double* grad_raw,
+                                      int32_t* info, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  return pgm_sm_mll_grad_staged_alpha_f64(x, n_valid, y, fixed_noise, raw, con_kind, con_lb,
+                                          con_ub, B, n_max, d, Q, kernel_kind,
+                                          flags | PGM_FLAG_TF32X3, mll, grad_raw, nullptr, info,
+                                          workspace, workspace_bytes, stream);
+}
+
+int pgm_sm_mll_grad_tf32x3_f32(const float* x, const int32_t* n_valid, const float* y,
+                               const float* fixed_noise, const float* raw,
+                               const int32_t* con_kind, const float* con_lb, const float* con_ub,
+                               int B, int n_max, int d, int Q, int kernel_kind, int flags,
+                               float* mll, float* grad_raw, int32_t* info, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  if (int r = check_common(B, n_max, d, Q, kernel_kind)) return r;
+  if (B == 0) return 0;
+  if (!x || !y || !raw || !con_kind || !con_lb || !con_ub || !mll || !info || !workspace)
+    return fail("null pointer argument");
+  if ((flags & PGM_FLAG_GRAD) && !grad_raw) return fail("PGM_FLAG_GRAD needs grad_raw");
+  const int P = host_param_count(d, Q, kernel_kind, flags);
+  const bool per_lc = (flags & PGM_FLAG_BOUNDS_PER_LC) != 0;
+  const size_t base = align256(pgm_staged_tf32x3_workspace_bytes(n_max, B));
+  const size_t need = base + pgm_f32_staging_bytes(B, n_max, d, Q, kernel_kind, flags, 0, 0);
+  if (workspace_bytes < need)
+    return fail("workspace too small (pgm_staged_tf32x3_workspace_bytes rounded up to 256 + "
+                "pgm_f32_staging_bytes)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Stage32 s = carve32(static_cast<char*>(workspace) + base, B, n_max, d, P, per_lc, 0, false);
+  const size_t Bn = (size_t)B * n_max, BP = (size_t)B * P;
+  widen(x, s.x, Bn * d, st); widen(y, s.y, Bn, st);
+  if (fixed_noise) widen(fixed_noise, s.fn, Bn, st);
+  widen(raw, s.raw, BP, st);
+  widen(con_lb, s.lb, per_lc ? BP : (size_t)P, st);
+  widen(con_ub, s.ub, per_lc ? BP : (size_t)P, st);
+  if (int r = pgm_sm_mll_grad_staged_alpha_f64(
+          s.x, n_valid, s.y, fixed_noise ? s.fn : nullptr, s.raw, con_kind, s.lb, s.ub, B, n_max, d,
+          Q, kernel_kind, flags | PGM_FLAG_JITTER_F32 | PGM_FLAG_TF32X3, s.mll,
+          (flags & PGM_FLAG_GRAD) ? s.grad : nullptr, nullptr, info, workspace, base, stream))
+    return r;
+  narrow(s.mll, mll, (size_t)B, st);
+  if (flags & PGM_FLAG_GRAD) narrow(s.grad, grad_raw, BP, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail("f32 staging", e);
   return 0;
 }
 

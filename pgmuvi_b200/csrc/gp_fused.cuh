@@ -183,8 +183,6 @@ __device__ __forceinline__ void load_exp_tab(double* tab) {
   if (threadIdx.x < EXP_TAB) tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
 }
 
-__constant__ int c_phase_ns = 0;
-__device__ int g_sm_slot[256];
 #ifdef PGM_DEBUG_HOOKS
 // -DPGM_DEBUG_HOOKS: per-phase clock64 totals of thread 0 and decomposition switches
 // (PGM_DEBUG_MODE: 0x100 no operand loads, 0x200 no MMAs, 0x400 no exp/cos epilogue work,
@@ -1600,20 +1598,6 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   const int P = param_count<KIND, QT, D>(A.Q, (A.flags & PGM_FLAG_LEARN_NOISE) != 0);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
-  if (c_phase_ns > 0) {   // EXPERIMENT: de-phase the two co-resident blocks of an SM
-    __shared__ int s_slot;
-    if (threadIdx.x == 0) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      s_slot = atomicAdd(&g_sm_slot[smid & 255], 1) & 1;
-      if (s_slot) {
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < (unsigned long long)c_phase_ns);
-      }
-    }
-    __syncthreads();
-  }
   for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
     double* gout = A.grad ? A.grad + (size_t)b * P : nullptr;
     const int info =

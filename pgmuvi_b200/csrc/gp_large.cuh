@@ -1007,7 +1007,9 @@ __global__ void __launch_bounds__(NTHREADS) lg_finish(LargeArgs A, int want_grad
     vv[C::NV + 2] += w.ldz[2 * jb + 1];
   }
   if (want_grad) {
-    const int njobs = N * (N + 1) / 2;
+    // per-tile partials: 64x64 tiles (lg_grad) or 128x128 tiles (lg_grad_tc, PGM_FLAG_TF32X3 = 16)
+    const int NTg = (A.flags & 16) ? (N + 1) / 2 : N;
+    const int njobs = NTg * (NTg + 1) / 2;
     for (int t = tid; t < njobs; t += NTHREADS)
 #pragma unroll
       for (int k = 0; k < C::NV; ++k) vv[k] += w.gpart[(size_t)t * LG_GP + k];

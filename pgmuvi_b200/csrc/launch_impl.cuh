@@ -3,6 +3,7 @@
 #pragma once
 #include "gp_fused.cuh"
 #include "gp_large.cuh"
+#include "gp_large_tc.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -31,11 +32,6 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
   if (grid > A.B) grid = A.B;
-  {
-    int ns = 0;
-    if (const char* f = getenv("PGM_PHASE_NS")) ns = atoi(f);
-    cudaMemcpyToSymbolAsync(pgm::c_phase_ns, &ns, sizeof(int), 0, cudaMemcpyHostToDevice, st);
-  }
 #ifdef PGM_DEBUG_HOOKS
   {
     int dbg = 0;
@@ -181,7 +177,27 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       lg_inv_all<<<dim3((unsigned)nblk), blk, LG_INV_SMEM, st>>>(A);
     }
     lg_alpha<<<dim3(N, B), blk, 0, st>>>(A);
-    if (!predict_only) k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
+    if (!predict_only && (A.flags & PGM_FLAG_TF32X3)) {
+      // G phase on tcgen05: X^T -> packed TF32 hi / lo operand images, then one CTA per 128x128
+      // tile of K~^-1 (3xTF32 products in tensor memory, FP64 contraction epilogue)
+      const int NT = (N + 1) / 2;
+      using TS_ = TcGradSmem<KIND, QT, D>;
+      auto k_tc = lg_grad_tc<KIND, QT, D>;
+      int nst = 3;
+      if (const char* f = getenv("PGM_TC_STAGES")) nst = std::min(3, std::max(1, atoi(f)));
+      while (nst > 1 && TS_::bytes(nst) > 227 * 1024) --nst;
+      if (TS_::bytes(nst) > 227 * 1024) return fail("lg_grad_tc does not fit in shared memory");
+      e = cudaFuncSetAttribute(k_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_::bytes(nst));
+      if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_grad_tc)", e);
+      lg_pack_tf32<<<dim3(N, 2 * NT, B), blk, 0, st>>>(A);
+      // pieces of 16 k (two truncating hi hi additions each) by default: accuracy first.  32-k pieces
+      // (PGM_TC_HALF_PIECES=0) halve the drain work - C4's G phase 170 -> 112 ms - at 1.8x the error.
+      int halfp = 1;
+      if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
+      k_tc<<<dim3(NT * (NT + 1) / 2, B), TC_THREADS, TS_::bytes(nst), st>>>(A, nst, halfp);
+    } else if (!predict_only) {
+      k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
+    }
   }
   if (predict_only) {
     lg_transpose<<<dim3(N * (N + 1) / 2, B), blk, 0, st>>>(A);

@@ -268,18 +268,29 @@ def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_
 def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
                        con_kind: Tensor, con_lb: Tensor, con_ub: Tensor,
                        n_valid: Optional[Tensor], kind: int, Q: int, learn_noise: bool,
-                       want_grad: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+                       want_grad: bool = True, tf32x3: bool = False
+                       ) -> Tuple[Tensor, Tensor, Tensor]:
     """Same contract as :func:`sm_mll_grad`, through the staged whole-device engine
     (``pgm_sm_mll_grad_staged_f64``): every light curve's K~ lives in HBM as 64x64 tiles and
-    the batch advances stage by stage.  Blocking."""
+    the batch advances stage by stage.  Blocking.
+
+    ``tf32x3=True``: the K~^-1 = X^T X products of the gradient run on the Blackwell tensor cores
+    (tcgen05, 3xTF32; ``pgm_sm_mll_grad_staged_tf32x3_f64`` for float64 tensors,
+    ``pgm_sm_mll_grad_tf32x3_f32`` for float32 tensors - the reference's default dtype)."""
     (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
         x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
-    if x.dtype != torch.float64:
-        raise RuntimeError("the staged engine takes float64 tensors")
+    f32 = x.dtype == torch.float32
+    if f32 and not tf32x3:
+        raise RuntimeError("the staged engine takes float64 tensors (float32: tf32x3=True)")
     if want_grad:
         flags |= FLAG_GRAD
     lib = _lib.load()
-    need = lib.pgm_staged_workspace_bytes(n, B)
+    if tf32x3:
+        need = lib.pgm_staged_tf32x3_workspace_bytes(n, B)
+        if f32:
+            need = ((need + 255) & ~255) + lib.pgm_f32_staging_bytes(B, n, d, Q, kind, flags, 0, 0)
+    else:
+        need = lib.pgm_staged_workspace_bytes(n, B)
     key = (x.device.index,)
     ws = _staged_ws.get(key)
     if ws is None or ws.numel() < need:
@@ -292,8 +303,10 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
     info = torch.zeros(B, dtype=torch.int32, device=x.device)
     if n_valid is not None:
         n_valid = n_valid.to(torch.int32).contiguous()
+    entry = (lib.pgm_sm_mll_grad_tf32x3_f32 if f32 else lib.pgm_sm_mll_grad_staged_tf32x3_f64
+             if tf32x3 else lib.pgm_sm_mll_grad_staged_f64)
     with torch.cuda.device(x.device):
-        check(lib.pgm_sm_mll_grad_staged_f64(
+        check(entry(
             ptr(x), ptr(n_valid), ptr(y), ptr(fixed_noise), ptr(raw), ptr(con_kind), ptr(con_lb),
             ptr(con_ub), B, n, d, Q, kind, flags, ptr(mll), ptr(grad), ptr(info), ptr(ws),
             ws.numel(), _stream()))

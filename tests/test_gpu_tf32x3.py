@@ -1,0 +1,139 @@
+"""GPU tests of the fp32-model tensor-core path (R1): ``pgm_sm_mll_grad_staged_tf32x3_f64`` /
+``pgm_sm_mll_grad_tf32x3_f32`` - the K~^-1 = X^T X products of the gradient on tcgen05 (3xTF32, FP32
+accumulators in tensor memory), contracted with dK/dtheta in FP64 straight out of TMEM.
+
+Bar (north star, fp32): error against the fp64 oracle <= max(1e-4 relative, the
+error of an fp32 torch restatement on the same inputs) - the restatement is the oracle itself run in
+float32 (live for the small goldens; ``tests/golden_large/fp32_restatement.json``, written by
+``python -m oracle.make_fp32_baseline``, at size).  The MLL stays on the FP64 path, so through the
+double-buffer entry it must equal the staged engine's value exactly; the gradient carries the
+3xTF32 product / FP32 accumulation error of K~^-1."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # north star: "1e-4 relative in fp32"
+
+
+def _fp32_restatement_grad_err(g, b):
+    """relative gradient error of the oracle run in float32 on light curve b of golden g"""
+    from oracle import ModelSpec, mll_and_grad_autograd
+    spec = ModelSpec(d=g["d"], Q=g["Q"], kind=g["kind"], learn_noise=g["learn_noise"])
+    nb = g["x"].shape[1] if g["n_valid"] is None else int(g["n_valid"][b])
+    c = lambda a: torch.tensor(np.asarray(a), dtype=torch.float32)
+    lb = g["lb"][b] if np.ndim(g["lb"]) == 2 else g["lb"]
+    ub = g["ub"][b] if np.ndim(g["ub"]) == 2 else g["ub"]
+    try:
+        _, gr, info = mll_and_grad_autograd(
+            c(g["x"][b][:nb]), c(g["y"][b][:nb]), None if g["noise"] is None else c(g["noise"][b][:nb]),
+            c(g["raw"][b]), torch.tensor(g["kinds"]), c(lb), c(ub), spec)
+    except Exception:
+        return float("inf")
+    ref = g["grad_autograd"][b]
+    if int(info) != int(g["info"][b]) or not torch.isfinite(gr).all():
+        return float("inf")
+    return float(np.abs(gr.double().numpy() - ref).max() / np.abs(ref).max())
+
+
+def _t(a, dev, dt=torch.float64):
+    return None if a is None else torch.tensor(np.asarray(a), dtype=dt, device=dev)
+
+
+def _args(g, dev, dt=torch.float64):
+    return (_t(g["x"], dev, dt), _t(g["y"], dev, dt), _t(g["noise"], dev, dt), _t(g["raw"], dev, dt),
+            _t(g["kinds"], dev, torch.int32), _t(g["lb"], dev, dt), _t(g["ub"], dev, dt),
+            None if g["n_valid"] is None else _t(g["n_valid"], dev, torch.int32))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_tf32x3_matches_goldens(name, cuda_device):
+    """every kernel kind / ragged batch / learned-noise golden of the oracle, double buffers"""
+    from pgmuvi_b200 import ops
+    g = load_golden(name)
+    a = _args(g, cuda_device)
+    mll, grad, info = ops.sm_mll_grad_staged(*a, g["kind"], g["Q"], g["learn_noise"], True,
+                                             tf32x3=True)
+    m0, g0, i0 = ops.sm_mll_grad_staged(*a, g["kind"], g["Q"], g["learn_noise"], True)
+    assert info.cpu().tolist() == [int(v) for v in g["info"]]
+    assert torch.equal(mll, m0)          # the MLL never leaves the FP64 path
+    ref = g["grad_autograd"]
+    got = grad.cpu().numpy()
+    for b in range(ref.shape[0]):
+        if int(g["info"][b]) < 0:
+            continue
+        err = np.abs(got[b] - ref[b]).max() / np.abs(ref[b]).max()
+        if err > TOL:      # the escape clause: no worse than float32 arithmetic itself
+            bar = _fp32_restatement_grad_err(g, b)
+            print(f"[tf32x3] {name}[{b}]: grad rel err {err:.2e}, fp32 restatement {bar:.2e}")
+            assert err <= bar, (name, b, err, bar)
+
+
+def test_tf32x3_float32_entry_c2_shape(cuda_device):
+    """pgm_sm_mll_grad_tf32x3_f32 on a C2-shaped batch (n = 512, SM-4, float32 buffers - the
+    reference's default dtype) against the live fp64 oracle on the SAME float32-rounded inputs."""
+    from pgmuvi_b200 import ops, synthetic as S
+    from oracle import ModelSpec, mll_and_grad_analytic, mll_and_grad_autograd
+    bt = S.make_batch_1d(6, 512, Q=4, seed0=31)
+    dev = cuda_device
+    f32 = {k: np.asarray(bt[k], dtype=np.float32) for k in ("x", "y", "noise", "raw", "lb", "ub")}
+    T = lambda a: torch.tensor(a, dtype=torch.float32, device=dev)
+    kinds = torch.tensor(bt["kinds"], dtype=torch.int32, device=dev)
+    mll, grad, info = ops.sm_mll_grad_staged(T(f32["x"]), T(f32["y"]), T(f32["noise"]), T(f32["raw"]),
+                                             kinds, T(f32["lb"]), T(f32["ub"]), None, 0, 4, False, True,
+                                             tf32x3=True)
+    assert mll.dtype == torch.float32 and grad.dtype == torch.float32
+    assert info.cpu().tolist() == [0] * 6
+    spec = ModelSpec(d=1, Q=4, kind=0, learn_noise=False)
+    c = lambda a: torch.tensor(np.asarray(a, dtype=np.float64))
+    for b in range(6):
+        lb = f32["lb"][b] if f32["lb"].ndim == 2 else f32["lb"]
+        ub = f32["ub"][b] if f32["ub"].ndim == 2 else f32["ub"]
+        mo, go, _ = mll_and_grad_analytic(c(f32["x"][b]), c(f32["y"][b]), c(f32["noise"][b]),
+                                          c(f32["raw"][b]), torch.tensor(bt["kinds"]), c(lb), c(ub),
+                                          spec)
+        assert abs(float(mll[b]) - float(mo)) <= TOL * abs(float(mo))
+        err = float((grad[b].cpu().double() - go).abs().max() / go.abs().max())
+        if err > TOL:      # no worse than the oracle itself run in float32
+            c32 = lambda a: torch.tensor(np.asarray(a, dtype=np.float32))
+            _, g32, _ = mll_and_grad_autograd(c32(f32["x"][b]), c32(f32["y"][b]), c32(f32["noise"][b]),
+                                              c32(f32["raw"][b]), torch.tensor(bt["kinds"]), c32(lb),
+                                              c32(ub), spec)
+            bar = float((g32.double() - go).abs().max() / go.abs().max())
+            print(f"[tf32x3 f32 entry] lc {b}: grad rel err {err:.2e}, fp32 restatement {bar:.2e}")
+            assert err <= bar
+
+
+LARGE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_large")
+
+
+@pytest.mark.parametrize("name", ["c3_2d_8x1000_q4", "panel_1d_n14000_q4", "c4_1d_n32768_q8"])
+def test_tf32x3_at_size(name, cuda_device):
+    """C3 / the n = 14000 panel case / C4 (K range up to 32768 per product) against the blocked fp64
+    oracle's goldens (tests/golden_large): the FP32 accumulation in tensor memory must hold the
+    fp32 bar at size too."""
+    from pgmuvi_b200 import ops
+    z = np.load(os.path.join(LARGE_DIR, name + ".npz"))
+    dev = cuda_device
+    u = lambda a, dt=torch.float64: _t(a, dev, dt).unsqueeze(0)
+    lb, ub = _t(z["lb"], dev), _t(z["ub"], dev)
+    mll, grad, info = ops.sm_mll_grad_staged(
+        u(z["x"]) if z["x"].ndim == 2 else u(z["x"]).unsqueeze(-1), u(z["y"]), u(z["noise"]),
+        u(z["raw"]), _t(z["kinds"], dev, torch.int32), lb, ub, None, int(z["kind"]), int(z["Q"]),
+        bool(z["learn_noise"]), True, tf32x3=True)
+    assert int(info[0]) == int(z["info"])
+    ref = float(z["mll"])
+    err_m = abs(float(mll[0]) - ref) / abs(ref)
+    gref = z["grad"]
+    err_g = float(np.abs(grad[0].cpu().numpy() - gref).max() / np.abs(gref).max())
+    with open(os.path.join(LARGE_DIR, "fp32_restatement.json")) as f:
+        bar = max(TOL, json.load(f)[name]["grad_rel_err"])
+    print(f"[tf32x3 at size] {name}: n={z['x'].shape[0]} mll rel err {err_m:.2e}, grad rel err {err_g:.2e} "
+          f"(bar {bar:.2e})")
+    assert err_m <= 1e-6 and err_g <= bar
