@@ -77,6 +77,10 @@ extern "C" {
 #define PGM_FLAG_TF32X3 16       /* staged engine: the K~^-1 = X^T X products of the gradient run on
                                     the Blackwell tensor cores (tcgen05, 3xTF32, FP32 accumulators in
                                     tensor memory); needs pgm_staged_tf32x3_workspace_bytes          */
+#define PGM_FLAG_TF32X3_CHOL 32  /* staged engine, panel schedule (n > 12800): the right-looking trailing
+                                    updates C -= L_panel L_panel^T run on tcgen05 (3xTF32) as well; the MLL
+                                    then carries fp32-class error (with PGM_FLAG_TF32X3 only, it is the
+                                    FP64 value)                                                        */
 #define PGM_FLAG_JITTER_F32 8    /* jitter ladder 1e-6, 1e-5, 1e-4 (GPyTorch's float32 cholesky_jitter)
                                     instead of 1e-8, 1e-7, 1e-6; set by the *_f32 entry points, and
                                     by f64 callers whose MODEL is float32                          */
@@ -260,7 +264,11 @@ int pgm_sm_fit_f32(const float* x, const int32_t* n_valid, const float* y,
  * 2^-21 relative per product), one CTA per 128x128 tile of K~^-1, contraction in FP64 straight out of
  * tensor memory (K~^-1 is never written anywhere).  The MLL value, the Cholesky factor, the solves and
  * the inverse factor stay on the FP64 path, so `mll` is the same number the _f64 entry returns; the
- * gradient meets the north star's fp32 bar (1e-4 relative against the fp64 oracle).
+ * gradient is held to the fp32 acceptance of SURVEY.md section 7 (error against the fp64 oracle <=
+ * max(1e-4 relative, the error of the oracle run in float32); tests/test_gpu_tf32x3.py).
+ * With PGM_FLAG_TF32X3_CHOL the trailing updates of the panel-schedule Cholesky (n > 12800: 90 % of
+ * the factorisation's flops) run on tcgen05 too - north star kernel (2); pgm_sm_mll_grad_tf32x3_f32
+ * sets it, the _f64 entry takes it from `flags`.
  *   pgm_sm_mll_grad_staged_tf32x3_f64  double buffers, = pgm_sm_mll_grad_staged_f64 | PGM_FLAG_TF32X3
  *   pgm_sm_mll_grad_tf32x3_f32         float buffers (the reference's default dtype,
  *                                      pgmuvi/lightcurve.py:2434-2446); workspace =

@@ -347,7 +347,7 @@ int pgm_sm_mll_grad_tf32x3_f32(const float* x, const int32_t* n_valid, const flo
   widen(con_ub, s.ub, per_lc ? BP : (size_t)P, st);
   if (int r = pgm_sm_mll_grad_staged_alpha_f64(
           s.x, n_valid, s.y, fixed_noise ? s.fn : nullptr, s.raw, con_kind, s.lb, s.ub, B, n_max, d,
-          Q, kernel_kind, flags | PGM_FLAG_JITTER_F32 | PGM_FLAG_TF32X3, s.mll,
+          Q, kernel_kind, flags | PGM_FLAG_JITTER_F32 | PGM_FLAG_TF32X3 | PGM_FLAG_TF32X3_CHOL, s.mll,
           (flags & PGM_FLAG_GRAD) ? s.grad : nullptr, nullptr, info, workspace, base, stream))
     return r;
   narrow(s.mll, mll, (size_t)B, st);

@@ -155,7 +155,21 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
         lg_diag<<<dim3(1, B), blk, LG_DIAG_SMEM, st>>>(A, j);
         if (j + 1 < N) lg_trsm<<<dim3(N - j - 1, B), blk, LG_TRSM_SMEM, st>>>(A, j);
       }
-      if (J1 < N) {
+      if (J1 < N && (A.flags & PGM_FLAG_TF32X3_CHOL) && !(J1 & 1)) {
+        // trailing update on tcgen05 (3xTF32): pack the panel's L tiles, one CTA per 128x128 tile
+        using TS_ = TcGradSmem<KIND, QT, D>;
+        auto k_utc = lg_update_tc<KIND, QT, D>;
+        int nst = 3;
+        while (nst > 1 && TS_::bytes(nst) > 227 * 1024) --nst;
+        if (TS_::bytes(nst) > 227 * 1024) return fail("lg_update_tc does not fit in shared memory");
+        e = cudaFuncSetAttribute(k_utc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_::bytes(nst));
+        if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_update_tc)", e);
+        int halfp = 1;
+        if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
+        const int NT = (N + 1) / 2, Mt = NT - J1 / 2;
+        lg_pack_panel_tf32<<<dim3(J1 - J0, 2 * NT - J1, B), blk, 0, st>>>(A, J0, J1);
+        k_utc<<<dim3(Mt * (Mt + 1) / 2, B), TC_THREADS, TS_::bytes(nst), st>>>(A, J0, J1, build, nst, halfp);
+      } else if (J1 < N) {
         const int M = N - J1;
         k_upd<<<dim3(M * (M + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build);
       }

@@ -268,7 +268,7 @@ def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_
 def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
                        con_kind: Tensor, con_lb: Tensor, con_ub: Tensor,
                        n_valid: Optional[Tensor], kind: int, Q: int, learn_noise: bool,
-                       want_grad: bool = True, tf32x3: bool = False
+                       want_grad: bool = True, tf32x3: bool = False, tf32x3_chol: bool = False
                        ) -> Tuple[Tensor, Tensor, Tensor]:
     """Same contract as :func:`sm_mll_grad`, through the staged whole-device engine
     (``pgm_sm_mll_grad_staged_f64``): every light curve's K~ lives in HBM as 64x64 tiles and
@@ -276,7 +276,9 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
 
     ``tf32x3=True``: the K~^-1 = X^T X products of the gradient run on the Blackwell tensor cores
     (tcgen05, 3xTF32; ``pgm_sm_mll_grad_staged_tf32x3_f64`` for float64 tensors,
-    ``pgm_sm_mll_grad_tf32x3_f32`` for float32 tensors - the reference's default dtype)."""
+    ``pgm_sm_mll_grad_tf32x3_f32`` for float32 tensors - the reference's default dtype).
+    ``tf32x3_chol=True`` (implied for float32 tensors): the trailing updates of the panel-schedule
+    Cholesky run there too."""
     (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
         x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
     f32 = x.dtype == torch.float32
@@ -284,6 +286,10 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
         raise RuntimeError("the staged engine takes float64 tensors (float32: tf32x3=True)")
     if want_grad:
         flags |= FLAG_GRAD
+    if tf32x3_chol:
+        if not tf32x3:
+            raise RuntimeError("tf32x3_chol needs tf32x3=True")
+        flags |= _lib.FLAG_TF32X3_CHOL
     lib = _lib.load()
     if tf32x3:
         need = lib.pgm_staged_tf32x3_workspace_bytes(n, B)

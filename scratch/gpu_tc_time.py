@@ -25,6 +25,11 @@ def run(name, bt, kind, Q, B):
             ms, (mll, grad, info) = timeit(lambda: ops.sm_mll_grad_staged(x, y, nz, raw, kinds, lb, ub, None, kind, Q, False, want, tf32x3=tf))
             res[(tf, want)] = (ms, grad)
             print(f'{name}: tf32x3={tf} grad={want}: {ms:9.3f} ms   {B / ms * 1e3:9.0f} evals/s  info!=0: {int((info != 0).sum())}', flush=True)
+    if bt['x'].shape[1] > 12800:
+        ms, (mll, grad, info) = timeit(lambda: ops.sm_mll_grad_staged(x, y, nz, raw, kinds, lb, ub, None, kind, Q, False, True, tf32x3=True, tf32x3_chol=True))
+        print(f'{name}: tf32x3 + chol grad=True: {ms:9.3f} ms   info!=0: {int((info != 0).sum())}', flush=True)
+        ms, _ = timeit(lambda: ops.sm_mll_grad_staged(x, y, nz, raw, kinds, lb, ub, None, kind, Q, False, False, tf32x3=True, tf32x3_chol=True))
+        print(f'{name}: tf32x3 + chol grad=False: {ms:9.3f} ms', flush=True)
     g0, g1 = res[(False, True)][1], res[(True, True)][1]
     print(f'{name}: max grad rel diff tf32x3 vs fp64 = {float(((g1 - g0).abs().amax(1) / g0.abs().amax(1)).max()):.2e}', flush=True)
 

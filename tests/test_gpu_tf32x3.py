@@ -137,3 +137,58 @@ def test_tf32x3_at_size(name, cuda_device):
     print(f"[tf32x3 at size] {name}: n={z['x'].shape[0]} mll rel err {err_m:.2e}, grad rel err {err_g:.2e} "
           f"(bar {bar:.2e})")
     assert err_m <= 1e-6 and err_g <= bar
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names()
+                                  if n.startswith(("sm1d_n512", "sm1d_ragged", "sm2d", "sep_rbf", "sep_mat"))])
+def test_tf32x3_chol_forced_panel_schedule_goldens(name, cuda_device, monkeypatch):
+    """PGM_FLAG_TF32X3_CHOL on small goldens: PGM_STAGED_CHOL_ALL_N=0 forces the right-looking panel
+    schedule (PGM_STAGED_NB=2: panels of 2 tile columns), whose trailing updates then run on tcgen05 (first panel: K~
+    generated in the tensor-core kernel's epilogue).  MLL within 1e-4 (measured ~1e-7), gradient
+    within max(1e-4, fp32 restatement)."""
+    if name not in golden_names():
+        pytest.skip("golden not present")
+    from pgmuvi_b200 import ops
+    monkeypatch.setenv("PGM_STAGED_CHOL_ALL_N", "0")
+    monkeypatch.setenv("PGM_STAGED_NB", "2")      # panels of 2 tile columns: trailing updates at J1 = 2, 4, ..
+    g = load_golden(name)
+    a = _args(g, cuda_device)
+    mll, grad, info = ops.sm_mll_grad_staged(*a, g["kind"], g["Q"], g["learn_noise"], True,
+                                             tf32x3=True, tf32x3_chol=True)
+    assert info.cpu().tolist() == [int(v) for v in g["info"]]
+    ref = g["grad_autograd"]
+    got = grad.cpu().numpy()
+    for b in range(ref.shape[0]):
+        if int(g["info"][b]) < 0:
+            continue
+        em = abs(float(mll[b]) - g["mll"][b]) / abs(g["mll"][b])
+        err = np.abs(got[b] - ref[b]).max() / np.abs(ref[b]).max()
+        print(f"[tf32x3 chol] {name}[{b}]: mll rel err {em:.2e}, grad rel err {err:.2e}")
+        assert em <= TOL
+        if err > TOL:
+            bar = _fp32_restatement_grad_err(g, b)
+            assert err <= bar, (name, b, err, bar)
+
+
+@pytest.mark.parametrize("name", ["panel_1d_n14000_q4", "c4_1d_n32768_q8"])
+def test_tf32x3_chol_at_size(name, cuda_device):
+    """the panel-schedule sizes with the trailing updates on tcgen05 (north star kernel 2, "TF32-refined")"""
+    from pgmuvi_b200 import ops
+    z = np.load(os.path.join(LARGE_DIR, name + ".npz"))
+    dev = cuda_device
+    u = lambda a, dt=torch.float64: _t(a, dev, dt).unsqueeze(0)
+    mll, grad, info = ops.sm_mll_grad_staged(
+        u(z["x"]) if z["x"].ndim == 2 else u(z["x"]).unsqueeze(-1), u(z["y"]), u(z["noise"]), u(z["raw"]),
+        _t(z["kinds"], dev, torch.int32), _t(z["lb"], dev), _t(z["ub"], dev), None, int(z["kind"]),
+        int(z["Q"]), bool(z["learn_noise"]), True, tf32x3=True, tf32x3_chol=True)
+    assert int(info[0]) == int(z["info"])
+    ref = float(z["mll"])
+    err_m = abs(float(mll[0]) - ref) / abs(ref)
+    gref = z["grad"]
+    err_g = float(np.abs(grad[0].cpu().numpy() - gref).max() / np.abs(gref).max())
+    with open(os.path.join(LARGE_DIR, "fp32_restatement.json")) as f:
+        rec = json.load(f)[name]
+    bar = max(TOL, rec["grad_rel_err"])
+    print(f"[tf32x3 chol at size] {name}: mll rel err {err_m:.2e} (fp32 restatement "
+          f"{rec['mll_rel_err']:.2e}), grad rel err {err_g:.2e} (bar {bar:.2e})")
+    assert err_m <= TOL and err_g <= bar
