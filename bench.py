@@ -214,6 +214,10 @@ def other_configs(dev, dmma_peak):
     from pgmuvi_b200 import ops, synthetic as S
     T = lambda a, dt=torch.float64: torch.tensor(np.asarray(a), dtype=dt, device=dev)
     out = {}
+    try:
+        tf32_peak = ops.peak_probe(4, 4096)
+    except Exception:
+        tf32_peak = None
 
     def ev_ms(fn, reps):
         best = 1e30
@@ -234,7 +238,20 @@ def other_configs(dev, dmma_peak):
         ms = ev_ms(lambda: ops.sm_mll_grad_large(x, y, nz, raw, kk, lo, hi, kind, Q, False, True),
                    reps)
         tf = (n ** 3 + 4 * n ** 2) / (ms * 1e-3) / 1e12
-        return {"n": n, "ms_per_eval": ms, "tflops": tf, "frac_of_dmma_peak": tf / dmma_peak}
+        rec = {"n": n, "ms_per_eval": ms, "tflops": tf, "frac_of_dmma_peak": tf / dmma_peak}
+        # float32 model (the reference's default dtype) through pgm_sm_mll_grad_tf32x3_f32: the
+        # trailing updates (n > 12800) and K~^-1 = X^T X on tcgen05 (3xTF32); same flop count
+        f = lambda t: None if t is None else t.float().unsqueeze(0)
+        x32 = f(x if x.dim() == 2 else x.unsqueeze(-1))
+        ms32 = ev_ms(lambda: ops.sm_mll_grad_staged(x32, f(y), f(nz), f(raw), kk, lo.float(),
+                                                    hi.float(), None, kind, Q, False, True,
+                                                    tf32x3=True), reps)
+        rec["f32_tf32x3"] = {"ms_per_eval": ms32, "tflops": tf * ms / ms32,
+                             "speedup_vs_f64": ms / ms32,
+                             "tf32_tcgen05_peak_tflops": tf32_peak,
+                             "note": "P trailing updates (panel schedule) + G products on tcgen05 "
+                                     "3xTF32; T phase, panels and solves FP64 DMMA"}
+        return rec
 
     try:
         import tempfile

@@ -332,7 +332,9 @@ int pgm_sm_psd_peak_f64(const double* freq, const double* fscale, const double* 
 /* Device yardsticks used by bench.py for the self-measured FP64 roofline: runs `iters`
  * dependent-free FP64 DMMA (kind 0), FP64 DFMA (kind 1), FP32 FFMA (kind 2) or interleaved
  * DMMA+DFMA (kind 3, equal flops each) instructions per thread on every SM and returns the
- * achieved TFLOP/s in *tflops (host pointer). */
+ * achieved TFLOP/s in *tflops (host pointer).  kind 4: dense TF32 tcgen05.mma (M = N = 128, one
+ * issuing thread per SM, operands resident in shared memory): the yardstick of the 3xTF32 path,
+ * whose effective peak is a third of it. */
 int pgm_peak_probe(int kind, int iters, double* tflops_host, void* stream);
 
 #ifdef __cplusplus

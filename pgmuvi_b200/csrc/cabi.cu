@@ -687,6 +687,50 @@ __global__ void __launch_bounds__(256) probe_ffma(int iters, double* out) {
   for (int i = 0; i < 16; ++i) s += acc[i];
   if (s == 123.456f) out[0] = s;
 }
+// dense TF32 tcgen05.mma rate (M = N = 128, K = 8 per instruction): one CTA per SM, one thread issues
+// `iters` rounds of 16 MMAs (4 k-steps x 2 accumulators x A/B image pairs) from a resident stage
+__global__ void __launch_bounds__(64, 1) probe_tcgen05_tf32(int iters, double* out) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  const unsigned base = (smem_u32(smraw) + 1023u) & ~1023u;
+  const unsigned bar = base + 2 * tc::IMG_BYTES, tslot = bar + 16;
+  float* img = reinterpret_cast<float*>(smraw + (base - smem_u32(smraw)));
+  for (int i = threadIdx.x; i < 2 * tc::IMG_FLOATS; i += 64) img[i] = 1e-3f * (float)((i * 37) % 101);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  if ((threadIdx.x >> 5) == 1) tc::tmem_alloc(tslot, 256);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  unsigned tmem;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem) : "r"(tslot));
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc = tc::idesc_tf32(128, 128);
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t a = tc::smem_desc_sw128(base + ks * 32);
+        const uint64_t b = tc::smem_desc_sw128(base + tc::IMG_BYTES + ks * 32);
+        tc::mma_tf32(tmem, a, b, idesc, (it | ks) ? 1u : 0u);
+        tc::mma_tf32(tmem + 128, b, a, idesc, (it | ks) ? 1u : 0u);
+        tc::mma_tf32(tmem, b, a, idesc, 1u);
+        tc::mma_tf32(tmem + 128, a, b, idesc, 1u);
+      }
+    tc::mma_commit(bar);
+    mbar_wait(bar, 0);
+    tc::fence_after_sync();
+  }
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    float v[16];
+    tc::tmem_ld16(tmem + ((unsigned)(32 * 1) << 16), v);
+    if (v[0] == 123.456f) out[0] = v[0];
+    tc::fence_before_sync();
+    tc::tmem_dealloc(tmem, 256);
+  }
+}
 }  // namespace pgm
 
 extern "C" int pgm_peak_probe(int kind, int iters, double* tflops_host, void* stream) {
@@ -699,12 +743,20 @@ extern "C" int pgm_peak_probe(int kind, int iters, double* tflops_host, void* st
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int blocks = sms * 8, threads = 256;
+  int blocks = sms * 8, threads = 256;
   double flops_per_thread_iter = 0.0;
   float best = 1e30f;
+  const size_t tc_smem = 2 * pgm::tc::IMG_BYTES + 1024 + 64;
+  if (kind == 4) {
+    blocks = sms; threads = 64;
+    cudaFuncSetAttribute(pgm::probe_tcgen05_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem);
+  }
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0, st);
-    if (kind == 0) {
+    if (kind == 4) {
+      pgm::probe_tcgen05_tf32<<<blocks, threads, tc_smem, st>>>(iters, dout);
+      flops_per_thread_iter = 16.0 * (128.0 * 128 * 8 * 2) / 64.0;
+    } else if (kind == 0) {
       pgm::probe_dmma<<<blocks, threads, 0, st>>>(iters, dout);
       flops_per_thread_iter = 8.0 * (8 * 8 * 4 * 2) / 32.0;
     } else if (kind == 1) {

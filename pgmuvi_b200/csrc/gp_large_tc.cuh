@@ -211,11 +211,33 @@ __device__ __forceinline__ void tc_drain(const TcCtx& cx, unsigned tlane, int nc
       tc::tmem_st16(tlane + T_MASTER + (unsigned)c0, pv);
       tc::tmem_st16(tlane + T_MLO + (unsigned)c0, lo);
     }
+    // (batching the six loads of 32 columns behind one wait was tried: no faster - the drain is bound
+    // by its instruction count, ~400 per thread and piece, not by the TMEM round trips - and spills)
     tc::tmem_wait_st();
     tc::fence_before_sync();
     __syncwarp();
     if (lane == 0) mbar_arrive(cx.bar_pempty + 8 * buf);
   }
+}
+
+// Block -> tile of a lower-triangular set of Mt x Mt 128-tiles, in SUPER-BLOCKS of S x S tiles: the
+// CTAs resident at the same time (one per SM) then cover a roughly square patch and share their A / B
+// operand panels through L2 (row-major order: one A panel + ~148 B panels = 300 MB per wave, super-
+// blocks of 12: 24 panels = 48 MB).  grid = nSB (nSB + 1) / 2 * S * S; blocks above the diagonal or
+// past the edge return false.
+__host__ __device__ inline int tc_super(int Mt) { return Mt < 12 ? Mt : 12; }
+__host__ __device__ inline unsigned tc_grid(int Mt) {
+  const int S = tc_super(Mt), nSB = (Mt + S - 1) / S;
+  return (unsigned)(nSB * (nSB + 1) / 2) * (unsigned)(S * S);
+}
+__device__ __forceinline__ bool tc_tile_of_block(unsigned bid, int Mt, int& a, int& b) {
+  const int S = tc_super(Mt);
+  const unsigned sb = bid / (unsigned)(S * S), within = bid - sb * (unsigned)(S * S);
+  int sI, sJ;
+  tri_unrank((int)sb, sI, sJ);
+  a = sI * S + (int)(within / (unsigned)S);
+  b = sJ * S + (int)(within % (unsigned)S);
+  return a < Mt && b <= a;
 }
 
 // per-point fields of the two 64-point sub-tiles of a side (128-block T128) -> vec, by the 256
@@ -271,10 +293,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lg_grad_tc(LargeArgs A, int nst
   if (v.st.state[v.b] != LG_FACTORED) return;
   const LargeWs& w = v.w;
   const int n = v.n, N = v.N, npad = v.npad;
-  int I, J;
-  tri_unrank(blockIdx.x, I, J);
-  if (I >= (N + 1) / 2) return;
   const int Nmax = (A.n_max + TS - 1) / TS, NTmax = (Nmax + 1) / 2, KCH = 2 * Nmax;
+  int I, J;
+  if (!tc_tile_of_block(blockIdx.x, NTmax, I, J) || I >= (N + 1) / 2) return;
   const float* phi = tc_pack_base(A.ws, A.n_max, A.B, v.b);
   const float* plo = phi + (size_t)NTmax * KCH * tc::IMG_FLOATS;
   const int kc0 = 4 * I, nchunks = 2 * N - kc0;      // U[128 I .., k] = 0 for k < 128 I
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lg_grad_tc(LargeArgs A, int nst
       double s = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * C::NV + et];
-      w.gpart[(size_t)blockIdx.x * LG_GP + et] = s;
+      w.gpart[((size_t)I * (I + 1) / 2 + J) * LG_GP + et] = s;
     }
   }
   tc_teardown(cx);
@@ -412,11 +433,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (v.st.state[v.b] != LG_ACTIVE || v.st.fail[v.b]) return;
   const LargeWs& w = v.w;
   const int n = v.n, N = v.N, npad = v.npad;
+  const int Nmax = (A.n_max + TS - 1) / TS, NTmax = (Nmax + 1) / 2, KCH = 2 * Nmax;
   int a, b;
-  tri_unrank(blockIdx.x, a, b);
+  if (!tc_tile_of_block(blockIdx.x, NTmax - (J1 >> 1), a, b)) return;
   const int I = (J1 >> 1) + a, J = (J1 >> 1) + b;
   if (I >= (N + 1) / 2) return;
-  const int Nmax = (A.n_max + TS - 1) / TS, NTmax = (Nmax + 1) / 2, KCH = 2 * Nmax;
   const float* phi = tc_pack_base(A.ws, A.n_max, A.B, v.b);
   const float* plo = phi + (size_t)NTmax * KCH * tc::IMG_FLOATS;
   const int nchunks = 2 * (J1 - J0);

@@ -168,7 +168,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
         if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
         const int NT = (N + 1) / 2, Mt = NT - J1 / 2;
         lg_pack_panel_tf32<<<dim3(J1 - J0, 2 * NT - J1, B), blk, 0, st>>>(A, J0, J1);
-        k_utc<<<dim3(Mt * (Mt + 1) / 2, B), TC_THREADS, TS_::bytes(nst), st>>>(A, J0, J1, build, nst, halfp);
+        k_utc<<<dim3(tc_grid(Mt), B), TC_THREADS, TS_::bytes(nst), st>>>(A, J0, J1, build, nst, halfp);
       } else if (J1 < N) {
         const int M = N - J1;
         k_upd<<<dim3(M * (M + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build);
@@ -208,7 +208,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       // (PGM_TC_HALF_PIECES=0) halve the drain work - C4's G phase 170 -> 112 ms - at 1.8x the error.
       int halfp = 1;
       if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
-      k_tc<<<dim3(NT * (NT + 1) / 2, B), TC_THREADS, TS_::bytes(nst), st>>>(A, nst, halfp);
+      k_tc<<<dim3(tc_grid(NT), B), TC_THREADS, TS_::bytes(nst), st>>>(A, nst, halfp);
     } else if (!predict_only) {
       k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
     }
