@@ -104,3 +104,28 @@ def fdr_bh(fap_values, alpha=0.05):
     if ok.any():
         res[order[: np.where(ok)[0].max() + 1]] = True
     return res
+
+
+def multiband_power(t, y, bands, dy, freq):
+    """astropy ``LombScargleMultiband(t, y, bands, dy).power(freq, method='fast')`` restated
+    (astropy/timeseries/periodograms/lombscargle_multiband/implementations/mbfast_impl.py, the
+    ``ls_method`` default of pgmuvi/multiband_ls_significance.py:136): a floating-mean single-band
+    periodogram per band, combined with the bands' reference chi-squares chi2_0b = sum w (y - ybar_w)^2
+    as weights.  astropy is absent from the image: parity with it is unpinned."""
+    t, y, bands = (np.asarray(a) for a in (t, y, bands))
+    dy = np.ones_like(t, dtype=np.float64) if dy is None else np.asarray(dy, np.float64)
+    ub = np.unique(bands)
+    powers, chi2 = [], []
+    for b in ub:
+        m = bands == b
+        powers.append(power_slow(t[m], y[m], dy[m], freq))
+        w = dy[m] ** -2.0
+        ybar = np.dot(w, y[m]) / w.sum()
+        chi2.append(np.dot(w, (y[m] - ybar) ** 2))
+    chi2 = np.asarray(chi2)
+    return np.dot(chi2 / chi2.sum(), np.asarray(powers))
+
+
+def multiband_fap_analytical(power_values, n_freq):
+    """pgmuvi/multiband_ls_significance.py:408-467"""
+    return np.clip(1.0 - (1.0 - np.exp(-np.asarray(power_values, np.float64))) ** (n_freq / 5.0), 0.0, 1.0)

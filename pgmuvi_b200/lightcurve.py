@@ -346,26 +346,50 @@ class Lightcurve(torch.nn.Module):
         scales = (1 / (2 * np.pi * sg[:, 0, 0])).numpy()
         return periods, w.numpy(), scales
 
-    def get_period_summary(self, n_grid=5000, min_freq=None, max_freq=None, **kwargs):
-        """First stage of ``get_period_summary`` (lightcurve.py:7860-7950, 8134-8305) on the GPU:
-        the summed spectral-mixture PSD on the log-spaced grid and its dominant peak.  Returns a
-        dict with ``dominant_period``, ``dominant_frequency``, ``peak_height``, ``n_peaks``,
-        ``freq_grid``, ``psd`` and the ``component_*`` diagnostics; the reference's basin-mass
-        interval and LSP flags are not computed."""
-        from .period_summary import period_summary_batch, sm_components
+    def get_period_summary(self, n_grid=5000, min_freq=None, max_freq=None, peak_threshold_rel=0.2,
+                           uncertainty="peak_mass", n_peaks=None, mass_level=0.68,
+                           classify_lsp=False):
+        """``get_period_summary`` of a fitted spectral-mixture model (lightcurve.py:7860-8130,
+        8134-8305): the summed PSD on the log-spaced grid and its dominant peak on the GPU
+        (``pgm_sm_psd_peak_f64``, re-evaluated while the half-maximum of the dominant peak is not
+        contained), then per-peak basins, peak-centred ``mass_level`` intervals, physical ranking
+        and optional LSP flags.  Returns a :class:`pgmuvi_b200.period_summary.PeriodSummary` (a
+        dict with the reference's keys plus ``peaks``; ``write_text`` / ``write_json``)."""
+        if uncertainty != "peak_mass":
+            raise NotImplementedError(f"uncertainty='{uncertainty}' is not yet implemented. "
+                                      "Supported values: ['peak_mass'].")
+        if getattr(self, "model", None) is None:
+            raise RuntimeError("Model not initialised.  Call set_model() first.")
+        from .period_summary import sm_components, summarise_batch
         mu, sg, w = sm_components(self)
         xr = self._xdata_raw[:, 0] if self.ndim > 1 else self._xdata_raw
-        span = torch.tensor([float(xr.max() - xr.min())])
-        f = lambda v: None if v is None else torch.tensor([float(v)])
-        out = period_summary_batch(mu[None], sg[None], w[None], t_span=span, fmin=f(min_freq),
-                                   fmax=f(max_freq), n_grid=n_grid, return_psd=True)
-        return dict(method="spectral_mixture_psd_peak", backend="spectral_mixture",
-                    dominant_period=float(out["dominant_period"][0]),
-                    dominant_frequency=float(out["dominant_frequency"][0]),
-                    peak_height=float(out["peak_height"][0]), n_peaks=int(out["n_peaks"][0]),
-                    freq_grid=out["freq_grid"][0], psd=out["psd"][0],
-                    component_frequencies=mu.numpy(), component_periods=(1.0 / mu).numpy(),
-                    component_frequency_scales=sg.numpy(), component_weights=w.numpy())
+        span = np.array([float(xr.max() - xr.min())])
+        f = lambda v: None if v is None else np.array([float(v)])
+        if n_peaks is None:
+            n_peaks = getattr(self, "_fit_num_mixtures_effective", None)
+        return summarise_batch(mu[None], sg[None], w[None], span, fmin=f(min_freq), fmax=f(max_freq),
+                               n_grid=n_grid, peak_threshold_rel=peak_threshold_rel, n_peaks=n_peaks,
+                               mass_level=mass_level, classify_lsp=classify_lsp)[0]
+
+    def write_period_summary_outputs(self, text_file=None, png_file=None, json_file=None, summary=None,
+                                     include_components=True, include_peaks=True,
+                                     include_psd_info=False, include_psd_in_json=False,
+                                     summary_kwargs=None, **kwargs):
+        """lightcurve.py:8862-8990: the text report and / or the JSON export of the period summary
+        (figures are outside the path: ``png_file`` raises)."""
+        if png_file is not None:
+            raise UnsupportedModel("write_period_summary_outputs: plotting is outside the B200 path")
+        if summary is None:
+            summary = self.get_period_summary(**(summary_kwargs or {}))
+        elif summary_kwargs:
+            warnings.warn("summary_kwargs are ignored because a pre-computed summary was supplied "
+                          "via the summary= argument.", UserWarning, stacklevel=2)
+        if text_file is not None:
+            summary.write_text(text_file, include_components=include_components,
+                               include_peaks=include_peaks, include_psd_info=include_psd_info)
+        if json_file is not None:
+            summary.write_json(json_file, include_psd=include_psd_in_json)
+        return summary
 
     # ---- posterior prediction (lightcurve.py:9607-9640, 9849-9880: the body of plot()) -----
     def predict(self, x_fine_raw=None, n_points=10000):
@@ -433,17 +457,37 @@ class Lightcurve(torch.nn.Module):
 
     # ---- Lomb-Scargle initialisation (lightcurve.py:4214-4611), on the GPU (N2) -----------
     def fit_LS(self, freq_only=False, num_peaks=1, single_threshold=0.05, Nyquist_factor=5,
-               return_full=False, device=None, **kwargs):
-        """1-D ``fit_LS``: the periodogram on astropy's ``autofrequency`` grid, the
-        ``num_peaks`` highest peaks ``Nyquist_factor`` samples apart and their significance mask
-        (Davies bound on the highest peak, Benjamini-Hochberg over the single-frequency FAPs).
-        Computed by ``pgm_lombscargle_f64`` / ``pgm_ls_peaks_f64`` (exact floating-mean
-        periodogram; the reference's astropy call uses its FFT approximation beyond 200
-        frequencies).  Multiband (2-D) periodograms are outside the path."""
+               return_full=False, device=None, fap_method=None, use_best_band_init=True,
+               n_samples=100, **kwargs):
+        """``fit_LS`` (pgmuvi/lightcurve.py:4214-4611): the periodogram on astropy's
+        ``autofrequency`` grid, the ``num_peaks`` highest peaks ``Nyquist_factor`` samples apart
+        and their significance mask (Benjamini-Hochberg over the per-peak false-alarm
+        probabilities, after a gate on the highest peak).  Computed by ``pgm_lombscargle_f64`` /
+        ``pgm_ls_peaks_f64`` (exact floating-mean periodogram; the reference's astropy call uses
+        its FFT approximation beyond 200 frequencies).
+        1-D: 'davies' bound on the maximum, single-frequency FAPs per peak.
+        2-D (multiband, ``:4372-4497``): ``use_best_band_init`` (default) takes grid and
+        periodogram from the most-sampled band, else the chi2-weighted multiband periodogram;
+        FAP method default 'phase_scramble' (``n_samples`` null periodograms in one launch;
+        also 'bootstrap', 'analytical', 'calibrated') - :mod:`pgmuvi_b200.lombscargle`."""
         from . import lombscargle as ls
-        if self.ndim > 1:
-            raise UnsupportedModel("fit_LS: the multiband periodogram is not on the B200 path")
         dev = torch.device(device) if device is not None else torch.device("cuda:0")
+        if self.ndim > 1:
+            xr = self._xdata_raw
+            has_err = getattr(self, "_yerr_transformed", None) is not None
+            pf, sm, freq, power = ls.fit_ls_multiband(
+                xr[:, 0].cpu().numpy(), self._ydata_raw.cpu().numpy(), xr[:, 1].cpu().numpy(),
+                self._yerr_raw.cpu().numpy() if has_err else None, num_peaks=num_peaks,
+                single_threshold=single_threshold, nyquist_factor=Nyquist_factor,
+                fap_method=fap_method, use_best_band_init=use_best_band_init,
+                n_samples=n_samples, device=dev)
+            o = lambda a, dt=None: torch.as_tensor(np.asarray(a), dtype=dt or self.xdata.dtype,
+                                                   device=self.xdata.device)
+            if freq_only:
+                return o(freq), o(power)
+            if return_full:
+                return o(pf), o(sm, torch.bool), o(freq), o(power)
+            return o(pf), o(sm, torch.bool)
         t = self._xdata_raw.to(dev, torch.float64).unsqueeze(0)
         y = self._ydata_raw.to(dev, torch.float64).unsqueeze(0)
         has_err = getattr(self, "_yerr_transformed", None) is not None

@@ -151,3 +151,83 @@ def test_gpu_fit_ls_batch_seeds_the_injected_periods(cuda_device):
             m = ols.fdr_bh(ols.fap_single(p[pk], n), 0.05); m[0] = True
             want = m[:3]
         assert np.array_equal(sig[b], want)
+
+
+# ---------------------------------------------------------------- N2 multiband (2-D fit_LS)
+def _multiband_case(seed=3, nb=3, period=37.0, amp=1.0):
+    rng = np.random.default_rng(seed)
+    t, y, b, dy = [], [], [], []
+    for k in range(nb):
+        n = 40 + 25 * k
+        tk = np.sort(rng.uniform(0, 400, n))
+        t.append(tk)
+        y.append(amp * (1 + 0.3 * k) * np.sin(2 * np.pi * tk / period + 0.4 * k) + 0.2 * k
+                 + 0.3 * rng.standard_normal(n))
+        b.append(np.full(n, 0.5 + k))
+        dy.append(np.full(n, 0.3) * (1 + 0.1 * k))
+    return tuple(np.concatenate(a) for a in (t, y, b, dy))
+
+
+def test_oracle_multiband_power_reduces_to_single_band_and_weights_by_chi2():
+    from oracle import lombscargle as ols
+    t, y, b, dy = _multiband_case()
+    f0, df, nf = ols.autofrequency(t, nyquist_factor=2)
+    freq = f0 + df * np.arange(0, nf, 7)
+    one = np.zeros_like(b)
+    assert np.allclose(ols.multiband_power(t, y, one, dy, freq), ols.power_slow(t, y, dy, freq),
+                       rtol=1e-13)
+    p = ols.multiband_power(t, y, b, dy, freq)
+    parts = [ols.power_slow(t[b == v], y[b == v], dy[b == v], freq) for v in np.unique(b)]
+    assert (p <= np.max(parts, 0) + 1e-12).all() and (p >= np.min(parts, 0) - 1e-12).all()
+    assert np.allclose(ols.multiband_fap_analytical([0.0, 50.0], 1000), [1.0, 0.0], atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_multiband_power_matches_oracle(cuda_device):
+    from oracle import lombscargle as ols
+    from pgmuvi_b200.lombscargle import MultibandLS
+    for use_dy in (True, False):
+        t, y, b, dy = _multiband_case(seed=11)
+        LS = MultibandLS(t, y, b, dy if use_dy else None, device=cuda_device)
+        freq = LS.autofrequency(nyquist_factor=3)
+        f0, df, nf = ols.autofrequency(t, nyquist_factor=3)
+        assert len(freq) == nf and np.allclose(freq[:3], f0 + df * np.arange(3), rtol=1e-14)
+        got = LS.power(freq)
+        ref = ols.multiband_power(t, y, b, dy if use_dy else None, freq)
+        assert np.abs(got - ref).max() < 1e-10
+        assert np.allclose(LS.false_alarm_probability(got[:5], "analytical", freq_grid=freq),
+                           ols.multiband_fap_analytical(got[:5], len(freq)))
+
+
+@pytest.mark.gpu
+def test_gpu_multiband_monte_carlo_fap_and_fit_ls_2d(cuda_device):
+    """bootstrap / phase-scramble null distributions in one launch: a strong common period is
+    significant (FAP 0 of 64 samples), pure noise is not; the 2-D fit_LS recovers the period."""
+    import torch
+    from pgmuvi_b200.lombscargle import MultibandLS, fit_ls_multiband
+    from pgmuvi_b200.lightcurve import Lightcurve
+    t, y, b, dy = _multiband_case(seed=5, period=41.0)
+    rng = np.random.default_rng(0)
+    LS = MultibandLS(t, y, b, dy, device=cuda_device)
+    freq = LS.autofrequency(nyquist_factor=2)
+    p = LS.power(freq)
+    for method in ("bootstrap", "phase_scramble"):
+        null = LS.null_max_powers(freq, method, 64, generator=rng)
+        assert null.shape == (64,) and (null > 0).all() and (null < 1).all()
+        assert LS.false_alarm_probability(p.max(), method, 64, freq, generator=rng) == 0.0
+    noise = MultibandLS(t, rng.standard_normal(len(t)), b, dy, device=cuda_device)
+    pn = noise.power(freq)
+    assert noise.false_alarm_probability(pn.max(), "bootstrap", 64, freq, generator=rng) > 0.05
+    for best in (True, False):
+        pf, sm, fg, pg = fit_ls_multiband(t, y, b, dy, num_peaks=3, fap_method="bootstrap",
+                                          use_best_band_init=best, n_samples=64,
+                                          device=cuda_device, generator=rng)
+        assert abs(1.0 / pf[0] - 41.0) < 1.0 and bool(sm[0]) and len(fg) == len(pg)
+    # the Lightcurve surface (reference defaults: best band, phase_scramble)
+    lc = Lightcurve(torch.tensor(np.stack([t, b], 1), dtype=torch.float32),
+                    torch.tensor(y, dtype=torch.float32), yerr=torch.tensor(dy, dtype=torch.float32))
+    pf, sm = lc.fit_LS(num_peaks=2, n_samples=32)
+    assert pf.dtype == torch.float32 and sm.dtype == torch.bool and len(pf) == len(sm) <= 2
+    assert abs(1.0 / float(pf[0]) - 41.0) < 1.0
+    fr, pw = lc.fit_LS(freq_only=True)
+    assert fr.shape == pw.shape
