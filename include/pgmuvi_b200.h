@@ -154,6 +154,11 @@ int pgm_sm_predict_f64(const double* x, const int32_t* n_valid, const double* y,
                        double* var, int32_t* info, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* Persistent grid of the fused kernels for this model family on the current device (SMs x resident
+ * blocks per SM): callers that balance the last wave of a batch (pgmuvi_b200/batch.py) need it.
+ * -1 on a bad argument. */
+int pgm_fused_grid(int d, int Q, int kernel_kind);
+
 /*
  * Staged engine: the same quantities as pgm_sm_mll_grad_f64 (same arguments), computed stage
  * by stage over the whole device: K~ of every light curve lives in HBM as the lower triangle

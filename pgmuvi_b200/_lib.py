@@ -50,7 +50,7 @@ EXPORTS = (
     "pgm_sm_mll_grad_alpha_f64", "pgm_sm_mll_grad_staged_alpha_f64",
     "pgm_sm_psd_peak_f64",
     "pgm_staged_tf32x3_workspace_bytes", "pgm_sm_mll_grad_staged_tf32x3_f64",
-    "pgm_sm_mll_grad_tf32x3_f32",
+    "pgm_sm_mll_grad_tf32x3_f32", "pgm_fused_grid",
 )
 
 _lib = None
@@ -93,6 +93,8 @@ def load():
     lib.pgm_staged_workspace_bytes.argtypes = [c_int, c_int]
     lib.pgm_sm_mll_grad_staged_f64.restype = c_int
     lib.pgm_sm_mll_grad_staged_f64.argtypes = lib.pgm_sm_mll_grad_f64.argtypes
+    lib.pgm_fused_grid.restype = c_int
+    lib.pgm_fused_grid.argtypes = [c_int, c_int, c_int]
     lib.pgm_staged_tf32x3_workspace_bytes.restype = c_size_t
     lib.pgm_staged_tf32x3_workspace_bytes.argtypes = [c_int, c_int]
     lib.pgm_sm_mll_grad_staged_tf32x3_f64.restype = c_int

@@ -18,7 +18,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import (KIND_SM1D, OPT_ADAM, OPT_ADAMW, OPT_SGD)
 
 OPTIM_KINDS = {"SGD": OPT_SGD, "Adam": OPT_ADAM, "AdamW": OPT_ADAMW}
@@ -114,10 +114,46 @@ class BatchEngine:
         return buf
 
     # -- device-resident calls -------------------------------------------------------------
+    def tail_split(self, B, d_in):
+        """How many light curves of a batch of B go to the staged engine so that the LAST WAVE of
+        the fused kernel's persistent grid stays balanced.  The fused kernel holds `grid` = SMs x 2
+        blocks, one light curve per block at a time; with r = B mod grid light curves in the last
+        wave and r > SMs, r - SMs SMs run two blocks while the others run one and then idle
+        (B = 512 on 148 SMs: 4.52 ms, the time of 592).  Handing those r - SMs light curves to the
+        staged engine on a second stream - whose tile-sized blocks fill the slots that free up on
+        EVERY SM when the blocks with no further light curve exit - finishes the shard in about the
+        time of B - (r - SMs) (measured: profiles/r02m_tail_balance.log).  0 = no split."""
+        import os
+        if os.environ.get("PGM_TAIL_BALANCE", "1") == "0" or B <= 0:
+            return 0
+        grid = _lib.load().pgm_fused_grid(int(d_in), self.Q, self.kind)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        if grid != 2 * sms or B <= grid:
+            return 0
+        r = B % grid
+        return r - sms if r > sms else 0
+
     def evaluate_device(self, d, want_grad=True):
-        return ops.sm_mll_grad(d["x"], d["y"], d["noise"], d["raw"], d["kinds"], d["lb"],
-                               d["ub"], d["n_valid"], self.kind, self.Q, self.learn_noise,
-                               want_grad)
+        B = d["y"].shape[0]
+        k = self.tail_split(B, d["x"].shape[2] if d["x"].dim() == 3 else 1)
+        args = (self.kind, self.Q, self.learn_noise, want_grad)
+        if k == 0:
+            return ops.sm_mll_grad(d["x"], d["y"], d["noise"], d["raw"], d["kinds"], d["lb"],
+                                   d["ub"], d["n_valid"], *args)
+        cut = lambda t, a, z: None if t is None else (t[a:z] if t.dim() and t.shape[0] == B else t)
+        part = lambda a, z: (cut(d["x"], a, z), cut(d["y"], a, z), cut(d["noise"], a, z),
+                             cut(d["raw"], a, z), d["kinds"],
+                             d["lb"][a:z] if d["lb"].dim() == 2 else d["lb"],
+                             d["ub"][a:z] if d["ub"].dim() == 2 else d["ub"], cut(d["n_valid"], a, z))
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        self._side.wait_stream(cur)
+        m0, g0, i0 = ops.sm_mll_grad(*part(0, B - k), *args)          # asynchronous
+        with torch.cuda.stream(self._side):                           # blocks on its own stream only
+            m1, g1, i1 = ops.sm_mll_grad_staged(*part(B - k, B), *args)
+        cur.wait_stream(self._side)
+        return torch.cat([m0, m1]), torch.cat([g0, g1]), torch.cat([i0, i1])
 
     def fit_device(self, d, maxiter=300, miniter=None, stop=1e-5, lr=0.1, optim="AdamW",
                    eps=1e-8, stopavg=30, keep_history=True):

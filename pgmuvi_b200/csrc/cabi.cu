@@ -202,6 +202,13 @@ int narrow(const double* src, float* dst, size_t n, cudaStream_t st) {
   return 0;
 }
 
+template <int KIND, int QT, int D>
+int fused_blocks_per_sm() { return pgm::Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024 ? 2 : 1; }
+int fused_occ_dispatch(int d, int Q, int kernel_kind) {
+  PGM_DISPATCH(fused_blocks_per_sm);
+  return 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -216,7 +223,8 @@ size_t pgm_workspace_bytes(int elem_size, int n_max, int d, int Q, int device) {
   else { int dv = 0; if (cudaGetDevice(&dv) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dv); }
   if (sms <= 0) sms = 148;
   const size_t per_block = pgm::scratch_elems(n_max, nf_for(d, Q));
-  return per_block * sizeof(double) * (size_t)sms * 2;  // up to 2 resident blocks per SM
+  // up to 2 resident blocks per SM, + the light-curve ticket counters of the fused kernels
+  return per_block * sizeof(double) * (size_t)sms * 2 + pgm::PGM_SCHED_INTS * sizeof(int);
 }
 
 int pgm_sm_mll_grad_f64(const double* x, const int32_t* n_valid, const double* y,
@@ -251,9 +259,17 @@ int pgm_sm_mll_grad_alpha_f64(const double* x, const int32_t* n_valid, const dou
   A.mll = mll; A.grad = grad_raw; A.info = info;
   A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
   A.alpha_out = alpha_out;
+  A.sched = reinterpret_cast<int*>(static_cast<char*>(workspace) + pgm_workspace_bytes(8, n_max, d, Q, -1)
+                                   - pgm::PGM_SCHED_INTS * sizeof(int));
+  A.sms = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PGM_DISPATCH(launch_eval, A, st);
   return 0;
+}
+
+int pgm_fused_grid(int d, int Q, int kernel_kind) {
+  if (check_common(1, 64, d, Q, kernel_kind)) return -1;
+  return pgm::device_sms() * fused_occ_dispatch(d, Q, kernel_kind);
 }
 
 size_t pgm_staged_workspace_bytes(int n_max, int B) {
@@ -465,6 +481,9 @@ int pgm_sm_fit_f64(const double* x, const int32_t* n_valid, const double* y,
   A.mll = nullptr; A.grad = nullptr; A.info = info;
   A.ws = static_cast<double*>(workspace); A.ws_per_block = per_block;
   A.alpha_out = nullptr;
+  A.sched = reinterpret_cast<int*>(static_cast<char*>(workspace) + pgm_workspace_bytes(8, n_max, d, Q, -1)
+                                   - pgm::PGM_SCHED_INTS * sizeof(int));
+  A.sms = 0;
   F.raw_io = raw; F.optim_kind = optim_kind; F.lr = lr; F.beta1 = beta1; F.beta2 = beta2;
   F.eps = eps; F.weight_decay = weight_decay; F.stop = stop; F.maxiter = maxiter;
   F.miniter = miniter; F.stopavg = stopavg; F.loss_hist = loss_hist; F.raw_hist = raw_hist;

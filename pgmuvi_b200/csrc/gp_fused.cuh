@@ -938,7 +938,55 @@ struct EvalArgs {
   double* ws;
   size_t ws_per_block;  // elements
   double* alpha_out;    // [B, n_max] or null: alpha = K~^-1 (y - mean)  (d MLL / d y = -alpha / n)
+  int* sched;           // [PGM_SCHED_INTS] zeroed before the launch, or null: light-curve tickets
+  int sms;              // SMs of the device (last-wave rule of next_lightcurve)
 };
+
+// Light curves are handed out by a ticket counter instead of a fixed stride, with one rule for the
+// LAST wave.  The hardware fills every SM with both of its resident blocks before moving on, so with
+// a fixed stride the left-over light curves of the last wave land two to an SM on the first SMs
+// while the others idle (B = 444 on 148 SMs took the time of 592).  Here every block learns which
+// of its SM's two slots it holds (atomic counter per %smid), and once no more than `sms` light
+// curves are left only the slot-0 blocks - one per SM - take them.  The tickets make the
+// assignment correct whatever the residency; the rule only balances.
+constexpr int PGM_SCHED_INTS = 1024;     // [0] next ticket, [8 + smid] blocks seen on that SM
+struct LcSched {
+  int slot;
+};
+__device__ __forceinline__ LcSched sched_init(const EvalArgs& A, int* s_bcast) {
+  LcSched sc{0};
+  if (!A.sched) return sc;
+  if (threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    *s_bcast = atomicAdd(A.sched + 8 + (smid % (PGM_SCHED_INTS - 8)), 1) & 1;
+  }
+  __syncthreads();
+  sc.slot = *s_bcast;
+  __syncthreads();
+  return sc;
+}
+// next light curve of this block (first = true: its first one), or -1
+__device__ __forceinline__ int next_lightcurve(const EvalArgs& A, const LcSched& sc, int prev,
+                                               int* s_bcast) {
+  if (!A.sched) {
+    const int b = prev < 0 ? (int)blockIdx.x : prev + (int)gridDim.x;
+    return b < A.B ? b : -1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int b = -1;
+    const bool defer = sc.slot == 1 && prev >= 0 &&
+                       A.B - atomicAdd(A.sched, 0) <= A.sms;   // leave the last ones to slot 0
+    if (!defer) {
+      b = atomicAdd(A.sched, 1);
+      if (b >= A.B) b = -1;
+    }
+    *s_bcast = b;
+  }
+  __syncthreads();
+  return *s_bcast;
+}
 
 struct FitArgs {
   EvalArgs e;
@@ -1598,7 +1646,11 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   const int P = param_count<KIND, QT, D>(A.Q, (A.flags & PGM_FLAG_LEARN_NOISE) != 0);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
-  for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+  // broadcast slot of the scheduler: in the spare words behind s_fail (static shared memory would
+  // push the block over the two-per-SM limit)
+  int* s_next = reinterpret_cast<int*>(sm + Cfg<KIND, QT, D>::SM_PAR + Cfg<KIND, QT, D>::PAR_END) + 4;
+  const LcSched lsc = sched_init(A, s_next);
+  for (int b = next_lightcurve(A, lsc, -1, s_next); b >= 0; b = next_lightcurve(A, lsc, b, s_next)) {
     double* gout = A.grad ? A.grad + (size_t)b * P : nullptr;
     const int info =
         eval_lightcurve<KIND, QT, D>(A, b, A.raw + (size_t)b * P, sm, sc, ps, A.mll + b, gout);
@@ -1719,7 +1771,11 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   const int tid = threadIdx.x;
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
-  for (int b = blockIdx.x; b < A.B; b += gridDim.x) {
+  // broadcast slot of the scheduler: in the spare words behind s_fail (static shared memory would
+  // push the block over the two-per-SM limit)
+  int* s_next = reinterpret_cast<int*>(sm + Cfg<KIND, QT, D>::SM_PAR + Cfg<KIND, QT, D>::PAR_END) + 4;
+  const LcSched lsc = sched_init(A, s_next);
+  for (int b = next_lightcurve(A, lsc, -1, s_next); b >= 0; b = next_lightcurve(A, lsc, b, s_next)) {
     __syncthreads();
     if (tid < P) {
       s_raw[tid] = F.raw_io[(size_t)b * P + tid];

@@ -32,6 +32,9 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
   if (grid > A.B) grid = A.B;
+  A.sms = device_sms();
+  if (A.sched && (occ != 2 || grid != 2 * A.sms || getenv("PGM_STATIC_STRIDE"))) A.sched = nullptr;
+  if (A.sched) cudaMemsetAsync(A.sched, 0, PGM_SCHED_INTS * sizeof(int), st);
 #ifdef PGM_DEBUG_HOOKS
   {
     int dbg = 0;
@@ -79,7 +82,11 @@ int launch_fit(const pgm::FitArgs& F, cudaStream_t st) {
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
   if (grid > F.e.B) grid = F.e.B;
-  kern<<<grid, pgm::NTHREADS, C::SMEM_BYTES, st>>>(F);
+  pgm::FitArgs F2 = F;
+  F2.e.sms = device_sms();
+  if (F2.e.sched && (occ != 2 || grid != 2 * F2.e.sms || getenv("PGM_STATIC_STRIDE"))) F2.e.sched = nullptr;
+  if (F2.e.sched) cudaMemsetAsync(F2.e.sched, 0, PGM_SCHED_INTS * sizeof(int), st);
+  kern<<<grid, pgm::NTHREADS, C::SMEM_BYTES, st>>>(F2);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("sm_fit_kernel launch", e);
   return 0;
