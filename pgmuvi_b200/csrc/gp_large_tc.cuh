@@ -179,44 +179,73 @@ __device__ __forceinline__ void tc_mma_issuer(const TcCtx& cx, int nchunks) {
   }
 }
 
-// the 8 epilogue warps: drain every piece into the master accumulator, (hi, lo) += piece by
-// Fast2Sum (|hi| >= |piece| but for the first few pieces, where the missed rounding error is of no
-// consequence).  tlane = TMEM address of this thread's lane at its first column.
-__device__ __forceinline__ void tc_drain(const TcCtx& cx, unsigned tlane, int nchunks) {
+// The 8 epilogue warps drain every piece: two levels.  Level 1: a running sum of `fold` consecutive
+// pieces in REGISTERS (64 floats per thread, plain round-to-nearest adds: `fold` = 4 keeps their error
+// at the level of one piece's own truncation) - 4 LDTM + 64 FADD per piece.  Level 2: every `fold`
+// pieces the running sum goes into the float-pair master accumulator in TMEM by Fast2Sum (|hi| >= |sum|
+// but for the first folds, where the missed rounding error is of no consequence).  Draining every piece
+// straight into the TMEM master (r02k: ~400 instructions per thread and piece, tensor pipe 18 % active)
+// made the drain, not the tensor pipe, the bound.  tlane = TMEM address of this thread's lane at its
+// first column.
+__device__ __forceinline__ void tc_drain(const TcCtx& cx, unsigned tlane, int nchunks, int fold) {
   const int lane = threadIdx.x & 31;
   const int npieces = nchunks * cx.ppc;
+  float m1[64];
+  int in_fold = 0, nfold = 0;
   for (int piece = 0; piece < npieces; ++piece) {
     const int buf = piece & 1;
     mbar_wait(cx.bar_pfull + 8 * buf, (piece >> 1) & 1);
     tc::fence_after_sync();
+    const bool first = in_fold == 0;
+    {
+      // all four loads in flight, one wait, and the piece buffer goes back to the MMA warp before
+      // the adds: the round trip pfull -> pempty, not the instruction count, paces the pipeline
+      float p0[16], p1[16], p2[16], p3[16];
+      const unsigned tpc = tlane + T_PIECE + 128u * (unsigned)buf;
+      tc::tmem_ld16_async(tpc, p0);
+      tc::tmem_ld16_async(tpc + 16, p1);
+      tc::tmem_ld16_async(tpc + 32, p2);
+      tc::tmem_ld16_async(tpc + 48, p3);
+      tc::tmem_wait_ld();
+      tc::tmem_tie(p0);
+      tc::tmem_tie(p1);
+      tc::tmem_tie(p2);
+      tc::tmem_tie(p3);
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(cx.bar_pempty + 8 * buf);
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      float pv[16], lo[16];
-      tc::tmem_ld16(tlane + T_PIECE + 128u * (unsigned)buf + (unsigned)c0, pv);
-      if (piece > 0) {
-        float hi[16];
-        tc::tmem_ld16(tlane + T_MASTER + (unsigned)c0, hi);
-        tc::tmem_ld16(tlane + T_MLO + (unsigned)c0, lo);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float s2 = __fadd_rn(hi[e], pv[e]);
-          const float er = __fsub_rn(pv[e], __fsub_rn(s2, hi[e]));
-          lo[e] = __fadd_rn(lo[e], er);
-          pv[e] = s2;
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) lo[e] = 0.f;
+      for (int e = 0; e < 16; ++e) {
+        m1[e] = first ? p0[e] : __fadd_rn(m1[e], p0[e]);
+        m1[16 + e] = first ? p1[e] : __fadd_rn(m1[16 + e], p1[e]);
+        m1[32 + e] = first ? p2[e] : __fadd_rn(m1[32 + e], p2[e]);
+        m1[48 + e] = first ? p3[e] : __fadd_rn(m1[48 + e], p3[e]);
       }
-      tc::tmem_st16(tlane + T_MASTER + (unsigned)c0, pv);
-      tc::tmem_st16(tlane + T_MLO + (unsigned)c0, lo);
     }
-    // (batching the six loads of 32 columns behind one wait was tried: no faster - the drain is bound
-    // by its instruction count, ~400 per thread and piece, not by the TMEM round trips - and spills)
-    tc::tmem_wait_st();
-    tc::fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(cx.bar_pempty + 8 * buf);
+    if (++in_fold == fold || piece == npieces - 1) {
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float hi[16], lo[16];
+        if (nfold > 0) {
+          tc::tmem_ld16(tlane + T_MASTER + (unsigned)c0, hi);
+          tc::tmem_ld16(tlane + T_MLO + (unsigned)c0, lo);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float s2 = __fadd_rn(hi[e], m1[c0 + e]);
+            lo[e] = __fadd_rn(lo[e], __fsub_rn(m1[c0 + e], __fsub_rn(s2, hi[e])));
+            hi[e] = s2;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { hi[e] = m1[c0 + e]; lo[e] = 0.f; }
+        }
+        tc::tmem_st16(tlane + T_MASTER + (unsigned)c0, hi);
+        tc::tmem_st16(tlane + T_MLO + (unsigned)c0, lo);
+      }
+      tc::tmem_wait_st();
+      in_fold = 0;
+      ++nfold;
+    }
   }
 }
 
@@ -282,7 +311,7 @@ struct TcGradSmem {
 };
 
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(TC_THREADS, 1) lg_grad_tc(LargeArgs A, int nst, int half_pieces) {
+__global__ void __launch_bounds__(TC_THREADS, 1) lg_grad_tc(LargeArgs A, int nst, int half_pieces, int fold) {
   using C = Cfg<KIND, QT, D>;
   using SM = TcGradSmem<KIND, QT, D>;
   constexpr int DS = C::DS;
@@ -344,7 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lg_grad_tc(LargeArgs A, int nst
     const int gi = I * 128 + r;
     const double al_i = rv[C::NFB * TS + rr];
     const unsigned tlane = cx.tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(half * 64);
-    tc_drain(cx, tlane, nchunks);
+    tc_drain(cx, tlane, nchunks, fold);
     // tcgen05.ld is warp-collective: the chunk loop is uniform over the warp (rows 32 q4 .. + 31),
     // the lower-triangle / n masks act per entry
     const int gi_hi = I * 128 + 32 * q4 + 31;
@@ -423,7 +452,7 @@ static __global__ void __launch_bounds__(NTHREADS) lg_pack_panel_tf32(LargeArgs 
 // per 128x128 tile; build: C_ij = K~_ij - sum (first panel), exactly as lg_update mode 1
 template <int KIND, int QT, int D>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    lg_update_tc(LargeArgs A, int J0, int J1, int build, int nst, int half_pieces) {
+    lg_update_tc(LargeArgs A, int J0, int J1, int build, int nst, int half_pieces, int fold) {
   using C = Cfg<KIND, QT, D>;
   using SM = TcGradSmem<KIND, QT, D>;
   constexpr int DS = C::DS;
@@ -483,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int ti = 2 * I + (r >> 6), tj = 2 * J + half;       // the 64x64 tile of this thread's entries
     const int gi = I * 128 + r;
     const unsigned tlane = cx.tmem + ((unsigned)(32 * q4) << 16) + (unsigned)(half * 64);
-    tc_drain(cx, tlane, nchunks);
+    tc_drain(cx, tlane, nchunks, fold);
     // every lane of the warp shares ti, tj (32 rows of one 64-row sub-tile)
     if (ti < N && tj <= ti) {
       double* out = lg_tile(w.tilesL, ti, tj);

@@ -107,6 +107,13 @@ int launch_dense(const pgm::EvalArgs& A, double* K, cudaStream_t st) {
 // dependency stage with B x (tiles of the stage) blocks; B = 1 is the single large GP.
 // Host-orchestrated on `st`; synchronises once per Cholesky pass to read how many light curves
 // must repeat it with more jitter (psd_safe_cholesky's ladder) - the call is blocking.
+// pieces per level-1 fold of the tcgen05 drain (gp_large_tc.cuh::tc_drain)
+inline int tc_fold() {
+  int f = 4;
+  if (const char* e = getenv("PGM_TC_FOLD")) f = std::max(1, atoi(e));
+  return f;
+}
+
 template <int KIND, int QT, int D>
 int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int predict_only = 0) {
   using C = pgm::Cfg<KIND, QT, D>;
@@ -175,7 +182,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
         if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
         const int NT = (N + 1) / 2, Mt = NT - J1 / 2;
         lg_pack_panel_tf32<<<dim3(J1 - J0, 2 * NT - J1, B), blk, 0, st>>>(A, J0, J1);
-        k_utc<<<dim3(tc_grid(Mt), B), TC_THREADS, TS_::bytes(nst), st>>>(A, J0, J1, build, nst, halfp);
+        k_utc<<<dim3(tc_grid(Mt), B), TC_THREADS, TS_::bytes(nst), st>>>(A, J0, J1, build, nst, halfp, tc_fold());
       } else if (J1 < N) {
         const int M = N - J1;
         k_upd<<<dim3(M * (M + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build);
@@ -215,7 +222,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       // (PGM_TC_HALF_PIECES=0) halve the drain work - C4's G phase 170 -> 112 ms - at 1.8x the error.
       int halfp = 1;
       if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
-      k_tc<<<dim3(tc_grid(NT), B), TC_THREADS, TS_::bytes(nst), st>>>(A, nst, halfp);
+      k_tc<<<dim3(tc_grid(NT), B), TC_THREADS, TS_::bytes(nst), st>>>(A, nst, halfp, tc_fold());
     } else if (!predict_only) {
       k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
     }
