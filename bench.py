@@ -377,6 +377,7 @@ def run_b200(args):
     hb = HostBatch.from_numpy(bt, pin=True)
     eng = BatchEngine(kind=ops.KIND_SM1D, Q=Q_MIX, learn_noise=False, device=dev)
     d = eng.upload(hb)
+    tail_k = eng.tail_split(B, 1)
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -495,7 +496,10 @@ def run_b200(args):
                         "h2d_bytes_per_step": hb.h2d_bytes(), "d2h_bytes_per_step": d2h,
                         "includes": "H2D of the shard, kernel, all-gather of the results over the "
                                     "ranks, D2H of all gathered results"},
-                "gpu_launches": args.steps, "roofline": roofline, "clocks": clocks,
+                # one fused-kernel launch per step, plus the 7 staged-engine launches of the
+                # tail-balancing split (batch.BatchEngine.tail_split) when the shard size needs it
+                "gpu_launches": args.steps * (1 + (7 if tail_k else 0)),
+                "tail_split_lightcurves": tail_k, "roofline": roofline, "clocks": clocks,
                 "cholesky_info_nonzero": bad, "wall_s_timed_loop": t_wall,
                 "step_ms": [round(v, 3) for v in step_ms], "c5": c5}
         if world == 1 and not args.no_cpu_baseline:

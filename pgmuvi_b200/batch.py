@@ -128,7 +128,8 @@ class BatchEngine:
             return 0
         grid = _lib.load().pgm_fused_grid(int(d_in), self.Q, self.kind)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        if grid != 2 * sms or B <= grid:
+        # worth it while the last wave is a noticeable share of the batch (B = 4096: 0.6 %)
+        if grid != 2 * sms or B <= grid or B > 8 * grid:
             return 0
         r = B % grid
         return r - sms if r > sms else 0
