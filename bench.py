@@ -278,6 +278,27 @@ def other_configs(dev, dmma_peak):
             best = min(best, time.perf_counter() - t0)
         out["C1_alfori_fit"] = {"n": 1000, "iterations": 300, "seconds": best,
                                 "final_loss": float(res["loss"][-1])}
+        # C2 for float32 models through the tensor-core path (staged engine; no trailing updates at
+        # n = 512, so only the K~^-1 products of the gradient run on tcgen05)
+        bt2 = S.make_batch_1d(64, N_POINTS, Q=Q_MIX, seed0=1000)
+        rep = lambda a: torch.tensor(np.concatenate([np.asarray(a)] * 64, 0), dtype=torch.float32,
+                                     device=dev)
+        x2, y2, n2, r2, l2, u2 = (rep(bt2[k]) for k in ("x", "y", "noise", "raw", "lb", "ub"))
+        k2 = T(bt2["kinds"], torch.int32)
+        ms2 = ev_ms(lambda: ops.sm_mll_grad_staged(x2, y2, n2, r2, k2, l2, u2, None, 0, Q_MIX, False,
+                                                   True, tf32x3=True), 3)
+        tf2 = 4096 * (N_POINTS ** 3 + 4 * N_POINTS ** 2) / (ms2 * 1e-3) / 1e12
+        out["C2_f32_tf32x3_staged"] = {
+            "lightcurves": 4096, "n": N_POINTS, "ms_per_eval_batch": ms2,
+            "evals_per_s": 4096 / ms2 * 1e3, "tflops": tf2,
+            "tf32_tcgen05_peak_tflops": tf32_peak,
+            "frac_of_3xtf32_peak": None if not tf32_peak else tf2 / (tf32_peak / 3.0),
+            "note": "pgm_sm_mll_grad_tf32x3_f32: float buffers; Cholesky / inverse FP64 DMMA (dataflow "
+                    "schedule), K~^-1 = X^T X on tcgen05 3xTF32 with the FP64 contraction epilogue; at "
+                    "n = 512 the epilogue outweighs the 16 chunks of MMAs per tile, the fused FP64 "
+                    "kernel (headline) is faster"}
+        del x2, y2, n2, r2, l2, u2
+        torch.cuda.empty_cache()
         out["C3_2d_n8000"] = single(S.make_batch_2d(1, 8, 1000, Q=4), 1, 4, 3)
         out["C4_1d_n32768_sm8"] = single(S.make_batch_1d(1, 32768, Q=8), 0, 8, 2)
     except Exception as exc:   # never let the side measurements break the headline line

@@ -240,13 +240,28 @@ __device__ __forceinline__ void lg_prefetch_side(double* vec, const LargeWs& w, 
   }
 }
 
+// Job index of a block of a one-launch dataflow phase: a ticket taken when the block STARTS, so that
+// the job order is the order in which blocks actually begin to run.  Every job only waits for jobs of
+// lower index, and a block holding ticket t started after the blocks holding 0 .. t-1 did, so waiting
+// can never deadlock whatever the hardware's dispatch order (MPS, preemption, debuggers) - the
+// decoupled look-back idiom.  `counter` is zeroed by the host before the launch.
+// `bcast`: any word of the block's (still unused) dynamic shared memory.
+__device__ __forceinline__ unsigned lg_ticket(int* counter, void* bcast) {
+  volatile unsigned* s_ticket = reinterpret_cast<volatile unsigned*>(bcast);
+  if (threadIdx.x == 0) *s_ticket = (unsigned)atomicAdd(counter, 1);
+  __syncthreads();
+  const unsigned t = *s_ticket;
+  __syncthreads();
+  return t;
+}
+
 // per-tile "final" flags of the one-launch phases (lg_chol_all, lg_inv_all)
 __device__ __forceinline__ void lg_wait_flag(const int* f) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
   if (!v) {
-    // Watchdog: the schedule relies on blocks being dispatched in index order (every awaited
-    // producer is then running or done).  Should that ever not hold, fail the launch after 20 s
+    // Watchdog: jobs come from a ticket taken at block start (lg_ticket), so every awaited producer
+    // is running or done.  Should that ever not hold, fail the launch after 20 s
     // of waiting instead of hanging the device.
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
@@ -548,8 +563,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
-  const unsigned tix = blockIdx.x / (unsigned)A.B;
-  const LcView v = lc_view(A, (int)(blockIdx.x - tix * (unsigned)A.B));
+  const unsigned job = lg_ticket(make_batch_state(A.ws, A.n_max, A.B).count + 1, sm);
+  const unsigned tix = job / (unsigned)A.B;
+  const LcView v = lc_view(A, (int)(job - tix * (unsigned)A.B));
   const int Nmax = (A.n_max + TS - 1) / TS;
   int i, j;
   col_unrank((int)tix, Nmax, i, j);
@@ -819,8 +835,9 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_all(LargeArgs A) {
   const int g = lane >> 2, tq = lane & 3, wm = warp >> 2, wn = warp & 3;
   // tile-major block order (all light curves' tile t before any tile t + 1): in a batch the
   // blocks adjacent in dispatch order are independent, a single GP gets plain row-major order
-  const unsigned tix = blockIdx.x / (unsigned)A.B;
-  const LcView v = lc_view(A, (int)(blockIdx.x - tix * (unsigned)A.B));
+  const unsigned job = lg_ticket(make_batch_state(A.ws, A.n_max, A.B).count + 2, sm);
+  const unsigned tix = job / (unsigned)A.B;
+  const LcView v = lc_view(A, (int)(job - tix * (unsigned)A.B));
   int i, j;
   tri_unrank((int)tix, i, j);   // (a, b), a >= b  ->  tile (a + 1, b)
   i += 1;

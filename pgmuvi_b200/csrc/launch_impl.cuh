@@ -143,7 +143,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   cudaMemsetAsync(bs.state, 0, (size_t)(3 * B + 4) * sizeof(int), st);
   const dim3 blk(NTHREADS);
   for (int pass = 0; pass <= 3; ++pass) {
-    cudaMemsetAsync(bs.count, 0, sizeof(int), st);
+    cudaMemsetAsync(bs.count, 0, 4 * sizeof(int), st);   // [0] repeat count, [1] / [2] job tickets
     lg_setup<KIND, QT, D><<<dim3((npad + NTHREADS - 1) / NTHREADS, B), blk, 0, st>>>(A);
     const long long ncb = (long long)(N * (N + 1) / 2) * B;
     // up to PGM_STAGED_CHOL_ALL_N tile rows (default 200) the left-looking one-launch schedule
@@ -200,6 +200,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       for (int i = 1; i < N; ++i) lg_inv_row<<<dim3(i, B), blk, LG_INV_SMEM, st>>>(A, i);
     } else if (N > 1) {                        // whole T phase in one launch, flag-ordered
       cudaMemsetAsync(bs.tflag, 0, (size_t)B * large_ntri(n) * sizeof(int), st);
+      cudaMemsetAsync(bs.count + 2, 0, sizeof(int), st);
       const long long nblk = (long long)(N * (N - 1) / 2) * B;
       if (nblk > 2147483647LL) return fail("staged engine: too many tiles x light curves");
       lg_inv_all<<<dim3((unsigned)nblk), blk, LG_INV_SMEM, st>>>(A);
