@@ -154,6 +154,8 @@ class BatchEngine:
         with torch.cuda.stream(self._side):                           # blocks on its own stream only
             m1, g1, i1 = ops.sm_mll_grad_staged(*part(B - k, B), *args)
         cur.wait_stream(self._side)
+        for t in (m1, g1, i1):          # allocated on the side stream, consumed on the current one
+            t.record_stream(cur)
         return torch.cat([m0, m1]), torch.cat([g0, g1]), torch.cat([i0, i1])
 
     def fit_device(self, d, maxiter=300, miniter=None, stop=1e-5, lr=0.1, optim="AdamW",

@@ -450,3 +450,40 @@ def test_non_constant_means_match_the_oracle(cuda_device, model, two_d):
                                pk.raw().detach().double(), pk.kinds, pk.lb, pk.ub, spec, xs)
     assert np.allclose(out["mean"], (mo + m_q).numpy(), rtol=1e-8, atol=1e-8)
     assert np.allclose(out["variance"], vo.numpy(), rtol=1e-6, atol=1e-9)
+
+
+def test_ticket_scheduler_and_tail_split_cover_every_light_curve(cuda_device, monkeypatch):
+    """r02 scheduling: (a) the fused kernel hands light curves out by tickets (last-wave rule), so a
+    batch larger than the persistent grid must still return every light curve exactly as the
+    fixed-stride launch does (PGM_STATIC_STRIDE=1), bit for bit; (b) BatchEngine's tail split
+    (fused kernel + staged engine on a second stream) returns the same values as the unsplit call
+    to 1e-10 and in the original order."""
+    import os
+    from pgmuvi_b200 import ops, synthetic as S
+    from pgmuvi_b200.batch import BatchEngine, HostBatch
+    dev = cuda_device
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    B = 3 * sms + sms // 2 + 7                    # > one grid, last wave with two per SM on some SMs
+    bt0 = S.make_batch_1d(16, 200, Q=2, seed0=99)
+    bt = {k: (np.concatenate([v] * (B // 16 + 1), 0)[:B] if isinstance(v, np.ndarray) and v.ndim
+              and v.shape[0] == 16 else v) for k, v in bt0.items()}
+    bt["raw"] = bt["raw"] + 1e-3 * np.arange(B)[:, None]      # every light curve distinct
+    T = lambda a, dt=torch.float64: torch.tensor(np.asarray(a), dtype=dt, device=dev)
+    args = (T(bt["x"]), T(bt["y"]), T(bt["noise"]), T(bt["raw"]), T(bt["kinds"], torch.int32),
+            T(bt["lb"]), T(bt["ub"]), None, 0, 2, False, True)
+    m1, g1, i1 = ops.sm_mll_grad(*args)
+    monkeypatch.setenv("PGM_STATIC_STRIDE", "1")
+    m0, g0, i0 = ops.sm_mll_grad(*args)
+    monkeypatch.delenv("PGM_STATIC_STRIDE")
+    assert torch.equal(m0, m1) and torch.equal(g0, g1) and torch.equal(i0, i1)
+    assert torch.isfinite(m1).all() and len(torch.unique(m1)) == B
+    eng = BatchEngine(kind=0, Q=2, learn_noise=False, device=dev)
+    d = eng.upload(HostBatch.from_numpy(bt, pin=True))
+    k = eng.tail_split(B, 1)
+    assert k == (B % (2 * sms)) - sms and k > 0
+    m2, g2, i2 = eng.evaluate_device(d, True)
+    torch.cuda.synchronize()
+    assert float(((m2 - m1) / m1).abs().max()) < 1e-10 and torch.equal(i2, i1)
+    assert float(((g2 - g1).abs().amax(1) / g1.abs().amax(1)).max()) < 1e-8
+    monkeypatch.setenv("PGM_TAIL_BALANCE", "0")
+    assert eng.tail_split(B, 1) == 0
