@@ -69,6 +69,9 @@ extern "C" {
 #define PGM_CON_NONE 0     /* value = raw                                         */
 #define PGM_CON_SOFTPLUS 1 /* Positive / GreaterThan(lb): softplus(raw) + lb      */
 #define PGM_CON_INTERVAL 2 /* Interval(lb, ub): lb + (ub - lb) * sigmoid(raw)     */
+#define PGM_CON_RSOFTPLUS 3 /* ub / (softplus(raw) + lb): a Positive / GreaterThan LENGTHSCALE l seen as the
+                              frequency scale 1 / (2 pi l) of a spectral-mixture component (ub = 1 / (2 pi)):
+                              the flicker term SMK + ScaleKernel(RBFKernel), pgmuvi/gps.py:992-1002          */
 
 /* flags */
 #define PGM_FLAG_GRAD 1          /* also compute d MLL / d raw (loss.backward, trainers.py:181) */

@@ -62,6 +62,7 @@ def stat_atoms(kind: int):
 # constraint kinds (A.2) ---------------------------------------------------------------
 CON_NONE = 0       # value = raw
 CON_SOFTPLUS = 1   # Positive / GreaterThan(lb): value = softplus(raw) + lb
+CON_RSOFTPLUS = 3  # value = ub / (softplus(raw) + lb)  (flicker term: sigma = 1 / (2 pi lengthscale))
 CON_INTERVAL = 2   # Interval(lb, ub):           value = lb + (ub - lb) * sigmoid(raw)
 
 TWO_PI = 2.0 * math.pi
@@ -127,6 +128,8 @@ def constrain(raw, kinds, lb, ub):
     iv = lb + (ub - lb) * torch.sigmoid(raw)
     out = torch.where(kinds == CON_SOFTPLUS, sp, raw)
     out = torch.where(kinds == CON_INTERVAL, iv, out)
+    # CON_RSOFTPLUS: ub / (softplus(raw) + lb) - a lengthscale seen as an SM frequency scale
+    out = torch.where(kinds == CON_RSOFTPLUS, ub / sp, out)
     return out
 
 
@@ -342,6 +345,8 @@ def constraint_jacobian(raw, kinds, lb, ub):
     j = torch.ones_like(raw)
     j = torch.where(kinds == CON_SOFTPLUS, s, j)
     j = torch.where(kinds == CON_INTERVAL, (ub - lb) * s * (1 - s), j)
+    v = torch.nn.functional.softplus(raw) + lb
+    j = torch.where(kinds == CON_RSOFTPLUS, -ub * s / (v * v), j)
     return j
 
 

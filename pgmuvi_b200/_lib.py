@@ -35,7 +35,7 @@ def stat_num_lam(kind):
     return (2, 2, 4, 6, 2, 2)[tk] + (0, 2, 2, 3, 1)[wk]
 
 
-CON_NONE, CON_SOFTPLUS, CON_INTERVAL = 0, 1, 2
+CON_NONE, CON_SOFTPLUS, CON_INTERVAL, CON_RSOFTPLUS = 0, 1, 2, 3
 FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC, FLAG_JITTER_F32, FLAG_TF32X3, FLAG_TF32X3_CHOL = (
     1, 2, 4, 8, 16, 32)
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2

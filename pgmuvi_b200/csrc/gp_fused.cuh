@@ -1189,6 +1189,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
       const double s = sigmoid_d(rv);
       th = lb + (ub - lb) * s;
       jc = (ub - lb) * s * (1.0 - s);
+    } else if (kd == 3) {   // PGM_CON_RSOFTPLUS: ub / (softplus(raw) + lb)
+      const double v = softplus_d(rv) + lb;
+      th = ub / v;
+      jc = -ub * sigmoid_d(rv) / (v * v);
     }
     theta[tid] = th;
     jac[tid] = jc;
@@ -1684,6 +1688,7 @@ __global__ void __launch_bounds__(NTHREADS)
     double th = rv;
     if (kd == 1) th = softplus_d(rv) + lb;
     else if (kd == 2) th = lb + (ub - lb) * sigmoid_d(rv);
+    else if (kd == 3) th = ub / (softplus_d(rv) + lb);
     theta[tid] = th;
   }
   load_exp_tab(tab);

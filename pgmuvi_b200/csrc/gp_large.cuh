@@ -172,6 +172,10 @@ __global__ void __launch_bounds__(NTHREADS) lg_setup(LargeArgs A) {
       const double s = sigmoid_d(rv);
       th = lb + (ub - lb) * s;
       jc = (ub - lb) * s * (1.0 - s);
+    } else if (kd == 3) {   // PGM_CON_RSOFTPLUS: ub / (softplus(raw) + lb)
+      const double v = softplus_d(rv) + lb;
+      th = ub / v;
+      jc = -ub * sigmoid_d(rv) / (v * v);
     }
     theta[tid] = th;
     jac[tid] = jc;

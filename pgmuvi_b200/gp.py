@@ -356,6 +356,8 @@ class AdditiveKernel(_ParamKernel):
 
 
 SpectralMixtureKernel.__mul__ = lambda self, other: ProductKernel(self, other)
+SpectralMixtureKernel.__add__ = lambda self, other: AdditiveKernel(self, other)
+AdditiveKernel.__mul__ = lambda self, other: ProductKernel(self, other)
 
 
 class _HomoskedasticNoise(Module):
@@ -506,12 +508,17 @@ def _make_qp_kernel(period):
     return ScaleKernel(ProductKernel(periodic_k, rbf_k))
 
 
-def _build_time_kernel(time_kernel_type, num_mixtures, period=None):
+def _build_time_kernel(time_kernel_type, num_mixtures, period=None, add_flicker=False):
     """pgmuvi/gps.py:938-1007: 'matern' (the reference's default), 'rbf', 'quasi_periodic',
-    'spectral_mixture' / 'sm'; the flicker term is outside the accelerated path."""
+    'spectral_mixture' / 'sm' (+ the flicker term ``SMK + ScaleKernel(RBFKernel)``, :992-1002)."""
     if isinstance(time_kernel_type, nn.Module):
         return time_kernel_type
     if time_kernel_type in ("spectral_mixture", "sm"):
+        if add_flicker:
+            warnings.warn("add_flicker=True is a work-in-progress feature whose stability has not yet "
+                          "been confirmed. Use with caution.", UserWarning, stacklevel=2)
+            return AdditiveKernel(SpectralMixtureKernel(num_mixtures=num_mixtures, ard_num_dims=1),
+                                  ScaleKernel(RBFKernel()))
         return SpectralMixtureKernel(num_mixtures=num_mixtures, ard_num_dims=1)
     if time_kernel_type == "matern":
         return ScaleKernel(MaternKernel(nu=1.5))
@@ -656,12 +663,11 @@ class WavelengthDependentGPModel(SeparableGPModel):
         if wavelength_lengthscale is None:
             wl_span = float(train_x[:, 1].max() - train_x[:, 1].min())
             wavelength_lengthscale = max(wl_span / 2.0, 1.0)       # gps.py:1576-1578
-        if add_flicker:
-            raise NotImplementedError("add_flicker is outside the accelerated path")
         if period is None:      # gps.py:1581-1583
             period = float(train_x[:, 0].max() - train_x[:, 0].min()) / 2.0
         super().__init__(train_x, train_y, likelihood,
-                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures, period),
+                         time_kernel=_build_time_kernel(time_kernel_type, num_mixtures, period,
+                                                        add_flicker=add_flicker),
                          wavelength_kernel=_build_wavelength_kernel(
                              wavelength_kernel_type, wavelength_lengthscale,
                              scaling=wavelength_scaling),

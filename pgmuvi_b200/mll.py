@@ -14,6 +14,7 @@ likelihood's noise modules and each ``raw_*_constraint``.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -22,6 +23,7 @@ import torch
 from . import ops
 from ._lib import (KIND_STAT_BASE, stat_kind, KIND_SEP_CONST, KIND_SEP_MATERN15, KIND_SEP_RBF, KIND_SEP_RQ, KIND_SM1D,
                    KIND_SM_ARD_PRODSUM, KIND_SM_ARD_SUMPROD)
+from ._lib import CON_INTERVAL, CON_RSOFTPLUS, CON_SOFTPLUS
 from .constraints import describe
 
 
@@ -62,7 +64,8 @@ class PackedModel:
         with torch.no_grad():
             for i, p in enumerate(self.params):
                 k = p.numel()
-                if not (self.external_mean and i == 0):      # the frozen zero stays zero
+                # frozen zeros (external mean slot, flicker mean frequency) are not Parameters
+                if not (self.external_mean and i == 0) and self.names[i] != "?":
                     p.copy_(flat[o:o + k].reshape(p.shape).to(dtype=p.dtype, device=p.device))
                 o += k
 
@@ -186,6 +189,16 @@ def _pack_stationary(model, likelihood, mean, cov, external_mean):
                        noise_index=noise_index)
 
 
+_FROZEN_ZERO = object()      # marks the frozen mean-frequency slot of the flicker component
+
+
+class _RSoftplus:
+    """marks a lengthscale slot the engine reads as an SM frequency scale (PGM_CON_RSOFTPLUS)"""
+
+    def __init__(self, inner):
+        self.inner = inner
+
+
 def pack_model(model, likelihood=None) -> PackedModel:
     """Recognise (mean, SpectralMixtureKernel [x wavelength kernel], Gaussian | FixedNoise
     likelihood).  ConstantMean is packed into slot 0; any other mean module (LinearMean,
@@ -202,11 +215,22 @@ def pack_model(model, likelihood=None) -> PackedModel:
     stat = _pack_stationary(model, likelihood, mean, cov, external_mean) if cov is not None else None
     if stat is not None:
         return stat
-    lam_params, lam_cons, sep_kind = [], [], None
+    lam_params, lam_cons, sep_kind, flick = [], [], None, None
     factors = getattr(cov, "kernels", None)
     if factors is not None:
         # ProductKernel(time_kernel, wavelength_kernel) with active_dims [0] / [1]
         # (pgmuvi/gps.py:1319-1333)
+        flick = None
+        f0 = factors[0] if len(factors) == 2 else None
+        if f0 is not None and type(f0).__name__ == "AdditiveKernel" and len(f0.kernels) == 2 \
+                and hasattr(f0.kernels[0], "raw_mixture_weights") \
+                and hasattr(f0.kernels[1], "raw_outputscale") \
+                and "RBF" in type(getattr(f0.kernels[1], "base_kernel", None)).__name__:
+            # flicker term (gps.py:992-1002): SMK(Q) + ScaleKernel(RBFKernel) in time.  An RBF term
+            # os * exp(-tau^2 / (2 l^2)) IS a spectral-mixture component with weight os, mean
+            # frequency 0 and frequency scale 1 / (2 pi l): packed as mixture Q + 1 (see below)
+            flick = f0.kernels[1]
+            factors = [f0.kernels[0], factors[1]]
         if len(factors) != 2 or not hasattr(factors[0], "raw_mixture_weights"):
             raise UnsupportedModelError(
                 "separable models need covar_module = SpectralMixtureKernel * wavelength kernel")
@@ -240,7 +264,7 @@ def pack_model(model, likelihood=None) -> PackedModel:
     for nm in ("raw_mixture_weights", "raw_mixture_means", "raw_mixture_scales"):
         if cov is None or not hasattr(cov, nm):
             raise UnsupportedModelError("covar_module must be a SpectralMixtureKernel")
-    Q = int(cov.raw_mixture_weights.numel())
+    Q = int(cov.raw_mixture_weights.numel()) + (1 if flick is not None else 0)
     d = int(cov.raw_mixture_means.shape[-1])
     if sep_kind is not None:
         if d != 1:
@@ -267,6 +291,15 @@ def pack_model(model, likelihood=None) -> PackedModel:
     cons = [None if external_mean else _constraint(mean, "raw_constant"),
             _constraint(cov, "raw_mixture_weights"), _constraint(cov, "raw_mixture_means"),
             _constraint(cov, "raw_mixture_scales")]
+    if flick is not None:
+        # [mean | w[Q-1], os_f | mu[Q-1], 0 (frozen) | sigma[Q-1], 1 / (2 pi l_f) | ...]
+        zero = torch.zeros(1, dtype=cov.raw_mixture_weights.dtype,
+                           device=cov.raw_mixture_weights.device)
+        base = flick.base_kernel
+        params = [slot0, cov.raw_mixture_weights, flick.raw_outputscale, cov.raw_mixture_means, zero,
+                  cov.raw_mixture_scales, base.raw_lengthscale]
+        cons = [cons[0], cons[1], _constraint(flick, "raw_outputscale"), cons[2], _FROZEN_ZERO,
+                cons[3], _RSoftplus(_constraint(base, "raw_lengthscale"))]
     fixed, learn, noise_index = None, False, None
     nc = getattr(likelihood, "noise_covar", None)
     snc = getattr(likelihood, "second_noise_covar", None)
@@ -288,7 +321,16 @@ def pack_model(model, likelihood=None) -> PackedModel:
     cons += lam_cons
     kinds, lb, ub = [], [], []
     for p, c in zip(params, cons):
-        k, lo, hi = describe(c)
+        if c is _FROZEN_ZERO:                 # Interval(0, 0): value 0, Jacobian 0 - never moves
+            k, lo, hi = CON_INTERVAL, 0.0, 0.0
+        elif isinstance(c, _RSoftplus):       # 1 / (2 pi (softplus(raw) + lb))
+            k0, lo, _ = describe(c.inner)
+            if k0 != CON_SOFTPLUS:
+                raise UnsupportedModelError("the flicker lengthscale needs a Positive / GreaterThan "
+                                            "constraint")
+            k, hi = CON_RSOFTPLUS, 1.0 / (2.0 * math.pi)
+        else:
+            k, lo, hi = describe(c)
         kinds += [k] * p.numel()
         lb += [lo] * p.numel()
         ub += [hi] * p.numel()

@@ -67,7 +67,7 @@ def history_from_raw(raw_hist, pk, model, lightcurve=None, transform=True):
         k = p.numel()
         vals = raw_hist[:, o:o + k].reshape((T,) + tuple(p.shape)).to(p.dtype)
         o += k
-        if getattr(pk, "external_mean", False) and i == 0:
+        if (getattr(pk, "external_mean", False) and i == 0) or name == "?":
             continue                                        # frozen zero, not a model parameter
         if lightcurve is None:
             out[name] = [v.numpy() for v in vals]           # raw values under the raw name

@@ -487,3 +487,49 @@ def test_ticket_scheduler_and_tail_split_cover_every_light_curve(cuda_device, mo
     assert float(((g2 - g1).abs().amax(1) / g1.abs().amax(1)).max()) < 1e-8
     monkeypatch.setenv("PGM_TAIL_BALANCE", "0")
     assert eng.tail_split(B, 1) == 0
+
+
+def test_flicker_model_parity_and_fit(cuda_device):
+    """N3 flicker term through the engine: MLL + gradient of the packed (Q + 1)-mixture model against
+    the oracle's autograd (the PGM_CON_RSOFTPLUS slot carries the chain rule to raw_lengthscale),
+    then a short fit through Lightcurve.fit: the loss falls, the frozen slot never moves."""
+    import warnings
+    from oracle import ModelSpec, mll_and_grad_autograd
+    from pgmuvi_b200 import ops, gp
+    from pgmuvi_b200.lightcurve import Lightcurve
+    from pgmuvi_b200.mll import pack_model
+    rng = np.random.default_rng(4)
+    nb, per = 3, 80
+    t = np.concatenate([np.sort(rng.uniform(0, 300, per)) for _ in range(nb)])
+    wl = np.repeat([0.5, 1.2, 2.2], per)
+    y = np.sin(2 * np.pi * t / 45.0) * (1 + 0.2 * wl) + 0.1 * rng.standard_normal(nb * per)
+    lc = Lightcurve(torch.tensor(np.stack([t, wl], 1), dtype=torch.float32),
+                    torch.tensor(y, dtype=torch.float32),
+                    yerr=torch.full((nb * per,), 0.1), xtransform="minmax")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        lc.set_model("2DWavelengthDependent", num_mixtures=3, time_kernel_type="sm", add_flicker=True,
+                     mean_module="constant")
+    pk = pack_model(lc.model, lc.likelihood)
+    assert pk.Q == 4
+    dev = cuda_device
+    T = lambda a, dt=torch.float64: a.detach().to(device=dev, dtype=dt)
+    x64, y64 = lc._xdata_transformed.double(), lc._ydata_transformed.double()
+    raw = pk.raw().detach().double()
+    mll, grad, info = ops.sm_mll_grad(T(x64)[None], T(y64)[None], T(pk.fixed_noise.double())[None],
+                                      T(raw)[None], pk.kinds.to(dev), T(pk.lb), T(pk.ub), None,
+                                      pk.kind, pk.Q, pk.learn_noise, True)
+    spec = ModelSpec(d=2, Q=4, kind=pk.kind, learn_noise=pk.learn_noise)
+    mo, go, io = mll_and_grad_autograd(x64, y64, pk.fixed_noise.double(), raw, pk.kinds, pk.lb, pk.ub, spec)
+    assert int(info[0]) == int(io) == 0
+    assert abs(float(mll[0]) - float(mo)) <= 1e-9 * abs(float(mo))
+    assert float((grad[0].cpu() - go).abs().max()) <= 1e-7 * float(go.abs().max())
+    assert float(grad[0, 8]) == 0.0                     # the frozen mean frequency of the flicker term
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = lc.fit(model="2DWavelengthDependent", num_mixtures=3, time_kernel_type="sm",
+                     add_flicker=True, mean_module="constant", training_iter=40, lr=0.05,
+                     use_mls_init=False)
+    assert res["loss"][-1] < res["loss"][0]
+    keys = [k for k in res if "lengthscale" in k or "outputscale" in k]
+    assert any("kernels.0.kernels.1" in k for k in keys)     # flicker parameters are in the history

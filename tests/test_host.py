@@ -402,3 +402,56 @@ def test_torch_optimizer_history_keys_follow_the_reference(cpu_engine, monkeypat
         snap[n] = key
     assert all(not k.startswith("mean_module.eights") for k in snap.values())
     assert set(snap.values()) <= set(lc.get_parameters())
+
+
+def test_flicker_term_packs_as_an_extra_spectral_mixture_component():
+    """N3: WavelengthDependentGPModel(time_kernel_type='sm', add_flicker=True) has the time kernel
+    SMK(Q) + ScaleKernel(RBFKernel) (gps.py:992-1002).  The RBF term IS an SM component (weight =
+    outputscale, mean frequency 0, frequency scale 1 / (2 pi lengthscale)): pack_model emits Q + 1
+    mixtures with a frozen zero and a PGM_CON_RSOFTPLUS slot.  Check the packed model's dense
+    covariance (oracle) against the explicit sum written with the modules' own parameters."""
+    import math
+    import warnings
+    from oracle import ModelSpec, constrain, kernel_dense
+    from pgmuvi_b200._lib import CON_INTERVAL, CON_RSOFTPLUS, KIND_SEP_RBF
+    torch.manual_seed(3)
+    n = 40
+    x = torch.stack([torch.sort(torch.rand(n) * 50).values, torch.randint(0, 3, (n,)) + 0.5], 1).float()
+    lik = gp.FixedNoiseGaussianLikelihood(noise=torch.full((n,), 0.01))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = gp.WavelengthDependentGPModel(x, torch.randn(n), lik, time_kernel_type="sm", num_mixtures=3,
+                                          add_flicker=True, mean_module="constant")
+    assert any("work-in-progress" in str(v.message) for v in w)
+    add = m.covar_module.kernels[0]
+    smk, fl, wl = add.kernels[0], add.kernels[1], m.covar_module.kernels[1]
+    with torch.no_grad():
+        smk.raw_mixture_weights.copy_(torch.tensor([0.3, -0.2, 0.1]))
+        smk.raw_mixture_means.copy_(torch.tensor([-2.0, -1.0, -3.0]).reshape(3, 1, 1))
+        smk.raw_mixture_scales.copy_(torch.tensor([-3.0, -2.5, -4.0]).reshape(3, 1, 1))
+        fl.raw_outputscale.fill_(0.4)
+        fl.base_kernel.raw_lengthscale.fill_(1.7)
+        wl.raw_outputscale.fill_(0.2)
+    pk = pack_model(m, lik)
+    assert (pk.kind, pk.Q, pk.d, pk.P) == (KIND_SEP_RBF, 4, 2, 15)
+    assert pk.kinds.tolist().count(CON_RSOFTPLUS) == 1 and pk.kinds[8] == CON_INTERVAL
+    assert pk.names[4] == "?" and float(pk.lb[8]) == float(pk.ub[8]) == 0.0
+    raw = pk.raw().detach().double()
+    theta = constrain(raw, pk.kinds, pk.lb, pk.ub)
+    xd = x.double()
+    K = kernel_dense(xd, xd, theta, ModelSpec(d=2, Q=4, kind=KIND_SEP_RBF, learn_noise=False))
+    sp = torch.nn.functional.softplus
+    tau = xd[:, :1] - xd[:, :1].T
+    wq, mu, sg = (sp(p.detach().double().reshape(-1)) for p in
+                  (smk.raw_mixture_weights, smk.raw_mixture_means, smk.raw_mixture_scales))
+    Kt = sum(wq[q] * torch.exp(-2 * math.pi ** 2 * sg[q] ** 2 * tau ** 2) * torch.cos(2 * math.pi * mu[q] * tau)
+             for q in range(3))
+    osf, ell = sp(fl.raw_outputscale.detach().double()), sp(fl.base_kernel.raw_lengthscale.detach().double())
+    Kt = Kt + osf * torch.exp(-0.5 * tau ** 2 / ell ** 2)
+    dl = xd[:, 1:] - xd[:, 1:].T
+    Kl = sp(wl.raw_outputscale.detach().double()) * torch.exp(
+        -0.5 * dl ** 2 / sp(wl.base_kernel.raw_lengthscale.detach().double()) ** 2)
+    assert torch.allclose(K, Kt * Kl, rtol=1e-12, atol=1e-14)
+    # scatter leaves the frozen slot alone and round-trips the real parameters
+    pk.scatter_raw_(raw + 0.25)
+    assert float(fl.base_kernel.raw_lengthscale) == pytest.approx(1.95)
