@@ -40,8 +40,8 @@ F_EVAL = N_POINTS ** 3 + 4 * N_POINTS ** 2          # algorithmic flops / eval (
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel on the C2 batch
 # (4096 light curves), from the `ncu --set full` capture summarised in
 # profiles/r01g_fused_ncu_summary.txt (43.57 GB + 10.35 GB); scales with light curves per GPU
-TRAFFIC_BYTES_PER_LC = (43.565392e9 + 10.345462e9) / 4096
-TRAFFIC_SOURCE = "profiles/r01g_fused_ncu_summary.txt"
+TRAFFIC_BYTES_PER_LC = 56.266e9 / 4096      # ncu dram__bytes_read + write of one C2 launch (r02s)
+TRAFFIC_SOURCE = "profiles/r02s_ncu_summary.txt"
 KERNEL_NAME = "pgm::sm_mll_grad_kernel<0,4,1>"
 PREWARM_STEPS = 30
 _OUT = sys.stdout      # replaced in main() by a private handle to the real stdout
