@@ -60,7 +60,9 @@ def parse():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default): the batch is split over the ranks; weak: per rank")
     ap.add_argument("--c5-sources", type=int, default=16384, help="global sources of the C5 line")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="light curves in the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=128,
+                    help="light curves in the CPU sample (128 x n=512: about 1.5 s per step and mode; "
+                         "r01's 32 gave +-8 %% run-to-run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short C1 / C3 / C4 / C5 timings appended to the N=1 line")
