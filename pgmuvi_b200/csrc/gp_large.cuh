@@ -327,6 +327,15 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
   Ring r2{bars, bars + 16, stages, 0};
+  double* out = lg_tile(w.tilesL, i, j);
+  double* Ct = sm + C::SM_S;              // the block's own C tile (free: no diagonal work here)
+  const unsigned cbar = bars + 8 * 10;
+  if (!build && tid == 0) {
+    // read-modify-write of C_ij through shared memory: one bulk load now (lands under the k-loop),
+    // one bulk store at the end, instead of 16 scattered 16-byte global accesses per thread
+    mbar_expect_tx(cbar, 2 * CHUNK_BYTES);
+    bulk_g2s(smem_u32(Ct), out, 2 * CHUNK_BYTES, cbar);
+  }
   double acc[4][2][2];
   zero_acc(acc);
   auto tA = [&](int kk) { return lg_tile(w.tilesL, i, k0 + kk); };
@@ -341,20 +350,26 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   if (i == j) gemm_stream<M_FULL, true, 2>(acc, r2, k1 - k0, tA, tB, 0, 0, none, none, pf);
   else gemm_stream<M_FULL, false, 2>(acc, r2, k1 - k0, tA, tB, 0, 0, none, none, pf);
   __syncthreads();
-  double* out = lg_tile(w.tilesL, i, j);
   if (!build) {
-    // read-modify-write of this block's own tile (thread-private entries)
+    mbar_wait(cbar, 0);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 2; ++ni) {
         const int r = frag_row(wm, mi, g), c = frag_col(wn, ni, tq, 0);
-        double2* p = reinterpret_cast<double2*>(out + img(r, c));
+        double2* p = reinterpret_cast<double2*>(Ct + img(r, c));
         double2 vv = *p;
         vv.x -= acc[mi][ni][0];
         vv.y -= acc[mi][ni][1];
         *p = vv;
       }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(out, smem_u32(Ct), 2 * OPBUF * sizeof(double));
+      bulk_commit();
+      bulk_wait_all();
+    }
     return;
   }
   double wreg[QT], areg[QT * DS], lam[4];
