@@ -84,6 +84,13 @@ extern "C" {
                                     updates C -= L_panel L_panel^T run on tcgen05 (3xTF32) as well; the MLL
                                     then carries fp32-class error (with PGM_FLAG_TF32X3 only, it is the
                                     FP64 value)                                                        */
+#define PGM_FLAG_NOSYNC 64       /* staged engine: do not synchronise the stream.  All four passes of the
+                                    jitter ladder are enqueued (kernels of a later pass return at once for a
+                                    light curve that is already factored); `info` is final when the stream has
+                                    drained.  Only where the Cholesky pass is one launch (B * N < 1024 tile rows
+                                    in total and N <= 200, i.e. single GPs up to n = 12800 and small batches);
+                                    other shapes return an error.  Makes a training loop over ONE GP
+                                    (pgmuvi/trainers.py:177-207) a pure enqueue loop.                          */
 #define PGM_FLAG_JITTER_F32 8    /* jitter ladder 1e-6, 1e-5, 1e-4 (GPyTorch's float32 cholesky_jitter)
                                     instead of 1e-8, 1e-7, 1e-6; set by the *_f32 entry points, and
                                     by f64 callers whose MODEL is float32                          */
@@ -174,7 +181,7 @@ int pgm_fused_grid(int d, int Q, int kernel_kind);
  * gpytorch.settings.fast_computations(False, False, False), i.e. the exact Cholesky branch
  * the reference takes only for n <= 800.
  * The call is BLOCKING: it synchronises `stream` once per Cholesky pass to learn whether any
- * light curve must repeat it with more jitter.  B <= 65535.
+ * light curve must repeat it with more jitter (unless PGM_FLAG_NOSYNC).  B <= 65535.
  */
 size_t pgm_staged_workspace_bytes(int n_max, int B);
 int pgm_sm_mll_grad_staged_f64(const double* x, const int32_t* n_valid, const double* y,

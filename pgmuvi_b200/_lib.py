@@ -36,8 +36,8 @@ def stat_num_lam(kind):
 
 
 CON_NONE, CON_SOFTPLUS, CON_INTERVAL, CON_RSOFTPLUS = 0, 1, 2, 3
-FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC, FLAG_JITTER_F32, FLAG_TF32X3, FLAG_TF32X3_CHOL = (
-    1, 2, 4, 8, 16, 32)
+FLAG_GRAD, FLAG_LEARN_NOISE, FLAG_BOUNDS_PER_LC, FLAG_JITTER_F32, FLAG_TF32X3, FLAG_TF32X3_CHOL, FLAG_NOSYNC = (
+    1, 2, 4, 8, 16, 32, 64)
 OPT_SGD, OPT_ADAM, OPT_ADAMW = 0, 1, 2
 
 EXPORTS = (

@@ -41,6 +41,7 @@ namespace pgm {
 
 #define PGM_FLAG_TF32X3 16   // G phase on tcgen05 (3xTF32); set by pgm_sm_mll_grad_tf32x3_f32
 #define PGM_FLAG_TF32X3_CHOL 32   /* ... and the trailing updates of the panel-schedule Cholesky */
+#define PGM_FLAG_NOSYNC 64        /* staged engine: no host synchronisation (one-launch schedule only) */
 
 constexpr int TC_THREADS = 320;        // producer warp + MMA warp + 8 epilogue warps
 constexpr int TC_EPI_THREADS = 256;

@@ -189,6 +189,12 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       }
     }
     lg_ladder<<<(B + 255) / 256, 256, 0, st>>>(A);
+    if (A.flags & PGM_FLAG_NOSYNC) {
+      // no host round trip: all four ladder passes are enqueued; for a light curve that is already
+      // factored (or failed) every kernel of a later pass returns at once
+      if (!one_launch) return fail("PGM_FLAG_NOSYNC needs the one-launch schedule (B * N < 1024, N <= 200)");
+      continue;
+    }
     int again = 0;
     e = cudaMemcpyAsync(&again, bs.count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);

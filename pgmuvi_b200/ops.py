@@ -268,8 +268,8 @@ def _(x, y, fixed_noise, raw, con_kind, con_lb, con_ub, n_valid, kind, Q, learn_
 def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
                        con_kind: Tensor, con_lb: Tensor, con_ub: Tensor,
                        n_valid: Optional[Tensor], kind: int, Q: int, learn_noise: bool,
-                       want_grad: bool = True, tf32x3: bool = False, tf32x3_chol: bool = False
-                       ) -> Tuple[Tensor, Tensor, Tensor]:
+                       want_grad: bool = True, tf32x3: bool = False, tf32x3_chol: bool = False,
+                       nosync: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """Same contract as :func:`sm_mll_grad`, through the staged whole-device engine
     (``pgm_sm_mll_grad_staged_f64``): every light curve's K~ lives in HBM as 64x64 tiles and
     the batch advances stage by stage.  Blocking.
@@ -278,7 +278,9 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
     (tcgen05, 3xTF32; ``pgm_sm_mll_grad_staged_tf32x3_f64`` for float64 tensors,
     ``pgm_sm_mll_grad_tf32x3_f32`` for float32 tensors - the reference's default dtype).
     ``tf32x3_chol=True`` (implied for float32 tensors): the trailing updates of the panel-schedule
-    Cholesky run there too."""
+    Cholesky run there too.
+    ``nosync=True``: no host synchronisation (``PGM_FLAG_NOSYNC``; single GPs up to n = 12800 and small
+    batches): ``info`` is final once the stream has drained."""
     (x, y, fixed_noise, raw, con_kind, con_lb, con_ub, B, n, d, P, flags) = _prep(
         x, y, fixed_noise, raw, con_kind, con_lb, con_ub, kind, Q, learn_noise)
     f32 = x.dtype == torch.float32
@@ -286,6 +288,8 @@ def sm_mll_grad_staged(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw:
         raise RuntimeError("the staged engine takes float64 tensors (float32: tf32x3=True)")
     if want_grad:
         flags |= FLAG_GRAD
+    if nosync:
+        flags |= _lib.FLAG_NOSYNC
     if tf32x3_chol:
         if not tf32x3:
             raise RuntimeError("tf32x3_chol needs tf32x3=True")
@@ -359,16 +363,18 @@ def sm_predict(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
 
 def sm_mll_grad_large(x: Tensor, y: Tensor, fixed_noise: Optional[Tensor], raw: Tensor,
                       con_kind: Tensor, con_lb: Tensor, con_ub: Tensor, kind: int, Q: int,
-                      learn_noise: bool, want_grad: bool = True):
+                      learn_noise: bool, want_grad: bool = True, nosync: bool = False):
     """ONE large GP (x [n, d], y [n], raw [P]) factored by the whole device: the staged engine
-    with B = 1.  Returns (mll 0-d tensor, grad [P], info int); blocking."""
+    with B = 1.  Returns (mll 0-d tensor, grad [P], info int); blocking.
+    ``nosync=True`` (n <= 12800): nothing is synchronised and ``info`` comes back as a 0-d DEVICE
+    tensor - the caller reads it when it has to."""
     if x.dim() == 1:
         x = x.unsqueeze(-1)
     mll, grad, info = sm_mll_grad_staged(
         x.unsqueeze(0), y.unsqueeze(0), None if fixed_noise is None else fixed_noise.unsqueeze(0),
         raw.reshape(1, -1), con_kind, con_lb.reshape(-1), con_ub.reshape(-1), None, kind, Q,
-        learn_noise, want_grad)
-    return mll[0], grad[0], int(info.item())
+        learn_noise, want_grad, nosync=nosync)
+    return mll[0], grad[0], (info[0] if nosync else int(info.item()))
 
 
 def peak_probe(kind: int, iters: int = 4096) -> float:

@@ -203,16 +203,29 @@ def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, sto
     mll_dev = []
     need_loss = bool(stop) and miniter < maxiter - 1
     host_losses = []
+    # without a possible early stop nothing has to come back per iteration: the staged engine runs
+    # without host synchronisation (PGM_FLAG_NOSYNC, n <= 12800) and the loop is a pure enqueue
+    # loop; the Cholesky info of every iteration is checked once at the end
+    nosync = (not need_loss) and x.shape[0] <= 12800
+    info_dev = []
+
+    def _raise(code, i):
+        pk.scatter_raw_(raw_dev[min(i, len(raw_dev) - 1)].cpu())
+        if code == -1:
+            raise NanError("cholesky_cpu: NaN values found in the covariance matrix "
+                           f"at training iteration {i}")
+        raise NotPSDError("Matrix not positive definite after repeatedly adding jitter up "
+                          f"to 1.0e-06 (training iteration {i}).")
+
     for i in range(maxiter):
         mll, grad, code = ops.sm_mll_grad_large(x, y, fixed, raw[0], kinds, lb, ub, pk.kind, pk.Q,
-                                                pk.learn_noise, True)
-        if code < 0:
-            pk.scatter_raw_(raw_dev[-1].cpu())
-            if code == -1:
-                raise NanError("cholesky_cpu: NaN values found in the covariance matrix "
-                               f"at training iteration {i}")
-            raise NotPSDError("Matrix not positive definite after repeatedly adding jitter up "
-                              f"to 1.0e-06 (training iteration {i}).")
+                                                pk.learn_noise, True, nosync=nosync)
+        if nosync:
+            info_dev.append(code)
+            # a failed factorisation returns NaN gradients: freeze the parameters from there on
+            grad = torch.where(code < 0, torch.zeros_like(grad), grad)
+        elif code < 0:
+            _raise(code, i)
         ops.optim_step(raw, grad.reshape(1, -1), m, v, None, od["optim_kind"], lr, od["beta1"],
                        od["beta2"], od["eps"], od["weight_decay"], i + 1)
         mll_dev.append(mll.reshape(()))
@@ -223,6 +236,11 @@ def _train_large(lightcurve, model, pk, x, y, raw, od, lr, maxiter, miniter, sto
                 print(f"""Average change in loss over the last {stopavg} iterations
                     was {np.std(host_losses[-stopavg:])}.\n This is < {stop}, so we will end training here.""")
                 break
+    if info_dev:
+        codes = torch.stack(info_dev).cpu()
+        bad = torch.nonzero(codes < 0)
+        if len(bad):
+            _raise(int(codes[int(bad[0])]), int(bad[0]))
     lh = (-torch.stack(mll_dev)).cpu().numpy()
     losses = [np.asarray(val, dtype=np_dt) for val in lh]      # history in the model's dtype
     raws = list(torch.stack(raw_dev).cpu())
