@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -40,12 +41,15 @@ int device_sms() {
 namespace pgm {
 __global__ void optim_step_kernel(double* raw, const double* grad_mll, double* m, double* v,
                                   const int32_t* active, int B, int P, int kind, double lr,
-                                  double b1, double b2, double eps, double wd, int step) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * P) return;
+                                  double b1, double b2, double eps, double wd, double bc1,
+                                  double bc2s) {
+  // HBM-bound: 4 reads + 3 writes of 8 bytes per parameter; the bias corrections (two pow per
+  // step) come from the host so that no transcendental is left in the kernel
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * P) return;
   if (active && !active[idx / P]) return;
   double mm = m ? m[idx] : 0.0, vv = v ? v[idx] : 0.0;
-  raw[idx] = optim_update(raw[idx], -grad_mll[idx], mm, vv, kind, lr, b1, b2, eps, wd, step);
+  raw[idx] = optim_update_bc(raw[idx], -grad_mll[idx], mm, vv, kind, lr, b1, b2, eps, wd, bc1, bc2s);
   if (m) m[idx] = mm;
   if (v) v[idx] = vv;
 }
@@ -443,11 +447,15 @@ int pgm_optim_step_f64(double* raw, const double* grad_mll, double* exp_avg, dou
     return fail("Adam / AdamW need exp_avg and exp_avg_sq");
   if (optim_kind < 0 || optim_kind > 2) return fail("unknown optim_kind");
   if (step < 1) return fail("step counts from 1");
-  const int total = B * P;
-  const int threads = 256, blocks = (total + threads - 1) / threads;
+  const size_t total = (size_t)B * P;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  // torch.optim computes the bias corrections in host double precision as well (1 - beta ** step)
+  const double bc1 = 1.0 - std::pow(beta1, (double)step);
+  const double bc2s = std::sqrt(1.0 - std::pow(beta2, (double)step));
   pgm::optim_step_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       raw, grad_mll, exp_avg, exp_avg_sq, active, B, P, optim_kind, lr, beta1, beta2, eps,
-      weight_decay, step);
+      weight_decay, bc1, bc2s);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("optim_step_kernel launch", e);
   return 0;

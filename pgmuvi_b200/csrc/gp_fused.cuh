@@ -276,8 +276,12 @@ struct Cfg {
   static constexpr int PAR_W = PAR_JAC + PMAX;
   static constexpr int PAR_A = PAR_W + QT;
   static constexpr int PAR_LAM = PAR_A + QT * DS;   // wavelength-kernel constants [4]
-  static constexpr int PAR_RED = PAR_LAM + 4;
-  static constexpr int PAR_FIN = PAR_RED + 8 * (NV + 2);
+  // the warp partials of block_reduce ([8][NV + 2]) live in the column-side field vector: every
+  // reduction runs after a block barrier behind the last epilogue that read the fields.  (Kept out
+  // of the parameter area so that the separable 2-D kinds fit two blocks per SM.)
+  static constexpr int RED_ELEMS = 8 * (NV + 2);
+  static_assert(RED_ELEMS <= NF * TS, "block_reduce scratch must fit the column field vector");
+  static constexpr int PAR_FIN = PAR_LAM + 4;
   static constexpr int PAR_ZJ = (PAR_FIN + NV + 4 + 1) & ~1;   // z_j of the current block column [64], 16-B aligned
   static constexpr int PAR_ZI = PAR_ZJ + TS;          // z_i of the current tile row / scratch [64]
   static constexpr int PAR_DINV = PAR_ZI + TS;        // 1 / L_kk of the current diagonal block [64]
@@ -1163,7 +1167,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double* wq = par + C::PAR_W;
   double* aq = par + C::PAR_A;
   double* lamq = par + C::PAR_LAM;
-  double* red = par + C::PAR_RED;
+  double* red = colv;          // block_reduce scratch (see Cfg::RED_ELEMS)
   double* fin = par + C::PAR_FIN;
   double* zj = par + C::PAR_ZJ;
   double* zi = par + C::PAR_ZI;
@@ -1743,19 +1747,25 @@ __global__ void __launch_bounds__(NTHREADS)
 }
 
 // torch.optim.{SGD,Adam,AdamW} step on one parameter (trainers.py:141-147 defaults; A.7).
-// g is d loss / d raw.
-__device__ __forceinline__ double optim_update(double p, double g, double& m, double& v,
-                                               int kind, double lr, double b1, double b2,
-                                               double eps, double wd, int step) {
+// g is d loss / d raw; bc1 = 1 - beta1^step and bc2s = sqrt(1 - beta2^step) are the bias
+// corrections of the step (the same for every parameter: computed once per step by the caller).
+__device__ __forceinline__ double optim_update_bc(double p, double g, double& m, double& v,
+                                                  int kind, double lr, double b1, double b2,
+                                                  double eps, double wd, double bc1, double bc2s) {
   if (kind == 0) return p - lr * g;
   if (kind == 2) p *= (1.0 - lr * wd);
   else if (wd != 0.0) g += wd * p;
   m = b1 * m + (1.0 - b1) * g;
   v = b2 * v + (1.0 - b2) * g * g;
-  const double bc1 = 1.0 - pow(b1, (double)step);
-  const double bc2 = 1.0 - pow(b2, (double)step);
-  const double denom = sqrt(v) / sqrt(bc2) + eps;
+  const double denom = sqrt(v) / bc2s + eps;
   return p - (lr / bc1) * (m / denom);
+}
+__device__ __forceinline__ double optim_update(double p, double g, double& m, double& v,
+                                               int kind, double lr, double b1, double b2,
+                                               double eps, double wd, int step) {
+  const double bc1 = 1.0 - pow(b1, (double)step);
+  const double bc2s = sqrt(1.0 - pow(b2, (double)step));
+  return optim_update_bc(p, g, m, v, kind, lr, b1, b2, eps, wd, bc1, bc2s);
 }
 
 // whole training loop of trainers.py:177-207 per light curve, on device

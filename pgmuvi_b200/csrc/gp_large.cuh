@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* rowv = sm + C::SM_ROW;
   double* colv = sm + C::SM_COL;
   double* par = sm + C::SM_PAR;
-  double* red = par + C::PAR_RED;
+  double* red = colv;          // block_reduce scratch: the fields are dead by then (Cfg::RED_ELEMS)
   double* fin = par + C::PAR_FIN;
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
@@ -1128,11 +1128,9 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* rowv = sm + C::SM_ROW;   // test tile fields
   double* colv = sm + C::SM_COL;   // train tile fields (+ alpha)
   double* par = sm + C::SM_PAR;
-  double* red = par + C::PAR_RED;  // >= 8 * 15 doubles; used as [4][64] below via S region
   double* scr = sm + C::SM_S;      // 34 KB free region: reductions
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
-  (void)red;
   load_exp_tab(tab);
   PipeState ps;
   pipe_init<KIND, QT, D>(sm, ps);
