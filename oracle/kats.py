@@ -5,6 +5,17 @@ path (the reference's own tests pin none); they pin the oracle's M
 likelihood / constraint construction and optimiser semantics to ~1e-3 (limited by the 4-7
 printed digits and by optimiser chaos), not to the 1e-6 of the generated goldens.
 
+K4 - Lomb-Scargle notebook, 1-D peak summary (N2)
+    /root/reference/docs/source/notebooks/PGMUVI_Lomb_Scargle.ipynb cells 6, 8, 10, 12: band 0 (38
+    points) of ``make_chromatic_sinusoid_2d(period=150, ...)``, ``fit_LS(num_peaks=5)`` -> peak
+    frequencies 0.006704, 0.039931, 0.061499, 0.248038, 0.069660 (ASTROPY's output), 475 grid
+    points.  The printed mask (first peak significant only) pre-dates the per-peak 'single' FAP now
+    at pgmuvi/lightcurve.py:4587-4596 (like K3 and F13): it is what Benjamini-Hochberg gives with
+    the multiple-frequency (Davies / Baluev) FAP per peak; today's rule marks all five.  Both are
+    restated (``significant`` = current code, ``significant_legacy`` = the notebook's).
+    Data from the reference's own generator
+    (oracle/make_golden_kats.py -> tests/golden_kats/ls_nb_data.npz).
+
 K3 - tutorial, second 1-D fit
     /root/reference/docs/source/notebooks/pgmuvi_tutorial.ipynb cells 3, 6, 8, 21, 23.
     Published (cell 23 output): loss -0.36470833, noise 0.00239522, constant 0.00569272,
@@ -159,3 +170,41 @@ def k2_run(param_dtype=torch.float32, iters=1000):
                 time_freqs=(float(th[spec.o_mu]), float(th[spec.o_mu + 2])),
                 n_iter=len(res["loss"]), means0=float(th0[spec.o_mu]),
                 weight0=float(th0[1]), constant0=float(th0[0]))
+
+
+# ---------------------------------------------------------------------------------------
+# K4: PGMUVI_Lomb_Scargle.ipynb cells 10 / 12 - the only astropy-produced numbers in the tree
+# ---------------------------------------------------------------------------------------
+K4_PUBLISHED = dict(n=38, grid=475,
+                    peak_freqs=(0.006704, 0.039931, 0.061499, 0.248038, 0.069660),
+                    peak_periods=(149.171, 25.043, 16.260, 4.032, 14.355),
+                    significant=(True, False, False, False, False))
+
+
+def k4_data():
+    """(t, y, yerr) of band 0 as float64 (the notebook's ``lc2d.select_bands(['band 0'])``)."""
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(here, "tests", "golden_kats", "ls_nb_data.npz"))
+    x, y, e = z["x"], z["y"], z["yerr"]
+    m = x[:, 1] == np.unique(x[:, 1])[0]
+    return x[m, 0].astype(np.float64), y[m].astype(np.float64), e[m].astype(np.float64)
+
+
+def k4_run():
+    """The oracle's route through Lightcurve.fit_LS's 1-D branch (lightcurve.py:4499-4611):
+    astropy autofrequency grid, exact floating-mean periodogram, scipy find_peaks(distance = 5)
+    sorted by height, Davies FAP of the maximum, Benjamini-Hochberg over the per-peak FAPs."""
+    from . import lombscargle as ols
+    t, y, dy = k4_data()
+    f0, df, nf = ols.autofrequency(t, nyquist_factor=5)
+    freq = f0 + df * np.arange(nf)
+    power = ols.power_slow(t, y, dy, freq)
+    pk = ols.top_peaks(power, 5, 10 ** 6)
+    sig = np.zeros(pk.size, dtype=bool)
+    if ols.fap_davies(power.max(), freq[-1], t, dy) <= 0.05:
+        sig = ols.fdr_bh(ols.fap_single(power[pk], t.size), 0.05)
+        sig[0] = True
+    legacy = ols.fdr_bh(np.minimum([ols.fap_davies(z, freq[-1], t, dy) for z in power[pk]], 1.0), 0.05)
+    return dict(n=t.size, grid=nf, freqs=freq[pk[:5]], power=power[pk[:5]], significant=sig[:5],
+                significant_legacy=legacy[:5])

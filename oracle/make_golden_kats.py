@@ -8,6 +8,10 @@ built from - and calls ``make_multi_sinusoid_chromatic_2d`` with the exact confi
 docs/source/notebooks/PGMUVI_comparison_with_other_codes.ipynb cell 7 (``MULTI_DATASET_CONFIG``).
 Output: ``tests/golden_kats/comparison_nb_data.npz`` (x [225, 2], y [225], yerr [225], float32
 as the reference stores them).  The notebook's printed band counts (89, 73, 63) are asserted.
+
+K4: ``make_chromatic_sinusoid_2d`` with ``SINGLE_DATASET_CONFIG`` of
+docs/source/notebooks/PGMUVI_Lomb_Scargle.ipynb cell 6 -> ``tests/golden_kats/ls_nb_data.npz``
+(x [106, 2], y, yerr); the notebook's "Number of points in 1D light curve: 38" (band 0) is asserted.
 """
 from __future__ import annotations
 
@@ -30,7 +34,7 @@ class _RecordingLightcurve:
         self.xdata, self.ydata, self.yerr = xdata, ydata, yerr
 
 
-def reference_generator():
+def reference_generator(which="comparison"):
     pkg = types.ModuleType("pgmuvi")
     pkg.__path__ = []
     lcmod = types.ModuleType("pgmuvi.lightcurve")
@@ -41,6 +45,10 @@ def reference_generator():
         spec = importlib.util.spec_from_file_location("pgmuvi_reference_synthetic", REF)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        if which == "ls":      # PGMUVI_Lomb_Scargle.ipynb cell 6 (SEED = 0)
+            return mod.make_chromatic_sinusoid_2d(
+                period=150, t_span=150 * 2.3, n_per_band=(25, 40), wavelengths=[0.8, 1.2, 2.2],
+                amplitude_law="extinction", seed=0)
         # notebook cell 7
         cfg = dict(
             components=[
@@ -68,6 +76,12 @@ def main():
     assert counts.tolist() == [89, 73, 63], counts          # notebook cell 7 output
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "comparison_nb_data.npz"), x=x, y=y, yerr=e)
+    print("wrote", x.shape, wl, counts)
+    lc = reference_generator("ls")
+    x, y, e = lc.xdata.numpy(), lc.ydata.numpy(), lc.yerr.numpy()
+    wl, counts = np.unique(x[:, 1], return_counts=True)
+    assert counts[0] == 38, counts                          # Lomb-Scargle notebook cell 8 output
+    np.savez_compressed(os.path.join(OUT, "ls_nb_data.npz"), x=x, y=y, yerr=e)
     print("wrote", x.shape, wl, counts)
 
 

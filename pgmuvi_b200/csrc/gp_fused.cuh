@@ -1667,23 +1667,48 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   if (threadIdx.x == 0) bulk_wait_all();  // no bulk store may outlive the block's shared memory
 }
 
-// dense K + D for parity tests / large-n path: one block per (light curve, 64x64 tile)
+// rank t of the lower triangle (row-major) -> (a, b), a >= b
+__device__ __forceinline__ void tri_unrank(int t, int& a, int& b) {
+  a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((a + 1) * (a + 2) / 2 <= t) ++a;
+  while (a * (a + 1) / 2 > t) --a;
+  b = t - a * (a + 1) / 2;
+}
+
+// dense K + D (north-star kernel 1 as a launch of its own; the fused and staged engines call the
+// same k_entry from their Cholesky epilogues and never write K).  One block per (light curve,
+// 64x64 tile of the LOWER triangle): the per-point fields of the 128 points are built by all 256
+// threads, every entry is evaluated once with the larger index as its row, written row-wise and -
+// for off-diagonal tiles - mirrored through a padded shared-memory tile so that both stores are
+// coalesced and K_ij, K_ji are the same bits.  FP64-pipe bound (n^2/2 Q exp / cos chains).
+template <int KIND, int QT, int D>
+struct DenseSmem {
+  using C = Cfg<KIND, QT, D>;
+  static constexpr int LDT = TS + 1;
+  static constexpr int ELEMS = 2 * C::NFB * TS + TS * LDT;
+  static constexpr size_t BYTES = (size_t)ELEMS * sizeof(double);
+};
 template <int KIND, int QT, int D>
 __global__ void __launch_bounds__(NTHREADS)
     sm_kernel_dense_kernel(EvalArgs A, double* __restrict__ Kout) {
   using C = Cfg<KIND, QT, D>;
   constexpr int DS = C::DS;
-  __shared__ __align__(16) double rowv[C::NFB * TS];
-  __shared__ __align__(16) double colv[C::NFB * TS];
+  constexpr int LDT = DenseSmem<KIND, QT, D>::LDT;
+  extern __shared__ __align__(16) double dsm[];
+  double* rowv = dsm;
+  double* colv = rowv + C::NFB * TS;
+  double* tl = colv + C::NFB * TS;
   __shared__ double theta[C::PMAX], wq[QT], aq[QT * DS], lamq[4], tab[EXP_TAB];
   const int tid = threadIdx.x;
-  const int b = blockIdx.z, ti = blockIdx.y, tj = blockIdx.x;
+  const int b = blockIdx.y;
+  int ti, tj;
+  tri_unrank(blockIdx.x, ti, tj);
   const int Q = A.Q;
   const bool learn_noise = (A.flags & PGM_FLAG_LEARN_NOISE) != 0;
   const int P = param_count<KIND, QT, D>(Q, learn_noise);
   const int o_noise = 1 + Q + 2 * Q * DS, o_lam = o_noise + (learn_noise ? 1 : 0);
   const int n = A.n_valid ? A.n_valid[b] : A.n_max;
-  if (ti * TS >= n || tj * TS >= n) return;
+  if (ti * TS >= n) return;
   if (tid < P) {
     const double rv = A.raw[(size_t)b * P + tid];
     const int kd = A.con_kind[tid];
@@ -1707,22 +1732,25 @@ __global__ void __launch_bounds__(NTHREADS)
     if constexpr (C::STAT) stat_setup<KIND>(theta + o_lam, wq, aq, lamq);
     else lam_setup<KIND>(theta + o_lam, lamq);
   }
+  // fields: item 0 of a point = its centred inputs, items 1.. = (cos, sin)(2 pi mu_qd x_d)
   const double* xb = A.x + (size_t)b * A.n_max * D;
-  for (int idx = tid; idx < 2 * TS; idx += NTHREADS) {
-    const int side = idx >> 6, r = idx & 63;
+  constexpr int ITEMS = 1 + DS * QT;
+  for (int idx = tid; idx < 2 * TS * ITEMS; idx += NTHREADS) {
+    const int item = idx / (2 * TS), pt = idx - item * (2 * TS);
+    const int side = pt >> 6, r = pt & 63;
     const int gi = (side ? tj : ti) * TS + r;
     double* vec = side ? colv : rowv;
     const bool valid = gi < n;
-    for (int dd = 0; dd < D; ++dd) {
-      const double xc = valid ? (xb[(size_t)gi * D + dd] - xb[dd]) : 0.0;
-      vec[dd * TS + r] = xc;
-      if (dd >= DS) continue;
-      for (int q = 0; q < QT; ++q) {
-        double sn = 0.0, cs = 1.0;
-        if (valid && q < Q) sincospi(2.0 * theta[1 + Q + q * DS + dd] * xc, &sn, &cs);
-        vec[D * TS + ((dd * QT + q) * TS + r) * 2] = cs;
-        vec[D * TS + ((dd * QT + q) * TS + r) * 2 + 1] = sn;
-      }
+    if (item == 0) {
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) vec[dd * TS + r] = valid ? (xb[(size_t)gi * D + dd] - xb[dd]) : 0.0;
+    } else {
+      const int f = item - 1, dd = f / QT, q = f - dd * QT;
+      double sn = 0.0, cs = 1.0;
+      if (valid && q < Q)
+        sincospi(2.0 * theta[1 + Q + q * DS + dd] * (xb[(size_t)gi * D + dd] - xb[dd]), &sn, &cs);
+      vec[D * TS + (f * TS + r) * 2] = cs;
+      vec[D * TS + (f * TS + r) * 2 + 1] = sn;
     }
   }
   __syncthreads();
@@ -1737,12 +1765,20 @@ __global__ void __launch_bounds__(NTHREADS)
     const int r = idx >> 6, c = idx & 63;
     const int gi = ti * TS + r, gj = tj * TS + c;
     if (gi < n && gj < n) {
-      // evaluate with the larger index as the row so that K_ij and K_ji are the same bits
+      // the larger index is the row (on a diagonal tile rowv and colv hold the same points)
       double kv = (gi >= gj) ? k_entry<KIND, QT, D>(rowv, colv, r, c, wreg, areg, lam, tab)
                              : k_entry<KIND, QT, D>(colv, rowv, c, r, wreg, areg, lam, tab);
       if (gi == gj) kv += (fnb ? fnb[gi] : 0.0) + lnoise;
       Kb[(size_t)gi * A.n_max + gj] = kv;
+      tl[r * LDT + c] = kv;
     }
+  }
+  if (ti == tj) return;
+  __syncthreads();
+  for (int idx = tid; idx < TT; idx += NTHREADS) {   // K_ji = K_ij, rows of the mirrored tile
+    const int c = idx >> 6, r = idx & 63;
+    const int gi = ti * TS + r, gj = tj * TS + c;
+    if (gi < n && gj < n) Kb[(size_t)gj * A.n_max + gi] = tl[r * LDT + c];
   }
 }
 

@@ -134,12 +134,7 @@ __device__ __forceinline__ double* lg_tile(double* base, int i, int j) {
   return base + ((size_t)i * (i + 1) / 2 + j) * TT;
 }
 // linear index t -> (a, b) with a >= b >= 0 (row-major lower triangle)
-__device__ __forceinline__ void tri_unrank(int t, int& a, int& b) {
-  a = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while ((a + 1) * (a + 2) / 2 <= t) ++a;
-  while (a * (a + 1) / 2 > t) --a;
-  b = t - a * (a + 1) / 2;
-}
+// tri_unrank: gp_fused.cuh
 
 // ------------------------------------------------------------------------------------
 // setup: constraints -> parameter block; per-point fields, rhs, noise diagonal

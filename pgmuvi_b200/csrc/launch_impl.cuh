@@ -95,9 +95,14 @@ int launch_fit(const pgm::FitArgs& F, cudaStream_t st) {
 template <int KIND, int QT, int D>
 int launch_dense(const pgm::EvalArgs& A, double* K, cudaStream_t st) {
   const int N = (A.n_max + pgm::TS - 1) / pgm::TS;
-  dim3 grid(N, N, A.B);
-  pgm::sm_kernel_dense_kernel<KIND, QT, D><<<grid, pgm::NTHREADS, 0, st>>>(A, K);
-  cudaError_t e = cudaGetLastError();
+  if (A.B > 65535) return fail("sm_kernel_dense: at most 65535 light curves per call");
+  auto kern = pgm::sm_kernel_dense_kernel<KIND, QT, D>;
+  const size_t smem = pgm::DenseSmem<KIND, QT, D>::BYTES;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(sm_kernel_dense_kernel)", e);
+  dim3 grid(N * (N + 1) / 2, A.B);
+  kern<<<grid, pgm::NTHREADS, smem, st>>>(A, K);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("sm_kernel_dense_kernel launch", e);
   return 0;
 }
