@@ -810,42 +810,99 @@ __device__ __forceinline__ double rcp_pos(double d) {   // 1/d for normal d > 0
   return fma(y, e, y);
 }
 
-// warp 0: factor columns c0..c0+7 (rows c0..63; lane holds rows c0+lane and c0+lane+32)
+// 1/d for normal d > 0: MUFU.RCP64H seed (|e| < 2^-20) + one cubic step e -> e^3 (3 dependent FMAs
+// instead of the 4 of two Newton steps; relative error < 2^-60 before the final rounding)
+__device__ __forceinline__ double rcp_pos3(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+
+// 1/sqrt(d) for normal d > 0: MUFU.RSQ64H seed + one cubic step (y (1 + e/2 + 3 e^2/8), e = 1 - d y^2):
+// 1 MUFU + 5 dependent-free-ish FMAs instead of the ~18 instructions of rsqrt() / sqrt()
+__device__ __forceinline__ double rsqrt_pos3(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = fma(0.375, e, 0.5) * e;
+  return fma(y, q, y);
+}
+
+// warp 0: factor columns c0..c0+7 (rows c0..63; lane holds rows c0+lane and c0+lane+32).
+// The serial chain (pivot -> reciprocal -> update of the next pivot) runs on the 8x8 pivot block,
+// which EVERY lane eliminates redundantly in its own registers (broadcast loads, no shuffle on the
+// chain); the lanes then eliminate their own two rows against the finished multipliers
+// u_ck = v_ck / d_k - 28 FMAs per row whose only chain is one FMA per column.  Rows are loaded and
+// stored as 16-byte vectors (LD_S = 68: 2-way instead of 8-way bank conflicts).
 __device__ __forceinline__ void potrf_panel8(double* __restrict__ S, double* __restrict__ dinv,
                                              int c0, int lane, int* fail) {
   const int r0 = c0 + lane, r1 = c0 + lane + 32;
-  double a0[8], a1[8], dp[8];
+  double P[8][8];      // lower triangle of the pivot block: v_ck -> u_ck; diagonal: d_k
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    a0[k] = (r0 < TS) ? S[r0 * LD_S + c0 + k] : 0.0;
-    a1[k] = (r1 < TS) ? S[r1 * LD_S + c0 + k] : 0.0;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j2 = 0; j2 <= i / 2; ++j2) {
+      const double2 v = *reinterpret_cast<const double2*>(S + (c0 + i) * LD_S + c0 + 2 * j2);
+      P[i][2 * j2] = v.x;
+      P[i][2 * j2 + 1] = v.y;          // (i, i + 1) for even i: unused upper entry
+    }
+  double a0[8], a1[8];
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) {
+    const double2 v0 = (r0 < TS) ? *reinterpret_cast<const double2*>(S + r0 * LD_S + c0 + 2 * k2)
+                                 : make_double2(0.0, 0.0);
+    const double2 v1 = (r1 < TS) ? *reinterpret_cast<const double2*>(S + r1 * LD_S + c0 + 2 * k2)
+                                 : make_double2(0.0, 0.0);
+    a0[2 * k2] = v0.x; a0[2 * k2 + 1] = v0.y;
+    a1[2 * k2] = v1.x; a1[2 * k2 + 1] = v1.y;
   }
   bool bad = false, isnan_ = false;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const double dpiv = shfl_d(a0[k], k);
+    double dpiv = P[k][k];
     if (!(dpiv > 0.0)) { bad = true; if (dpiv != dpiv) isnan_ = true; }
-    dp[k] = bad ? 1.0 : dpiv;
-    const double rd = rcp_pos(dp[k]);
+    dpiv = bad ? 1.0 : dpiv;
+    P[k][k] = dpiv;
+    const double rd = rcp_pos3(dpiv);
 #pragma unroll
     for (int c = k + 1; c < 8; ++c) {
-      const double u = shfl_d(a0[k], c) * rd;      // v_ck / d_k
-      a0[c] = fma(-a0[k], u, a0[c]);
-      a1[c] = fma(-a1[k], u, a1[c]);
+      const double v = P[c][k];
+      const double u = v * rd;                  // v_ck / d_k
+#pragma unroll
+      for (int c2 = k + 1; c2 < c; ++c2) P[c][c2] = fma(-P[c2][k], v, P[c][c2]);   // P[c2][k] is u_c2k
+      P[c][c] = fma(-v, u, P[c][c]);
+      P[c][k] = u;
     }
+  }
+  // own rows: v_rc = a_rc - sum_{k<c} v_rk u_ck  (rows of the pivot block reproduce its elimination)
+#pragma unroll
+  for (int c = 1; c < 8; ++c) {
+    double s0 = a0[c], s1 = a1[c];
+#pragma unroll
+    for (int k = 0; k < c; ++k) {
+      s0 = fma(-a0[k], P[c][k], s0);
+      s1 = fma(-a1[k], P[c][k], s1);
+    }
+    a0[c] = s0;
+    a1[c] = s1;
   }
   double myrs = 0.0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const double rs = rsqrt(dp[k]);
+    const double rs = rsqrt_pos3(P[k][k]);      // 1 / L_kk
     if (lane == k) myrs = rs;
     a0[k] *= rs;
     a1[k] *= rs;
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (r0 < TS) S[r0 * LD_S + c0 + k] = a0[k];
-    if (r1 < TS) S[r1 * LD_S + c0 + k] = a1[k];
+  for (int k2 = 0; k2 < 4; ++k2) {
+    if (r0 < TS)
+      *reinterpret_cast<double2*>(S + r0 * LD_S + c0 + 2 * k2) = make_double2(a0[2 * k2], a0[2 * k2 + 1]);
+    if (r1 < TS)
+      *reinterpret_cast<double2*>(S + r1 * LD_S + c0 + 2 * k2) = make_double2(a1[2 * k2], a1[2 * k2 + 1]);
   }
   if (lane < 8) dinv[c0 + lane] = myrs;
   if (lane == 0 && bad) atomicOr(fail, isnan_ ? 2 : 1);

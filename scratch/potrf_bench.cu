@@ -8,9 +8,70 @@
 #include <vector>
 using namespace pgm;
 
-#ifndef POTRF
-#define POTRF potrf_inv_64
+// timing variants of potrf_inv_64 (results are wrong unless VAR == 0):
+//   1: panel factorisations only   2: no inverse rows (step 2b)   3: no trailing step 2a   4: panels + step 1 only
+template <int VAR>
+__device__ __forceinline__ void potrf_var(double* __restrict__ S, double* __restrict__ S2,
+                                          double* __restrict__ dinv, int* fail) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  if (warp == 0) potrf_panel8(S, dinv, 0, lane, fail);
+  for (int p = 0; p < 8; ++p) {
+    const int c0 = p * 8;
+    __syncthreads();
+    if (VAR != 1 && p < 7 && warp < 7 - p) potrf_syrk_tile(S, c0, p + 1 + warp, p + 1, g, tq);
+    __syncthreads();
+    if (p < 7 && warp == 0) {
+      potrf_panel8(S, dinv, c0 + 8, lane, fail);
+    } else if (VAR != 1 && VAR != 4) {
+      const int nw = (p < 7) ? 7 : 8, w = (p < 7) ? warp - 1 : warp;
+      const int m8 = 6 - p;
+      const int cnt = (m8 > 0) ? m8 * (m8 + 1) / 2 : 0;
+      if (VAR != 3)
+      for (int t = w; t < cnt; t += nw) {
+        int a_ = 0;
+        while ((a_ + 1) * (a_ + 2) / 2 <= t) ++a_;
+        const int b_ = t - a_ * (a_ + 1) / 2;
+        potrf_syrk_tile(S, c0, p + 2 + a_, p + 2 + b_, g, tq);
+      }
+      if (VAR != 2)
+      for (int nt = w; nt <= p; nt += nw) {
+        double c2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) c2[e] = (c0 + g == 8 * nt + 2 * tq + e) ? 1.0 : 0.0;
+        for (int kt = nt; kt < p; ++kt) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+            mma_f64(c2, -S[(c0 + g) * LD_S + 8 * kt + 4 * s + tq],
+                    S2[(8 * kt + 4 * s + tq) * LD_S + 8 * nt + g]);
+        }
+        *reinterpret_cast<double2*>(S2 + (c0 + g) * LD_S + 8 * nt + 2 * tq) = make_double2(c2[0], c2[1]);
+        __syncwarp();
+        if (lane < 8) {
+          const int c = 8 * nt + lane;
+          double v[8];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) v[rr] = S2[(c0 + rr) * LD_S + c];
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            double sacc = v[rr];
+#pragma unroll
+            for (int kk = 0; kk < rr; ++kk) sacc -= S[(c0 + rr) * LD_S + c0 + kk] * v[kk];
+            v[rr] = sacc * dinv[c0 + rr];
+          }
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) S2[(c0 + rr) * LD_S + c] = v[rr];
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncthreads();
+}
+#ifndef PVAR
+#define PVAR 0
 #endif
+#define POTRF potrf_var<PVAR>
 
 __global__ void __launch_bounds__(256, 2) bench(const double* A, int iters, long long* cyc, double* Lout,
                                                 double* Xout, int* failout) {
