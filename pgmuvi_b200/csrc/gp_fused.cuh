@@ -350,8 +350,7 @@ __host__ __device__ __forceinline__ int img(int r, int k) {
 }
 
 __device__ __forceinline__ int frag_mt(int wm, int mi) {
-  return wm ? ((mi == 0) ? 1 : (mi == 1) ? 2 : (mi == 2) ? 5 : 6)
-            : ((mi == 0) ? 0 : (mi == 1) ? 3 : (mi == 2) ? 4 : 7);
+  return 2 * mi + ((mi ^ wm) & 1);   // {0,3,4,7} | {1,2,5,6}, branch-free (rolled epilogue loops)
 }
 __device__ __forceinline__ int frag_nt(int wn, int ni) { return ni ? 7 - wn : wn; }
 __device__ __forceinline__ int frag_row(int wm, int mi, int g) { return 8 * frag_mt(wm, mi) + g; }
