@@ -275,9 +275,32 @@ __device__ __forceinline__ void lg_wait_flag(const int* f) {
   }
   fence_proxy_async();   // the tile was written, and will be read, through the async proxy
 }
+// Non-blocking look at a flag: the acquire load is issued here, its value is consumed one k-tile later
+// (lg_wait_flag_pf), so that the L2 round trip of the poll hides under the products of the tile in
+// between (r02y: the blocking poll per operand tile paced the k-loops of the one-launch phases).
+__device__ __forceinline__ int lg_peek_flag(const int* f) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+  return v;
+}
+// wait for a flag whose value was peeked earlier (0 = not yet set then: poll); no proxy fence
+__device__ __forceinline__ void lg_wait_flag_pf(const int* f, int peeked) {
+  if (peeked) return;
+  int v;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+  do {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory");
+    if (!v) {
+      __nanosleep(40);
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) __trap();
+    }
+  } while (!v);
+}
 __device__ __forceinline__ void lg_set_flag(int* f) {
   fence_proxy_async();
-  __threadfence();
+  // st.release.gpu is a gpu-scope release fence + store: no separate __threadfence() in front of it
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(1) : "memory");
 }
 
@@ -617,38 +640,86 @@ __global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
   }
   __syncthreads();
   Ring r2{bars, bars + 16, stages, 0};
+  double wreg[QT], areg[QT * DS], lam[4];
+#pragma unroll
+  for (int q = 0; q < QT; ++q) wreg[q] = w.par[LG_PAR_WQ + q];
+#pragma unroll
+  for (int q = 0; q < QT * DS; ++q) areg[q] = w.par[LG_PAR_AQ + q];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) lam[q] = w.par[LG_PAR_LM + q];
+  if (i == j) {
+    // Diagonal job = the critical path of the factorisation (column j + 1 cannot start before it):
+    // K~_jj (+ noise, jitter) does not depend on the operands this block is about to wait for, so it
+    // is generated into S BEFORE the k-loop (fields through stage 0, which the ring takes over
+    // afterwards); behind the k-loop only C = K~ - acc is left (r02y).
+    lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 1
+    for (int p8 = 0; p8 < 8; ++p8) {
+      const int mi = p8 >> 1, ni2 = p8 & 1;
+      if (frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+      const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
+      const int gi = i * TS + r;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = j * TS + c0 + e;
+        double kv = k_entry<KIND, QT, D>(rowv, rowv, r, c0 + e, wreg, areg, lam, tab);
+        kv = (gi < n && gj <= gi) ? kv : 0.0;
+        if (gi == gj) kv = (gi < n) ? (kv + w.dn[gi] + jitter) : 1.0;
+        S[r * LD_S + c0 + e] = kv;
+      }
+    }
+    __syncthreads();      // everyone is done with the fields in stage 0
+  }
   double acc[4][2][2];
   zero_acc(acc);
   auto tA = [&](int kk) { return lg_tile(w.tilesL, i, kk); };
   auto tB = [&](int kk) { return lg_tile(w.tilesL, j, kk); };
   auto none = [&](int) { return (double*)nullptr; };
-  auto ready = [&](int kk) {            // producer thread only
-    lg_wait_flag(flag_of(j, kk));
-    if (i != j) lg_wait_flag(flag_of(i, kk));
+  // producer thread only: both operand tiles of k-tile kk must be final; the flags of k-tile kk + 1 are
+  // peeked here and looked at one k-tile later
+  int pk_k = -1, pk_j = 0, pk_i = 0;
+  auto ready = [&](int kk) {
+    const bool have = (pk_k == kk);
+    lg_wait_flag_pf(flag_of(j, kk), have ? pk_j : 0);
+    if (i != j) lg_wait_flag_pf(flag_of(i, kk), have ? pk_i : 0);
+    fence_proxy_async();   // the tiles were written, and will be read, through the async proxy
+    if (kk + 1 < j) {
+      pk_j = lg_peek_flag(flag_of(j, kk + 1));
+      pk_i = (i != j) ? lg_peek_flag(flag_of(i, kk + 1)) : 1;
+      pk_k = kk + 1;
+    }
   };
   if (i == j) gemm_stream_r<M_FULL, true, 2>(acc, r2, j, tA, tB, 0, 0, none, none, []() {}, ready);
   else gemm_stream_r<M_FULL, false, 2>(acc, r2, j, tA, tB, 0, 0, none, none, []() {}, ready);
   __syncthreads();
-  // the stages are idle now: per-point fields of tile row i / column j into stage 0
-  lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
-  if (i != j) lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, false);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  // epilogue: C = K~_ij - acc  (off-diagonal: image in stage 1; diagonal: S, lower MMA tiles)
-  {
-    double wreg[QT], areg[QT * DS], lam[4];
+  if (i == j) {
+    // C = K~ - acc on the lower MMA tiles; every thread revisits the entries it wrote itself
 #pragma unroll
-    for (int q = 0; q < QT; ++q) wreg[q] = w.par[LG_PAR_WQ + q];
+    for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-    for (int q = 0; q < QT * DS; ++q) areg[q] = w.par[LG_PAR_AQ + q];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) lam[q] = w.par[LG_PAR_LM + q];
+      for (int ni2 = 0; ni2 < 2; ++ni2) {
+        if (frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
+        double2* sp = reinterpret_cast<double2*>(S + frag_row(wm, mi, g) * LD_S + frag_col(wn, ni2, tq, 0));
+        double2 kv = *sp;
+        kv.x -= acc[mi][ni2][0];
+        kv.y -= acc[mi][ni2][1];
+        *sp = kv;
+      }
+  } else {
+    // the stages are idle now: per-point fields of tile row i / column j into stage 0 / S
+    lg_prefetch_side<KIND, QT, D>(rowv, w, npad, i, false);
+    lg_prefetch_side<KIND, QT, D>(colv, w, npad, j, false);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // epilogue: C = K~_ij - acc, image in stage 1
     store_acc_tile(acc, Cst, 1.0);
 #pragma unroll 1
     for (int p8 = 0; p8 < 8; ++p8) {
       const int mi = p8 >> 1, ni2 = p8 & 1;
-      if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
       const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
       const int gi = i * TS + r;
       double2* cp = reinterpret_cast<double2*>(Cst + img(r, c0));
@@ -659,15 +730,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
         const int gj = j * TS + c0 + e;
         double kv = k_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab);
         kv = (gi < n && gj <= gi) ? kv : 0.0;
-        if (gi == gj) kv = (gi < n) ? (kv + w.dn[gi] + jitter) : 1.0;
         o2[e] = kv - (e ? cv.y : cv.x);
       }
-      if (i == j) {
-        S[r * LD_S + c0] = o2[0];
-        S[r * LD_S + c0 + 1] = o2[1];
-      } else {
-        *cp = make_double2(o2[0], o2[1]);
-      }
+      *cp = make_double2(o2[0], o2[1]);
     }
   }
   if (i == j) {
@@ -682,21 +747,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
     if (!earlier_failure) potrf_inv_64(S, S2, dinv, s_fail);
     const bool ok = !earlier_failure && (*s_fail == 0);
     if (!earlier_failure && *s_fail && tid == 0) atomicOr(v.st.fail + v.b, *s_fail);
+    // What column j's other blocks wait for goes out FIRST (X_jj in the L array's diagonal slot and
+    // z_j), then the flag; the copies later phases read (X_jj / X_jj^T for the inverse and the
+    // gradient, the log-det / quadratic-form partials) follow behind the flag (r02y).
+    double* tl = lg_tile(w.tilesL, j, j);
     if (ok) {
-      double* tl = lg_tile(w.tilesL, j, j);
-      double* tx = lg_tile(w.tilesX, j, j);
-      double* tt = w.tilesT + (size_t)j * TT;
       for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
         const int r = idx >> 5, c2 = (idx & 31) * 2;
-        double2 vv, vt;
+        double2 vv;
         vv.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
         vv.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
-        vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
-        vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
-        const int o = img(r, c2);
-        *reinterpret_cast<double2*>(tl + o) = vv;
-        *reinterpret_cast<double2*>(tx + o) = vv;
-        *reinterpret_cast<double2*>(tt + o) = vt;
+        *reinterpret_cast<double2*>(tl + img(r, c2)) = vv;
       }
       {
         const int r = tid >> 2, l4 = tid & 3;
@@ -710,16 +771,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) lg_chol_all(LargeArgs A) {
           red2[TS + r] = -log(dinv[r]);
         }
       }
-      __syncthreads();
-      if (tid < 2) {
-        double s = 0.0;
-        for (int r = 0; r < TS; ++r) s += red2[tid * TS + r];
-        w.ldz[2 * j + (tid ? 0 : 1)] = s;   // ldz[2j] = sum log L_kk, ldz[2j+1] = z_j^T z_j
-      }
     }
-    fence_proxy_async();   // the tiles written above are read by bulk copies of other blocks
+    fence_proxy_async();   // the tile written above is read by bulk copies of other blocks
     __syncthreads();
     if (tid == 0) lg_set_flag(flag_of(j, j));
+    if (ok) {
+      double* tx = lg_tile(w.tilesX, j, j);
+      double* tt = w.tilesT + (size_t)j * TT;
+      for (int idx = tid; idx < TT / 2; idx += NTHREADS) {
+        const int r = idx >> 5, c2 = (idx & 31) * 2;
+        double2 vv, vt;
+        vv.x = (c2 <= r) ? S2[r * LD_S + c2] : 0.0;
+        vv.y = (c2 + 1 <= r) ? S2[r * LD_S + c2 + 1] : 0.0;
+        vt.x = (r <= c2) ? S2[c2 * LD_S + r] : 0.0;
+        vt.y = (r <= c2 + 1) ? S2[(c2 + 1) * LD_S + r] : 0.0;
+        const int o = img(r, c2);
+        *reinterpret_cast<double2*>(tx + o) = vv;
+        *reinterpret_cast<double2*>(tt + o) = vt;
+      }
+      if (tid < 2) {
+        double s2 = 0.0;
+        for (int r = 0; r < TS; ++r) s2 += red2[tid * TS + r];
+        w.ldz[2 * j + (tid ? 0 : 1)] = s2;   // ldz[2j] = sum log L_kk, ldz[2j+1] = z_j^T z_j
+      }
+      fence_proxy_async();   // tilesX / tilesT are read by bulk copies of the following kernels
+    }
     return;
   }
   // ---- off-diagonal tile: L_ij = C X_jj^T once the diagonal tile is final
@@ -786,6 +862,35 @@ static __global__ void lg_ladder(LargeArgs A) {
 // row i of X = L^-1:  X_ij^T = -(sum_{k=j}^{i-1} X_kj^T L_ik^T) X_ii^T,  j = blockIdx.x < i
 // (reads L from tilesL, writes X^T tiles to tilesX: blocks of one launch never conflict)
 // ------------------------------------------------------------------------------------
+// alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i: the products X_ij^T z_i ride along with the T phase
+// (the tile is in the accumulators as -X_ij^T; 4 partials per row over the warp columns, summed in
+// a fixed order) and land in fpart - dead after the P phase -, so that lg_alpha only adds N of
+// them per point instead of walking the tile column (r02y: 32 -> 6 us at n = 1000).
+__device__ __forceinline__ void lg_inv_partial(const double (&acc)[4][2][2], const double* __restrict__ zi,
+                                               double* red /* [4][64], stage 0 is idle */, int wm, int wn,
+                                               int g, int tq) {
+  double zc[2][2];
+#pragma unroll
+  for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) zc[ni][e] = __ldcg(zi + frag_col(wn, ni, tq, e));
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+    double s = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) s -= acc[mi][ni][e] * zc[ni][e];
+    s += shfl_xor_d(s, 1);
+    s += shfl_xor_d(s, 2);
+    if (tq == 0) red[wn * TS + frag_row(wm, mi, g)] = s;
+  }
+}
+__device__ __forceinline__ void lg_inv_partial_store(double* __restrict__ dst, const double* red) {
+  const int tid = threadIdx.x;
+  if (tid < TS) dst[tid] = (red[tid] + red[TS + tid]) + (red[2 * TS + tid] + red[3 * TS + tid]);
+}
+
 constexpr size_t LG_INV_SMEM = (size_t)(6 * OPBUF + 16) * sizeof(double);
 static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(LargeArgs A, int i) {
   extern __shared__ __align__(16) double sm[];
@@ -825,8 +930,10 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_row(LargeArgs A, in
   zero_acc(acc);
   compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
   compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
-  store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);
+  lg_inv_partial(acc, w.z + i * TS, stages, wm, wn, g, tq);
+  store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);   // its barriers also publish the partials
   if (tid == 0) bulk_wait_all();
+  lg_inv_partial_store(w.fpart + ((size_t)i * (i + 1) / 2 + j) * TS, stages);
 }
 
 // ------------------------------------------------------------------------------------
@@ -875,8 +982,18 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_all(LargeArgs A) {
   auto tA = [&](int kk) { return kk == 0 ? w.tilesT + (size_t)j * TT : lg_tile(w.tilesX, j + kk, j); };
   auto tB = [&](int kk) { return lg_tile(w.tilesL, i, j + kk); };
   auto none = [&](int) { return (double*)nullptr; };
-  auto ready = [&](int kk) {   // producer thread only: X_{j+kk, j} must be final
-    if (kk > 0) lg_wait_flag(flags + ((size_t)(j + kk) * (j + kk + 1) / 2 + j));
+  // producer thread only: X_{j+kk, j} must be final; the flag of k-tile kk + 1 is peeked one tile ahead
+  int pk_k = -1, pk_v = 0;
+  auto xflag = [&](int kk) { return flags + ((size_t)(j + kk) * (j + kk + 1) / 2 + j); };
+  auto ready = [&](int kk) {
+    if (kk > 0) {
+      lg_wait_flag_pf(xflag(kk), (pk_k == kk) ? pk_v : 0);
+      fence_proxy_async();
+    }
+    if (kk + 1 < i - j) {
+      pk_v = lg_peek_flag(xflag(kk + 1));
+      pk_k = kk + 1;
+    }
   };
   gemm_stream_r<M_A_GE, false, 2>(acc, r2, i - j, tA, tB, 0, 0, none, none, []() {}, ready);
   __syncthreads();
@@ -886,11 +1003,13 @@ static __global__ void __launch_bounds__(NTHREADS, 2) lg_inv_all(LargeArgs A) {
   zero_acc(acc);
   compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
   compute_chunk<M_B_LE, false>(acc, Cst + OPBUF, R + OPBUF, KC / 8, wm, wn, g, tq);
-  store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);
+  lg_inv_partial(acc, w.z + i * TS, stages, wm, wn, g, tq);
+  store_tile_bulk(acc, Cst, lg_tile(w.tilesX, i, j), -1.0);   // its barriers also publish the partials
   if (tid == 0) {
     bulk_wait_all();
     lg_set_flag(flags + ((size_t)i * (i + 1) / 2 + j));
   }
+  lg_inv_partial_store(w.fpart + ((size_t)i * (i + 1) / 2 + j) * TS, stages);   // behind the flag
 }
 
 // alpha_j = X_jj^T z_j + sum_{i>j} X_ij^T z_i   (tilesX holds X_jj and the X_ij^T tiles)
@@ -909,12 +1028,8 @@ static __global__ void __launch_bounds__(NTHREADS) lg_alpha(LargeArgs A) {
 #pragma unroll 4
     for (int r = part * 16; r < part * 16 + 16; ++r) s += Xd[img(r, m)] * zz[r];
   }
-  for (int i = j + 1; i < N; ++i) {
-    const double* Xt = lg_tile(w.tilesX, i, j);
-    const double* zz = w.z + i * TS;
-#pragma unroll 4
-    for (int c = part * 16; c < part * 16 + 16; ++c) s += Xt[img(m, c)] * zz[c];
-  }
+  // the off-diagonal products were left in fpart by the T phase (lg_inv_partial)
+  for (int i = j + 1 + part; i < N; i += 4) s += w.fpart[((size_t)i * (i + 1) / 2 + j) * TS + m];
   scr[part * TS + m] = s;
   __syncthreads();
   if (tid < TS)
