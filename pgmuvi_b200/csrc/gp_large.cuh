@@ -1039,10 +1039,24 @@ static __global__ void __launch_bounds__(NTHREADS) lg_alpha(LargeArgs A) {
 // ------------------------------------------------------------------------------------
 // gradient partials of tile (i, j), i >= j:  K^-1_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}
 // ------------------------------------------------------------------------------------
+// Shared memory of lg_grad: one tile job per block and no look-ahead, so the ring is idle behind the
+// k-loop and the K^-1 tile is parked in stage 1 - no separate 34 KB work tile.  That brings the ARD
+// 2-D kinds (19 per-point fields per side) under the two-blocks-per-SM limit (r02z); two blocks are
+// only asked for while the gradient accumulators leave room in 128 registers (NG <= 24).
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+struct GradSmem {
+  using C = Cfg<KIND, QT, D>;
+  static constexpr int ROW_OFF = STAGE_ELEMS;
+  static constexpr int COL_OFF = ROW_OFF + C::NF * TS;
+  static constexpr int PAR_OFF = COL_OFF + C::NF * TS;
+  static constexpr size_t BYTES = (size_t)(PAR_OFF + C::PAR_END + 8) * sizeof(double);
+  static constexpr int MIN_BLOCKS = (BYTES <= 113 * 1024 && C::NG <= 24) ? 2 : 1;
+};
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, GradSmem<KIND, QT, D>::MIN_BLOCKS)
     lg_grad(LargeArgs A) {
   using C = Cfg<KIND, QT, D>;
+  using L = GradSmem<KIND, QT, D>;
   constexpr int DS = C::DS;
   static_assert(C::NV <= LG_GP, "gradient partial slot too small");
   extern __shared__ __align__(16) double sm[];
@@ -1055,18 +1069,22 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   int i, j;
   tri_unrank(blockIdx.x, i, j);
   if (i >= N) return;
-  double* stages = sm + C::SM_STAGES;
-  double* R = sm + C::SM_S;
-  double* rowv = sm + C::SM_ROW;
-  double* colv = sm + C::SM_COL;
-  double* par = sm + C::SM_PAR;
+  double* stages = sm;
+  double* R = stages + 2 * OPBUF;   // K^-1 tile parked in stage 1 (the ring is idle by then)
+  double* rowv = sm + L::ROW_OFF;
+  double* colv = sm + L::COL_OFF;
+  double* par = sm + L::PAR_OFF;
   double* red = colv;          // block_reduce scratch: the fields are dead by then (Cfg::RED_ELEMS)
   double* fin = par + C::PAR_FIN;
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
   load_exp_tab(tab);
-  PipeState ps;
-  pipe_init<KIND, QT, D>(sm, ps);
+  if (tid == 0) {   // mbarriers of the 2-stage ring (full / empty)
+    for (int s2 = 0; s2 < 2; ++s2) { mbar_init(bars + 8 * s2, 1); mbar_init(bars + 8 * (2 + s2), NTHREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
   Ring r2{bars, bars + 16, stages, 0};
   double acc[4][2][2];
   zero_acc(acc);

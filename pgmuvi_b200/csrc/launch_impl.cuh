@@ -138,7 +138,8 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_update)", e);
   constexpr size_t CHOL_SMEM = CholAllSmem<KIND, QT, D>::BYTES;
   cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM);
-  e = cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+  constexpr size_t GRAD_SMEM = GradSmem<KIND, QT, D>::BYTES;
+  e = cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAD_SMEM);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_grad)", e);
   cudaFuncSetAttribute(lg_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_DIAG_SMEM);
   cudaFuncSetAttribute(lg_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LG_TRSM_SMEM);
@@ -236,7 +237,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       if (const char* f = getenv("PGM_TC_HALF_PIECES")) halfp = atoi(f) ? 1 : 0;
       k_tc<<<dim3(tc_grid(NT), B), TC_THREADS, TS_::bytes(nst), st>>>(A, nst, halfp, tc_fold());
     } else if (!predict_only) {
-      k_grad<<<dim3(N * (N + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A);
+      k_grad<<<dim3(N * (N + 1) / 2, B), blk, GRAD_SMEM, st>>>(A);
     }
   }
   if (predict_only) {
