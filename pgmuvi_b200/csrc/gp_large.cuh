@@ -309,10 +309,24 @@ __device__ __forceinline__ void lg_set_flag(int* f) {
 //   mode 0: one tile column j = jj, i = jj + blockIdx.x
 //   mode 1: the whole trailing triangle i >= j >= jj, blockIdx.x -> (i - jj, j - jj)
 // ------------------------------------------------------------------------------------
+// Shared memory of lg_update: ring + ONE 32 KB region that is the block's own C tile when the launch
+// updates an existing tile (read-modify-write) and the per-point fields when it builds K~ (first
+// touch; the result is then formed in stage 1) - never both.  102-105 KB for every kind, i.e. two
+// blocks per SM also for SM-8 (C4's trailing updates) and the ARD 2-D kinds (r02z).
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+struct UpdSmem {
+  using C = Cfg<KIND, QT, D>;
+  static constexpr int CT_OFF = STAGE_ELEMS;
+  static constexpr int UNION = (2 * C::NF * TS > 2 * OPBUF) ? 2 * C::NF * TS : 2 * OPBUF;
+  static constexpr int PAR_OFF = CT_OFF + UNION;
+  static constexpr size_t BYTES = (size_t)(PAR_OFF + C::PAR_END + 8) * sizeof(double);
+  static constexpr int MIN_BLOCKS = (BYTES <= 113 * 1024) ? 2 : 1;
+};
+template <int KIND, int QT, int D>
+__global__ void __launch_bounds__(NTHREADS, UpdSmem<KIND, QT, D>::MIN_BLOCKS)
     lg_update(LargeArgs A, int mode, int jj, int k0, int k1, int build) {
   using C = Cfg<KIND, QT, D>;
+  using L = UpdSmem<KIND, QT, D>;
   constexpr int DS = C::DS;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -334,20 +348,25 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   if (i >= N || j >= N) return;
   if (v.st.fail[v.b]) return;
   const double jitter = lg_jitter(v.st.attempt[v.b], A.flags);
-  double* stages = sm + C::SM_STAGES;
+  double* stages = sm;
   double* Cst = stages + 2 * OPBUF;
-  double* rowv = sm + C::SM_ROW;
-  double* colv = sm + C::SM_COL;
-  double* par = sm + C::SM_PAR;
+  double* Ct = sm + L::CT_OFF;            // !build: the block's own C tile
+  double* rowv = Ct;                      // build: per-point fields (same region)
+  double* colv = rowv + C::NF * TS;
+  double* par = sm + L::PAR_OFF;
   double* tab = par + C::PAR_TAB;
   const unsigned bars = smem_u32(par + C::PAR_BAR);
+  const unsigned cbar = bars + 8 * 10;
   load_exp_tab(tab);
-  PipeState ps;
-  pipe_init<KIND, QT, D>(sm, ps);
+  if (tid == 0) {   // mbarriers: 2-stage ring (full / empty) + the C-tile barrier
+    for (int s2 = 0; s2 < 2; ++s2) { mbar_init(bars + 8 * s2, 1); mbar_init(bars + 8 * (2 + s2), NTHREADS / 32); }
+    mbar_init(cbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
   Ring r2{bars, bars + 16, stages, 0};
   double* out = lg_tile(w.tilesL, i, j);
-  double* Ct = sm + C::SM_S;              // the block's own C tile (free: no diagonal work here)
-  const unsigned cbar = bars + 8 * 10;
   if (!build && tid == 0) {
     // read-modify-write of C_ij through shared memory: one bulk load now (lands under the k-loop),
     // one bulk store at the end, instead of 16 scattered 16-byte global accesses per thread

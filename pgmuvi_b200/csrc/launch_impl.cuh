@@ -134,7 +134,8 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
   auto k_grad = lg_grad<KIND, QT, D>;
   auto k_chol = lg_chol_all<KIND, QT, D>;
   cudaError_t e;
-  e = cudaFuncSetAttribute(k_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+  constexpr size_t UPD_SMEM = UpdSmem<KIND, QT, D>::BYTES;
+  e = cudaFuncSetAttribute(k_upd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UPD_SMEM);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(lg_update)", e);
   constexpr size_t CHOL_SMEM = CholAllSmem<KIND, QT, D>::BYTES;
   cudaFuncSetAttribute(k_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM);
@@ -171,7 +172,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
       const int build = (J0 == 0) ? 1 : 0;
       for (int j = J0; j < J1; ++j) {
         if (build || j > J0)
-          k_upd<<<dim3(N - j, B), blk, C::SMEM_BYTES, st>>>(A, 0, j, J0, j, build);
+          k_upd<<<dim3(N - j, B), blk, UPD_SMEM, st>>>(A, 0, j, J0, j, build);
         lg_diag<<<dim3(1, B), blk, LG_DIAG_SMEM, st>>>(A, j);
         if (j + 1 < N) lg_trsm<<<dim3(N - j - 1, B), blk, LG_TRSM_SMEM, st>>>(A, j);
       }
@@ -191,7 +192,7 @@ int launch_large(const pgm::LargeArgs& A, int want_grad, cudaStream_t st, int pr
         k_utc<<<dim3(tc_grid(Mt), B), TC_THREADS, TS_::bytes(nst), st>>>(A, J0, J1, build, nst, halfp, tc_fold());
       } else if (J1 < N) {
         const int M = N - J1;
-        k_upd<<<dim3(M * (M + 1) / 2, B), blk, C::SMEM_BYTES, st>>>(A, 1, J1, J0, J1, build);
+        k_upd<<<dim3(M * (M + 1) / 2, B), blk, UPD_SMEM, st>>>(A, 1, J1, J0, J1, build);
       }
     }
     lg_ladder<<<(B + 255) / 256, 256, 0, st>>>(A);
