@@ -207,7 +207,7 @@ int narrow(const double* src, float* dst, size_t n, cudaStream_t st) {
 }
 
 template <int KIND, int QT, int D>
-int fused_blocks_per_sm() { return pgm::Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024 ? 2 : 1; }
+int fused_blocks_per_sm() { return pgm::Cfg<KIND, QT, D>::F_BYTES <= 113 * 1024 ? 2 : 1; }
 int fused_occ_dispatch(int d, int Q, int kernel_kind) {
   PGM_DISPATCH(fused_blocks_per_sm);
   return 1;

@@ -291,6 +291,16 @@ struct Cfg {
   static constexpr int PAR_END = PAR_BAR + 12;
   static constexpr int SM_TOTAL = SM_PAR + PAR_END + 8;
   static constexpr size_t SMEM_BYTES = (size_t)SM_TOTAL * sizeof(double);
+  // Layout of the FUSED kernels (sm_mll_grad_kernel / sm_fit_kernel).  Kinds whose full layout does
+  // not fit two blocks per SM (ARD 2-D SM-4, SM-8, ...) run LEAN when their fields fit one ring stage:
+  // the per-point fields live in stage 0, fetched behind the k-loop (as lg_chol_all does), at the
+  // price of the look-ahead across job boundaries in the P and G phases - two resident blocks
+  // overlap more than the look-ahead did (r02z: C5 share 113.1 -> see DESIGN.md 4.1).
+  static constexpr bool LEAN = (SMEM_BYTES > 113 * 1024) && (2 * NF * TS <= 2 * OPBUF);
+  static constexpr int F_ROW = LEAN ? SM_STAGES : SM_ROW;
+  static constexpr int F_COL = F_ROW + NF * TS;
+  static constexpr int F_PAR = LEAN ? SM_ROW : SM_PAR;     // SM_ROW = first offset behind the S tile
+  static constexpr size_t F_BYTES = (size_t)(F_PAR + PAR_END + 8) * sizeof(double);
 };
 
 // per-block global scratch layout (doubles)
@@ -1173,9 +1183,15 @@ struct PipeState {
 };
 
 template <int KIND, int QT, int D>
+__device__ __forceinline__ void pipe_init_at(double* par, PipeState& ps);
+template <int KIND, int QT, int D>
 __device__ __forceinline__ void pipe_init(double* sm, PipeState& ps) {
+  pipe_init_at<KIND, QT, D>(sm + Cfg<KIND, QT, D>::SM_PAR, ps);
+}
+template <int KIND, int QT, int D>
+__device__ __forceinline__ void pipe_init_at(double* par, PipeState& ps) {
   using C = Cfg<KIND, QT, D>;
-  const unsigned bars = smem_u32(sm + C::SM_PAR + C::PAR_BAR);
+  const unsigned bars = smem_u32(par + C::PAR_BAR);
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 8 * (2 + s), NTHREADS / 32); }
     for (int s = 0; s < 3; ++s) { mbar_init(bars + 8 * (4 + s), 1); mbar_init(bars + 8 * (7 + s), NTHREADS / 32); }
@@ -1215,9 +1231,9 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double* R = S;               // afterwards: resident X_jj / X_ii operand image (= stage 2 in G)
   double* Cst = stages + 2 * OPBUF;   // stage 1: staging of the register-resident A operand
   double* scr = stages + S_ELEMS;     // 256 doubles behind S2
-  double* rowv = sm + C::SM_ROW;
-  double* colv = sm + C::SM_COL;
-  double* par = sm + C::SM_PAR;
+  double* rowv = sm + C::F_ROW;
+  double* colv = sm + C::F_COL;
+  double* par = sm + C::F_PAR;
   double* theta = par + C::PAR_THETA;
   double* jac = par + C::PAR_JAC;
   double* wq = par + C::PAR_W;
@@ -1229,9 +1245,10 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
   double* zi = par + C::PAR_ZI;
   double* dinv = par + C::PAR_DINV;
   double* tab = par + C::PAR_TAB;
-  int* s_fail = reinterpret_cast<int*>(sm + C::SM_PAR + C::PAR_END);
+  int* s_fail = reinterpret_cast<int*>(sm + C::F_PAR + C::PAR_END);
   const unsigned bars = smem_u32(par + C::PAR_BAR);
   const unsigned rbar = bars + 8 * 10;
+  constexpr bool LEAN = C::LEAN;
 
   PGM_PROF_START();
   __syncthreads();
@@ -1361,15 +1378,22 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         // done.  No look-ahead across diagonal jobs (S2 aliases the stages there).
         int ni = i + 1, nj = j;
         if (ni >= N) { ni = j + 1; nj = j + 1; }
-        const int nnk = (j >= 1 && i != j && ni < N) ? nj : 0;
+        const int nnk = (!LEAN && j >= 1 && i != j && ni < N) ? nj : 0;
         auto tA = [&](int k) { return tile(i, k); };
         auto tB = [&](int k) { return tile(j, k); };
         auto nA = [&](int k) { return tile(ni, k); };
         auto nB = [&](int k) { return tile(nj, k); };
-        auto pf = [&]() { prefetch_side(rowv, i, false); prefetch_side(colv, j, false); };
+        auto pf = [&]() { if (!LEAN) { prefetch_side(rowv, i, false); prefetch_side(colv, j, false); } };
         if (i == j) pre = gemm_stream<M_FULL, true, 2>(acc, r2, j, tA, tB, pre, nnk, nA, nB, pf);
         else pre = gemm_stream<M_FULL, false, 2>(acc, r2, j, tA, tB, pre, nnk, nA, nB, pf);
         __syncthreads();
+        if (LEAN) {   // the ring is idle (no look-ahead): the fields of this job go into stage 0
+          prefetch_side(rowv, i, false);
+          prefetch_side(colv, j, false);
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncthreads();
+        }
         PGM_PROF(1);
         // epilogue: C = Ktilde_ij - acc (diagonal tiles: lower triangle only).  The
         // accumulators are parked in stage 1 (the image the next product reads as its A
@@ -1599,16 +1623,23 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         zero_acc(acc);
         int ni = i, nj = j + 1;
         if (nj > i) { ni = i + 1; nj = 0; }
-        const int nnk = (ni < N) ? N - ni : 0;
+        const int nnk = (!LEAN && ni < N) ? N - ni : 0;
         // Kinv_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}: both operands are the stored X^T tiles
         auto tA = [&](int kk) { return kk == 0 ? tileT(i) : tile(i + kk, i); };
         auto tB = [&](int kk) { return (kk == 0 && i == j) ? tileT(j) : tile(i + kk, j); };
         auto nA = [&](int kk) { return kk == 0 ? tileT(ni) : tile(ni + kk, ni); };
         auto nB = [&](int kk) { return (kk == 0 && ni == nj) ? tileT(nj) : tile(ni + kk, nj); };
-        auto pf = [&]() { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); };
+        auto pf = [&]() { if (!LEAN) { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); } };
         if (i == j) pre = gemm_stream<M_A_GE, true, 2>(acc, r2, N - i, tA, tB, pre, nnk, nA, nB, pf);
         else pre = gemm_stream<M_A_GE, false, 2>(acc, r2, N - i, tA, tB, pre, nnk, nA, nB, pf);
         __syncthreads();
+        if (LEAN) {
+          prefetch_side(rowv, i, true);
+          prefetch_side(colv, j, true);
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncthreads();
+        }
         PGM_PROF(10);
         // K^-1 tile parked in R (free in this phase); rolled, branch-free contraction
         store_acc_tile(acc, R, 1.0);
@@ -1703,16 +1734,16 @@ __device__ __forceinline__ Scratch make_scratch(double* base, int n_max) {
 // kernels
 // ------------------------------------------------------------------------------------
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::F_BYTES <= 113 * 1024) ? 2 : 1)
     sm_mll_grad_kernel(EvalArgs A) {
   extern __shared__ __align__(16) double sm[];
   Scratch sc = make_scratch<KIND, QT, D>(A.ws + (size_t)blockIdx.x * A.ws_per_block, A.n_max);
   const int P = param_count<KIND, QT, D>(A.Q, (A.flags & PGM_FLAG_LEARN_NOISE) != 0);
   PipeState ps;
-  pipe_init<KIND, QT, D>(sm, ps);
+  pipe_init_at<KIND, QT, D>(sm + Cfg<KIND, QT, D>::F_PAR, ps);
   // broadcast slot of the scheduler: in the spare words behind s_fail (static shared memory would
   // push the block over the two-per-SM limit)
-  int* s_next = reinterpret_cast<int*>(sm + Cfg<KIND, QT, D>::SM_PAR + Cfg<KIND, QT, D>::PAR_END) + 4;
+  int* s_next = reinterpret_cast<int*>(sm + Cfg<KIND, QT, D>::F_PAR + Cfg<KIND, QT, D>::PAR_END) + 4;
   const LcSched lsc = sched_init(A, s_next);
   for (int b = next_lightcurve(A, lsc, -1, s_next); b >= 0; b = next_lightcurve(A, lsc, b, s_next)) {
     double* gout = A.grad ? A.grad + (size_t)b * P : nullptr;
@@ -1862,14 +1893,14 @@ __device__ __forceinline__ double optim_update(double p, double g, double& m, do
 
 // whole training loop of trainers.py:177-207 per light curve, on device
 template <int KIND, int QT, int D>
-__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::F_BYTES <= 113 * 1024) ? 2 : 1)
     sm_fit_kernel(FitArgs F) {
   using C = Cfg<KIND, QT, D>;
   extern __shared__ __align__(16) double sm[];
   const EvalArgs& A = F.e;
   Scratch sc = make_scratch<KIND, QT, D>(A.ws + (size_t)blockIdx.x * A.ws_per_block, A.n_max);
   const int P = param_count<KIND, QT, D>(A.Q, (A.flags & PGM_FLAG_LEARN_NOISE) != 0);
-  double* par = sm + C::SM_PAR;
+  double* par = sm + C::F_PAR;
   double* s_raw = par + C::PAR_RAW;
   double* s_m = s_raw + C::PMAX;
   double* s_v = s_m + C::PMAX;
@@ -1877,10 +1908,10 @@ __global__ void __launch_bounds__(NTHREADS, (Cfg<KIND, QT, D>::SMEM_BYTES <= 113
   double* s_mll = par + C::PAR_FIN + C::NV + 2;
   const int tid = threadIdx.x;
   PipeState ps;
-  pipe_init<KIND, QT, D>(sm, ps);
+  pipe_init_at<KIND, QT, D>(sm + Cfg<KIND, QT, D>::F_PAR, ps);
   // broadcast slot of the scheduler: in the spare words behind s_fail (static shared memory would
   // push the block over the two-per-SM limit)
-  int* s_next = reinterpret_cast<int*>(sm + Cfg<KIND, QT, D>::SM_PAR + Cfg<KIND, QT, D>::PAR_END) + 4;
+  int* s_next = reinterpret_cast<int*>(sm + Cfg<KIND, QT, D>::F_PAR + Cfg<KIND, QT, D>::PAR_END) + 4;
   const LcSched lsc = sched_init(A, s_next);
   for (int b = next_lightcurve(A, lsc, -1, s_next); b >= 0; b = next_lightcurve(A, lsc, b, s_next)) {
     __syncthreads();

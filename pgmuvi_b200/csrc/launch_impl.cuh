@@ -21,7 +21,7 @@ int launch_eval(const pgm::EvalArgs& A0, cudaStream_t st) {
   using C = pgm::Cfg<KIND, QT, D>;
   pgm::EvalArgs A = A0;
   auto kern = pgm::sm_mll_grad_kernel<KIND, QT, D>;
-  size_t smem = C::SMEM_BYTES;
+  size_t smem = C::F_BYTES;
   if (const char* f = getenv("PGM_DEBUG_SMEM_KB")) smem = std::max(smem, (size_t)atoi(f) * 1024);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
@@ -74,10 +74,10 @@ int launch_fit(const pgm::FitArgs& F, cudaStream_t st) {
   using C = pgm::Cfg<KIND, QT, D>;
   auto kern = pgm::sm_fit_kernel<KIND, QT, D>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)C::SMEM_BYTES);
+                                       (int)C::F_BYTES);
   if (e != cudaSuccess) return cuda_fail("cudaFuncSetAttribute", e);
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pgm::NTHREADS, C::SMEM_BYTES);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, pgm::NTHREADS, C::F_BYTES);
   if (e != cudaSuccess) return cuda_fail("occupancy", e);
   if (occ < 1) return fail("kernel does not fit on an SM");
   int grid = device_sms() * occ;
@@ -86,7 +86,7 @@ int launch_fit(const pgm::FitArgs& F, cudaStream_t st) {
   F2.e.sms = device_sms();
   if (F2.e.sched && (occ != 2 || grid != 2 * F2.e.sms || getenv("PGM_STATIC_STRIDE"))) F2.e.sched = nullptr;
   if (F2.e.sched) cudaMemsetAsync(F2.e.sched, 0, PGM_SCHED_INTS * sizeof(int), st);
-  kern<<<grid, pgm::NTHREADS, C::SMEM_BYTES, st>>>(F2);
+  kern<<<grid, pgm::NTHREADS, C::F_BYTES, st>>>(F2);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail("sm_fit_kernel launch", e);
   return 0;
