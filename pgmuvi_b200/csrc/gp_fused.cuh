@@ -510,6 +510,21 @@ __device__ __forceinline__ int gemm_stream(double (&acc)[4][2][2], Ring& rg, int
                                           extra_prefetch, [](int) {});
 }
 
+// Late look-ahead (LEAN layout): thread 0 issues the FIRST chunk of the next job at the ring's current
+// position - always stage 0, every job consumes an even number of chunks - once stage 0 is free again;
+// the following gemm_stream call is told `pre = 1`.
+__device__ __forceinline__ void ring_issue_first(const Ring& rg, const double* ga, const double* gb) {
+  const int q = rg.gq, s = q % 2, use = q / 2;
+  if (use > 0) mbar_wait(rg.empty + 8 * s, (use - 1) & 1);
+  const unsigned bar = rg.full + 8 * s;
+  const unsigned dst = smem_u32(rg.stages + s * 2 * OPBUF);
+  fence_proxy_async_smem();   // stage 0 was last written by cp.async (the per-point fields)
+  if (PGM_DBG(0x100)) { mbar_arrive(bar); return; }
+  mbar_expect_tx(bar, 2 * CHUNK_BYTES);
+  bulk_g2s(dst, ga, CHUNK_BYTES, bar);
+  bulk_g2s(dst + CHUNK_BYTES, gb, CHUNK_BYTES, bar);
+}
+
 __device__ __forceinline__ void zero_acc(double (&acc)[4][2][2]) {
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
@@ -1479,6 +1494,12 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         } else {
           // L_ij = C * X_jj^T  straight from shared memory (C in stage 1, X_jj resident)
           __syncthreads();
+          if (LEAN && j >= 1 && ni < N) {
+            // the epilogue is done with the fields in stage 0: the next job's first chunk (k-tile 0 of
+            // rows ni / nj, final since column 0) travels under the triangular solve and the tile store
+            if (tid == 0) ring_issue_first(r2, nA(0), nB(0));
+            pre = 1;
+          }
           zero_acc(acc);
           if (!PGM_DBG(0x4000)) {
             compute_chunk<M_B_LE, false>(acc, Cst, R, 0, wm, wn, g, tq);
