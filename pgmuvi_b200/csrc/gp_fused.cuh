@@ -1636,6 +1636,13 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
 #pragma unroll
   for (int t = 0; t < C::NG; ++t) ga[t] = 0.0;
   double trW = 0.0;
+  // G phase of the LEAN layout: no tile is resident in this phase, so the fields take the S / R region
+  // (prefetched under the k-loop as in the full layout) and the K^-1 tile is parked in stage 1, which
+  // the one-chunk look-ahead (always stage 0) never touches - the look-ahead stays on
+  static_assert(!LEAN || 2 * C::NF * TS <= S_ELEMS, "LEAN: the fields must fit the S region in the G phase");
+  double* rowg = LEAN ? S : rowv;
+  double* colg = LEAN ? S + C::NF * TS : colv;
+  double* parkg = LEAN ? Cst : R;
   {
     int pre = 0;
     if (tid == 0) bulk_wait_all();
@@ -1644,35 +1651,28 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
         zero_acc(acc);
         int ni = i, nj = j + 1;
         if (nj > i) { ni = i + 1; nj = 0; }
-        const int nnk = (!LEAN && ni < N) ? N - ni : 0;
+        const int nnk = (ni < N) ? N - ni : 0;
         // Kinv_ij = sum_kk X_{i+kk,i}^T X_{i+kk,j}: both operands are the stored X^T tiles
         auto tA = [&](int kk) { return kk == 0 ? tileT(i) : tile(i + kk, i); };
         auto tB = [&](int kk) { return (kk == 0 && i == j) ? tileT(j) : tile(i + kk, j); };
         auto nA = [&](int kk) { return kk == 0 ? tileT(ni) : tile(ni + kk, ni); };
         auto nB = [&](int kk) { return (kk == 0 && ni == nj) ? tileT(nj) : tile(ni + kk, nj); };
-        auto pf = [&]() { if (!LEAN) { prefetch_side(rowv, i, true); prefetch_side(colv, j, true); } };
+        auto pf = [&]() { prefetch_side(rowg, i, true); prefetch_side(colg, j, true); };
         if (i == j) pre = gemm_stream<M_A_GE, true, 2>(acc, r2, N - i, tA, tB, pre, nnk, nA, nB, pf);
         else pre = gemm_stream<M_A_GE, false, 2>(acc, r2, N - i, tA, tB, pre, nnk, nA, nB, pf);
         __syncthreads();
-        if (LEAN) {
-          prefetch_side(rowv, i, true);
-          prefetch_side(colv, j, true);
-          cp_async_commit();
-          cp_async_wait<0>();
-          __syncthreads();
-        }
         PGM_PROF(10);
-        // K^-1 tile parked in R (free in this phase); rolled, branch-free contraction
-        store_acc_tile(acc, R, 1.0);
-        const double* al_r = rowv + C::NFB * TS;
-        const double* al_c = colv + C::NFB * TS;
+        // K^-1 tile parked (R, free in this phase; LEAN: stage 1); rolled, branch-free contraction
+        store_acc_tile(acc, parkg, 1.0);
+        const double* al_r = rowg + C::NFB * TS;
+        const double* al_c = colg + C::NFB * TS;
 #pragma unroll 1
         for (int p8 = PGM_DBG(0x8000) ? 8 : 0; p8 < 8; ++p8) {
           const int mi = p8 >> 1, ni2 = p8 & 1;
           if (i == j && frag_mt(wm, mi) < frag_nt(wn, ni2)) continue;
           const int r = frag_row(wm, mi, g), c0 = frag_col(wn, ni2, tq, 0);
           const int gi = i * TS + r;
-          const double2 kinv = *reinterpret_cast<const double2*>(R + img(r, c0));
+          const double2 kinv = *reinterpret_cast<const double2*>(parkg + img(r, c0));
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int gj = j * TS + c0 + e;
@@ -1681,7 +1681,7 @@ __device__ int eval_lightcurve(const EvalArgs& A, int b, const double* raw, doub
             if (gi == gj) trW += W;
             const double wgt = (gi == gj) ? W : 2.0 * W;
             if (!PGM_DBG(0x400))
-              k_grad_entry<KIND, QT, D>(rowv, colv, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
+              k_grad_entry<KIND, QT, D>(rowg, colg, r, c0 + e, wreg, areg, lam, tab, wgt, ga);
           }
         }
         PGM_PROF(11);
