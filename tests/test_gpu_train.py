@@ -533,3 +533,44 @@ def test_flicker_model_parity_and_fit(cuda_device):
     assert res["loss"][-1] < res["loss"][0]
     keys = [k for k in res if "lengthscale" in k or "outputscale" in k]
     assert any("kernels.0.kernels.1" in k for k in keys)     # flicker parameters are in the history
+
+
+@pytest.mark.parametrize("name,kind,Q", [("sm8_1d", 0, 8), ("ard2d_prodsum", 1, 4),
+                                         ("ard2d_sumprod", 2, 4), ("sep_sm8_rbf", 3, 8)])
+def test_one_launch_fit_of_the_lean_kinds_equals_a_loop_of_evaluations(cuda_device, name, kind, Q):
+    """The kinds whose fused kernels run in the LEAN shared-memory layout (per-point fields in the idle
+    ring stage, two blocks per SM: ARD 2-D SM-4, SM-8, separable SM-8): the whole AdamW loop in one
+    launch (`pgm_sm_fit_f64`) must reproduce a host loop of `pgm_sm_mll_grad_f64` +
+    `pgm_optim_step_f64`, and the evaluation must agree with the staged engine (own kernels, own
+    layouts)."""
+    from pgmuvi_b200 import ops, synthetic as S
+    if kind == 0:
+        bt = S.make_batch_1d(3, 200, Q=Q, seed0=77)
+    elif kind in (1, 2):
+        bt = S.make_batch_2d(3, 3, 60, Q=Q, seed0=77)
+    else:
+        bt = S.make_batch_sep(3, 3, 60, Q=Q, kind=kind, seed0=77)
+    T = lambda a, dt=torch.float64: torch.tensor(np.asarray(a), dtype=dt, device=cuda_device)
+    x, y, nz, raw0, lb, ub = (T(bt[k]) for k in ("x", "y", "noise", "raw", "lb", "ub"))
+    kinds = T(bt["kinds"], torch.int32)
+    m_f, g_f, i_f = ops.sm_mll_grad(x, y, nz, raw0, kinds, lb, ub, None, kind, Q, False, True)
+    m_s, g_s, i_s = ops.sm_mll_grad_staged(x, y, nz, raw0, kinds, lb, ub, None, kind, Q, False, True)
+    assert int(i_f.abs().sum()) == 0 and int(i_s.abs().sum()) == 0
+    assert torch.allclose(m_f, m_s, rtol=1e-12, atol=1e-13)
+    assert float(((g_f - g_s).abs().amax(1) / g_s.abs().amax(1)).max()) < 1e-9
+    iters, lr = 6, 0.05
+    raw_fit = raw0.clone()
+    loss_hist, raw_hist, n_iter, info = ops.sm_fit(x, y, nz, raw_fit, kinds, lb, ub, None, kind, Q, False,
+                                                  2, lr, 0.9, 0.999, 1e-8, 0.01, iters, iters, 0.0, 30,
+                                                  True)
+    raw = raw0.clone()
+    m, v = torch.zeros_like(raw), torch.zeros_like(raw)
+    losses = []
+    for it in range(iters):
+        mll, grad, code = ops.sm_mll_grad(x, y, nz, raw, kinds, lb, ub, None, kind, Q, False, True)
+        losses.append(-mll)
+        ops.optim_step(raw, grad, m, v, None, 2, lr, 0.9, 0.999, 1e-8, 0.01, it + 1)
+    assert int(info.abs().sum()) == 0 and n_iter.tolist() == [iters] * 3
+    assert torch.allclose(loss_hist, torch.stack(losses), rtol=1e-10, atol=1e-12)
+    assert torch.allclose(raw_fit, raw, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(raw_hist[-1], raw, rtol=1e-10, atol=1e-12)
