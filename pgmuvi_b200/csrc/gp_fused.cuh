@@ -921,6 +921,7 @@ __device__ __forceinline__ void potrf_panel8(double* __restrict__ S, double* __r
     a0[k] *= rs;
     a1[k] *= rs;
   }
+  __syncwarp();   // every lane has read the pivot block (top) before lanes 0..7 overwrite its rows
 #pragma unroll
   for (int k2 = 0; k2 < 4; ++k2) {
     if (r0 < TS)
